@@ -1,0 +1,101 @@
+/* lcrsim.h -- C-ABI of liblcrsim.so: the B200 batched replacement for the per-step hot path of
+ * gym_lowcostrobot.envs.{ReachCube,PushCube,LiftCube,PickPlaceCube,StackTwoCubes}Env.
+ *
+ * Every entry point below replaces a piece of the reference's Python->MuJoCo interface; the
+ * reference file:line it stands in for is cited per function.  All `d_*` pointers are BORROWED
+ * DEVICE pointers (owned by the caller, e.g. torch tensors); the library never frees them and
+ * never synchronises the host -- each call only enqueues work on `stream` (a cudaStream_t passed
+ * as void*; NULL = the legacy default stream).  Calls return 0 on success, non-zero on error with
+ * a message available from lcr_last_error().  One handle per device; a handle is not thread-safe,
+ * distinct handles are independent.  No torch types appear in any signature.
+ */
+#ifndef LCRSIM_H_
+#define LCRSIM_H_
+
+#include <stdint.h>
+#include "lcr_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct LcrSim LcrSim;
+
+enum { LCR_F32 = 0, LCR_F64 = 1 };
+
+/* Observation record written by lcr_step/lcr_reset, row-major [n_envs][obs_dim] float32
+ * (reference get_observation, reach_cube_env.py:281-295, push_cube_env.py:291-306,
+ * stack_two_cubes_env.py:290-305; all `.astype(np.float32)`):
+ *   Reach/Lift      : arm_qpos[6] arm_qvel[6] cube_pos[3]                      (15)
+ *   Push/PickPlace  : arm_qpos[6] arm_qvel[6] target_pos[3] cube_pos[3]        (18)
+ *   Stack           : arm_qpos[6] arm_qvel[6] cube_red_pos[3] cube_blue_pos[3] (18) */
+int lcr_obs_dim(int task);
+/* Action width: {joint:5, ee:3} + (block_gripper ? 0 : 1)   (reach_cube_env.py:95-97). */
+int lcr_action_dim(const LcrEnvCfg* cfg);
+
+/* Replaces MjModel.from_xml_path + MjData(model) (reach_cube_env.py:89-90 and the same two lines
+ * in the other four envs): uploads the compiled model constants and allocates the SoA state of
+ * n_envs instances on `device`.  `hull_verts` is a HOST array [model->nvert][3] (body frame).
+ * `precision` LCR_F32 is the product path; LCR_F64 runs the same kernels in double for
+ * verification against the CPU oracle.  State is initialised like mj_resetData (qpos0, zeros). */
+int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg* cfg, int n_envs, int device,
+               int precision, LcrSim** out);
+int lcr_destroy(LcrSim* sim);
+
+/* Replaces Env.reset(seed=...)'s seeding (gymnasium: np_random = Generator(PCG64(SeedSequence(seed)))).
+ * `h_state` is a HOST array [n_envs][4] of uint64 = (state_hi, state_lo, inc_hi, inc_lo) of each
+ * env's numpy PCG64 bit generator; the device continues that exact stream for every later draw. */
+int lcr_seed(LcrSim* sim, const uint64_t* h_state, void* stream);
+
+/* Replaces Env.reset (reach_cube_env.py:297-311, push_cube_env.py:308-328, lift_cube_env.py:306-320,
+ * pick_place_cube_env.py:316-336, stack_two_cubes_env.py:307-324): for every env with
+ * d_mask[i] != 0 (all envs if d_mask is NULL) draw cube (and target / second cube) positions
+ * from the env's PCG64 stream, write qpos, run mj_forward, and write the observation row.
+ * Like the reference it does NOT reset qvel / ctrl / warmstart / time.  Rows of unmasked envs in
+ * d_obs are left untouched. */
+int lcr_reset(LcrSim* sim, const uint8_t* d_mask, float* d_obs, void* stream);
+
+/* Replaces Env.step (reach_cube_env.py:313-333 = apply_action :223-279 incl. inverse_kinematics
+ * :148-221 and the 20x mj_step loop :276-277, get_observation :281-295, is_success/compute_reward
+ * :335-348; and the same methods of the other four envs) plus TimeLimit (gym_lowcostrobot/__init__.py).
+ * d_actions: [n_envs][action_dim] float32.  Outputs: d_obs [n_envs][obs_dim] f32, d_reward [n_envs]
+ * f32, d_terminated / d_truncated / d_success [n_envs] uint8. */
+int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated,
+             uint8_t* d_truncated, uint8_t* d_success, void* stream);
+
+/* Replaces direct reads/writes of MjData the reference performs (data.qpos / data.qvel / data.ctrl,
+ * reach_cube_env.py:182,185,252,273,285-294,305-306) and provides checkpoint/resume.  Row-major
+ * DEVICE arrays of float64 regardless of precision: qpos [n][nq], qvel [n][nv], ctrl [n][6],
+ * warm (qacc_warmstart) [n][nv], aux [n][LCR_NAUX] = time, target[3], site_xpos[3],
+ * cube_xpos[3*2]; ints [n][LCR_NINT] = elapsed_steps, needs_reset.  Any pointer may be NULL. */
+#define LCR_NAUX 13
+#define LCR_NINT 2
+int lcr_get_state(LcrSim* sim, double* d_qpos, double* d_qvel, double* d_ctrl, double* d_warm, double* d_aux,
+                  int32_t* d_ints, void* stream);
+int lcr_set_state(LcrSim* sim, const double* d_qpos, const double* d_qvel, const double* d_ctrl,
+                  const double* d_warm, const double* d_aux, const int32_t* d_ints, void* stream);
+
+/* Advance `n` raw substeps (mujoco.mj_step, reach_cube_env.py:277) with the current ctrl, or with
+ * n == 0 run mj_forward only (reach_cube_env.py:186,309).  Used by parity tests of the one-substep map. */
+int lcr_substeps(LcrSim* sim, int n, void* stream);
+
+/* Batched equivalent of the IK helper (inverse_kinematics, reach_cube_env.py:148-221; same text in all
+ * envs; legacy interface SimulatedRobot.inverse_kinematics_reg, simulated_robot.py:139-186):
+ * damped-least-squares iterations from the env's current arm qpos towards d_ee_target [n][3] f32,
+ * result in d_q_out [n][6] f32.  Does not modify the simulation state (unlike the in-step IK). */
+int lcr_ik(LcrSim* sim, const float* d_ee_target, float* d_q_out, void* stream);
+
+/* Diagnostics of the last lcr_step/lcr_substeps: DEVICE array [n][LCR_NDIAG] int32 =
+ * ncon, nefc, solver iterations (last substep), max nefc over the step, overflow count, nan resets. */
+#define LCR_NDIAG 6
+int lcr_get_diag(LcrSim* sim, int32_t* d_diag, void* stream);
+
+int lcr_n_envs(const LcrSim* sim);
+int lcr_kernel_launches(const LcrSim* sim); /* kernels launched by this handle so far */
+const char* lcr_last_error(void);
+const char* lcr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCRSIM_H_ */
