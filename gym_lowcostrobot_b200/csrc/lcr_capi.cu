@@ -1,0 +1,311 @@
+// lcr_capi.cu -- host side of liblcrsim.so: the C-ABI declared in include/lcrsim.h.
+// Builds the device model (incl. the contact-parameter classes from MuJoCo's geom mixing rule),
+// owns the SoA state buffers, and enqueues the kernels of lcr_kernels.cuh.  No CPU fallback: if
+// CUDA is unavailable every call fails with an error.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lcr_device.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& msg) { g_err = msg; return 1; }
+#define CUDA_OK(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));   \
+  } while (0)
+
+constexpr double kMinVal = 1e-15, kMinImp = 1e-4, kMaxImp = 0.9999, kMinMu = 1e-5;
+
+struct Mixed {
+  int dim;
+  double fr[3], solref[2], solimp[5];
+};
+
+// MuJoCo contact parameter mixing: higher priority wins; on a tie max condim, element-wise max
+// friction, solmix-weighted solref / solimp.
+Mixed mix(const LcrModel& m, int g1, int g2) {
+  Mixed o;
+  const int p1 = m.geom_priority[g1], p2 = m.geom_priority[g2];
+  if (p1 != p2) {
+    const int g = p1 > p2 ? g1 : g2;
+    o.dim = m.geom_condim[g];
+    std::copy(m.geom_friction[g], m.geom_friction[g] + 3, o.fr);
+    std::copy(m.geom_solref[g], m.geom_solref[g] + 2, o.solref);
+    std::copy(m.geom_solimp[g], m.geom_solimp[g] + 5, o.solimp);
+    return o;
+  }
+  o.dim = std::max(m.geom_condim[g1], m.geom_condim[g2]);
+  for (int k = 0; k < 3; k++) o.fr[k] = std::max(m.geom_friction[g1][k], m.geom_friction[g2][k]);
+  const double s1 = m.geom_solmix[g1], s2 = m.geom_solmix[g2];
+  double w;
+  if (s1 >= kMinVal && s2 >= kMinVal) w = s1 / (s1 + s2);
+  else if (s1 < kMinVal && s2 < kMinVal) w = 0.5;
+  else w = s1 < kMinVal ? 0.0 : 1.0;
+  const bool pos = m.geom_solref[g1][0] > 0 && m.geom_solref[g2][0] > 0;
+  for (int k = 0; k < 2; k++)
+    o.solref[k] = pos ? w * m.geom_solref[g1][k] + (1 - w) * m.geom_solref[g2][k] : std::min(m.geom_solref[g1][k], m.geom_solref[g2][k]);
+  for (int k = 0; k < 5; k++) o.solimp[k] = w * m.geom_solimp[g1][k] + (1 - w) * m.geom_solimp[g2][k];
+  return o;
+}
+
+template <typename T>
+void fill_par(CPar<T>& p, int dim, const double* fr3, const double* solref, const double* solimp, double timestep) {
+  const double f[5] = {std::max(kMinMu, fr3[0]), std::max(kMinMu, fr3[0]), std::max(kMinMu, fr3[1]), std::max(kMinMu, fr3[2]),
+                       std::max(kMinMu, fr3[2])};
+  for (int k = 0; k < 5; k++) p.fr[k] = (T)f[k];
+  const double si[5] = {std::min(std::max(solimp[0], kMinImp), kMaxImp), std::min(std::max(solimp[1], kMinImp), kMaxImp),
+                        std::max(0.0, solimp[2]), std::min(std::max(solimp[3], kMinImp), kMaxImp), std::max(1.0, solimp[4])};
+  for (int k = 0; k < 5; k++) p.si[k] = (T)si[k];
+  const double dmax = si[1];
+  double K, B;
+  if (solref[0] > 0) {
+    const double tc = std::max(solref[0], 2 * timestep), dr = solref[1];  // refsafe
+    K = 1 / std::max(kMinVal, dmax * dmax * tc * tc * dr * dr);
+    B = 2 / std::max(kMinVal, dmax * tc);
+  } else {
+    K = -solref[0] / std::max(kMinVal, dmax * dmax);
+    B = -solref[1] / std::max(kMinVal, dmax);
+  }
+  p.K = (T)K; p.B = (T)B; p.dim = dim;
+}
+
+template <typename T>
+void build_model(const LcrModel& m, const LcrEnvCfg& c, DevModel<T>& d) {
+  std::memset(&d, 0, sizeof d);
+  d.task = m.task; d.ncube = m.ncube; d.nq = m.nq; d.nv = m.nv; d.nmesh = m.nmesh; d.nvert = m.nvert; d.npair = m.npair;
+  d.site_body = m.site_body; d.iterations = m.iterations; d.ls_iterations = m.ls_iterations;
+  d.timestep = (T)m.timestep; d.impratio = (T)m.impratio; d.tolerance = (T)m.tolerance; d.ls_tolerance = (T)m.ls_tolerance;
+  d.meaninertia = (T)m.meaninertia;
+  for (int k = 0; k < 3; k++) { d.gravity[k] = (T)m.gravity[k]; d.site_pos[k] = (T)m.site_pos[k]; }
+  for (int b = 0; b < LCR_NABODY; b++) {
+    for (int k = 0; k < 3; k++) { d.body_pos[b][k] = (T)m.body_pos[b][k]; d.body_ipos[b][k] = (T)m.body_ipos[b][k]; d.body_inertia[b][k] = (T)m.body_inertia[b][k]; }
+    for (int k = 0; k < 4; k++) { d.body_quat[b][k] = (T)m.body_quat[b][k]; d.body_iquat[b][k] = (T)m.body_iquat[b][k]; }
+    d.body_mass[b] = (T)m.body_mass[b];
+    d.body_invweight0[b][0] = (T)m.body_invweight0[b][0]; d.body_invweight0[b][1] = (T)m.body_invweight0[b][1];
+  }
+  static const double qpos0[5][2][3] = {{{0, 0.2, 0.01}}, {{0, 0.2, 0.01}}, {{0, 0.2, 0.01}}, {{0, 0.2, 0.01}}, {{0.1, 0.1, 0.01}, {-0.1, -0.1, 0.01}}};
+  for (int cb = 0; cb < m.ncube; cb++) {
+    d.body_invweight0[LCR_NABODY + cb][0] = (T)m.cube_invweight0[cb][0]; d.body_invweight0[LCR_NABODY + cb][1] = (T)m.cube_invweight0[cb][1];
+    d.cube_mass[cb] = (T)m.cube_mass[cb]; d.cube_inertia[cb] = (T)m.cube_inertia[cb][0];
+    for (int k = 0; k < 3; k++) { d.cube_size[cb][k] = (T)m.cube_size[cb][k]; d.cube_qpos0[cb][k] = (T)qpos0[m.task][cb][k]; }
+  }
+  for (int j = 0; j < LCR_NARM; j++) {
+    for (int k = 0; k < 3; k++) d.jnt_axis[j][k] = (T)m.jnt_axis[j][k];
+    for (int k = 0; k < 2; k++) { d.jnt_range[j][k] = (T)m.jnt_range[j][k]; d.jnt_frcrange[j][k] = (T)m.jnt_frcrange[j][k]; d.act_ctrlrange[j][k] = (T)m.act_ctrlrange[j][k]; }
+    d.jnt_armature[j] = (T)m.jnt_armature[j]; d.jnt_damping[j] = (T)m.jnt_damping[j]; d.dof_invweight0[j] = (T)m.dof_invweight0[j];
+    d.act_kp[j] = (T)m.act_kp[j]; d.act_kv[j] = (T)m.act_kv[j];
+    const double fr[3] = {1, 0.005, 0.0001};
+    fill_par(d.par_limit[j], 1, fr, m.jnt_solref[j], m.jnt_solimp[j], m.timestep);
+  }
+  for (int g = 0; g < m.nmesh; g++) {
+    d.mesh_body[g] = m.mesh_body[g]; d.mesh_vertadr[g] = m.mesh_vertadr[g]; d.mesh_vertnum[g] = m.mesh_vertnum[g];
+    for (int k = 0; k < 3; k++) { d.mesh_center[g][k] = (T)m.mesh_center[g][k]; d.mesh_half[g][k] = (T)m.mesh_half[g][k]; }
+    d.mesh_rbound[g] = (T)m.mesh_rbound[g];
+  }
+  const int gfloor = m.nmesh;
+  for (int cb = 0; cb < m.ncube; cb++) {
+    Mixed x = mix(m, gfloor, gfloor + 1 + cb);
+    fill_par(d.par_floor_cube[cb], x.dim, x.fr, x.solref, x.solimp, m.timestep);
+    for (int g = 0; g < m.nmesh; g++) {
+      // geom order follows MuJoCo's type ordering: box (cube) is geom1, mesh is geom2
+      Mixed y = mix(m, gfloor + 1 + cb, g);
+      fill_par(d.par_cube_mesh[cb][g], y.dim, y.fr, y.solref, y.solimp, m.timestep);
+    }
+  }
+  if (m.ncube == 2) {
+    Mixed x = mix(m, gfloor + 1, gfloor + 2);
+    fill_par(d.par_cube_cube, x.dim, x.fr, x.solref, x.solimp, m.timestep);
+  }
+  for (int g = 0; g < m.nmesh; g++) {
+    Mixed x = mix(m, gfloor, g);
+    fill_par(d.par_floor_mesh[g], x.dim, x.fr, x.solref, x.solimp, m.timestep);
+  }
+  for (int p = 0; p < m.npair; p++) {
+    d.pair_g1[p] = m.pair_g1[p]; d.pair_g2[p] = m.pair_g2[p];
+    Mixed x = mix(m, m.pair_g1[p], m.pair_g2[p]);
+    fill_par(d.par_mesh_mesh[p], x.dim, x.fr, x.solref, x.solimp, m.timestep);
+  }
+  d.action_mode = c.action_mode; d.block_gripper = c.block_gripper; d.reward_type = c.reward_type; d.n_substeps = c.n_substeps;
+  d.max_episode_steps = c.max_episode_steps; d.autoreset = c.autoreset; d.collision_mask = c.collision_mask;
+  d.distance_threshold = (T)c.distance_threshold; d.height_threshold = (T)c.height_threshold;
+  for (int k = 0; k < 3; k++) { d.cube_low[k] = c.cube_low[k]; d.cube_high[k] = c.cube_high[k]; d.target_low[k] = c.target_low[k]; d.target_high[k] = c.target_high[k]; }
+}
+
+template <typename T>
+struct Impl {
+  DevModel<T>* dm = nullptr;
+  T* verts = nullptr;
+  DevState<T> s{};
+  int nf = 0;
+
+  int create(const LcrModel& m, const double* hv, const LcrEnvCfg& c, int n) {
+    DevModel<T> h;
+    build_model(m, c, h);
+    CUDA_OK(cudaMalloc(&dm, sizeof h));
+    CUDA_OK(cudaMemcpy(dm, &h, sizeof h, cudaMemcpyHostToDevice));
+    std::vector<T> v(4 * (size_t)std::max(m.nvert, 1), (T)0);
+    for (int i = 0; i < m.nvert; i++) for (int k = 0; k < 3; k++) v[4 * (size_t)i + k] = (T)hv[3 * (size_t)i + k];
+    CUDA_OK(cudaMalloc(&verts, v.size() * sizeof(T)));
+    CUDA_OK(cudaMemcpy(verts, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    nf = m.nq + 2 * m.nv + LCR_NARM + LCR_NAUX;
+    s.n = n;
+    CUDA_OK(cudaMalloc(&s.st, sizeof(T) * (size_t)nf * n));
+    CUDA_OK(cudaMalloc(&s.ints, sizeof(int32_t) * LCR_NINT * (size_t)n));
+    CUDA_OK(cudaMalloc(&s.rng, sizeof(unsigned long long) * 4 * (size_t)n));
+    CUDA_OK(cudaMalloc(&s.diag, sizeof(int32_t) * LCR_NDIAG * (size_t)n));
+    lcr::Launch<T>::prepare(m.ncube);
+    lcr::Launch<T>::init_state(m.ncube, dm, s, 0);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+  }
+  void destroy() {
+    cudaFree(dm); cudaFree(verts); cudaFree(s.st); cudaFree(s.ints); cudaFree(s.rng); cudaFree(s.diag);
+  }
+};
+
+}  // namespace
+
+struct LcrSim {
+  int precision, device, n, ncube, task, launches;
+  LcrModel model;
+  LcrEnvCfg cfg;
+  Impl<float> f;
+  Impl<double> d;
+};
+
+#define WITH_DEVICE(sim)                                  \
+  if (!(sim)) return fail("null handle");                 \
+  CUDA_OK(cudaSetDevice((sim)->device));
+
+extern "C" {
+
+int lcr_obs_dim(int task) { return (task == LCR_TASK_REACH || task == LCR_TASK_LIFT) ? 15 : 18; }
+int lcr_action_dim(const LcrEnvCfg* cfg) { return (cfg->action_mode ? 3 : 5) + (cfg->block_gripper ? 0 : 1); }
+
+int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg* cfg, int n_envs, int device, int precision, LcrSim** out) {
+  if (!model || !cfg || !out || (!hull_verts && model->nvert > 0)) return fail("lcr_create: null argument");
+  if (n_envs <= 0) return fail("lcr_create: n_envs must be positive");
+  if (model->ncube < 1 || model->ncube > LCR_MAXCUBE || model->nmesh > LCR_MAXMESH || model->npair > LCR_MAXPAIR)
+    return fail("lcr_create: model exceeds compiled caps");
+  if (precision != LCR_F32 && precision != LCR_F64) return fail("lcr_create: precision must be LCR_F32 or LCR_F64");
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("lcr_create: no such CUDA device");
+  CUDA_OK(cudaSetDevice(device));
+  LcrSim* s = new LcrSim();
+  s->precision = precision; s->device = device; s->n = n_envs; s->ncube = model->ncube; s->task = model->task; s->launches = 0;
+  s->model = *model; s->cfg = *cfg;
+  int rc = precision == LCR_F32 ? s->f.create(*model, hull_verts, *cfg, n_envs) : s->d.create(*model, hull_verts, *cfg, n_envs);
+  if (rc) { delete s; return rc; }
+  s->launches = 1;
+  *out = s;
+  return 0;
+}
+
+int lcr_destroy(LcrSim* sim) {
+  if (!sim) return 0;
+  cudaSetDevice(sim->device);
+  if (sim->precision == LCR_F32) sim->f.destroy(); else sim->d.destroy();
+  delete sim;
+  return 0;
+}
+
+int lcr_seed(LcrSim* sim, const uint64_t* h_state, void* stream) {
+  WITH_DEVICE(sim);
+  if (!h_state) return fail("lcr_seed: null state");
+  const size_t n = sim->n;
+  std::vector<unsigned long long> soa(4 * n);
+  for (size_t e = 0; e < n; e++) for (int k = 0; k < 4; k++) soa[k * n + e] = h_state[4 * e + k];
+  unsigned long long* dst = sim->precision == LCR_F32 ? sim->f.s.rng : sim->d.s.rng;
+  CUDA_OK(cudaMemcpyAsync(dst, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));  // soa is a temporary
+  return 0;
+}
+
+int lcr_reset(LcrSim* sim, const uint8_t* d_mask, float* d_obs, void* stream) {
+  WITH_DEVICE(sim);
+  if (sim->precision == LCR_F32) lcr::Launch<float>::reset(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_mask, d_obs, (cudaStream_t)stream);
+  else lcr::Launch<double>::reset(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_mask, d_obs, (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated,
+             uint8_t* d_success, void* stream) {
+  WITH_DEVICE(sim);
+  if (!d_actions || !d_obs || !d_reward || !d_terminated || !d_truncated || !d_success) return fail("lcr_step: null buffer");
+  if (sim->precision == LCR_F32)
+    lcr::Launch<float>::step(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
+  else
+    lcr::Launch<double>::step(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_get_state(LcrSim* sim, double* q, double* v, double* c, double* w, double* a, int32_t* i, void* stream) {
+  WITH_DEVICE(sim);
+  if (sim->precision == LCR_F32) lcr::Launch<float>::get_state(sim->ncube, sim->f.s, q, v, c, w, a, i, (cudaStream_t)stream);
+  else lcr::Launch<double>::get_state(sim->ncube, sim->d.s, q, v, c, w, a, i, (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_set_state(LcrSim* sim, const double* q, const double* v, const double* c, const double* w, const double* a, const int32_t* i, void* stream) {
+  WITH_DEVICE(sim);
+  if (sim->precision == LCR_F32) lcr::Launch<float>::set_state(sim->ncube, sim->f.s, q, v, c, w, a, i, (cudaStream_t)stream);
+  else lcr::Launch<double>::set_state(sim->ncube, sim->d.s, q, v, c, w, a, i, (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_substeps(LcrSim* sim, int n, void* stream) {
+  WITH_DEVICE(sim);
+  if (n < 0) return fail("lcr_substeps: n < 0");
+  if (sim->precision == LCR_F32) lcr::Launch<float>::substeps(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, n, (cudaStream_t)stream);
+  else lcr::Launch<double>::substeps(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, n, (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_ik(LcrSim* sim, const float* d_ee_target, float* d_q_out, void* stream) {
+  WITH_DEVICE(sim);
+  if (!d_ee_target || !d_q_out) return fail("lcr_ik: null buffer");
+  if (sim->precision == LCR_F32) lcr::Launch<float>::ik(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_ee_target, d_q_out, (cudaStream_t)stream);
+  else lcr::Launch<double>::ik(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_ee_target, d_q_out, (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_get_diag(LcrSim* sim, int32_t* d_diag, void* stream) {
+  WITH_DEVICE(sim);
+  if (!d_diag) return fail("lcr_get_diag: null buffer");
+  const int32_t* src = sim->precision == LCR_F32 ? sim->f.s.diag : sim->d.s.diag;
+  // device layout is [LCR_NDIAG][n]; callers get [n][LCR_NDIAG] via a strided 2-D copy
+  for (int k = 0; k < LCR_NDIAG; k++)
+    CUDA_OK(cudaMemcpy2DAsync(d_diag + k, sizeof(int32_t) * LCR_NDIAG, src + (size_t)k * sim->n, sizeof(int32_t), sizeof(int32_t), sim->n,
+                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int lcr_n_envs(const LcrSim* sim) { return sim ? sim->n : 0; }
+int lcr_kernel_launches(const LcrSim* sim) { return sim ? sim->launches : 0; }
+const char* lcr_last_error(void) { return g_err.c_str(); }
+const char* lcr_version(void) { return "lcrsim 0.1 (sm_100a)"; }
+int lcr_sizeof_model(void) { return (int)sizeof(LcrModel); }
+int lcr_sizeof_cfg(void) { return (int)sizeof(LcrEnvCfg); }
+
+}  // extern "C"

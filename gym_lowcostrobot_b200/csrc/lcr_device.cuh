@@ -1,0 +1,121 @@
+// lcr_device.cuh -- device-side data structures of liblcrsim (sm_100a).
+//
+// Execution model: ONE WARP PER ENVIRONMENT.  A CTA of LCR_WPB warps stages the SoA state of its
+// LCR_WPB consecutive envs from HBM into shared memory with 128-bit loads (one float4 = one field
+// of 4 consecutive envs), each warp then runs the whole control step (action map / IK -> n_substeps
+// x mj_step -> observation / reward) out of its private shared-memory workspace, and the CTA
+// stages the state back.  Small dense algebra is done with lanes <-> rows/columns and warp
+// shuffles; there is no tensor-core work on this path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lcr_model.h"
+#include "../../include/lcrsim.h"
+
+#define LCR_WPB 4          // warps (= envs) per CTA
+#define FULLMASK 0xffffffffu
+
+// contact parameter classes, precomputed on the host by the MuJoCo mixing rule
+template <typename T>
+struct CPar {
+  T fr[5];      // friction: slide, slide, spin, roll, roll
+  T K, B;       // reference stiffness / damping from solref (refsafe) and clamped dmax
+  T si[5];      // clamped solimp
+  int dim;
+};
+
+template <typename T>
+struct DevModel {
+  int task, ncube, nq, nv, nmesh, nvert, npair, site_body, iterations, ls_iterations;
+  T timestep, impratio, tolerance, ls_tolerance, meaninertia, gravity[3];
+  T body_pos[LCR_NABODY][3], body_quat[LCR_NABODY][4], body_ipos[LCR_NABODY][3], body_iquat[LCR_NABODY][4];
+  T body_mass[LCR_NABODY], body_inertia[LCR_NABODY][3], body_invweight0[LCR_NABODY + LCR_MAXCUBE][2];
+  T jnt_axis[LCR_NARM][3], jnt_range[LCR_NARM][2], jnt_armature[LCR_NARM], jnt_damping[LCR_NARM];
+  T jnt_frcrange[LCR_NARM][2], dof_invweight0[LCR_NARM], act_kp[LCR_NARM], act_kv[LCR_NARM], act_ctrlrange[LCR_NARM][2];
+  T site_pos[3];
+  T cube_mass[LCR_MAXCUBE], cube_inertia[LCR_MAXCUBE], cube_size[LCR_MAXCUBE][3], cube_qpos0[LCR_MAXCUBE][3];
+  int mesh_body[LCR_MAXMESH], mesh_vertadr[LCR_MAXMESH], mesh_vertnum[LCR_MAXMESH];
+  T mesh_center[LCR_MAXMESH][3], mesh_half[LCR_MAXMESH][3], mesh_rbound[LCR_MAXMESH];
+  int pair_g1[LCR_MAXPAIR], pair_g2[LCR_MAXPAIR];
+  // contact parameter classes
+  CPar<T> par_limit[LCR_NARM];
+  CPar<T> par_floor_cube[LCR_MAXCUBE];
+  CPar<T> par_cube_cube;
+  CPar<T> par_floor_mesh[LCR_MAXMESH];
+  CPar<T> par_cube_mesh[LCR_MAXCUBE][LCR_MAXMESH];
+  CPar<T> par_mesh_mesh[LCR_MAXPAIR];
+  // env config
+  int action_mode, block_gripper, reward_type, n_substeps, max_episode_steps, autoreset, collision_mask;
+  T distance_threshold, height_threshold;
+  double cube_low[3], cube_high[3], target_low[3], target_high[3];  // reset draws are float64 like numpy
+};
+
+// Global (HBM) state, SoA [field][env].  Field order of `st` (type T): qpos[nq] | qvel[nv] | ctrl[6] |
+// warm[nv] | aux[LCR_NAUX] (time, target[3], site_xpos[3], cube_xpos[6]).
+template <typename T>
+struct DevState {
+  T* st;                    // [NF][n]
+  int32_t* ints;            // [LCR_NINT][n]  elapsed, needs_reset
+  unsigned long long* rng;  // [4][n]         PCG64 state_hi, state_lo, inc_hi, inc_lo
+  int32_t* diag;            // [LCR_NDIAG][n]
+  int n;
+};
+
+template <typename T, int NC>
+struct Ws {  // per-warp shared-memory workspace
+  static constexpr int NQ = LCR_NARM + 7 * NC, NVV = LCR_NARM + 6 * NC, NB = LCR_NABODY + NC;
+  static constexpr int NF = NQ + 2 * NVV + LCR_NARM + LCR_NAUX;
+  static constexpr int JS = NVV + 1;  // padded row stride of J (odd -> conflict-free row-parallel access)
+  T st[NF];
+  unsigned long long rng[4];
+  int ints[LCR_NINT];
+  int diag[LCR_NDIAG];
+  // kinematics
+  T xpos[NB][3], xquat[NB][4], xmat[NB][9], xipos[LCR_NABODY][3], ximat[LCR_NABODY][9], axis[LCR_NARM][3];
+  T Iw[LCR_NABODY][6];
+  T rw[LCR_NABODY][3], ral[LCR_NABODY][3], ra[LCR_NABODY][3], F[LCR_NABODY][3], Nn[LCR_NABODY][3];
+  T M[LCR_NARM][LCR_NARM], Lm[LCR_NARM][LCR_NARM + 1];
+  T bias[NVV], smooth[NVV], qacc_smooth[NVV], qacc[NVV], Ma[NVV], grad[NVV], search[NVV], Mv[NVV];
+  T H[NVV][NVV + 1];
+  // contacts
+  T c_pos[LCR_MAXCON][3], c_frame[LCR_MAXCON][9], c_dist[LCR_MAXCON], c_mu[LCR_MAXCON], c_c1[LCR_MAXCON], c_c2[LCR_MAXCON];
+  const CPar<T>* c_par[LCR_MAXCON];
+  short c_efc[LCR_MAXCON];
+  signed char c_b1[LCR_MAXCON], c_b2[LCR_MAXCON];
+  // constraint rows
+  T J[LCR_MAXEFC][JS];
+  T e_pos[LCR_MAXEFC], e_D[LCR_MAXEFC], e_aref[LCR_MAXEFC], e_jar[LCR_MAXEFC], e_jv[LCR_MAXEFC], e_force[LCR_MAXEFC];
+  T e_w[LCR_MAXEFC], e_g[LCR_MAXEFC], e_p[LCR_MAXEFC];  // Hessian pieces, see contact_eval
+  short e_unit[LCR_MAXEFC];  // >= 0: contact index; < 0: limit row of joint -1-e_unit
+  signed char e_r[LCR_MAXEFC];  // row index within its contact
+  int ncon, nefc, nlim;
+
+  __device__ T* qpos() { return st; }
+  __device__ T* qvel() { return st + NQ; }
+  __device__ T* ctrl() { return st + NQ + NVV; }
+  __device__ T* warm() { return st + NQ + NVV + LCR_NARM; }
+  __device__ T* aux() { return st + NQ + 2 * NVV + LCR_NARM; }
+  __device__ T* target() { return aux() + 1; }
+  __device__ T* site_xpos() { return aux() + 4; }
+  __device__ T* cube_xpos(int c) { return aux() + 7 + 3 * c; }
+};
+
+// host-side launchers, instantiated in lcr_kernels_f32.cu / lcr_kernels_f64.cu
+namespace lcr {
+template <typename T>
+struct Launch {
+  static void prepare(int ncube);
+  static size_t smem_bytes(int ncube);
+  static void reset(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const uint8_t* mask, float* obs, cudaStream_t st);
+  static void step(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
+                   uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st);
+  static void substeps(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, int n, cudaStream_t st);
+  static void ik(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* target, float* q_out, cudaStream_t st);
+  static void get_state(int ncube, DevState<T> s, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,
+                        cudaStream_t st);
+  static void set_state(int ncube, DevState<T> s, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
+                        const double* aux, const int32_t* ints, cudaStream_t st);
+  static void init_state(int ncube, const DevModel<T>* dm, DevState<T> s, cudaStream_t st);
+};
+}  // namespace lcr

@@ -1,0 +1,1286 @@
+// lcr_kernels.cuh -- the env.step() hot path as warp-per-env CUDA (sm_100a).  Templated on the
+// arithmetic type (float = product, double = verification build) and the number of cubes.
+//
+// Pipeline per substep (what mujoco.mj_step does for this model family; the reference calls it 20x
+// per env.step at reach_cube_env.py:276-277):
+//   kinematics -> inertia (CRB form, arm 6x6 + diagonal cubes) -> bias (RNE) -> collision ->
+//   constraint rows (limits + elliptic contacts: Jacobian, impedance, regularisation, aref) ->
+//   smooth forces (damping, position servos with +-frcrange) -> primal Newton solve with exact
+//   line search -> implicitfast velocity update -> semi-implicit position update.
+// Around it: apply_action incl. the damped-least-squares IK (reach_cube_env.py:148-279),
+// get_observation (:281-295), reward / success (:313-348), reset (:297-311), TimeLimit(50).
+#pragma once
+#include "lcr_device.cuh"
+
+namespace lcr {
+
+#define LANE (threadIdx.x & 31)
+#define DI __device__ __forceinline__
+
+template <typename T> DI T c_minval() { return (T)1e-15; }
+
+// ---------------------------------------------------------------- warp helpers
+template <typename T> DI T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+// first-index argmax: larger value wins, ties go to the smaller index
+template <typename T> DI void warp_argmax(T& v, int& idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    T ov = __shfl_xor_sync(FULLMASK, v, o);
+    int oi = __shfl_xor_sync(FULLMASK, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+}
+
+// ---------------------------------------------------------------- small math
+template <typename T> DI T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <typename T> DI void cross3(T* r, const T* a, const T* b) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> DI void quat_mul(T* r, const T* a, const T* b) {
+  T w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  T x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  T y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  T z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+template <typename T> DI void quat_to_mat(T* m, const T* q) {
+  T w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+template <typename T> DI void quat_normalize(T* q) {
+  T n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < c_minval<T>()) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  T inv = 1 / n;
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+template <typename T> DI void mat_vec(T* r, const T* m, const T* v) {
+  T x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
+    z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> DI void matT_vec(T* r, const T* m, const T* v) {
+  T x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2],
+    z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> DI T clampT(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// ---------------------------------------------------------------- PCG64 (numpy) on the device
+DI unsigned long long pcg64_next(unsigned long long* s) {
+  const unsigned long long mh = 0x2360ED051FC65DA4ULL, ml = 0x4385DF649FCCF645ULL;
+  unsigned long long sh = s[0], sl = s[1];
+  unsigned long long lo = sl * ml;
+  unsigned long long hi = __umul64hi(sl, ml) + sh * ml + sl * mh;
+  unsigned long long nlo = lo + s[3];
+  unsigned long long nhi = hi + s[2] + (nlo < lo ? 1ULL : 0ULL);
+  s[0] = nhi; s[1] = nlo;
+  unsigned long long x = nhi ^ nlo;
+  unsigned rot = (unsigned)(nhi >> 58);
+  return (x >> rot) | (x << ((64 - rot) & 63));
+}
+DI double pcg64_double(unsigned long long* s) { return (double)(pcg64_next(s) >> 11) * (1.0 / 9007199254740992.0); }
+
+// ---------------------------------------------------------------- warp-cooperative dense SPD solves
+// In-place Cholesky of the leading n x n block of A (row stride ld) in shared memory: lower
+// triangle becomes L.  Lane i owns row i (n <= 32).
+template <typename T> DI void warp_cholesky(T* A, int ld, int n) {
+  const int i = LANE;
+  for (int k = 0; k < n; k++) {
+    T akk = A[k * ld + k];
+    if (akk < c_minval<T>()) akk = c_minval<T>();
+    T piv = sqrt(akk), lik = 0;
+    if (i > k && i < n) { lik = A[i * ld + k] / piv; A[i * ld + k] = lik; }
+    if (i == k) A[k * ld + k] = piv;
+    __syncwarp();
+    if (i > k && i < n)
+      for (int j = k + 1; j <= i; j++) A[i * ld + j] -= lik * A[j * ld + k];
+    __syncwarp();
+  }
+}
+// Solve L L^T x = b; lane i passes b_i and receives x_i (lanes >= n pass anything, receive 0).
+template <typename T> DI T warp_chol_solve(const T* L, int ld, int n, T b) {
+  const int i = LANE;
+  T y = (i < n) ? b : (T)0;
+  for (int k = 0; k < n; k++) {
+    T yk = __shfl_sync(FULLMASK, y, k) / L[k * ld + k];
+    if (i == k) y = yk;
+    else if (i > k && i < n) y -= L[i * ld + k] * yk;
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    T xk = __shfl_sync(FULLMASK, y, k) / L[k * ld + k];
+    if (i == k) y = xk;
+    else if (i < k) y -= L[k * ld + i] * xk;
+  }
+  return y;
+}
+
+// ---------------------------------------------------------------- kinematics
+template <typename T, int NC>
+__device__ __noinline__ void kinematics(Ws<T, NC>& w, const DevModel<T>& m) {
+  const int lane = LANE;
+  T p[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0};
+  const T* qpos = w.qpos();
+#pragma unroll 1
+  for (int b = 0; b < LCR_NABODY; b++) {  // serial chain, computed redundantly by every lane
+    T R[9], t[3], bq[4] = {m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]};
+    T bp[3] = {m.body_pos[b][0], m.body_pos[b][1], m.body_pos[b][2]};
+    quat_to_mat(R, q);
+    mat_vec(t, R, bp);
+    p[0] += t[0]; p[1] += t[1]; p[2] += t[2];
+    quat_mul(q, q, bq);
+    if (b >= 1) {
+      const int j = b - 1;
+      T ja[3] = {m.jnt_axis[j][0], m.jnt_axis[j][1], m.jnt_axis[j][2]}, ax[3], ql[4], sn, cs;
+      quat_to_mat(R, q);
+      mat_vec(ax, R, ja);
+      sincos((T)0.5 * qpos[j], &sn, &cs);
+      ql[0] = cs; ql[1] = sn * ja[0]; ql[2] = sn * ja[1]; ql[3] = sn * ja[2];
+      quat_mul(q, q, ql);
+      if (lane == 0) { w.axis[j][0] = ax[0]; w.axis[j][1] = ax[1]; w.axis[j][2] = ax[2]; }
+    }
+    if (lane == 0) {
+      w.xpos[b][0] = p[0]; w.xpos[b][1] = p[1]; w.xpos[b][2] = p[2];
+      w.xquat[b][0] = q[0]; w.xquat[b][1] = q[1]; w.xquat[b][2] = q[2]; w.xquat[b][3] = q[3];
+    }
+  }
+  __syncwarp();
+  if (lane < LCR_NABODY) {
+    const int b = lane;
+    T qq[4] = {w.xquat[b][0], w.xquat[b][1], w.xquat[b][2], w.xquat[b][3]}, R[9], t[3], qi[4];
+    quat_to_mat(R, qq);
+    T ip[3] = {m.body_ipos[b][0], m.body_ipos[b][1], m.body_ipos[b][2]};
+    T iq[4] = {m.body_iquat[b][0], m.body_iquat[b][1], m.body_iquat[b][2], m.body_iquat[b][3]};
+    mat_vec(t, R, ip);
+#pragma unroll
+    for (int k = 0; k < 9; k++) w.xmat[b][k] = R[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) w.xipos[b][k] = w.xpos[b][k] + t[k];
+    quat_mul(qi, qq, iq);
+    T Ri[9];
+    quat_to_mat(Ri, qi);
+#pragma unroll
+    for (int k = 0; k < 9; k++) w.ximat[b][k] = Ri[k];
+    // world inertia Iw = Ri diag(I) Ri^T, symmetric storage xx xy xz yy yz zz
+    T I0 = m.body_inertia[b][0], I1 = m.body_inertia[b][1], I2 = m.body_inertia[b][2];
+    w.Iw[b][0] = Ri[0] * I0 * Ri[0] + Ri[1] * I1 * Ri[1] + Ri[2] * I2 * Ri[2];
+    w.Iw[b][1] = Ri[0] * I0 * Ri[3] + Ri[1] * I1 * Ri[4] + Ri[2] * I2 * Ri[5];
+    w.Iw[b][2] = Ri[0] * I0 * Ri[6] + Ri[1] * I1 * Ri[7] + Ri[2] * I2 * Ri[8];
+    w.Iw[b][3] = Ri[3] * I0 * Ri[3] + Ri[4] * I1 * Ri[4] + Ri[5] * I2 * Ri[5];
+    w.Iw[b][4] = Ri[3] * I0 * Ri[6] + Ri[4] * I1 * Ri[7] + Ri[5] * I2 * Ri[8];
+    w.Iw[b][5] = Ri[6] * I0 * Ri[6] + Ri[7] * I1 * Ri[7] + Ri[8] * I2 * Ri[8];
+    if (b == m.site_body) {
+      T sp[3] = {m.site_pos[0], m.site_pos[1], m.site_pos[2]};
+      mat_vec(t, R, sp);
+      T* s = w.site_xpos();
+      s[0] = w.xpos[b][0] + t[0]; s[1] = w.xpos[b][1] + t[1]; s[2] = w.xpos[b][2] + t[2];
+    }
+  } else if (lane < LCR_NABODY + NC) {
+    const int c = lane - LCR_NABODY, b = lane;
+    const T* qp = qpos + LCR_NARM + 7 * c;
+    T qq[4] = {qp[3], qp[4], qp[5], qp[6]}, R[9];
+    quat_normalize(qq);
+    quat_to_mat(R, qq);
+    T* cx = w.cube_xpos(c);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { w.xpos[b][k] = qp[k]; cx[k] = qp[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) w.xquat[b][k] = qq[k];
+#pragma unroll
+    for (int k = 0; k < 9; k++) w.xmat[b][k] = R[k];
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- arm inertia matrix + bias forces
+template <typename T, int NC>
+__device__ __noinline__ void inertia_and_bias(Ws<T, NC>& w, const DevModel<T>& m) {
+  const int lane = LANE;
+  // M: lane e < 21 -> lower-triangle entry (i, j), i >= j
+  if (lane < 21) {
+    int i = 0, e = lane;
+    while (e > i) { e -= i + 1; i++; }
+    const int j = e;
+    T zi[3] = {w.axis[i][0], w.axis[i][1], w.axis[i][2]}, zj[3] = {w.axis[j][0], w.axis[j][1], w.axis[j][2]};
+    T acc = 0;
+    for (int b = i + 1; b < LCR_NABODY; b++) {
+      T ri[3], rj[3], ci[3], cj[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { ri[k] = w.xipos[b][k] - w.xpos[i + 1][k]; rj[k] = w.xipos[b][k] - w.xpos[j + 1][k]; }
+      cross3(ci, zi, ri);
+      cross3(cj, zj, rj);
+      const T* I = w.Iw[b];
+      T Iz[3] = {I[0] * zj[0] + I[1] * zj[1] + I[2] * zj[2], I[1] * zj[0] + I[3] * zj[1] + I[4] * zj[2],
+                 I[2] * zj[0] + I[4] * zj[1] + I[5] * zj[2]};
+      acc += m.body_mass[b] * dot3(ci, cj) + dot3(zi, Iz);
+    }
+    if (i == j) acc += m.jnt_armature[i];
+    w.M[i][j] = acc;
+    w.M[j][i] = acc;
+  }
+  // RNE forward recursion (serial; every lane computes it, lane 0 stores)
+  {
+    T wv[3] = {0, 0, 0}, al[3] = {0, 0, 0}, a[3] = {-m.gravity[0], -m.gravity[1], -m.gravity[2]};
+    const T* qvel = w.qvel();
+#pragma unroll 1
+    for (int b = 1; b < LCR_NABODY; b++) {
+      const int j = b - 1;
+      T zq[3] = {w.axis[j][0] * qvel[j], w.axis[j][1] * qvel[j], w.axis[j][2] * qvel[j]}, r[3], t1[3], t2[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) r[k] = w.xpos[b][k] - w.xpos[b - 1][k];
+      cross3(t1, al, r);
+      cross3(t2, wv, r);
+      cross3(t2, wv, t2);
+#pragma unroll
+      for (int k = 0; k < 3; k++) a[k] += t1[k] + t2[k];  // uses w, al of the parent
+      cross3(t1, wv, zq);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { al[k] += t1[k]; wv[k] += zq[k]; }
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { w.rw[b][k] = wv[k]; w.ral[b][k] = al[k]; w.ra[b][k] = a[k]; }
+      }
+    }
+  }
+  __syncwarp();
+  if (lane >= 1 && lane < LCR_NABODY) {
+    const int b = lane;
+    T wv[3] = {w.rw[b][0], w.rw[b][1], w.rw[b][2]}, al[3] = {w.ral[b][0], w.ral[b][1], w.ral[b][2]};
+    T rc[3], t1[3], t2[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) rc[k] = w.xipos[b][k] - w.xpos[b][k];
+    cross3(t1, al, rc);
+    cross3(t2, wv, rc);
+    cross3(t2, wv, t2);
+    T mass = m.body_mass[b];
+#pragma unroll
+    for (int k = 0; k < 3; k++) w.F[b][k] = mass * (w.ra[b][k] + t1[k] + t2[k]);
+    const T* I = w.Iw[b];
+    T Iww[3] = {I[0] * wv[0] + I[1] * wv[1] + I[2] * wv[2], I[1] * wv[0] + I[3] * wv[1] + I[4] * wv[2],
+                I[2] * wv[0] + I[4] * wv[1] + I[5] * wv[2]};
+    T Iwa[3] = {I[0] * al[0] + I[1] * al[1] + I[2] * al[2], I[1] * al[0] + I[3] * al[1] + I[4] * al[2],
+                I[2] * al[0] + I[4] * al[1] + I[5] * al[2]};
+    cross3(t1, wv, Iww);
+#pragma unroll
+    for (int k = 0; k < 3; k++) w.Nn[b][k] = Iwa[k] + t1[k];
+  }
+  __syncwarp();
+  if (lane < LCR_NARM) {
+    const int j = lane;
+    T tq[3] = {0, 0, 0};
+    for (int b = j + 1; b < LCR_NABODY; b++) {
+      T r[3], t[3], F[3] = {w.F[b][0], w.F[b][1], w.F[b][2]};
+#pragma unroll
+      for (int k = 0; k < 3; k++) r[k] = w.xipos[b][k] - w.xpos[j + 1][k];
+      cross3(t, r, F);
+#pragma unroll
+      for (int k = 0; k < 3; k++) tq[k] += w.Nn[b][k] + t[k];
+    }
+    w.bias[j] = w.axis[j][0] * tq[0] + w.axis[j][1] * tq[1] + w.axis[j][2] * tq[2];
+  } else if (lane < Ws<T, NC>::NVV) {
+    const int d = lane - LCR_NARM, c = d / 6, k = d % 6;
+    w.bias[lane] = (k < 3) ? -m.cube_mass[c] * m.gravity[k] : (T)0;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- collision
+template <typename T> DI void make_frame(T* f) {
+  T y[3] = {0, 0, 0};
+  if (f[1] < (T)0.5 && f[1] > (T)-0.5) y[1] = 1; else y[2] = 1;
+  T d = dot3(f, y);
+#pragma unroll
+  for (int k = 0; k < 3; k++) y[k] -= d * f[k];
+  T inv = 1 / sqrt(dot3(y, y));
+#pragma unroll
+  for (int k = 0; k < 3; k++) f[3 + k] = y[k] * inv;
+  cross3(f + 6, f, f + 3);
+}
+
+// Append one contact (warp-uniform arguments; lane 0 writes).  ncon / nefc are warp-uniform
+// registers owned by make_constraints.  Returns true if stored.
+template <typename T, int NC>
+DI bool add_contact(Ws<T, NC>& w, int& ncon, int& nefc, const CPar<T>* par, int b1, int b2, const T* pos, const T* normal, T dist) {
+  const int dim = par->dim;
+  if (ncon >= LCR_MAXCON || nefc + dim > LCR_MAXEFC) {
+    if (LANE == 0) w.diag[4]++;
+    return false;
+  }
+  const int ci = ncon;
+  if (LANE == 0) {
+    T f[9];
+    f[0] = normal[0]; f[1] = normal[1]; f[2] = normal[2];
+    make_frame(f);
+#pragma unroll
+    for (int k = 0; k < 3; k++) w.c_pos[ci][k] = pos[k];
+#pragma unroll
+    for (int k = 0; k < 9; k++) w.c_frame[ci][k] = f[k];
+    w.c_dist[ci] = dist;
+    w.c_par[ci] = par;
+    w.c_b1[ci] = (signed char)b1;
+    w.c_b2[ci] = (signed char)b2;
+    w.c_efc[ci] = (short)nefc;
+  }
+  ncon = ci + 1;
+  nefc += dim;
+  return true;
+}
+
+template <typename T, int NC>
+DI void collide_floor_cube(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, int c) {
+  const int lane = LANE, b = LCR_NABODY + c, i = lane & 7;
+  T v[3] = {m.cube_size[c][0] * ((i & 1) ? 1 : -1), m.cube_size[c][1] * ((i & 2) ? 1 : -1), m.cube_size[c][2] * ((i & 4) ? 1 : -1)};
+  T wv[3];
+  mat_vec(wv, w.xmat[b], v);
+  const T dist = w.xpos[b][2], ld = wv[2], d = dist + ld;
+  const bool hit = lane < 8 && !(d > 0 || ld > 0) && d < 0;
+  unsigned mask = __ballot_sync(FULLMASK, hit);
+  int cnt = 0;
+  const T n[3] = {0, 0, 1};
+  while (mask && cnt < 4) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    T pos[3], dd = __shfl_sync(FULLMASK, d, src);
+    pos[0] = w.xpos[b][0] + __shfl_sync(FULLMASK, wv[0], src);
+    pos[1] = w.xpos[b][1] + __shfl_sync(FULLMASK, wv[1], src);
+    pos[2] = w.xpos[b][2] + __shfl_sync(FULLMASK, wv[2], src) - (T)0.5 * dd;
+    if (add_contact(w, ncon, nefc, &m.par_floor_cube[c], -1, b, pos, n, dd)) cnt++;
+  }
+}
+
+// support vertices of mesh g along 4 world directions at once (warp-cooperative, lane-strided)
+template <typename T, int NC>
+DI void mesh_support4(const Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int g, const T (*dirs)[3],
+                      int* idx, T (*pts)[3]) {
+  const int lane = LANE, b = m.mesh_body[g], adr = m.mesh_vertadr[g], num = m.mesh_vertnum[g];
+  T dl[4][3], bv[4];
+  int bi[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) { matT_vec(dl[t], w.xmat[b], dirs[t]); bv[t] = (T)-1e30; bi[t] = 0x7fffffff; }
+  for (int i = lane; i < num; i += 32) {
+    const T* v = verts + 4 * (size_t)(adr + i);
+    T vx = v[0], vy = v[1], vz = v[2];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      T s = vx * dl[t][0] + vy * dl[t][1] + vz * dl[t][2];
+      if (s > bv[t]) { bv[t] = s; bi[t] = i; }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    warp_argmax(bv[t], bi[t]);
+    idx[t] = bi[t];
+    const T* v = verts + 4 * (size_t)(adr + bi[t]);
+    T vl[3] = {v[0], v[1], v[2]};
+    mat_vec(pts[t], w.xmat[b], vl);
+#pragma unroll
+    for (int k = 0; k < 3; k++) pts[t][k] += w.xpos[b][k];
+  }
+}
+
+template <typename T, int NC>
+DI void collide_floor_meshes(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc) {
+  const int lane = LANE;
+  bool cand = false;
+  if (lane < m.nmesh && m.mesh_body[lane] != 0) {
+    const int b = m.mesh_body[lane];
+    T cz = w.xmat[b][6] * m.mesh_center[lane][0] + w.xmat[b][7] * m.mesh_center[lane][1] + w.xmat[b][8] * m.mesh_center[lane][2];
+    cand = !(w.xpos[b][2] + cz - m.mesh_rbound[lane] > 0);
+  }
+  unsigned mask = __ballot_sync(FULLMASK, cand);
+  const T n[3] = {0, 0, 1};
+  const T dirs[4][3] = {{0, 0, -1}, {(T)1e-3, 0, -1}, {(T)-0.5e-3, (T)0.8660254037844386e-3, -1}, {(T)-0.5e-3, (T)-0.8660254037844386e-3, -1}};
+  while (mask) {
+    const int g = __ffs(mask) - 1;
+    mask &= mask - 1;
+    int idx[4];
+    T pts[4][3];
+    mesh_support4(w, m, verts, g, dirs, idx, pts);
+    if (pts[0][2] >= 0) continue;
+    int used[4], cnt = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      T d = pts[t][2];
+      if (d >= 0) continue;
+      bool dup = false;
+      for (int k = 0; k < cnt; k++) dup |= (used[k] == idx[t]);
+      if (dup) continue;
+      T pos[3] = {pts[t][0], pts[t][1], pts[t][2] - (T)0.5 * d};
+      if (add_contact(w, ncon, nefc, &m.par_floor_mesh[g], -1, m.mesh_body[g], pos, n, d)) used[cnt++] = idx[t];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- constraint rows
+template <typename T> DI T impedance(const T* si, T pos) {
+  if (si[0] == si[1] || si[2] <= c_minval<T>()) return (T)0.5 * (si[0] + si[1]);
+  T x = fabs(pos) / si[2];
+  if (x >= 1) return si[1];
+  if (x <= 0) return si[0];
+  T y;
+  if (si[4] == 1) y = x;
+  else if (si[4] == 2) y = (x <= si[3]) ? x * x / si[3] : 1 - (1 - x) * (1 - x) / (1 - si[3]);
+  else if (x <= si[3]) y = pow(x, si[4]) / pow(si[3], si[4] - 1);
+  else y = 1 - pow(1 - x, si[4]) / pow(1 - si[3], si[4] - 1);
+  return si[0] + y * (si[1] - si[0]);
+}
+
+template <typename T, int NC> DI T body_invweight(const DevModel<T>& m, int b, int rot) { return b < 0 ? (T)0 : m.body_invweight0[b][rot]; }
+
+// J entry of a contact row: axis . (Jac_b(pos)[:, d]) for a body b, translational (rot=0) or rotational
+template <typename T, int NC>
+DI T jac_entry(const Ws<T, NC>& w, int b, int d, const T* pos, const T* ax, bool rot) {
+  if (b < 0) return 0;
+  if (b < LCR_NABODY) {
+    if (d >= b) return 0;  // also excludes cube dofs (d >= 6 >= b)
+    const T* z = w.axis[d];
+    if (rot) return dot3(ax, z);
+    T r[3] = {pos[0] - w.xpos[d + 1][0], pos[1] - w.xpos[d + 1][1], pos[2] - w.xpos[d + 1][2]}, c[3];
+    cross3(c, z, r);
+    return dot3(ax, c);
+  }
+  const int d0 = LCR_NARM + 6 * (b - LCR_NABODY), k = d - d0;
+  if (k < 0 || k >= 6) return 0;
+  if (k < 3) return rot ? (T)0 : ax[k];
+  const int kk = k - 3;
+  T bx[3] = {w.xmat[b][kk], w.xmat[b][3 + kk], w.xmat[b][6 + kk]};
+  if (rot) return dot3(ax, bx);
+  T r[3] = {pos[0] - w.xpos[b][0], pos[1] - w.xpos[b][1], pos[2] - w.xpos[b][2]}, c[3];
+  cross3(c, bx, r);
+  return dot3(ax, c);
+}
+
+template <typename T, int NC>
+__device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts) {
+  constexpr int NVV = Ws<T, NC>::NVV;
+  const int lane = LANE;
+  const T* qpos = w.qpos();
+  const T* qvel = w.qvel();
+  int ncon = 0, nefc = 0, nlim = 0;
+  if (lane == 0) w.diag[4] = 0;
+  // joint limits: lane l < 12 -> (joint l/2, side l&1)
+  {
+    bool viol = false;
+    T dist = 0;
+    const int j = lane >> 1, side = lane & 1;
+    if (lane < 2 * LCR_NARM) {
+      dist = side == 0 ? qpos[j] - m.jnt_range[j][0] : m.jnt_range[j][1] - qpos[j];
+      viol = dist < 0;
+    }
+    const unsigned vmask = __ballot_sync(FULLMASK, viol);
+    if (viol) {
+      const int i = __popc(vmask & ((1u << lane) - 1));
+      for (int d = 0; d < NVV; d++) w.J[i][d] = 0;
+      w.J[i][j] = side == 0 ? (T)1 : (T)-1;
+      w.e_unit[i] = (short)(-1 - j);
+      w.e_r[i] = 0;
+      w.e_pos[i] = dist;
+    }
+    nefc = nlim = __popc(vmask);
+  }
+  __syncwarp();
+  const int cmask = m.collision_mask;
+  if (cmask & LCR_COLLIDE_FLOOR_CUBE)
+    for (int c = 0; c < NC; c++) collide_floor_cube(w, m, ncon, nefc, c);
+  if (cmask & LCR_COLLIDE_FLOOR_MESH) collide_floor_meshes(w, m, verts, ncon, nefc);
+  if (lane == 0) { w.ncon = ncon; w.nefc = nefc; w.nlim = nlim; }
+  __syncwarp();
+  // contact rows: lane <-> row
+  for (int ci = lane; ci < ncon; ci += 32) {
+    const int dim = w.c_par[ci]->dim, e0 = w.c_efc[ci];
+    for (int r = 0; r < dim; r++) { w.e_unit[e0 + r] = (short)ci; w.e_r[e0 + r] = (signed char)r; }
+  }
+  __syncwarp();
+  for (int i = nlim + lane; i < nefc; i += 32) {
+    const int ci = w.e_unit[i], r = w.e_r[i], b1 = w.c_b1[ci], b2 = w.c_b2[ci];
+    const T* ax = w.c_frame[ci] + 3 * (r % 3);
+    const T* pos = w.c_pos[ci];
+    const bool rot = r >= 3;
+    for (int d = 0; d < NVV; d++) w.J[i][d] = jac_entry(w, b2, d, pos, ax, rot) - jac_entry(w, b1, d, pos, ax, rot);
+    w.e_pos[i] = r == 0 ? w.c_dist[ci] : (T)0;
+  }
+  __syncwarp();
+  // impedance, regularisation R (stored in e_D for now), reference acceleration
+  for (int i = lane; i < nefc; i += 32) {
+    T v = 0;
+    for (int d = 0; d < NVV; d++) v += w.J[i][d] * qvel[d];
+    const int u = w.e_unit[i];
+    const CPar<T>* par;
+    T diagA;
+    if (u < 0) { par = &m.par_limit[-1 - u]; diagA = m.dof_invweight0[-1 - u]; }
+    else {
+      par = w.c_par[u];
+      const int rot = w.e_r[i] >= 3;
+      diagA = body_invweight<T, NC>(m, w.c_b1[u], rot) + body_invweight<T, NC>(m, w.c_b2[u], rot);
+    }
+    const T pos = w.e_pos[i], imp = impedance(par->si, pos);
+    T R = (1 - imp) * diagA / imp;
+    if (R < c_minval<T>()) R = c_minval<T>();
+    w.e_D[i] = R;
+    w.e_aref[i] = -par->B * v - par->K * imp * pos;
+  }
+  __syncwarp();
+  // elliptic friction rows: R from the normal row and impratio; mu
+  T Rnew = 0;
+  for (int i = nlim + lane; i < nefc + 31; i += 32) {  // two-phase per 32-row chunk: read, sync, write
+    const bool act = i < nefc;
+    if (act) {
+      const int u = w.e_unit[i], r = w.e_r[i];
+      const CPar<T>* par = w.c_par[u];
+      const T R0 = w.e_D[w.c_efc[u]];
+      T ir = m.impratio < c_minval<T>() ? c_minval<T>() : m.impratio;
+      const T R1 = R0 / ir;
+      if (r == 0) { Rnew = R0; w.c_mu[u] = par->dim > 1 ? par->fr[0] * sqrt(R1 / R0) : (T)0; }
+      else Rnew = R1 * par->fr[0] * par->fr[0] / (par->fr[r - 1] * par->fr[r - 1]);
+    }
+    __syncwarp();
+    if (act) w.e_D[i] = Rnew;
+    __syncwarp();
+  }
+  for (int i = lane; i < nefc; i += 32) w.e_D[i] = 1 / w.e_D[i];
+  if (lane == 0) {
+    w.diag[0] = ncon; w.diag[1] = nefc;
+    if (nefc > w.diag[3]) w.diag[3] = nefc;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- smooth forces
+template <typename T, int NC>
+__device__ __noinline__ void smooth_forces(Ws<T, NC>& w, const DevModel<T>& m) {
+  constexpr int NVV = Ws<T, NC>::NVV;
+  const int lane = LANE;
+  const T* qpos = w.qpos();
+  const T* qvel = w.qvel();
+  T sm = 0;
+  if (lane < LCR_NARM) {
+    const int j = lane;
+    T u = clampT(w.ctrl()[j], m.act_ctrlrange[j][0], m.act_ctrlrange[j][1]);
+    T f = m.act_kp[j] * (u - qpos[j]) - m.act_kv[j] * qvel[j];
+    f = clampT(f, m.jnt_frcrange[j][0], m.jnt_frcrange[j][1]);
+    sm = -m.jnt_damping[j] * qvel[j] - w.bias[j] + f;
+  } else if (lane < NVV) sm = -w.bias[lane];
+  if (lane < NVV) w.smooth[lane] = sm;
+  // factor the arm block once per substep: Lm = chol(M_arm)
+  if (lane < LCR_NARM)
+    for (int j = 0; j < LCR_NARM; j++) w.Lm[lane][j] = w.M[lane][j];
+  __syncwarp();
+  warp_cholesky(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM);
+  T x = warp_chol_solve(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM, sm);
+  if (lane >= LCR_NARM && lane < NVV) {
+    const int d = lane - LCR_NARM, c = d / 6;
+    x = sm / ((d % 6) < 3 ? m.cube_mass[c] : m.cube_inertia[c]);
+  }
+  if (lane < NVV) w.qacc_smooth[lane] = x;
+  __syncwarp();
+}
+
+// y_lane = (M x)_lane with M = blockdiag(M_arm, cube diagonals); x read from shared memory
+template <typename T, int NC> DI T mul_M(const Ws<T, NC>& w, const DevModel<T>& m, const T* x) {
+  const int lane = LANE;
+  T a = 0;
+  if (lane < LCR_NARM) {
+#pragma unroll
+    for (int d = 0; d < LCR_NARM; d++) a += w.M[lane][d] * x[d];
+  } else if (lane < Ws<T, NC>::NVV) {
+    const int d = lane - LCR_NARM, c = d / 6;
+    a = ((d % 6) < 3 ? m.cube_mass[c] : m.cube_inertia[c]) * x[lane];
+  }
+  return a;
+}
+
+// ---------------------------------------------------------------- primal Newton solver
+// Evaluate one elliptic contact at x = jar + alpha*jv.  zone: 0 top (satisfied), 1 bottom (quadratic
+// in all rows), 2 middle (cone).  Mirrors the cost used by MuJoCo's primal solvers.
+// With FULL the lane also publishes, per row k of the contact, the force and the pieces of the
+// Hessian in the factored form
+//     J_c^T Hc J_c = sum_k wrow_k J_k J_k^T + c1 (J_c^T g)(J_c^T g)^T - c2 (J_c^T p)(J_c^T p)^T
+// (bottom zone: wrow = D, c1 = c2 = 0;  middle zone: wrow_0 = 0, wrow_k = c2 f_k^2,
+//  g = dNT/djar, p_k = f_k u_k / T, c1 = Dm, c2 = -mu NT Dm / T >= 0).
+template <typename T, int NC, bool FULL>
+DI int contact_eval(Ws<T, NC>& w, int ci, T alpha, bool with_jv, T& cost, T& d1, T& d2) {
+  const CPar<T>* par = w.c_par[ci];
+  const int dim = par->dim, i0 = w.c_efc[ci];
+  const T mu = w.c_mu[ci];
+  T x[6], u[6], fri[6], jv[6];
+  cost = d1 = d2 = 0;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    if (j < dim) {
+      jv[j] = with_jv ? w.e_jv[i0 + j] : (T)0;
+      x[j] = w.e_jar[i0 + j] + alpha * jv[j];
+    } else { jv[j] = 0; x[j] = 0; }
+  }
+  fri[0] = mu;
+  T T2 = 0;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    if (j > 0) fri[j] = j < dim ? par->fr[j - 1] : (T)0;
+    u[j] = x[j] * fri[j];
+    if (j > 0) T2 += u[j] * u[j];
+  }
+  const T N = u[0], Tn = sqrt(T2);
+  int zone;
+  if (dim == 1) zone = x[0] < 0 ? 1 : 0;
+  else if (N >= mu * Tn || (Tn <= 0 && N >= 0)) zone = 0;
+  else if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) zone = 1;
+  else zone = 2;
+  if (zone == 0) {
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < 6; j++) if (j < dim) { w.e_force[i0 + j] = 0; w.e_w[i0 + j] = 0; }
+      w.c_c1[ci] = 0; w.c_c2[ci] = 0;
+    }
+    return 0;
+  }
+  if (zone == 1) {
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+      if (j < dim) {
+        const T D = w.e_D[i0 + j];
+        cost += (T)0.5 * D * x[j] * x[j]; d1 += D * x[j] * jv[j]; d2 += D * jv[j] * jv[j];
+        if (FULL) { w.e_force[i0 + j] = -D * x[j]; w.e_w[i0 + j] = D; }
+      }
+    if (FULL) { w.c_c1[ci] = 0; w.c_c2[ci] = 0; }
+    return 1;
+  }
+  const T Dm = w.e_D[i0] / (mu * mu * (1 + mu * mu)), NT = N - mu * Tn, iT = 1 / Tn;
+  cost = (T)0.5 * Dm * NT * NT;
+  if (with_jv) {
+    T N1 = mu * jv[0], T1 = 0, up2 = 0;
+#pragma unroll
+    for (int j = 1; j < 6; j++) { T up = fri[j] * jv[j]; T1 += u[j] * up; up2 += up * up; }
+    T1 *= iT;
+    const T T2d = up2 * iT - T1 * T1 * iT, NT1 = N1 - mu * T1, NT2 = -mu * T2d;
+    d1 = Dm * NT * NT1;
+    d2 = Dm * (NT1 * NT1 + NT * NT2);
+  }
+  if (FULL) {
+    const T f0 = -Dm * NT * mu, c2 = -mu * NT * iT * Dm;
+    w.e_force[i0] = f0; w.e_w[i0] = 0; w.e_g[i0] = mu; w.e_p[i0] = 0;
+#pragma unroll
+    for (int j = 1; j < 6; j++)
+      if (j < dim) {
+        const T pj = fri[j] * u[j] * iT;
+        w.e_force[i0 + j] = -f0 * pj;
+        w.e_w[i0 + j] = c2 * fri[j] * fri[j];
+        w.e_g[i0 + j] = -mu * pj;
+        w.e_p[i0 + j] = pj;
+      }
+    w.c_c1[ci] = Dm; w.c_c2[ci] = c2;
+  }
+  return 2;
+}
+
+// cost at qacc: fills e_jar, Ma; if FULL also e_force, grad and the Hessian pieces (e_w, e_g, e_p, c_c1, c_c2)
+template <typename T, int NC, bool FULL>
+__device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T* qacc) {
+  constexpr int NVV = Ws<T, NC>::NVV;
+  const int lane = LANE, nefc = w.nefc, ncon = w.ncon, nlim = w.nlim;
+  for (int i = lane; i < nefc; i += 32) {
+    T a = -w.e_aref[i];
+#pragma unroll
+    for (int d = 0; d < NVV; d++) a += w.J[i][d] * qacc[d];
+    w.e_jar[i] = a;
+  }
+  T ma = mul_M(w, m, qacc), cost = 0;
+  if (lane < NVV) { w.Ma[lane] = ma; cost = (T)0.5 * (ma - w.smooth[lane]) * (qacc[lane] - w.qacc_smooth[lane]); }
+  __syncwarp();
+  if (lane < nlim) {
+    const T x = w.e_jar[lane];
+    T f = 0, ww = 0;
+    if (x < 0) { cost += (T)0.5 * w.e_D[lane] * x * x; f = -w.e_D[lane] * x; ww = w.e_D[lane]; }
+    if (FULL) { w.e_force[lane] = f; w.e_w[lane] = ww; }
+  }
+  for (int ci = lane; ci < ncon; ci += 32) {
+    T c, d1, d2;
+    contact_eval<T, NC, FULL>(w, ci, (T)0, false, c, d1, d2);
+    cost += c;
+  }
+  cost = warp_sum(cost);
+  if (FULL) {
+    __syncwarp();
+    if (lane < NVV) {
+      T g = w.Ma[lane] - w.smooth[lane];
+      for (int i = 0; i < nefc; i++) {
+        const T f = w.e_force[i];
+        if (f != 0) g -= w.J[i][lane] * f;
+      }
+      w.grad[lane] = g;
+    }
+  }
+  __syncwarp();
+  return cost;
+}
+
+template <typename T, int NC>
+__device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& m, T tol) {
+  constexpr int NVV = Ws<T, NC>::NVV;
+  constexpr int NENT = NVV * (NVV + 1) / 2, EPL = (NENT + 31) / 32;
+  const int lane = LANE, nefc = w.nefc, ncon = w.ncon, nlim = w.nlim;
+  T* warm = w.warm();
+  if (nefc == 0) {
+    if (lane < NVV) { T a = w.qacc_smooth[lane]; w.qacc[lane] = a; warm[lane] = a; }
+    if (lane == 0) w.diag[2] = 0;
+    __syncwarp();
+    return;
+  }
+  const T cw = total_cost<T, NC, false>(w, m, warm);
+  const T cs = total_cost<T, NC, false>(w, m, w.qacc_smooth);
+  if (lane < NVV) w.qacc[lane] = cw < cs ? warm[lane] : w.qacc_smooth[lane];
+  __syncwarp();
+  const T scale = 1 / (m.meaninertia * (T)NVV);
+  T cost = total_cost<T, NC, true>(w, m, w.qacc);
+  // lower-triangle entries owned by this lane
+  int ea[EPL], eb[EPL];
+#pragma unroll
+  for (int k = 0; k < EPL; k++) {
+    int e = lane + 32 * k, a = 0;
+    if (e >= NENT) e = 0;
+    while (e > a) { e -= a + 1; a++; }
+    ea[k] = a; eb[k] = e;
+  }
+  int niter = 0;
+  for (int iter = 0; iter < m.iterations; iter++) {
+    // ---- Hessian H = M + sum_rows w_i J_i J_i^T + sum_cone-contacts (c1 G G^T - c2 P P^T)
+    T h[EPL];
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+      const int a = ea[k], b = eb[k];
+      T v = 0;
+      if (a < LCR_NARM) v = w.M[a][b];
+      else if (a == b) { const int d = a - LCR_NARM, c = d / 6; v = (d % 6) < 3 ? m.cube_mass[c] : m.cube_inertia[c]; }
+      h[k] = v;
+    }
+    for (int i = 0; i < nefc; i++) {
+      const T ww = w.e_w[i];
+      if (ww == 0) continue;  // warp-uniform
+#pragma unroll
+      for (int k = 0; k < EPL; k++) h[k] += ww * w.J[i][ea[k]] * w.J[i][eb[k]];
+    }
+    for (int ci = 0; ci < ncon; ci++) {
+      const T c1 = w.c_c1[ci];
+      if (c1 == 0) continue;  // warp-uniform
+      const T c2 = w.c_c2[ci];
+      const int i0 = w.c_efc[ci], dim = w.c_par[ci]->dim;
+      T G = 0, P = 0;
+      if (lane < NVV)
+        for (int k = 0; k < dim; k++) { const T jk = w.J[i0 + k][lane]; G += w.e_g[i0 + k] * jk; P += w.e_p[i0 + k] * jk; }
+#pragma unroll
+      for (int k = 0; k < EPL; k++) {
+        const T Ga = __shfl_sync(FULLMASK, G, ea[k]), Gb = __shfl_sync(FULLMASK, G, eb[k]);
+        const T Pa = __shfl_sync(FULLMASK, P, ea[k]), Pb = __shfl_sync(FULLMASK, P, eb[k]);
+        h[k] += c1 * Ga * Gb - c2 * Pa * Pb;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < EPL; k++)
+      if (lane + 32 * k < NENT) w.H[ea[k]][eb[k]] = h[k];
+    __syncwarp();
+    warp_cholesky(&w.H[0][0], NVV + 1, NVV);
+    T s = -warp_chol_solve(&w.H[0][0], NVV + 1, NVV, lane < NVV ? w.grad[lane] : (T)0);
+    if (lane < NVV) w.search[lane] = s;
+    const T snorm = sqrt(warp_sum(lane < NVV ? s * s : (T)0));
+    __syncwarp();
+    if (snorm < c_minval<T>()) break;
+    // ---- exact line search (safeguarded Newton on alpha)
+    T mv = mul_M(w, m, w.search);
+    if (lane < NVV) w.Mv[lane] = mv;
+    for (int i = lane; i < nefc; i += 32) {
+      T a = 0;
+#pragma unroll
+      for (int d = 0; d < NVV; d++) a += w.J[i][d] * w.search[d];
+      w.e_jv[i] = a;
+    }
+    T g1 = 0, g2 = 0;
+    if (lane < NVV) { g1 = s * (w.Ma[lane] - w.smooth[lane]); g2 = s * mv; }
+    g1 = warp_sum(g1);
+    g2 = warp_sum(g2);
+    __syncwarp();
+    const T gtol = tol * m.ls_tolerance * snorm / scale;
+    T alpha = 0, lo = 0, hi = -1;
+    for (int ls = 0; ls <= m.ls_iterations; ls++) {
+      T d1 = 0, d2 = 0;
+      if (lane < nlim) {
+        const T jv = w.e_jv[lane], x = w.e_jar[lane] + alpha * jv;
+        if (x < 0) { d1 = w.e_D[lane] * x * jv; d2 = w.e_D[lane] * jv * jv; }
+      }
+      for (int ci = lane; ci < ncon; ci += 32) {
+        T c, a1, a2;
+        contact_eval<T, NC, false>(w, ci, alpha, true, c, a1, a2);
+        d1 += a1; d2 += a2;
+      }
+      d1 = warp_sum(d1) + g1 + alpha * g2;
+      d2 = warp_sum(d2) + g2;
+      if (fabs(d1) < gtol || ls == m.ls_iterations) break;
+      if (d1 < 0) lo = alpha; else hi = alpha;
+      T an = alpha - d1 / d2;
+      if (hi >= 0 && (an <= lo || an >= hi)) an = (T)0.5 * (lo + hi);
+      if (an == alpha) break;
+      alpha = an;
+    }
+    if (!(alpha > 0)) break;
+    if (lane < NVV) w.qacc[lane] += alpha * s;
+    __syncwarp();
+    const T old = cost;
+    cost = total_cost<T, NC, true>(w, m, w.qacc);
+    niter = iter + 1;
+    const T gn = sqrt(warp_sum(lane < NVV ? w.grad[lane] * w.grad[lane] : (T)0));
+    if (scale * (old - cost) < tol || scale * gn < tol) break;
+  }
+  if (lane < NVV) warm[lane] = w.qacc[lane];
+  if (lane == 0) w.diag[2] = niter;
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- mj_forward / mj_step
+template <typename T> DI T solver_tol(const DevModel<T>& m);
+template <> DI double solver_tol<double>(const DevModel<double>& m) { return m.tolerance; }
+template <> DI float solver_tol<float>(const DevModel<float>& m) { return fmaxf(m.tolerance, 1e-6f); }
+
+template <typename T, int NC>
+__device__ __noinline__ void forward(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts) {
+  kinematics(w, m);
+  inertia_and_bias(w, m);
+  make_constraints(w, m, verts);
+  smooth_forces(w, m);
+  solve_constraints(w, m, solver_tol<T>(m));
+}
+
+template <typename T, int NC> DI void reset_data(Ws<T, NC>& w, const DevModel<T>& m) {  // mj_resetData
+  const int lane = LANE;
+  for (int i = lane; i < Ws<T, NC>::NF - LCR_NAUX + 1; i += 32) w.st[i] = 0;  // qpos qvel ctrl warm time
+  __syncwarp();
+  if (lane < NC) {
+    T* qp = w.qpos() + LCR_NARM + 7 * lane;
+    qp[0] = m.cube_qpos0[lane][0]; qp[1] = m.cube_qpos0[lane][1]; qp[2] = m.cube_qpos0[lane][2]; qp[3] = 1;
+  }
+  __syncwarp();
+}
+
+template <typename T> DI bool bad_val(T x) { return !(x == x) || x > (T)1e10 || x < (T)-1e10; }
+
+template <typename T, int NC>
+__device__ __noinline__ void substep(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts) {
+  constexpr int NVV = Ws<T, NC>::NVV, NQ = Ws<T, NC>::NQ;
+  const int lane = LANE;
+  T* qpos = w.qpos();
+  T* qvel = w.qvel();
+  bool bad = (lane < NQ && bad_val(qpos[lane])) || (lane < NVV && bad_val(qvel[lane]));
+  if (__any_sync(FULLMASK, bad)) { reset_data(w, m); if (lane == 0) w.diag[5]++; }
+  forward(w, m, verts);
+  bad = lane < NVV && bad_val(w.qacc[lane]);
+  if (__any_sync(FULLMASK, bad)) { reset_data(w, m); if (lane == 0) w.diag[5]++; forward(w, m, verts); }
+  const T h = m.timestep;
+  // implicitfast: (M + h diag(damping + kv)) a = M qacc on the arm block; cubes keep qacc
+  T rhs = mul_M(w, m, w.qacc);
+  if (lane < LCR_NARM) {
+    for (int j = 0; j < LCR_NARM; j++) w.Lm[lane][j] = w.M[lane][j];
+    w.Lm[lane][lane] += h * (m.jnt_damping[lane] + m.act_kv[lane]);
+  }
+  __syncwarp();
+  warp_cholesky(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM);
+  T a = warp_chol_solve(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM, rhs);
+  if (lane >= LCR_NARM && lane < NVV) a = w.qacc[lane];
+  if (lane < NVV) qvel[lane] += h * a;
+  __syncwarp();
+  if (lane < LCR_NARM) qpos[lane] += h * qvel[lane];
+  else if (lane < LCR_NARM + NC) {
+    const int c = lane - LCR_NARM;
+    T* qp = qpos + LCR_NARM + 7 * c;
+    const T* qv = qvel + LCR_NARM + 6 * c;
+    qp[0] += h * qv[0]; qp[1] += h * qv[1]; qp[2] += h * qv[2];
+    T q[4] = {qp[3], qp[4], qp[5], qp[6]};
+    quat_normalize(q);
+    const T wn = sqrt(qv[3] * qv[3] + qv[4] * qv[4] + qv[5] * qv[5]);
+    if (wn * h > 0) {
+      T sn, cs;
+      sincos((T)0.5 * wn * h, &sn, &cs);
+      sn /= wn;
+      T dq[4] = {cs, sn * qv[3], sn * qv[4], sn * qv[5]}, r[4];
+      quat_mul(r, q, dq);
+      quat_normalize(r);
+      q[0] = r[0]; q[1] = r[1]; q[2] = r[2]; q[3] = r[3];
+    }
+    qp[3] = q[0]; qp[4] = q[1]; qp[5] = q[2]; qp[6] = q[3];
+  }
+  if (lane == 0) w.aux()[0] += h;
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- env glue
+template <typename T, int NC> DI void write_obs(Ws<T, NC>& w, const DevModel<T>& m, float* obs) {
+  const int lane = LANE, task = m.task;
+  const T* qpos = w.qpos();
+  const T* qvel = w.qvel();
+  const bool has_target = task == LCR_TASK_PUSH || task == LCR_TASK_PICK_PLACE;
+  const int od = (task == LCR_TASK_REACH || task == LCR_TASK_LIFT) ? 15 : 18;
+  if (lane < od) {
+    T v;
+    if (lane < 6) v = qpos[lane];
+    else if (lane < 12) v = qvel[lane - 6];
+    else if (lane < 15) v = has_target ? w.target()[lane - 12] : qpos[6 + lane - 12];
+    else v = has_target ? qpos[6 + lane - 15] : qpos[13 + lane - 15];
+    obs[lane] = (float)v;
+  }
+}
+
+template <typename T, int NC>
+__device__ __noinline__ void env_reset(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts) {
+  const int lane = LANE, task = m.task;
+  T* qpos = w.qpos();
+  if (lane == 0) {
+    for (int j = 0; j < 6; j++) qpos[j] = 0;
+    for (int c = 0; c < NC; c++) {
+      T* qp = qpos + 6 + 7 * c;
+      for (int k = 0; k < 3; k++) qp[k] = (T)(m.cube_low[k] + (m.cube_high[k] - m.cube_low[k]) * pcg64_double(w.rng));
+      qp[3] = 1; qp[4] = qp[5] = qp[6] = 0;
+    }
+    if (task == LCR_TASK_PUSH || task == LCR_TASK_PICK_PLACE)
+      for (int k = 0; k < 3; k++)
+        w.target()[k] = (T)(float)(m.target_low[k] + (m.target_high[k] - m.target_low[k]) * pcg64_double(w.rng));
+    w.ints[0] = 0;
+    w.ints[1] = 0;
+  }
+  __syncwarp();
+  forward(w, m, verts);
+}
+
+// damped least squares IK (reach_cube_env.py:148-221); teleport = faithful in-step behaviour
+template <typename T, int NC>
+__device__ __noinline__ void inverse_kinematics(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const T* target,
+                                                T* q_out, bool teleport) {
+  const int lane = LANE;
+  T* qpos = w.qpos();
+  T q = lane < 6 ? qpos[lane] : (T)0;
+  const T save = q;
+  for (int it = 0; it < 10; it++) {
+    if (lane < 6) qpos[lane] = q;
+    __syncwarp();
+    if (teleport) forward(w, m, verts); else kinematics(w, m);
+    const T* site = w.site_xpos();
+    T err[3] = {target[0] - site[0], target[1] - site[1], target[2] - site[2]};
+    if (sqrt(dot3(err, err)) < (T)0.01) break;
+    // lane a < 6: Jacobian column a, A[a][:] = J^T J + 0.15 I, rhs_a = J^T err
+    T col[3] = {0, 0, 0};
+    if (lane < m.site_body && lane < 6) {
+      T r[3] = {site[0] - w.xpos[lane + 1][0], site[1] - w.xpos[lane + 1][1], site[2] - w.xpos[lane + 1][2]};
+      cross3(col, w.axis[lane], r);
+    }
+    T rhs = dot3(col, err);
+    for (int b = 0; b < 6; b++) {
+      T cb[3] = {__shfl_sync(FULLMASK, col[0], b), __shfl_sync(FULLMASK, col[1], b), __shfl_sync(FULLMASK, col[2], b)};
+      if (lane < 6) w.Lm[lane][b] = dot3(col, cb) + (lane == b ? (T)0.15 : (T)0);
+    }
+    __syncwarp();
+    warp_cholesky(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM);
+    T qd = warp_chol_solve(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM, rhs);
+    const T n = sqrt(warp_sum(lane < 6 ? qd * qd : (T)0));
+    if (n > 1) qd /= n;
+    if (lane < 6) q = clampT(q + (T)0.5 * qd, m.jnt_range[lane][0], m.jnt_range[lane][1]);
+    __syncwarp();
+  }
+  if (lane < 6) q_out[lane] = q;
+  if (!teleport) {
+    if (lane < 6) qpos[lane] = save;
+    __syncwarp();
+  }
+  __syncwarp();
+}
+
+__device__ const double kTargetLow[6] = {-3.14159, -1.5708, -1.48353, -1.91986, -2.96706, -1.74533};
+__device__ const double kTargetHigh[6] = {3.14159, 1.22173, 1.74533, 1.91986, 2.96706, 0.0523599};
+
+template <typename T, int NC>
+__device__ __noinline__ void env_step(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const float* action, float* obs,
+                                      float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ) {
+  const int lane = LANE, task = m.task;
+  if (m.autoreset && w.ints[1]) {
+    env_reset(w, m, verts);
+    write_obs(w, m, obs);
+    if (lane == 0) { *reward = 0; *term = 0; *trunc = 0; *succ = 0; }
+    return;
+  }
+  if (lane == 0) w.diag[3] = 0;
+  const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
+  const bool gripper_task = task == LCR_TASK_LIFT || task == LCR_TASK_PICK_PLACE || task == LCR_TASK_STACK;
+  T* qpos = w.qpos();
+  T a = lane < na ? clampT((T)action[lane], (T)-1, (T)1) : (T)0;
+  T tq = 0;
+  if (m.action_mode == 1) {
+    __shared__ T ik_scratch[LCR_WPB][8];
+    T* sc = ik_scratch[threadIdx.x >> 5];
+    const T* site = w.site_xpos();
+    if (lane < 3) { T t = site[lane] + a * (T)0.05; if (lane == 2 && t < 0) t = 0; sc[lane] = t; }
+    __syncwarp();
+    T tgt[3] = {sc[0], sc[1], sc[2]};
+    __syncwarp();
+    inverse_kinematics(w, m, verts, tgt, sc, true);
+    __syncwarp();
+    if (lane < 6) tq = sc[lane];
+    if (lane == 5 && !gripper_task) tq = 0;
+    // gripper (lift_cube_env.py:253-257): q6 + 0.2*a[3] clipped to ctrlrange
+    const T ga = na > 3 ? __shfl_sync(FULLMASK, a, 3) : (T)0;
+    if (lane == 5 && gripper_task) tq = clampT(qpos[5] + ga * (T)0.2, m.act_ctrlrange[5][0], m.act_ctrlrange[5][1]);
+  } else {
+    const T alast = __shfl_sync(FULLMASK, a, na - 1);
+    if (lane < 5) tq = clampT(a + qpos[lane], (T)kTargetLow[lane], (T)kTargetHigh[lane]);
+    else if (lane == 5) tq = gripper_task ? clampT(alast + qpos[5], (T)kTargetLow[5], (T)kTargetHigh[5]) : (T)0;
+  }
+  if (lane < 6) w.ctrl()[lane] = tq;
+  __syncwarp();
+#pragma unroll 1
+  for (int k = 0; k < m.n_substeps; k++) substep(w, m, verts);
+  write_obs(w, m, obs);
+  if (lane == 0) {
+    T pa[3], pb[3];
+    const T* site = w.site_xpos();
+    const T* c0 = w.cube_xpos(0);
+    if (task == LCR_TASK_REACH || task == LCR_TASK_LIFT) { for (int k = 0; k < 3; k++) { pa[k] = site[k]; pb[k] = c0[k]; } }
+    else if (task == LCR_TASK_STACK) { const T* c1 = w.cube_xpos(NC - 1); for (int k = 0; k < 3; k++) { pa[k] = c1[k]; pb[k] = c0[k]; } pb[2] += (T)0.03; }
+    else { for (int k = 0; k < 3; k++) { pa[k] = c0[k]; pb[k] = w.target()[k]; } }
+    T dx = pa[0] - pb[0], dy = pa[1] - pb[1], dz = pa[2] - pb[2];
+    T d = sqrt(dx * dx + dy * dy + dz * dz);
+    bool te = false, su = false;
+    float r;
+    if (task == LCR_TASK_LIFT) r = (float)((c0[2] - m.height_threshold) + d);
+    else {
+      su = d < m.distance_threshold;
+      te = su;
+      r = m.reward_type == 0 ? -(float)(d > m.distance_threshold) : (float)(-d);
+    }
+    const int el = ++w.ints[0];
+    const bool tr = m.max_episode_steps > 0 && el >= m.max_episode_steps;
+    w.ints[1] = (te || tr) ? 1 : 0;
+    *reward = r; *term = te; *trunc = tr; *succ = su;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- state staging HBM <-> shared
+template <typename T, int NC>
+DI void load_state(Ws<T, NC>* ws, const DevState<T>& s, int env0) {
+  constexpr int NF = Ws<T, NC>::NF;
+  const int n = s.n, tid = threadIdx.x, nthr = blockDim.x;
+  if (sizeof(T) == 4 && (n & 3) == 0 && env0 + LCR_WPB <= n && LCR_WPB == 4) {
+    for (int f = tid; f < NF; f += nthr) {  // one 128-bit load = field f of 4 consecutive envs
+      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(s.st) + (size_t)f * n + env0);
+      reinterpret_cast<float*>(ws[0].st)[f] = v.x; reinterpret_cast<float*>(ws[1].st)[f] = v.y;
+      reinterpret_cast<float*>(ws[2].st)[f] = v.z; reinterpret_cast<float*>(ws[3].st)[f] = v.w;
+    }
+  } else {
+    for (int idx = tid; idx < NF * LCR_WPB; idx += nthr) {
+      const int f = idx / LCR_WPB, e = idx % LCR_WPB;
+      if (env0 + e < n) ws[e].st[f] = s.st[(size_t)f * n + env0 + e];
+    }
+  }
+  for (int idx = tid; idx < (LCR_NINT + LCR_NDIAG + 4) * LCR_WPB; idx += nthr) {
+    const int f = idx / LCR_WPB, e = idx % LCR_WPB;
+    if (env0 + e >= n) continue;
+    if (f < LCR_NINT) ws[e].ints[f] = s.ints[(size_t)f * n + env0 + e];
+    else if (f < LCR_NINT + LCR_NDIAG) ws[e].diag[f - LCR_NINT] = s.diag[(size_t)(f - LCR_NINT) * n + env0 + e];
+    else ws[e].rng[f - LCR_NINT - LCR_NDIAG] = s.rng[(size_t)(f - LCR_NINT - LCR_NDIAG) * n + env0 + e];
+  }
+}
+template <typename T, int NC>
+DI void store_state(Ws<T, NC>* ws, const DevState<T>& s, int env0) {
+  constexpr int NF = Ws<T, NC>::NF;
+  const int n = s.n, tid = threadIdx.x, nthr = blockDim.x;
+  if (sizeof(T) == 4 && (n & 3) == 0 && env0 + LCR_WPB <= n && LCR_WPB == 4) {
+    for (int f = tid; f < NF; f += nthr) {
+      float4 v;
+      v.x = reinterpret_cast<float*>(ws[0].st)[f]; v.y = reinterpret_cast<float*>(ws[1].st)[f];
+      v.z = reinterpret_cast<float*>(ws[2].st)[f]; v.w = reinterpret_cast<float*>(ws[3].st)[f];
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(s.st) + (size_t)f * n + env0) = v;
+    }
+  } else {
+    for (int idx = tid; idx < NF * LCR_WPB; idx += nthr) {
+      const int f = idx / LCR_WPB, e = idx % LCR_WPB;
+      if (env0 + e < n) s.st[(size_t)f * n + env0 + e] = ws[e].st[f];
+    }
+  }
+  for (int idx = tid; idx < (LCR_NINT + LCR_NDIAG + 4) * LCR_WPB; idx += nthr) {
+    const int f = idx / LCR_WPB, e = idx % LCR_WPB;
+    if (env0 + e >= n) continue;
+    if (f < LCR_NINT) s.ints[(size_t)f * n + env0 + e] = ws[e].ints[f];
+    else if (f < LCR_NINT + LCR_NDIAG) s.diag[(size_t)(f - LCR_NINT) * n + env0 + e] = ws[e].diag[f - LCR_NINT];
+    else s.rng[(size_t)(f - LCR_NINT - LCR_NDIAG) * n + env0 + e] = ws[e].rng[f - LCR_NINT - LCR_NDIAG];
+  }
+}
+
+// ---------------------------------------------------------------- kernels
+extern __shared__ __align__(16) unsigned char lcr_smem[];
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(LCR_WPB * 32) k_step(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                                      const float* __restrict__ actions, float* __restrict__ obs,
+                                                      float* __restrict__ reward, uint8_t* __restrict__ term,
+                                                      uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ) {
+  Ws<T, NC>* ws = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env0 = blockIdx.x * LCR_WPB, wid = threadIdx.x >> 5, env = env0 + wid;
+  load_state(ws, s, env0);
+  __syncthreads();
+  if (env < s.n) {
+    const DevModel<T>& m = *dm;
+    const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
+    const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+    env_step(ws[wid], m, verts, actions + (size_t)env * na, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
+  }
+  __syncthreads();
+  store_state(ws, s, env0);
+}
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(LCR_WPB * 32) k_reset(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                                       const uint8_t* __restrict__ mask, float* __restrict__ obs) {
+  Ws<T, NC>* ws = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env0 = blockIdx.x * LCR_WPB, wid = threadIdx.x >> 5, env = env0 + wid;
+  load_state(ws, s, env0);
+  __syncthreads();
+  if (env < s.n && (mask == nullptr || mask[env])) {
+    const DevModel<T>& m = *dm;
+    const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+    env_reset(ws[wid], m, verts);
+    if (obs) write_obs(ws[wid], m, obs + (size_t)env * od);
+  }
+  __syncthreads();
+  store_state(ws, s, env0);
+}
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(LCR_WPB * 32) k_substeps(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s, int nsub) {
+  Ws<T, NC>* ws = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env0 = blockIdx.x * LCR_WPB, wid = threadIdx.x >> 5, env = env0 + wid;
+  load_state(ws, s, env0);
+  __syncthreads();
+  if (env < s.n) {
+    if ((threadIdx.x & 31) == 0) ws[wid].diag[3] = 0;
+    if (nsub == 0) forward(ws[wid], *dm, verts);
+    for (int k = 0; k < nsub; k++) substep(ws[wid], *dm, verts);
+  }
+  __syncthreads();
+  store_state(ws, s, env0);
+}
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(LCR_WPB * 32) k_ik(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                                    const float* __restrict__ target, float* __restrict__ q_out) {
+  Ws<T, NC>* ws = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  __shared__ T outq[LCR_WPB][8];
+  const int env0 = blockIdx.x * LCR_WPB, wid = threadIdx.x >> 5, env = env0 + wid, lane = threadIdx.x & 31;
+  load_state(ws, s, env0);
+  __syncthreads();
+  if (env < s.n) {
+    T tgt[3] = {(T)target[3 * (size_t)env], (T)target[3 * (size_t)env + 1], (T)target[3 * (size_t)env + 2]};
+    inverse_kinematics(ws[wid], *dm, verts, tgt, outq[wid], false);
+    __syncwarp();
+    if (lane < 6) q_out[6 * (size_t)env + lane] = (float)outq[wid][lane];
+  }
+  // state is not written back: lcr_ik leaves the simulation untouched
+}
+
+// row-major float64 <-> SoA T
+template <typename T>
+__global__ void k_get_state(DevState<T> s, int nq, int nv, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x, n = s.n;
+  if (e >= n) return;
+  int f = 0;
+  for (int k = 0; k < nq; k++, f++) if (qpos) qpos[(size_t)e * nq + k] = (double)s.st[(size_t)f * n + e];
+  for (int k = 0; k < nv; k++, f++) if (qvel) qvel[(size_t)e * nv + k] = (double)s.st[(size_t)f * n + e];
+  for (int k = 0; k < 6; k++, f++) if (ctrl) ctrl[(size_t)e * 6 + k] = (double)s.st[(size_t)f * n + e];
+  for (int k = 0; k < nv; k++, f++) if (warm) warm[(size_t)e * nv + k] = (double)s.st[(size_t)f * n + e];
+  for (int k = 0; k < LCR_NAUX; k++, f++) if (aux) aux[(size_t)e * LCR_NAUX + k] = (double)s.st[(size_t)f * n + e];
+  if (ints) for (int k = 0; k < LCR_NINT; k++) ints[(size_t)e * LCR_NINT + k] = s.ints[(size_t)k * n + e];
+}
+template <typename T>
+__global__ void k_set_state(DevState<T> s, int nq, int nv, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
+                            const double* aux, const int32_t* ints) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x, n = s.n;
+  if (e >= n) return;
+  int f = 0;
+  for (int k = 0; k < nq; k++, f++) if (qpos) s.st[(size_t)f * n + e] = (T)qpos[(size_t)e * nq + k];
+  for (int k = 0; k < nv; k++, f++) if (qvel) s.st[(size_t)f * n + e] = (T)qvel[(size_t)e * nv + k];
+  for (int k = 0; k < 6; k++, f++) if (ctrl) s.st[(size_t)f * n + e] = (T)ctrl[(size_t)e * 6 + k];
+  for (int k = 0; k < nv; k++, f++) if (warm) s.st[(size_t)f * n + e] = (T)warm[(size_t)e * nv + k];
+  for (int k = 0; k < LCR_NAUX; k++, f++) if (aux) s.st[(size_t)f * n + e] = (T)aux[(size_t)e * LCR_NAUX + k];
+  if (ints) for (int k = 0; k < LCR_NINT; k++) s.ints[(size_t)k * n + e] = ints[(size_t)e * LCR_NINT + k];
+}
+template <typename T>
+__global__ void k_init_state(const DevModel<T>* dm, DevState<T> s, int nq, int nv) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x, n = s.n;
+  if (e >= n) return;
+  const int nf = nq + 2 * nv + LCR_NARM + LCR_NAUX;
+  for (int f = 0; f < nf; f++) s.st[(size_t)f * n + e] = 0;
+  for (int c = 0; c < dm->ncube; c++) {
+    for (int k = 0; k < 3; k++) s.st[(size_t)(6 + 7 * c + k) * n + e] = dm->cube_qpos0[c][k];
+    s.st[(size_t)(6 + 7 * c + 3) * n + e] = 1;
+  }
+  for (int k = 0; k < LCR_NINT; k++) s.ints[(size_t)k * n + e] = 0;
+  for (int k = 0; k < LCR_NDIAG; k++) s.diag[(size_t)k * n + e] = 0;
+  s.rng[(size_t)0 * n + e] = 0; s.rng[(size_t)1 * n + e] = 1; s.rng[(size_t)2 * n + e] = 0; s.rng[(size_t)3 * n + e] = 1;
+}
+
+// ---------------------------------------------------------------- launchers
+template <typename T, int NC> static void set_smem_attr() {
+  static bool done = false;  // per process; attributes are per device but identical
+  const int bytes = (int)(sizeof(Ws<T, NC>) * LCR_WPB);
+  (void)done;
+  cudaFuncSetAttribute(k_step<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_reset<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_substeps<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_ik<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+template <typename T>
+void Launch<T>::prepare(int ncube) {
+  if (ncube == 1) set_smem_attr<T, 1>(); else set_smem_attr<T, 2>();
+}
+template <typename T>
+size_t Launch<T>::smem_bytes(int ncube) { return (ncube == 1 ? sizeof(Ws<T, 1>) : sizeof(Ws<T, 2>)) * LCR_WPB; }
+
+#define LCR_GRID(s) (((s).n + LCR_WPB - 1) / LCR_WPB)
+#define LCR_LAUNCH(KERNEL, ...)                                                                          \
+  do {                                                                                                   \
+    if (ncube == 1) KERNEL<T, 1><<<LCR_GRID(s), LCR_WPB * 32, sizeof(Ws<T, 1>) * LCR_WPB, st>>>(__VA_ARGS__); \
+    else KERNEL<T, 2><<<LCR_GRID(s), LCR_WPB * 32, sizeof(Ws<T, 2>) * LCR_WPB, st>>>(__VA_ARGS__);           \
+  } while (0)
+
+template <typename T>
+void Launch<T>::reset(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const uint8_t* mask, float* obs, cudaStream_t st) {
+  LCR_LAUNCH(k_reset, dm, verts, s, mask, obs);
+}
+template <typename T>
+void Launch<T>::step(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
+                     uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st) {
+  LCR_LAUNCH(k_step, dm, verts, s, actions, obs, reward, term, trunc, succ);
+}
+template <typename T>
+void Launch<T>::substeps(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, int n, cudaStream_t st) {
+  LCR_LAUNCH(k_substeps, dm, verts, s, n);
+}
+template <typename T>
+void Launch<T>::ik(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* target, float* q_out, cudaStream_t st) {
+  LCR_LAUNCH(k_ik, dm, verts, s, target, q_out);
+}
+template <typename T>
+void Launch<T>::get_state(int ncube, DevState<T> s, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,
+                          cudaStream_t st) {
+  k_get_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, 6 + 7 * ncube, 6 + 6 * ncube, qpos, qvel, ctrl, warm, aux, ints);
+}
+template <typename T>
+void Launch<T>::set_state(int ncube, DevState<T> s, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
+                          const double* aux, const int32_t* ints, cudaStream_t st) {
+  k_set_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, 6 + 7 * ncube, 6 + 6 * ncube, qpos, qvel, ctrl, warm, aux, ints);
+}
+template <typename T>
+void Launch<T>::init_state(int ncube, const DevModel<T>* dm, DevState<T> s, cudaStream_t st) {
+  k_init_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(dm, s, 6 + 7 * ncube, 6 + 6 * ncube);
+}
+
+}  // namespace lcr

@@ -1,0 +1,230 @@
+"""Batched drop-in for ``gym_lowcostrobot.envs`` (state observations, joint / ee actions).
+
+Each class mirrors the constructor kwargs, ``reset`` / ``step`` / ``close`` interface, observation
+keys and action shapes of its reference counterpart
+(``gym_lowcostrobot/envs/{reach,push,lift,pick_place}_cube_env.py``, ``stack_two_cubes_env.py``) but
+holds ``num_envs`` instances on one GPU and returns batched torch tensors.  Everything behind
+``step`` runs in liblcrsim.so (hand-written sm_100a CUDA); torch only owns the buffers and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi, config, model, spaces
+
+_OBS_LAYOUT = {
+    "reach": (("arm_qpos", 6), ("arm_qvel", 6), ("cube_pos", 3)),
+    "lift": (("arm_qpos", 6), ("arm_qvel", 6), ("cube_pos", 3)),
+    "push": (("arm_qpos", 6), ("arm_qvel", 6), ("target_pos", 3), ("cube_pos", 3)),
+    "pick_place": (("arm_qpos", 6), ("arm_qvel", 6), ("target_pos", 3), ("cube_pos", 3)),
+    "stack": (("arm_qpos", 6), ("arm_qvel", 6), ("cube_red_pos", 3), ("cube_blue_pos", 3)),
+}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def pcg64_states(seeds):
+    """[n,4] uint64 (state_hi, state_lo, inc_hi, inc_lo) of numpy ``PCG64(seed)`` for every seed.
+
+    gymnasium's ``Env.reset(seed=s)`` sets ``np_random = Generator(PCG64(SeedSequence(s)))``; the
+    device continues exactly that stream (reference reach_cube_env.py:299-302).
+    """
+    out = np.empty((len(seeds), 4), dtype=np.uint64)
+    m64 = (1 << 64) - 1
+    for i, s in enumerate(seeds):
+        st = np.random.PCG64(int(s)).state["state"]
+        out[i] = (st["state"] >> 64, st["state"] & m64, st["inc"] >> 64, st["inc"] & m64)
+    return out
+
+
+class BatchedLowCostRobotEnv:
+    """``num_envs`` independent copies of one reference env, stepped in lockstep on one GPU."""
+
+    task = None
+    metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 25}
+
+    def __init__(self, num_envs=1, device="cuda:0", observation_mode="state", action_mode="joint", reward_type="sparse",
+                 block_gripper=None, distance_threshold=0.05, height_threshold=0.1, cube_xy_range=0.3,
+                 target_xy_range=0.3, goal_z_range=0.1, n_substeps=20, render_mode=None, max_episode_steps=50,
+                 autoreset=False, precision="float32", assets_path=None, collision_mask=model.COLLIDE_ALL,
+                 env_offset=0):
+        if observation_mode != "state":
+            raise NotImplementedError("only observation_mode='state' is implemented (image rendering is out of scope)")
+        if render_mode is not None:
+            raise NotImplementedError("rendering is out of scope")
+        if not torch.cuda.is_available():
+            raise capi.LcrError("CUDA device required: the simulator has no CPU fallback")
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        self.observation_mode, self.action_mode, self.reward_type = observation_mode, action_mode, reward_type
+        self.cfg = config.make_cfg(self.task, action_mode=action_mode, reward_type=reward_type, block_gripper=block_gripper,
+                                   distance_threshold=distance_threshold, height_threshold=height_threshold,
+                                   cube_xy_range=cube_xy_range, target_xy_range=target_xy_range, goal_z_range=goal_z_range,
+                                   n_substeps=n_substeps, max_episode_steps=max_episode_steps, autoreset=autoreset,
+                                   collision_mask=collision_mask)
+        self.block_gripper = bool(self.cfg.block_gripper)
+        self.compiled = model.load_compiled(self.task, assets_path)
+        self.cmodel, self.verts = model.pack_model(self.compiled)
+        self.nq, self.nv = self.cmodel.nq, self.cmodel.nv
+        self.action_dim, self.obs_dim = config.action_dim(self.cfg), config.obs_dim(self.task)
+        self.precision = {"float32": capi.F32, "float64": capi.F64}[precision]
+        self.env_offset = int(env_offset)  # global index of local env 0 (multi-GPU sharding)
+        self._L = capi.lib()
+        h = C.c_void_p()
+        capi.check(self._L.lcr_create(C.byref(self.cmodel), self.verts.ctypes.data_as(C.c_void_p), C.byref(self.cfg),
+                                      self.num_envs, self.device.index or 0, self.precision, C.byref(h)))
+        self._h = h
+        n, dev = self.num_envs, self.device
+        self._obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, device=dev)
+        self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._flags = torch.zeros(3, n, dtype=torch.uint8, device=dev)
+        self.single_action_space = spaces.Box(-1.0, 1.0, (self.action_dim,), np.float32)
+        sub = {"arm_qpos": spaces.Box(-np.pi, np.pi, (6,)), "arm_qvel": spaces.Box(-10.0, 10.0, (6,))}
+        for key, width in _OBS_LAYOUT[self.task][2:]:
+            sub[key] = spaces.Box(-10.0, 10.0, (width,))
+        self.single_observation_space = spaces.Dict(sub)
+        self.action_space = spaces.batch_space(self.single_action_space, n)
+        self.observation_space = spaces.batch_space(self.single_observation_space, n)
+        self.seed(0)
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _split(self, flat):
+        out, k = {}, 0
+        for key, width in _OBS_LAYOUT[self.task]:
+            out[key] = flat[:, k:k + width]
+            k += width
+        return out
+
+    def seed(self, seed):
+        """Env ``i`` gets the stream of ``np.random.default_rng(seed + env_offset + i)``."""
+        base = int(seed) + self.env_offset
+        st = pcg64_states(range(base, base + self.num_envs))
+        capi.check(self._L.lcr_seed(self._h, st.ctypes.data_as(C.c_void_p), self._stream()))
+
+    # -- gymnasium-style API -----------------------------------------------------------------
+    def reset(self, seed=None, options=None, mask=None):
+        """Reference ``reset`` (reach_cube_env.py:297-311).  ``mask`` (bool[num_envs]) resets a subset."""
+        if seed is not None:
+            self.seed(seed)
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            if m.shape != (self.num_envs,):
+                raise ValueError("mask must have shape (num_envs,)")
+        with torch.cuda.device(self.device):
+            capi.check(self._L.lcr_reset(self._h, _ptr(m), _ptr(self._obs), self._stream()))
+        return self._split(self._obs.clone()), {}
+
+    def step_flat(self, actions):
+        """One control step; returns views of the internal output buffers (no copies)."""
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions), device=self.device)
+        if tuple(actions.shape) != (self.num_envs, self.action_dim):
+            raise ValueError("Action dimension mismatch")  # reach_cube_env.py:231-232
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        f = self._flags
+        with torch.cuda.device(self.device):
+            capi.check(self._L.lcr_step(self._h, _ptr(a), _ptr(self._obs), _ptr(self._reward), _ptr(f[0]), _ptr(f[1]),
+                                        _ptr(f[2]), self._stream()))
+        return self._obs, self._reward, f[0], f[1], f[2]
+
+    def step(self, actions):
+        obs, reward, te, tr, su = self.step_flat(actions)
+        info = {} if self.task == "lift" else {"is_success": su.bool()}  # lift_cube_env.py:337
+        return self._split(obs.clone()), reward.clone(), te.bool(), tr.bool(), info
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.lcr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self):
+        raise NotImplementedError("rendering is out of scope")
+
+    # -- state access (replaces env.data.qpos / qvel / ctrl pokes; checkpoint / resume) ----------
+    def get_state(self):
+        n, dev = self.num_envs, self.device
+        z = lambda w, dt=torch.float64: torch.zeros(n, w, dtype=dt, device=dev)
+        st = dict(qpos=z(self.nq), qvel=z(self.nv), ctrl=z(6), warm=z(self.nv), aux=z(model.NAUX),
+                  ints=z(model.NINT, torch.int32))
+        with torch.cuda.device(self.device):
+            capi.check(self._L.lcr_get_state(self._h, *[_ptr(st[k]) for k in ("qpos", "qvel", "ctrl", "warm", "aux", "ints")],
+                                             self._stream()))
+        return st
+
+    def set_state(self, qpos=None, qvel=None, ctrl=None, warm=None, aux=None, ints=None):
+        def prep(x, w, dt=torch.float64):
+            if x is None:
+                return None
+            t = torch.as_tensor(x).to(device=self.device, dtype=dt).contiguous()
+            if tuple(t.shape) != (self.num_envs, w):
+                raise ValueError(f"expected shape {(self.num_envs, w)}, got {tuple(t.shape)}")
+            return t
+        args = [prep(qpos, self.nq), prep(qvel, self.nv), prep(ctrl, 6), prep(warm, self.nv), prep(aux, model.NAUX),
+                prep(ints, model.NINT, torch.int32)]
+        with torch.cuda.device(self.device):
+            capi.check(self._L.lcr_set_state(self._h, *[_ptr(a) for a in args], self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()  # args are temporaries
+
+    def substeps(self, n):
+        """``n`` raw ``mj_step`` calls with the current ctrl (``n == 0``: ``mj_forward`` only)."""
+        with torch.cuda.device(self.device):
+            capi.check(self._L.lcr_substeps(self._h, int(n), self._stream()))
+
+    def inverse_kinematics(self, ee_target_pos):
+        """Batched damped-least-squares IK from the current arm pose (reach_cube_env.py:148-221)."""
+        t = torch.as_tensor(ee_target_pos).to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(t.shape) != (self.num_envs, 3):
+            raise ValueError("ee_target_pos must have shape (num_envs, 3)")
+        q = torch.zeros(self.num_envs, 6, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            capi.check(self._L.lcr_ik(self._h, _ptr(t), _ptr(q), self._stream()))
+        return q
+
+    def diagnostics(self):
+        d = torch.zeros(self.num_envs, model.NDIAG, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            capi.check(self._L.lcr_get_diag(self._h, _ptr(d), self._stream()))
+        return dict(zip(("ncon", "nefc", "niter", "max_nefc", "overflow", "nan_resets"), d.unbind(1)))
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.lcr_kernel_launches(self._h))
+
+
+class ReachCubeEnv(BatchedLowCostRobotEnv):
+    task = "reach"
+
+
+class PushCubeEnv(BatchedLowCostRobotEnv):
+    task = "push"
+
+
+class LiftCubeEnv(BatchedLowCostRobotEnv):
+    task = "lift"
+
+
+class PickPlaceCubeEnv(BatchedLowCostRobotEnv):
+    task = "pick_place"
+
+
+class StackTwoCubesEnv(BatchedLowCostRobotEnv):
+    task = "stack"
+
+
+ENV_CLASSES = {"reach": ReachCubeEnv, "push": PushCubeEnv, "lift": LiftCubeEnv, "pick_place": PickPlaceCubeEnv,
+               "stack": StackTwoCubesEnv}

@@ -94,6 +94,9 @@ int lcr_n_envs(const LcrSim* sim);
 int lcr_kernel_launches(const LcrSim* sim); /* kernels launched by this handle so far */
 const char* lcr_last_error(void);
 const char* lcr_version(void);
+/* sizeof(LcrModel) / sizeof(LcrEnvCfg) as compiled, so that FFI mirrors can verify their layout */
+int lcr_sizeof_model(void);
+int lcr_sizeof_cfg(void);
 
 #ifdef __cplusplus
 }
