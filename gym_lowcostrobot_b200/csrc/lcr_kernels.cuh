@@ -527,9 +527,10 @@ __device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m
   }
   __syncwarp();
   // elliptic friction rows: R from the normal row and impratio; mu
-  T Rnew = 0;
-  for (int i = nlim + lane; i < nefc + 31; i += 32) {  // two-phase per 32-row chunk: read, sync, write
+  for (int base = nlim; base < nefc; base += 32) {  // warp-uniform trip count; per chunk: read, sync, write
+    const int i = base + lane;
     const bool act = i < nefc;
+    T Rnew = 0;
     if (act) {
       const int u = w.e_unit[i], r = w.e_r[i];
       const CPar<T>* par = w.c_par[u];
