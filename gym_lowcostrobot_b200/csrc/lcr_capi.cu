@@ -106,7 +106,7 @@ void build_model(const LcrModel& m, const LcrEnvCfg& c, DevModel<T>& d) {
   }
   for (int g = 0; g < m.nmesh; g++) {
     d.mesh_body[g] = m.mesh_body[g]; d.mesh_vertadr[g] = m.mesh_vertadr[g]; d.mesh_vertnum[g] = m.mesh_vertnum[g];
-    for (int k = 0; k < 3; k++) { d.mesh_center[g][k] = (T)m.mesh_center[g][k]; d.mesh_half[g][k] = (T)m.mesh_half[g][k]; }
+    for (int k = 0; k < 3; k++) { d.mesh_center[g][k] = (T)m.mesh_center[g][k]; d.mesh_half[g][k] = (T)m.mesh_half[g][k]; d.mesh_com[g][k] = (T)m.mesh_com[g][k]; }
     d.mesh_rbound[g] = (T)m.mesh_rbound[g];
   }
   const int gfloor = m.nmesh;
@@ -156,10 +156,9 @@ struct Impl {
     CUDA_OK(cudaMemcpy(verts, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     nf = m.nq + 2 * m.nv + LCR_NARM + LCR_NAUX;
     s.n = n;
-    CUDA_OK(cudaMalloc(&s.st, sizeof(T) * (size_t)nf * n));
-    CUDA_OK(cudaMalloc(&s.ints, sizeof(int32_t) * LCR_NINT * (size_t)n));
-    CUDA_OK(cudaMalloc(&s.rng, sizeof(unsigned long long) * 4 * (size_t)n));
-    CUDA_OK(cudaMalloc(&s.diag, sizeof(int32_t) * LCR_NDIAG * (size_t)n));
+    s.nfp = (nf + 3) & ~3;
+    CUDA_OK(cudaMalloc(&s.st, sizeof(T) * (size_t)s.nfp * n));
+    CUDA_OK(cudaMalloc(&s.ib, sizeof(int32_t) * LCR_IB_WORDS * (size_t)n));
     lcr::Launch<T>::prepare(m.ncube);
     lcr::Launch<T>::init_state(m.ncube, dm, s, 0);
     CUDA_OK(cudaGetLastError());
@@ -167,7 +166,7 @@ struct Impl {
     return 0;
   }
   void destroy() {
-    cudaFree(dm); cudaFree(verts); cudaFree(s.st); cudaFree(s.ints); cudaFree(s.rng); cudaFree(s.diag);
+    cudaFree(dm); cudaFree(verts); cudaFree(s.st); cudaFree(s.ib);
   }
 };
 
@@ -222,11 +221,14 @@ int lcr_seed(LcrSim* sim, const uint64_t* h_state, void* stream) {
   WITH_DEVICE(sim);
   if (!h_state) return fail("lcr_seed: null state");
   const size_t n = sim->n;
-  std::vector<unsigned long long> soa(4 * n);
-  for (size_t e = 0; e < n; e++) for (int k = 0; k < 4; k++) soa[k * n + e] = h_state[4 * e + k];
-  unsigned long long* dst = sim->precision == LCR_F32 ? sim->f.s.rng : sim->d.s.rng;
-  CUDA_OK(cudaMemcpyAsync(dst, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));  // soa is a temporary
+  unsigned long long* tmp = nullptr;
+  CUDA_OK(cudaMalloc(&tmp, 32 * n));
+  CUDA_OK(cudaMemcpyAsync(tmp, h_state, 32 * n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  if (sim->precision == LCR_F32) lcr::Launch<float>::seed(sim->f.s, tmp, (cudaStream_t)stream);
+  else lcr::Launch<double>::seed(sim->d.s, tmp, (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  CUDA_OK(cudaFree(tmp));
   return 0;
 }
 
@@ -293,11 +295,20 @@ int lcr_ik(LcrSim* sim, const float* d_ee_target, float* d_q_out, void* stream) 
 int lcr_get_diag(LcrSim* sim, int32_t* d_diag, void* stream) {
   WITH_DEVICE(sim);
   if (!d_diag) return fail("lcr_get_diag: null buffer");
-  const int32_t* src = sim->precision == LCR_F32 ? sim->f.s.diag : sim->d.s.diag;
-  // device layout is [LCR_NDIAG][n]; callers get [n][LCR_NDIAG] via a strided 2-D copy
-  for (int k = 0; k < LCR_NDIAG; k++)
-    CUDA_OK(cudaMemcpy2DAsync(d_diag + k, sizeof(int32_t) * LCR_NDIAG, src + (size_t)k * sim->n, sizeof(int32_t), sizeof(int32_t), sim->n,
-                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (sim->precision == LCR_F32) lcr::Launch<float>::get_diag(sim->f.s, d_diag, (cudaStream_t)stream);
+  else lcr::Launch<double>::get_diag(sim->d.s, d_diag, (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_debug_contacts(LcrSim* sim, double* d_contacts, int32_t* d_ncon, void* stream) {
+  WITH_DEVICE(sim);
+  if (!d_contacts || !d_ncon) return fail("lcr_debug_contacts: null buffer");
+  if (sim->precision == LCR_F32) lcr::Launch<float>::debug_contacts(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_contacts, d_ncon, (cudaStream_t)stream);
+  else lcr::Launch<double>::debug_contacts(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_contacts, d_ncon, (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
   return 0;
 }
 

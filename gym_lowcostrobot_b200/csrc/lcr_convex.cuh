@@ -1,0 +1,475 @@
+// lcr_convex.cuh -- warp-cooperative convex narrowphase: Minkowski Portal Refinement for box-mesh and
+// mesh-mesh pairs, SAT + face clipping for box-box, and the sphere / oriented-box broadphase.
+//
+// MPR follows the published algorithm of libccd's ccdMPRPenetration, which MuJoCo 3.2.x calls from
+// mjc_Convex for every box/mesh pair (inside mujoco.mj_step, reference reach_cube_env.py:277).  The
+// portal logic is scalar and runs redundantly (warp-uniform) in every lane; the support function of
+// a mesh is the parallel part: lanes stride over the hull vertices and a shuffle butterfly picks the
+// first maximum.  All of this is cold code (only reached when a broadphase test passes), kept out
+// of line so that the per-substep hot path stays small.
+#pragma once
+#include "lcr_device.cuh"
+
+namespace lcr {
+
+template <typename T> DI T ccd_eps();
+template <> DI float ccd_eps<float>() { return 1.1920929e-07f; }
+template <> DI double ccd_eps<double>() { return 2.220446049250313e-16; }
+template <typename T> DI bool is_zero(T x) { return fabs(x) < ccd_eps<T>(); }
+template <typename T> DI bool ccd_eq(T a, T b) {
+  const T ab = fabs(a - b);
+  if (ab < ccd_eps<T>()) return true;
+  const T fa = fabs(a), fb = fabs(b);
+  return ab < ccd_eps<T>() * (fb > fa ? fb : fa);
+}
+template <typename T> DI bool vec_is_origin(const T* a) { return ccd_eq(a[0], (T)0) && ccd_eq(a[1], (T)0) && ccd_eq(a[2], (T)0); }
+template <typename T> DI void normalize3(T* v) {
+  const T n = sqrt(dot3(v, v));
+  if (n > 0) { const T inv = 1 / n; v[0] *= inv; v[1] *= inv; v[2] *= inv; }
+}
+
+template <typename T>
+struct Shape {  // warp-uniform descriptor
+  int kind;     // 0 box, 1 mesh
+  int body;     // index into w.xpos / w.xmat
+  int adr, num; // mesh vertex range
+  T half[3];    // box half sizes
+  T center[3];  // interior point (geom centre), world
+};
+template <typename T> struct SPoint { T v[3], v1[3], v2[3]; };
+
+// support point of one shape along world direction d (all lanes get the same result)
+template <typename T, int NC>
+__device__ __noinline__ void shape_support(const Ws<T, NC>& w, const T* __restrict__ verts, const Shape<T>& sh, const T* d, T* out) {
+  T dl[3], p[3];
+  const T* R = w.xmat[sh.body];
+  matT_vec(dl, R, d);
+  if (sh.kind == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) p[k] = dl[k] >= 0 ? sh.half[k] : -sh.half[k];
+  } else {
+    T bv = (T)-1e30;
+    int bi = 0x7fffffff;
+    for (int i = LANE; i < sh.num; i += 32) {
+      const T* v = verts + 4 * (size_t)(sh.adr + i);
+      const T s = v[0] * dl[0] + v[1] * dl[1] + v[2] * dl[2];
+      if (s > bv) { bv = s; bi = i; }
+    }
+    warp_argmax(bv, bi);
+    const T* v = verts + 4 * (size_t)(sh.adr + bi);
+    p[0] = v[0]; p[1] = v[1]; p[2] = v[2];
+  }
+  mat_vec(out, R, p);
+#pragma unroll
+  for (int k = 0; k < 3; k++) out[k] += w.xpos[sh.body][k];
+}
+
+template <typename T, int NC>
+DI void md_support(const Ws<T, NC>& w, const T* __restrict__ verts, const Shape<T>& A, const Shape<T>& B, const T* dir, SPoint<T>& p) {
+  T nd[3] = {-dir[0], -dir[1], -dir[2]};
+  shape_support(w, verts, A, dir, p.v1);
+  shape_support(w, verts, B, nd, p.v2);
+#pragma unroll
+  for (int k = 0; k < 3; k++) p.v[k] = p.v1[k] - p.v2[k];
+}
+
+template <typename T> DI void portal_dir(const SPoint<T>* P, T* dir) {
+  T a[3], b[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { a[k] = P[2].v[k] - P[1].v[k]; b[k] = P[3].v[k] - P[1].v[k]; }
+  cross3(dir, a, b);
+  normalize3(dir);
+}
+template <typename T> DI bool reach_tolerance(const SPoint<T>* P, const SPoint<T>& v4, const T* dir, T tol) {
+  const T dv1 = dot3(P[1].v, dir), dv2 = dot3(P[2].v, dir), dv3 = dot3(P[3].v, dir), dv4 = dot3(v4.v, dir);
+  T d = dv4 - dv1;
+  if (dv4 - dv2 < d) d = dv4 - dv2;
+  if (dv4 - dv3 < d) d = dv4 - dv3;
+  return ccd_eq(d, tol) || d < tol;
+}
+template <typename T> DI void expand_portal(SPoint<T>* P, const SPoint<T>& v4) {
+  T c[3];
+  cross3(c, v4.v, P[0].v);
+  if (dot3(P[1].v, c) > 0) {
+    if (dot3(P[2].v, c) > 0) P[1] = v4; else P[3] = v4;
+  } else {
+    if (dot3(P[3].v, c) > 0) P[2] = v4; else P[1] = v4;
+  }
+}
+template <typename T> DI T origin_tri_dist2(const T* a, const T* b, const T* c, T* wit) {
+  T ab[3], ac[3], ap[3] = {-a[0], -a[1], -a[2]}, bp[3] = {-b[0], -b[1], -b[2]}, cp[3] = {-c[0], -c[1], -c[2]};
+#pragma unroll
+  for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; }
+  const T d1 = dot3(ab, ap), d2 = dot3(ac, ap), d3 = dot3(ab, bp), d4 = dot3(ac, bp), d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+  const T vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
+  if (d1 <= 0 && d2 <= 0) { wit[0] = a[0]; wit[1] = a[1]; wit[2] = a[2]; }
+  else if (d3 >= 0 && d4 <= d3) { wit[0] = b[0]; wit[1] = b[1]; wit[2] = b[2]; }
+  else if (vc <= 0 && d1 >= 0 && d3 <= 0) { const T v = d1 / (d1 - d3); for (int k = 0; k < 3; k++) wit[k] = a[k] + v * ab[k]; }
+  else if (d6 >= 0 && d5 <= d6) { wit[0] = c[0]; wit[1] = c[1]; wit[2] = c[2]; }
+  else if (vb <= 0 && d2 >= 0 && d6 <= 0) { const T ww = d2 / (d2 - d6); for (int k = 0; k < 3; k++) wit[k] = a[k] + ww * ac[k]; }
+  else if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+    const T ww = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+    for (int k = 0; k < 3; k++) wit[k] = b[k] + ww * (c[k] - b[k]);
+  } else {
+    const T den = 1 / (va + vb + vc), v = vb * den, ww = vc * den;
+    for (int k = 0; k < 3; k++) wit[k] = a[k] + ab[k] * v + ac[k] * ww;
+  }
+  return dot3(wit, wit);
+}
+template <typename T> DI void find_pos(const SPoint<T>* P, T* pos) {
+  T dir[3], b[4], c[3];
+  portal_dir(P, dir);
+  cross3(c, P[1].v, P[2].v); b[0] = dot3(c, P[3].v);
+  cross3(c, P[3].v, P[2].v); b[1] = dot3(c, P[0].v);
+  cross3(c, P[0].v, P[1].v); b[2] = dot3(c, P[3].v);
+  cross3(c, P[2].v, P[1].v); b[3] = dot3(c, P[0].v);
+  T sum = b[0] + b[1] + b[2] + b[3];
+  if (is_zero(sum) || sum < 0) {
+    b[0] = 0;
+    cross3(c, P[2].v, P[3].v); b[1] = dot3(c, dir);
+    cross3(c, P[3].v, P[1].v); b[2] = dot3(c, dir);
+    cross3(c, P[1].v, P[2].v); b[3] = dot3(c, dir);
+    sum = b[1] + b[2] + b[3];
+  }
+  const T inv = 1 / sum;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    T p1 = 0, p2 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { p1 += b[i] * P[i].v1[k]; p2 += b[i] * P[i].v2[k]; }
+    pos[k] = (T)0.5 * (p1 + p2) * inv;
+  }
+}
+
+// returns true and fills depth / pdir / pos if the shapes penetrate (warp-uniform)
+template <typename T, int NC>
+__device__ __noinline__ bool mpr_penetration(const Ws<T, NC>& w, const T* __restrict__ verts, const Shape<T>& A, const Shape<T>& B, T& depth,
+                                             T* pdir, T* pos) {
+  const T tol = (T)1e-6;
+  SPoint<T> P[4], v4;
+  T dir[3], va[3], vb[3], d;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { P[0].v1[k] = A.center[k]; P[0].v2[k] = B.center[k]; P[0].v[k] = A.center[k] - B.center[k]; }
+  if (vec_is_origin(P[0].v)) P[0].v[0] += ccd_eps<T>() * 10;
+#pragma unroll
+  for (int k = 0; k < 3; k++) dir[k] = -P[0].v[k];
+  normalize3(dir);
+  md_support(w, verts, A, B, dir, P[1]);
+  d = dot3(P[1].v, dir);
+  if (is_zero(d) || d < 0) return false;
+  cross3(dir, P[0].v, P[1].v);
+  if (is_zero(dot3(dir, dir))) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) pos[k] = (T)0.5 * (P[1].v1[k] + P[1].v2[k]);
+    if (vec_is_origin(P[1].v)) { depth = 0; pdir[0] = pdir[1] = pdir[2] = 0; return true; }
+    depth = sqrt(dot3(P[1].v, P[1].v));
+    pdir[0] = P[1].v[0]; pdir[1] = P[1].v[1]; pdir[2] = P[1].v[2];
+    normalize3(pdir);
+    return true;
+  }
+  normalize3(dir);
+  md_support(w, verts, A, B, dir, P[2]);
+  d = dot3(P[2].v, dir);
+  if (is_zero(d) || d < 0) return false;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { va[k] = P[1].v[k] - P[0].v[k]; vb[k] = P[2].v[k] - P[0].v[k]; }
+  cross3(dir, va, vb);
+  normalize3(dir);
+  if (dot3(dir, P[0].v) > 0) {
+    const SPoint<T> t = P[1]; P[1] = P[2]; P[2] = t;
+    dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2];
+  }
+#pragma unroll 1
+  for (int guard = 0;; guard++) {
+    if (guard > 100) return false;
+    md_support(w, verts, A, B, dir, P[3]);
+    d = dot3(P[3].v, dir);
+    if (is_zero(d) || d < 0) return false;
+    bool cont = false;
+    cross3(va, P[1].v, P[3].v); d = dot3(va, P[0].v);
+    if (d < 0 && !is_zero(d)) { P[2] = P[3]; cont = true; }
+    if (!cont) {
+      cross3(va, P[3].v, P[2].v); d = dot3(va, P[0].v);
+      if (d < 0 && !is_zero(d)) { P[1] = P[3]; cont = true; }
+    }
+    if (!cont) break;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { va[k] = P[1].v[k] - P[0].v[k]; vb[k] = P[2].v[k] - P[0].v[k]; }
+    cross3(dir, va, vb);
+    normalize3(dir);
+  }
+#pragma unroll 1
+  for (int guard = 0;; guard++) {
+    if (guard > 100) return false;
+    portal_dir(P, dir);
+    d = dot3(dir, P[1].v);
+    if (is_zero(d) || d > 0) break;
+    md_support(w, verts, A, B, dir, v4);
+    d = dot3(v4.v, dir);
+    if (!(is_zero(d) || d > 0) || reach_tolerance(P, v4, dir, tol)) return false;
+    expand_portal(P, v4);
+  }
+#pragma unroll 1
+  for (int it = 0;; it++) {
+    portal_dir(P, dir);
+    md_support(w, verts, A, B, dir, v4);
+    if (reach_tolerance(P, v4, dir, tol) || it > 50) {
+      T wit[3];
+      depth = sqrt(origin_tri_dist2(P[1].v, P[2].v, P[3].v, wit));
+      if (is_zero(wit[0]) && is_zero(wit[1]) && is_zero(wit[2])) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; }
+      else { pdir[0] = wit[0]; pdir[1] = wit[1]; pdir[2] = wit[2]; }
+      normalize3(pdir);
+      find_pos(P, pos);
+      return true;
+    }
+    expand_portal(P, v4);
+  }
+}
+
+template <typename T, int NC> DI void mesh_shape(const Ws<T, NC>& w, const DevModel<T>& m, int g, Shape<T>& sh) {
+  const int b = m.mesh_body[g];
+  sh.kind = 1; sh.body = b; sh.adr = m.mesh_vertadr[g]; sh.num = m.mesh_vertnum[g];
+  sh.half[0] = sh.half[1] = sh.half[2] = 0;
+  T c[3] = {m.mesh_com[g][0], m.mesh_com[g][1], m.mesh_com[g][2]};
+  mat_vec(sh.center, w.xmat[b], c);
+#pragma unroll
+  for (int k = 0; k < 3; k++) sh.center[k] += w.xpos[b][k];
+}
+template <typename T, int NC> DI void cube_shape(const Ws<T, NC>& w, const DevModel<T>& m, int c, Shape<T>& sh) {
+  const int b = LCR_NABODY + c;
+  sh.kind = 0; sh.body = b; sh.adr = 0; sh.num = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { sh.half[k] = m.cube_size[c][k]; sh.center[k] = w.xpos[b][k]; }
+}
+
+// oriented-box overlap test (15 axes) between the body-frame bounding boxes of two mesh geoms; conservative
+template <typename T, int NC>
+DI bool obb_apart(const Ws<T, NC>& w, const DevModel<T>& m, int g1, int g2) {
+  const int b1 = m.mesh_body[g1], b2 = m.mesh_body[g2];
+  const T* RA = w.xmat[b1];
+  const T* RB = w.xmat[b2];
+  const T eps = (T)1e-6;
+  T a[3] = {m.mesh_half[g1][0] + eps, m.mesh_half[g1][1] + eps, m.mesh_half[g1][2] + eps};
+  T b[3] = {m.mesh_half[g2][0] + eps, m.mesh_half[g2][1] + eps, m.mesh_half[g2][2] + eps};
+  T tw[3] = {w.gc[g2][0] - w.gc[g1][0], w.gc[g2][1] - w.gc[g1][1], w.gc[g2][2] - w.gc[g1][2]};
+  T R[3][3], AR[3][3], t[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    t[i] = tw[0] * RA[i] + tw[1] * RA[3 + i] + tw[2] * RA[6 + i];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      R[i][j] = RA[i] * RB[j] + RA[3 + i] * RB[3 + j] + RA[6 + i] * RB[6 + j];
+      AR[i][j] = fabs(R[i][j]) + eps;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    if (fabs(t[i]) > a[i] + b[0] * AR[i][0] + b[1] * AR[i][1] + b[2] * AR[i][2]) return true;
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    if (fabs(t[0] * R[0][j] + t[1] * R[1][j] + t[2] * R[2][j]) > a[0] * AR[0][j] + a[1] * AR[1][j] + a[2] * AR[2][j] + b[j]) return true;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const T ra = a[i1] * AR[i2][j] + a[i2] * AR[i1][j], rb = b[j1] * AR[i][j2] + b[j2] * AR[i][j1];
+      if (fabs(t[i2] * R[i1][j] - t[i1] * R[i2][j]) > ra + rb) return true;
+    }
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------- box-box (cube 0 vs cube 1): SAT + clipping
+template <typename T, int NC>
+__device__ __noinline__ void collide_cube_cube(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc) {
+  const int bA = LCR_NABODY, bB = LCR_NABODY + 1;
+  const T* pA = w.xpos[bA];
+  const T* pB = w.xpos[bB];
+  const T* RA = w.xmat[bA];
+  const T* RB = w.xmat[bB];
+  T hA[3] = {m.cube_size[0][0], m.cube_size[0][1], m.cube_size[0][2]}, hB[3] = {m.cube_size[1][0], m.cube_size[1][1], m.cube_size[1][2]};
+  T t[3] = {pB[0] - pA[0], pB[1] - pA[1], pB[2] - pA[2]};
+  {
+    const T r = sqrt(dot3(hA, hA)) + sqrt(dot3(hB, hB));
+    if (dot3(t, t) > r * r) return;
+  }
+  T axA[3][3], axB[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) { axA[i][k] = RA[3 * k + i]; axB[i][k] = RB[3 * k + i]; }
+  T best = (T)1e30, bestn[3] = {0, 0, 0};
+  int code = -1;
+#pragma unroll 1
+  for (int a = 0; a < 15; a++) {
+    T L[3];
+    if (a < 3) { L[0] = axA[a][0]; L[1] = axA[a][1]; L[2] = axA[a][2]; }
+    else if (a < 6) { L[0] = axB[a - 3][0]; L[1] = axB[a - 3][1]; L[2] = axB[a - 3][2]; }
+    else {
+      cross3(L, axA[(a - 6) / 3], axB[(a - 6) % 3]);
+      const T n = sqrt(dot3(L, L));
+      if (n < (T)1e-8) continue;
+      const T inv = 1 / n;
+      L[0] *= inv; L[1] *= inv; L[2] *= inv;
+    }
+    T rA = 0, rB = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { rA += hA[i] * fabs(dot3(axA[i], L)); rB += hB[i] * fabs(dot3(axB[i], L)); }
+    const T dist = dot3(t, L), ov = rA + rB - fabs(dist);
+    if (ov < 0) return;
+    const T pen = a < 6 ? ov : ov * (T)1.05 + (T)1e-9;
+    if (pen < best) {
+      best = pen; code = a;
+#pragma unroll
+      for (int k = 0; k < 3; k++) bestn[k] = dist < 0 ? -L[k] : L[k];
+    }
+  }
+  if (code < 0) return;
+  const CPar<T>* par = &m.par_cube_cube;
+  if (code >= 6) {
+    const int ia = (code - 6) / 3, ib = (code - 6) % 3;
+    T ea[3] = {pA[0], pA[1], pA[2]}, eb[3] = {pB[0], pB[1], pB[2]};
+    for (int i = 0; i < 3; i++) {
+      if (i != ia) { const T sg = dot3(axA[i], bestn) > 0 ? (T)1 : (T)-1; for (int k = 0; k < 3; k++) ea[k] += sg * hA[i] * axA[i][k]; }
+      if (i != ib) { const T sg = dot3(axB[i], bestn) > 0 ? (T)-1 : (T)1; for (int k = 0; k < 3; k++) eb[k] += sg * hB[i] * axB[i][k]; }
+    }
+    const T* ua = axA[ia];
+    const T* ub = axB[ib];
+    T ww[3] = {ea[0] - eb[0], ea[1] - eb[1], ea[2] - eb[2]};
+    const T uaub = dot3(ua, ub), q1 = dot3(ua, ww), q2 = dot3(ub, ww), den = 1 - uaub * uaub;
+    T sa = 0, sb = 0;
+    if (den > (T)1e-12) { sa = (uaub * q2 - q1) / den; sb = (q2 - uaub * q1) / den; }
+    sa = clampT(sa, -hA[ia], hA[ia]); sb = clampT(sb, -hB[ib], hB[ib]);
+    T pos[3];
+    for (int k = 0; k < 3; k++) pos[k] = (T)0.5 * (ea[k] + sa * ua[k] + eb[k] + sb * ub[k]);
+    add_contact(w, ncon, nefc, par, bA, bB, pos, bestn, -(best / (T)1.05));
+    return;
+  }
+  const bool refA = code < 3;
+  // explicit copies of the reference / incident box (no pointer selects into local arrays)
+  T pR[3], pI[3], hR[3], hI[3], axR[3][3], axI[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    pR[i] = refA ? pA[i] : pB[i]; pI[i] = refA ? pB[i] : pA[i];
+    hR[i] = refA ? hA[i] : hB[i]; hI[i] = refA ? hB[i] : hA[i];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { axR[i][k] = refA ? axA[i][k] : axB[i][k]; axI[i][k] = refA ? axB[i][k] : axA[i][k]; }
+  }
+  const int ir = refA ? code : code - 3;
+  T nr[3] = {refA ? bestn[0] : -bestn[0], refA ? bestn[1] : -bestn[1], refA ? bestn[2] : -bestn[2]};
+  // incident face: the face of I most anti-parallel to nr
+  const T dI0 = axI[0][0] * nr[0] + axI[0][1] * nr[1] + axI[0][2] * nr[2];
+  const T dI1 = axI[1][0] * nr[0] + axI[1][1] * nr[1] + axI[1][2] * nr[2];
+  const T dI2 = axI[2][0] * nr[0] + axI[2][1] * nr[1] + axI[2][2] * nr[2];
+  // (the running |max| is tracked in its own variable: nvcc 12.9 drops the |.| of `fabs(mn)` when mn is a
+  //  select of the previous candidates, which picked the wrong face)
+  const T aI0 = fabs(dI0), aI1 = fabs(dI1), aI2 = fabs(dI2);
+  int ii = 0;
+  T mn = dI0, ma = aI0;
+  if (aI1 > ma) { ma = aI1; mn = dI1; ii = 1; }
+  if (aI2 > ma) { ma = aI2; mn = dI2; ii = 2; }
+  const T sgI = mn > 0 ? (T)-1 : (T)1;
+  T fc[3];
+  for (int k = 0; k < 3; k++) fc[k] = pI[k] + sgI * hI[ii] * axI[ii][k];
+  const int i1 = (ii + 1) % 3, i2 = (ii + 2) % 3;
+  // the clip polygon lives in the (cold) e_jv / e_force scratch rows of the workspace: 2 x 16 x 3 values
+  T (*poly)[3] = reinterpret_cast<T(*)[3]>(w.e_jv);
+  T (*tmp)[3] = reinterpret_cast<T(*)[3]>(w.e_force);
+  int np = 4;
+  const T sx[4] = {1, -1, -1, 1}, sy[4] = {1, 1, -1, -1};
+  __syncwarp();
+  if (LANE == 0)
+    for (int v = 0; v < 4; v++)
+      for (int k = 0; k < 3; k++) poly[v][k] = fc[k] + sx[v] * hI[i1] * axI[i1][k] + sy[v] * hI[i2] * axI[i2][k];
+  __syncwarp();
+  const int r1 = (ir + 1) % 3, r2 = (ir + 2) % 3;
+#pragma unroll 1
+  for (int side = 0; side < 4; side++) {
+    const T* ax = axR[side < 2 ? r1 : r2];
+    const T sg = (side & 1) ? (T)-1 : (T)1, lim = hR[side < 2 ? r1 : r2];
+    int nn = 0;
+    for (int v = 0; v < np; v++) {  // warp-uniform: every lane walks the polygon, lane 0 stores
+      const T* p = poly[v];
+      const T* q = poly[(v + 1) % np];
+      T rp[3] = {p[0] - pR[0], p[1] - pR[1], p[2] - pR[2]}, rq[3] = {q[0] - pR[0], q[1] - pR[1], q[2] - pR[2]};
+      const T dp = sg * dot3(rp, ax) - lim, dq = sg * dot3(rq, ax) - lim;
+      if (dp <= 0) { if (LANE == 0) { tmp[nn][0] = p[0]; tmp[nn][1] = p[1]; tmp[nn][2] = p[2]; } nn++; }
+      if ((dp < 0 && dq > 0) || (dp > 0 && dq < 0)) {
+        const T u = dp / (dp - dq);
+        if (LANE == 0) for (int k = 0; k < 3; k++) tmp[nn][k] = p[k] + u * (q[k] - p[k]);
+        nn++;
+      }
+    }
+    __syncwarp();
+    np = nn;
+    if (LANE == 0) for (int v = 0; v < np; v++) { poly[v][0] = tmp[v][0]; poly[v][1] = tmp[v][1]; poly[v][2] = tmp[v][2]; }
+    __syncwarp();
+    if (np == 0) return;
+  }
+  int cnt = 0;
+  for (int v = 0; v < np && cnt < 8; v++) {
+    T rp[3] = {poly[v][0] - pR[0], poly[v][1] - pR[1], poly[v][2] - pR[2]};
+    const T depth = hR[ir] - dot3(rp, nr);
+    if (depth <= 0) continue;
+    T pos[3] = {poly[v][0] + (T)0.5 * depth * nr[0], poly[v][1] + (T)0.5 * depth * nr[1], poly[v][2] + (T)0.5 * depth * nr[2]};
+    if (add_contact(w, ncon, nefc, par, bA, bB, pos, bestn, -depth)) cnt++;
+  }
+}
+
+// ---------------------------------------------------------------- pair drivers
+template <typename T, int NC>
+__device__ __noinline__ void collide_cube_meshes(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc, int c) {
+  const int lane = LANE, bc = LCR_NABODY + c;
+  bool cand = false;
+  if (lane < m.nmesh) {
+    T hc[3] = {m.cube_size[c][0], m.cube_size[c][1], m.cube_size[c][2]};
+    const T r = m.mesh_rbound[lane] + sqrt(dot3(hc, hc));
+    T d[3] = {w.gc[lane][0] - w.xpos[bc][0], w.gc[lane][1] - w.xpos[bc][1], w.gc[lane][2] - w.xpos[bc][2]};
+    cand = !(dot3(d, d) > r * r);
+  }
+  unsigned mask = __ballot_sync(FULLMASK, cand);
+  while (mask) {
+    const int g = __ffs(mask) - 1;
+    mask &= mask - 1;
+    Shape<T> A, B;
+    cube_shape(w, m, c, A);
+    mesh_shape(w, m, g, B);
+    T depth, dir[3], pos[3];
+    if (!mpr_penetration(w, verts, A, B, depth, dir, pos)) continue;
+    if (dir[0] == 0 && dir[1] == 0 && dir[2] == 0) continue;
+    add_contact(w, ncon, nefc, &m.par_cube_mesh[c][g], bc, m.mesh_body[g], pos, dir, -depth);
+  }
+}
+
+template <typename T, int NC>
+__device__ __noinline__ void collide_mesh_meshes(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc) {
+  const int lane = LANE;
+  for (int base = 0; base < m.npair; base += 32) {
+    const int p = base + lane;
+    bool cand = false;
+    if (p < m.npair) {
+      const int g1 = m.pair_g1[p], g2 = m.pair_g2[p];
+      const T r = m.mesh_rbound[g1] + m.mesh_rbound[g2];
+      T d[3] = {w.gc[g1][0] - w.gc[g2][0], w.gc[g1][1] - w.gc[g2][1], w.gc[g1][2] - w.gc[g2][2]};
+      cand = !(dot3(d, d) > r * r);
+      if (cand) cand = !obb_apart(w, m, g1, g2);
+    }
+    unsigned mask = __ballot_sync(FULLMASK, cand);
+    while (mask) {
+      const int pp = base + __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int g1 = m.pair_g1[pp], g2 = m.pair_g2[pp];
+      Shape<T> A, B;
+      mesh_shape(w, m, g1, A);
+      mesh_shape(w, m, g2, B);
+      T depth, dir[3], pos[3];
+      if (!mpr_penetration(w, verts, A, B, depth, dir, pos)) continue;
+      if (dir[0] == 0 && dir[1] == 0 && dir[2] == 0) continue;
+      add_contact(w, ncon, nefc, &m.par_mesh_mesh[pp], m.mesh_body[g1], m.mesh_body[g2], pos, dir, -depth);
+    }
+  }
+}
+
+}  // namespace lcr

@@ -1,11 +1,13 @@
 // lcr_device.cuh -- device-side data structures of liblcrsim (sm_100a).
 //
-// Execution model: ONE WARP PER ENVIRONMENT.  A CTA of LCR_WPB warps stages the SoA state of its
-// LCR_WPB consecutive envs from HBM into shared memory with 128-bit loads (one float4 = one field
-// of 4 consecutive envs), each warp then runs the whole control step (action map / IK -> n_substeps
-// x mj_step -> observation / reward) out of its private shared-memory workspace, and the CTA
-// stages the state back.  Small dense algebra is done with lanes <-> rows/columns and warp
-// shuffles; there is no tensor-core work on this path.
+// Execution model: ONE WARP PER ENVIRONMENT, one 32-thread CTA per warp (envs finish at different
+// times -- solver iterations and contact counts are data dependent -- so warps must not wait for
+// each other; the hardware CTA scheduler does the load balancing).  The persistent state of an env
+// is one contiguous, 16-byte aligned record in HBM; the warp stages it into shared memory with
+// coalesced 128-bit loads (lane l moves uint4 #l of the record), runs the whole control step
+// (action map / IK -> n_substeps x mj_step -> observation / reward) out of its private
+// shared-memory workspace, and writes the record back the same way.  Small dense algebra is done
+// with lanes <-> rows/columns and warp shuffles; there is no tensor-core work on this path.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,7 +15,7 @@
 #include "../../include/lcr_model.h"
 #include "../../include/lcrsim.h"
 
-#define LCR_WPB 4          // warps (= envs) per CTA
+#define LCR_WPB 1          // warps (= envs) per CTA: every env is an independent 32-thread CTA
 #define FULLMASK 0xffffffffu
 
 // contact parameter classes, precomputed on the host by the MuJoCo mixing rule
@@ -36,7 +38,7 @@ struct DevModel {
   T site_pos[3];
   T cube_mass[LCR_MAXCUBE], cube_inertia[LCR_MAXCUBE], cube_size[LCR_MAXCUBE][3], cube_qpos0[LCR_MAXCUBE][3];
   int mesh_body[LCR_MAXMESH], mesh_vertadr[LCR_MAXMESH], mesh_vertnum[LCR_MAXMESH];
-  T mesh_center[LCR_MAXMESH][3], mesh_half[LCR_MAXMESH][3], mesh_rbound[LCR_MAXMESH];
+  T mesh_center[LCR_MAXMESH][3], mesh_half[LCR_MAXMESH][3], mesh_rbound[LCR_MAXMESH], mesh_com[LCR_MAXMESH][3];
   int pair_g1[LCR_MAXPAIR], pair_g2[LCR_MAXPAIR];
   // contact parameter classes
   CPar<T> par_limit[LCR_NARM];
@@ -51,15 +53,15 @@ struct DevModel {
   double cube_low[3], cube_high[3], target_low[3], target_high[3];  // reset draws are float64 like numpy
 };
 
-// Global (HBM) state, SoA [field][env].  Field order of `st` (type T): qpos[nq] | qvel[nv] | ctrl[6] |
-// warm[nv] | aux[LCR_NAUX] (time, target[3], site_xpos[3], cube_xpos[6]).
+// Global (HBM) state: one record per env.  `st` [n][NFP] of T, fields qpos[nq] | qvel[nv] | ctrl[6] |
+// warm[nv] | aux[LCR_NAUX] (time, target[3], site_xpos[3], cube_xpos[6]) | pad to a multiple of 16 B.
+// `ib` [n][16] int32: elapsed, needs_reset | diag[6] | PCG64 state_hi, state_lo, inc_hi, inc_lo (4 x u64).
+#define LCR_IB_WORDS 16
 template <typename T>
 struct DevState {
-  T* st;                    // [NF][n]
-  int32_t* ints;            // [LCR_NINT][n]  elapsed, needs_reset
-  unsigned long long* rng;  // [4][n]         PCG64 state_hi, state_lo, inc_hi, inc_lo
-  int32_t* diag;            // [LCR_NDIAG][n]
-  int n;
+  T* st;
+  int32_t* ib;
+  int n, nfp;
 };
 
 template <typename T, int NC>
@@ -67,13 +69,15 @@ struct Ws {  // per-warp shared-memory workspace
   static constexpr int NQ = LCR_NARM + 7 * NC, NVV = LCR_NARM + 6 * NC, NB = LCR_NABODY + NC;
   static constexpr int NF = NQ + 2 * NVV + LCR_NARM + LCR_NAUX;
   static constexpr int JS = NVV + 1;  // padded row stride of J (odd -> conflict-free row-parallel access)
-  T st[NF];
-  unsigned long long rng[4];
-  int ints[LCR_NINT];
+  static constexpr int NFP = (NF + 3) & ~3;  // record length in T, multiple of 16 bytes
+  alignas(16) T st[NFP];
+  alignas(16) int ints[LCR_NINT];  // ints | diag | rng are contiguous = the 64-byte `ib` record
   int diag[LCR_NDIAG];
+  unsigned long long rng[4];
   // kinematics
   T xpos[NB][3], xquat[NB][4], xmat[NB][9], xipos[LCR_NABODY][3], ximat[LCR_NABODY][9], axis[LCR_NARM][3];
   T Iw[LCR_NABODY][6];
+  T gc[LCR_MAXMESH][3];  // world centres of the mesh bounding spheres / boxes
   T rw[LCR_NABODY][3], ral[LCR_NABODY][3], ra[LCR_NABODY][3], F[LCR_NABODY][3], Nn[LCR_NABODY][3];
   T M[LCR_NARM][LCR_NARM], Lm[LCR_NARM][LCR_NARM + 1];
   T bias[NVV], smooth[NVV], qacc_smooth[NVV], qacc[NVV], Ma[NVV], grad[NVV], search[NVV], Mv[NVV];
@@ -117,5 +121,8 @@ struct Launch {
   static void set_state(int ncube, DevState<T> s, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
                         const double* aux, const int32_t* ints, cudaStream_t st);
   static void init_state(int ncube, const DevModel<T>* dm, DevState<T> s, cudaStream_t st);
+  static void get_diag(DevState<T> s, int32_t* out, cudaStream_t st);
+  static void debug_contacts(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, double* out, int32_t* ncon, cudaStream_t st);
+  static void seed(DevState<T> s, const unsigned long long* d_state, cudaStream_t st);
 };
 }  // namespace lcr

@@ -90,7 +90,7 @@ DI double pcg64_double(unsigned long long* s) { return (double)(pcg64_next(s) >>
 // ---------------------------------------------------------------- warp-cooperative dense SPD solves
 // In-place Cholesky of the leading n x n block of A (row stride ld) in shared memory: lower
 // triangle becomes L.  Lane i owns row i (n <= 32).
-template <typename T> DI void warp_cholesky(T* A, int ld, int n) {
+template <typename T> __device__ __noinline__ void warp_cholesky(T* A, int ld, int n) {
   const int i = LANE;
   for (int k = 0; k < n; k++) {
     T akk = A[k * ld + k];
@@ -105,7 +105,7 @@ template <typename T> DI void warp_cholesky(T* A, int ld, int n) {
   }
 }
 // Solve L L^T x = b; lane i passes b_i and receives x_i (lanes >= n pass anything, receive 0).
-template <typename T> DI T warp_chol_solve(const T* L, int ld, int n, T b) {
+template <typename T> __device__ __noinline__ T warp_chol_solve(const T* L, int ld, int n, T b) {
   const int i = LANE;
   T y = (i < n) ? b : (T)0;
   for (int k = 0; k < n; k++) {
@@ -354,6 +354,10 @@ DI void collide_floor_cube(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& n
   }
 }
 
+}  // namespace lcr
+#include "lcr_convex.cuh"
+namespace lcr {
+
 // support vertices of mesh g along 4 world directions at once (warp-cooperative, lane-strided)
 template <typename T, int NC>
 DI void mesh_support4(const Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int g, const T (*dirs)[3],
@@ -385,14 +389,10 @@ DI void mesh_support4(const Ws<T, NC>& w, const DevModel<T>& m, const T* __restr
 }
 
 template <typename T, int NC>
-DI void collide_floor_meshes(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc) {
+__device__ __noinline__ void collide_floor_meshes(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc) {
   const int lane = LANE;
   bool cand = false;
-  if (lane < m.nmesh && m.mesh_body[lane] != 0) {
-    const int b = m.mesh_body[lane];
-    T cz = w.xmat[b][6] * m.mesh_center[lane][0] + w.xmat[b][7] * m.mesh_center[lane][1] + w.xmat[b][8] * m.mesh_center[lane][2];
-    cand = !(w.xpos[b][2] + cz - m.mesh_rbound[lane] > 0);
-  }
+  if (lane < m.nmesh && m.mesh_body[lane] != 0) cand = !(w.gc[lane][2] - m.mesh_rbound[lane] > 0);
   unsigned mask = __ballot_sync(FULLMASK, cand);
   const T n[3] = {0, 0, 1};
   const T dirs[4][3] = {{0, 0, -1}, {(T)1e-3, 0, -1}, {(T)-0.5e-3, (T)0.8660254037844386e-3, -1}, {(T)-0.5e-3, (T)-0.8660254037844386e-3, -1}};
@@ -433,27 +433,48 @@ template <typename T> DI T impedance(const T* si, T pos) {
 
 template <typename T, int NC> DI T body_invweight(const DevModel<T>& m, int b, int rot) { return b < 0 ? (T)0 : m.body_invweight0[b][rot]; }
 
-// J entry of a contact row: axis . (Jac_b(pos)[:, d]) for a body b, translational (rot=0) or rotational
+// Fill row i of J for contact row (axis ax, point pos, bodies b1 -> b2): ax . (Jac_b2 - Jac_b1).
 template <typename T, int NC>
-DI T jac_entry(const Ws<T, NC>& w, int b, int d, const T* pos, const T* ax, bool rot) {
-  if (b < 0) return 0;
-  if (b < LCR_NABODY) {
-    if (d >= b) return 0;  // also excludes cube dofs (d >= 6 >= b)
+DI void fill_jac_row(Ws<T, NC>& w, int i, int b1, int b2, const T* pos, const T* ax, bool rot) {
+  constexpr int NVV = Ws<T, NC>::NVV;
+  T* row = w.J[i];
+#pragma unroll
+  for (int d = 0; d < NVV; d++) row[d] = 0;
+  const int n1 = (b1 > 0 && b1 < LCR_NABODY) ? b1 : 0, n2 = (b2 > 0 && b2 < LCR_NABODY) ? b2 : 0;
+  const int nmax = n1 > n2 ? n1 : n2;
+#pragma unroll 1
+  for (int d = 0; d < nmax; d++) {  // hinge d moves arm body b iff d < b
+    const int sgn = (d < n2 ? 1 : 0) - (d < n1 ? 1 : 0);
+    if (sgn == 0) continue;
     const T* z = w.axis[d];
-    if (rot) return dot3(ax, z);
-    T r[3] = {pos[0] - w.xpos[d + 1][0], pos[1] - w.xpos[d + 1][1], pos[2] - w.xpos[d + 1][2]}, c[3];
-    cross3(c, z, r);
-    return dot3(ax, c);
+    T val;
+    if (rot) val = dot3(ax, z);
+    else {
+      T r[3] = {pos[0] - w.xpos[d + 1][0], pos[1] - w.xpos[d + 1][1], pos[2] - w.xpos[d + 1][2]}, c[3];
+      cross3(c, z, r);
+      val = dot3(ax, c);
+    }
+    row[d] = sgn > 0 ? val : -val;
   }
-  const int d0 = LCR_NARM + 6 * (b - LCR_NABODY), k = d - d0;
-  if (k < 0 || k >= 6) return 0;
-  if (k < 3) return rot ? (T)0 : ax[k];
-  const int kk = k - 3;
-  T bx[3] = {w.xmat[b][kk], w.xmat[b][3 + kk], w.xmat[b][6 + kk]};
-  if (rot) return dot3(ax, bx);
-  T r[3] = {pos[0] - w.xpos[b][0], pos[1] - w.xpos[b][1], pos[2] - w.xpos[b][2]}, c[3];
-  cross3(c, bx, r);
-  return dot3(ax, c);
+#pragma unroll 1
+  for (int side = 0; side < 2; side++) {
+    const int b = side ? b1 : b2;
+    if (b < LCR_NABODY) continue;
+    const T sg = side ? (T)-1 : (T)1;
+    T* rc = row + LCR_NARM + 6 * (b - LCR_NABODY);
+    T r[3] = {pos[0] - w.xpos[b][0], pos[1] - w.xpos[b][1], pos[2] - w.xpos[b][2]};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      T bx[3] = {w.xmat[b][k], w.xmat[b][3 + k], w.xmat[b][6 + k]};
+      if (rot) rc[3 + k] += sg * dot3(ax, bx);
+      else {
+        T c[3];
+        cross3(c, bx, r);
+        rc[k] += sg * ax[k];
+        rc[3 + k] += sg * dot3(ax, c);
+      }
+    }
+  }
 }
 
 template <typename T, int NC>
@@ -486,9 +507,21 @@ __device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m
   }
   __syncwarp();
   const int cmask = m.collision_mask;
+  if (lane < m.nmesh) {  // world centres of the mesh bounding spheres / boxes
+    const int b = m.mesh_body[lane];
+    T c[3] = {m.mesh_center[lane][0], m.mesh_center[lane][1], m.mesh_center[lane][2]}, t[3];
+    mat_vec(t, w.xmat[b], c);
+    w.gc[lane][0] = w.xpos[b][0] + t[0]; w.gc[lane][1] = w.xpos[b][1] + t[1]; w.gc[lane][2] = w.xpos[b][2] + t[2];
+  }
+  __syncwarp();
+  // generation order (= drop order at the caps): floor-cube, cube-cube, cube-mesh, floor-mesh, mesh-mesh
   if (cmask & LCR_COLLIDE_FLOOR_CUBE)
     for (int c = 0; c < NC; c++) collide_floor_cube(w, m, ncon, nefc, c);
+  if (NC == 2 && (cmask & LCR_COLLIDE_CUBE_CUBE)) collide_cube_cube(w, m, ncon, nefc);
+  if (cmask & LCR_COLLIDE_CUBE_MESH)
+    for (int c = 0; c < NC; c++) collide_cube_meshes(w, m, verts, ncon, nefc, c);
   if (cmask & LCR_COLLIDE_FLOOR_MESH) collide_floor_meshes(w, m, verts, ncon, nefc);
+  if (cmask & LCR_COLLIDE_MESH_MESH) collide_mesh_meshes(w, m, verts, ncon, nefc);
   if (lane == 0) { w.ncon = ncon; w.nefc = nefc; w.nlim = nlim; }
   __syncwarp();
   // contact rows: lane <-> row
@@ -502,7 +535,7 @@ __device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m
     const T* ax = w.c_frame[ci] + 3 * (r % 3);
     const T* pos = w.c_pos[ci];
     const bool rot = r >= 3;
-    for (int d = 0; d < NVV; d++) w.J[i][d] = jac_entry(w, b2, d, pos, ax, rot) - jac_entry(w, b1, d, pos, ax, rot);
+    fill_jac_row(w, i, b1, b2, pos, ax, rot);
     w.e_pos[i] = r == 0 ? w.c_dist[ci] : (T)0;
   }
   __syncwarp();
@@ -604,8 +637,10 @@ template <typename T, int NC> DI T mul_M(const Ws<T, NC>& w, const DevModel<T>& 
 //     J_c^T Hc J_c = sum_k wrow_k J_k J_k^T + c1 (J_c^T g)(J_c^T g)^T - c2 (J_c^T p)(J_c^T p)^T
 // (bottom zone: wrow = D, c1 = c2 = 0;  middle zone: wrow_0 = 0, wrow_k = c2 f_k^2,
 //  g = dNT/djar, p_k = f_k u_k / T, c1 = Dm, c2 = -mu NT Dm / T >= 0).
-template <typename T, int NC, bool FULL>
-DI int contact_eval(Ws<T, NC>& w, int ci, T alpha, bool with_jv, T& cost, T& d1, T& d2) {
+template <typename T> struct Eval3 { T cost, d1, d2; };
+template <typename T, int NC>
+__device__ __noinline__ Eval3<T> contact_eval(Ws<T, NC>& w, int ci, T alpha, bool with_jv, bool FULL) {
+  T cost, d1, d2;
   const CPar<T>* par = w.c_par[ci];
   const int dim = par->dim, i0 = w.c_efc[ci];
   const T mu = w.c_mu[ci];
@@ -638,7 +673,7 @@ DI int contact_eval(Ws<T, NC>& w, int ci, T alpha, bool with_jv, T& cost, T& d1,
       for (int j = 0; j < 6; j++) if (j < dim) { w.e_force[i0 + j] = 0; w.e_w[i0 + j] = 0; }
       w.c_c1[ci] = 0; w.c_c2[ci] = 0;
     }
-    return 0;
+    return Eval3<T>{cost, d1, d2};
   }
   if (zone == 1) {
 #pragma unroll
@@ -649,7 +684,7 @@ DI int contact_eval(Ws<T, NC>& w, int ci, T alpha, bool with_jv, T& cost, T& d1,
         if (FULL) { w.e_force[i0 + j] = -D * x[j]; w.e_w[i0 + j] = D; }
       }
     if (FULL) { w.c_c1[ci] = 0; w.c_c2[ci] = 0; }
-    return 1;
+    return Eval3<T>{cost, d1, d2};
   }
   const T Dm = w.e_D[i0] / (mu * mu * (1 + mu * mu)), NT = N - mu * Tn, iT = 1 / Tn;
   cost = (T)0.5 * Dm * NT * NT;
@@ -676,12 +711,12 @@ DI int contact_eval(Ws<T, NC>& w, int ci, T alpha, bool with_jv, T& cost, T& d1,
       }
     w.c_c1[ci] = Dm; w.c_c2[ci] = c2;
   }
-  return 2;
+  return Eval3<T>{cost, d1, d2};
 }
 
 // cost at qacc: fills e_jar, Ma; if FULL also e_force, grad and the Hessian pieces (e_w, e_g, e_p, c_c1, c_c2)
-template <typename T, int NC, bool FULL>
-__device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T* qacc) {
+template <typename T, int NC>
+__device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T* qacc, bool FULL) {
   constexpr int NVV = Ws<T, NC>::NVV;
   const int lane = LANE, nefc = w.nefc, ncon = w.ncon, nlim = w.nlim;
   for (int i = lane; i < nefc; i += 32) {
@@ -700,9 +735,7 @@ __device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T
     if (FULL) { w.e_force[lane] = f; w.e_w[lane] = ww; }
   }
   for (int ci = lane; ci < ncon; ci += 32) {
-    T c, d1, d2;
-    contact_eval<T, NC, FULL>(w, ci, (T)0, false, c, d1, d2);
-    cost += c;
+    cost += contact_eval<T, NC>(w, ci, (T)0, false, FULL).cost;
   }
   cost = warp_sum(cost);
   if (FULL) {
@@ -732,12 +765,12 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
     __syncwarp();
     return;
   }
-  const T cw = total_cost<T, NC, false>(w, m, warm);
-  const T cs = total_cost<T, NC, false>(w, m, w.qacc_smooth);
+  const T cw = total_cost<T, NC>(w, m, warm, false);
+  const T cs = total_cost<T, NC>(w, m, w.qacc_smooth, false);
   if (lane < NVV) w.qacc[lane] = cw < cs ? warm[lane] : w.qacc_smooth[lane];
   __syncwarp();
   const T scale = 1 / (m.meaninertia * (T)NVV);
-  T cost = total_cost<T, NC, true>(w, m, w.qacc);
+  T cost = total_cost<T, NC>(w, m, w.qacc, true);
   // lower-triangle entries owned by this lane
   int ea[EPL], eb[EPL];
 #pragma unroll
@@ -813,9 +846,8 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
         if (x < 0) { d1 = w.e_D[lane] * x * jv; d2 = w.e_D[lane] * jv * jv; }
       }
       for (int ci = lane; ci < ncon; ci += 32) {
-        T c, a1, a2;
-        contact_eval<T, NC, false>(w, ci, alpha, true, c, a1, a2);
-        d1 += a1; d2 += a2;
+        const Eval3<T> ev = contact_eval<T, NC>(w, ci, alpha, true, false);
+        d1 += ev.d1; d2 += ev.d2;
       }
       d1 = warp_sum(d1) + g1 + alpha * g2;
       d2 = warp_sum(d2) + g2;
@@ -830,7 +862,7 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
     if (lane < NVV) w.qacc[lane] += alpha * s;
     __syncwarp();
     const T old = cost;
-    cost = total_cost<T, NC, true>(w, m, w.qacc);
+    cost = total_cost<T, NC>(w, m, w.qacc, true);
     niter = iter + 1;
     const T gn = sqrt(warp_sum(lane < NVV ? w.grad[lane] * w.grad[lane] : (T)0));
     if (scale * (old - cost) < tol || scale * gn < tol) break;
@@ -1015,8 +1047,8 @@ __device__ __noinline__ void env_step(Ws<T, NC>& w, const DevModel<T>& m, const 
   T a = lane < na ? clampT((T)action[lane], (T)-1, (T)1) : (T)0;
   T tq = 0;
   if (m.action_mode == 1) {
-    __shared__ T ik_scratch[LCR_WPB][8];
-    T* sc = ik_scratch[threadIdx.x >> 5];
+    __shared__ T ik_scratch[8];
+    T* sc = ik_scratch;
     const T* site = w.site_xpos();
     if (lane < 3) { T t = site[lane] + a * (T)0.05; if (lane == 2 && t < 0) t = 0; sc[lane] = t; }
     __syncwarp();
@@ -1065,166 +1097,156 @@ __device__ __noinline__ void env_step(Ws<T, NC>& w, const DevModel<T>& m, const 
 }
 
 // ---------------------------------------------------------------- state staging HBM <-> shared
+// One warp moves its env's record with coalesced 128-bit accesses: lane l <-> uint4 #l.
 template <typename T, int NC>
-DI void load_state(Ws<T, NC>* ws, const DevState<T>& s, int env0) {
-  constexpr int NF = Ws<T, NC>::NF;
-  const int n = s.n, tid = threadIdx.x, nthr = blockDim.x;
-  if (sizeof(T) == 4 && (n & 3) == 0 && env0 + LCR_WPB <= n && LCR_WPB == 4) {
-    for (int f = tid; f < NF; f += nthr) {  // one 128-bit load = field f of 4 consecutive envs
-      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(s.st) + (size_t)f * n + env0);
-      reinterpret_cast<float*>(ws[0].st)[f] = v.x; reinterpret_cast<float*>(ws[1].st)[f] = v.y;
-      reinterpret_cast<float*>(ws[2].st)[f] = v.z; reinterpret_cast<float*>(ws[3].st)[f] = v.w;
-    }
-  } else {
-    for (int idx = tid; idx < NF * LCR_WPB; idx += nthr) {
-      const int f = idx / LCR_WPB, e = idx % LCR_WPB;
-      if (env0 + e < n) ws[e].st[f] = s.st[(size_t)f * n + env0 + e];
-    }
-  }
-  for (int idx = tid; idx < (LCR_NINT + LCR_NDIAG + 4) * LCR_WPB; idx += nthr) {
-    const int f = idx / LCR_WPB, e = idx % LCR_WPB;
-    if (env0 + e >= n) continue;
-    if (f < LCR_NINT) ws[e].ints[f] = s.ints[(size_t)f * n + env0 + e];
-    else if (f < LCR_NINT + LCR_NDIAG) ws[e].diag[f - LCR_NINT] = s.diag[(size_t)(f - LCR_NINT) * n + env0 + e];
-    else ws[e].rng[f - LCR_NINT - LCR_NDIAG] = s.rng[(size_t)(f - LCR_NINT - LCR_NDIAG) * n + env0 + e];
-  }
+DI void load_state(Ws<T, NC>& w, const DevState<T>& s, int env) {
+  constexpr int NV4 = Ws<T, NC>::NFP * (int)sizeof(T) / 16;
+  const uint4* src = reinterpret_cast<const uint4*>(s.st + (size_t)env * Ws<T, NC>::NFP);
+  uint4* dst = reinterpret_cast<uint4*>(w.st);
+  for (int i = LANE; i < NV4; i += 32) dst[i] = src[i];
+  if (LANE < LCR_IB_WORDS / 4)
+    reinterpret_cast<uint4*>(w.ints)[LANE] = reinterpret_cast<const uint4*>(s.ib + (size_t)env * LCR_IB_WORDS)[LANE];
+  __syncwarp();
 }
 template <typename T, int NC>
-DI void store_state(Ws<T, NC>* ws, const DevState<T>& s, int env0) {
-  constexpr int NF = Ws<T, NC>::NF;
-  const int n = s.n, tid = threadIdx.x, nthr = blockDim.x;
-  if (sizeof(T) == 4 && (n & 3) == 0 && env0 + LCR_WPB <= n && LCR_WPB == 4) {
-    for (int f = tid; f < NF; f += nthr) {
-      float4 v;
-      v.x = reinterpret_cast<float*>(ws[0].st)[f]; v.y = reinterpret_cast<float*>(ws[1].st)[f];
-      v.z = reinterpret_cast<float*>(ws[2].st)[f]; v.w = reinterpret_cast<float*>(ws[3].st)[f];
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(s.st) + (size_t)f * n + env0) = v;
-    }
-  } else {
-    for (int idx = tid; idx < NF * LCR_WPB; idx += nthr) {
-      const int f = idx / LCR_WPB, e = idx % LCR_WPB;
-      if (env0 + e < n) s.st[(size_t)f * n + env0 + e] = ws[e].st[f];
-    }
-  }
-  for (int idx = tid; idx < (LCR_NINT + LCR_NDIAG + 4) * LCR_WPB; idx += nthr) {
-    const int f = idx / LCR_WPB, e = idx % LCR_WPB;
-    if (env0 + e >= n) continue;
-    if (f < LCR_NINT) s.ints[(size_t)f * n + env0 + e] = ws[e].ints[f];
-    else if (f < LCR_NINT + LCR_NDIAG) s.diag[(size_t)(f - LCR_NINT) * n + env0 + e] = ws[e].diag[f - LCR_NINT];
-    else s.rng[(size_t)(f - LCR_NINT - LCR_NDIAG) * n + env0 + e] = ws[e].rng[f - LCR_NINT - LCR_NDIAG];
-  }
+DI void store_state(Ws<T, NC>& w, const DevState<T>& s, int env) {
+  constexpr int NV4 = Ws<T, NC>::NFP * (int)sizeof(T) / 16;
+  __syncwarp();
+  uint4* dst = reinterpret_cast<uint4*>(s.st + (size_t)env * Ws<T, NC>::NFP);
+  const uint4* src = reinterpret_cast<const uint4*>(w.st);
+  for (int i = LANE; i < NV4; i += 32) dst[i] = src[i];
+  if (LANE < LCR_IB_WORDS / 4)
+    reinterpret_cast<uint4*>(s.ib + (size_t)env * LCR_IB_WORDS)[LANE] = reinterpret_cast<const uint4*>(w.ints)[LANE];
 }
 
-// ---------------------------------------------------------------- kernels
+// ---------------------------------------------------------------- kernels (grid = n_envs CTAs of one warp)
 extern __shared__ __align__(16) unsigned char lcr_smem[];
 
 template <typename T, int NC>
-__global__ void __launch_bounds__(LCR_WPB * 32) k_step(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
-                                                      const float* __restrict__ actions, float* __restrict__ obs,
-                                                      float* __restrict__ reward, uint8_t* __restrict__ term,
-                                                      uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ) {
-  Ws<T, NC>* ws = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env0 = blockIdx.x * LCR_WPB, wid = threadIdx.x >> 5, env = env0 + wid;
-  load_state(ws, s, env0);
-  __syncthreads();
-  if (env < s.n) {
-    const DevModel<T>& m = *dm;
-    const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
-    const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
-    env_step(ws[wid], m, verts, actions + (size_t)env * na, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
-  }
-  __syncthreads();
-  store_state(ws, s, env0);
+__global__ void __launch_bounds__(32, 16) k_step(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                             const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
+                                             uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ) {
+  Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env = blockIdx.x;
+  load_state(w, s, env);
+  const DevModel<T>& m = *dm;
+  const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
+  const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+  env_step(w, m, verts, actions + (size_t)env * na, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
+  store_state(w, s, env);
 }
 
 template <typename T, int NC>
-__global__ void __launch_bounds__(LCR_WPB * 32) k_reset(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
-                                                       const uint8_t* __restrict__ mask, float* __restrict__ obs) {
-  Ws<T, NC>* ws = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env0 = blockIdx.x * LCR_WPB, wid = threadIdx.x >> 5, env = env0 + wid;
-  load_state(ws, s, env0);
-  __syncthreads();
-  if (env < s.n && (mask == nullptr || mask[env])) {
-    const DevModel<T>& m = *dm;
-    const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
-    env_reset(ws[wid], m, verts);
-    if (obs) write_obs(ws[wid], m, obs + (size_t)env * od);
-  }
-  __syncthreads();
-  store_state(ws, s, env0);
+__global__ void __launch_bounds__(32, 16) k_reset(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                              const uint8_t* __restrict__ mask, float* __restrict__ obs) {
+  Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env = blockIdx.x;
+  if (mask != nullptr && !mask[env]) return;
+  load_state(w, s, env);
+  const DevModel<T>& m = *dm;
+  const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+  env_reset(w, m, verts);
+  if (obs) write_obs(w, m, obs + (size_t)env * od);
+  store_state(w, s, env);
 }
 
 template <typename T, int NC>
-__global__ void __launch_bounds__(LCR_WPB * 32) k_substeps(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s, int nsub) {
-  Ws<T, NC>* ws = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env0 = blockIdx.x * LCR_WPB, wid = threadIdx.x >> 5, env = env0 + wid;
-  load_state(ws, s, env0);
-  __syncthreads();
-  if (env < s.n) {
-    if ((threadIdx.x & 31) == 0) ws[wid].diag[3] = 0;
-    if (nsub == 0) forward(ws[wid], *dm, verts);
-    for (int k = 0; k < nsub; k++) substep(ws[wid], *dm, verts);
-  }
-  __syncthreads();
-  store_state(ws, s, env0);
+__global__ void __launch_bounds__(32, 16) k_substeps(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s, int nsub) {
+  Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env = blockIdx.x;
+  load_state(w, s, env);
+  if (LANE == 0) w.diag[3] = 0;
+  if (nsub == 0) forward(w, *dm, verts);
+  for (int k = 0; k < nsub; k++) substep(w, *dm, verts);
+  store_state(w, s, env);
 }
 
 template <typename T, int NC>
-__global__ void __launch_bounds__(LCR_WPB * 32) k_ik(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
-                                                    const float* __restrict__ target, float* __restrict__ q_out) {
-  Ws<T, NC>* ws = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  __shared__ T outq[LCR_WPB][8];
-  const int env0 = blockIdx.x * LCR_WPB, wid = threadIdx.x >> 5, env = env0 + wid, lane = threadIdx.x & 31;
-  load_state(ws, s, env0);
-  __syncthreads();
-  if (env < s.n) {
-    T tgt[3] = {(T)target[3 * (size_t)env], (T)target[3 * (size_t)env + 1], (T)target[3 * (size_t)env + 2]};
-    inverse_kinematics(ws[wid], *dm, verts, tgt, outq[wid], false);
-    __syncwarp();
-    if (lane < 6) q_out[6 * (size_t)env + lane] = (float)outq[wid][lane];
-  }
+__global__ void __launch_bounds__(32) k_ik(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                           const float* __restrict__ target, float* __restrict__ q_out) {
+  Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  __shared__ T outq[8];
+  const int env = blockIdx.x, lane = LANE;
+  load_state(w, s, env);
+  T tgt[3] = {(T)target[3 * (size_t)env], (T)target[3 * (size_t)env + 1], (T)target[3 * (size_t)env + 2]};
+  inverse_kinematics(w, *dm, verts, tgt, outq, false);
+  __syncwarp();
+  if (lane < 6) q_out[6 * (size_t)env + lane] = (float)outq[lane];
   // state is not written back: lcr_ik leaves the simulation untouched
 }
 
-// row-major float64 <-> SoA T
+// debug / test hook: mj_forward on the current state (not written back) and dump of the contact list
+template <typename T, int NC>
+__global__ void __launch_bounds__(32, 16) k_debug_contacts(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                                           double* __restrict__ out, int32_t* __restrict__ ncon_out) {
+  Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env = blockIdx.x;
+  load_state(w, s, env);
+  forward(w, *dm, verts);
+  const int ncon = w.ncon;
+  if (LANE == 0) ncon_out[env] = ncon;
+  for (int ci = LANE; ci < ncon; ci += 32) {
+    double* o = out + ((size_t)env * LCR_MAXCON + ci) * 12;
+    for (int k = 0; k < 3; k++) { o[k] = (double)w.c_pos[ci][k]; o[3 + k] = (double)w.c_frame[ci][k]; }
+    o[6] = (double)w.c_dist[ci]; o[7] = w.c_b1[ci]; o[8] = w.c_b2[ci]; o[9] = w.c_par[ci]->dim; o[10] = (double)w.c_mu[ci]; o[11] = w.c_efc[ci];
+  }
+}
+
+// row-major float64 <-> per-env records of T
 template <typename T>
 __global__ void k_get_state(DevState<T> s, int nq, int nv, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x, n = s.n;
-  if (e >= n) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= s.n) return;
+  const T* r = s.st + (size_t)e * s.nfp;
   int f = 0;
-  for (int k = 0; k < nq; k++, f++) if (qpos) qpos[(size_t)e * nq + k] = (double)s.st[(size_t)f * n + e];
-  for (int k = 0; k < nv; k++, f++) if (qvel) qvel[(size_t)e * nv + k] = (double)s.st[(size_t)f * n + e];
-  for (int k = 0; k < 6; k++, f++) if (ctrl) ctrl[(size_t)e * 6 + k] = (double)s.st[(size_t)f * n + e];
-  for (int k = 0; k < nv; k++, f++) if (warm) warm[(size_t)e * nv + k] = (double)s.st[(size_t)f * n + e];
-  for (int k = 0; k < LCR_NAUX; k++, f++) if (aux) aux[(size_t)e * LCR_NAUX + k] = (double)s.st[(size_t)f * n + e];
-  if (ints) for (int k = 0; k < LCR_NINT; k++) ints[(size_t)e * LCR_NINT + k] = s.ints[(size_t)k * n + e];
+  for (int k = 0; k < nq; k++, f++) if (qpos) qpos[(size_t)e * nq + k] = (double)r[f];
+  for (int k = 0; k < nv; k++, f++) if (qvel) qvel[(size_t)e * nv + k] = (double)r[f];
+  for (int k = 0; k < 6; k++, f++) if (ctrl) ctrl[(size_t)e * 6 + k] = (double)r[f];
+  for (int k = 0; k < nv; k++, f++) if (warm) warm[(size_t)e * nv + k] = (double)r[f];
+  for (int k = 0; k < LCR_NAUX; k++, f++) if (aux) aux[(size_t)e * LCR_NAUX + k] = (double)r[f];
+  if (ints) for (int k = 0; k < LCR_NINT; k++) ints[(size_t)e * LCR_NINT + k] = s.ib[(size_t)e * LCR_IB_WORDS + k];
 }
 template <typename T>
 __global__ void k_set_state(DevState<T> s, int nq, int nv, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
                             const double* aux, const int32_t* ints) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x, n = s.n;
-  if (e >= n) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= s.n) return;
+  T* r = s.st + (size_t)e * s.nfp;
   int f = 0;
-  for (int k = 0; k < nq; k++, f++) if (qpos) s.st[(size_t)f * n + e] = (T)qpos[(size_t)e * nq + k];
-  for (int k = 0; k < nv; k++, f++) if (qvel) s.st[(size_t)f * n + e] = (T)qvel[(size_t)e * nv + k];
-  for (int k = 0; k < 6; k++, f++) if (ctrl) s.st[(size_t)f * n + e] = (T)ctrl[(size_t)e * 6 + k];
-  for (int k = 0; k < nv; k++, f++) if (warm) s.st[(size_t)f * n + e] = (T)warm[(size_t)e * nv + k];
-  for (int k = 0; k < LCR_NAUX; k++, f++) if (aux) s.st[(size_t)f * n + e] = (T)aux[(size_t)e * LCR_NAUX + k];
-  if (ints) for (int k = 0; k < LCR_NINT; k++) s.ints[(size_t)k * n + e] = ints[(size_t)e * LCR_NINT + k];
+  for (int k = 0; k < nq; k++, f++) if (qpos) r[f] = (T)qpos[(size_t)e * nq + k];
+  for (int k = 0; k < nv; k++, f++) if (qvel) r[f] = (T)qvel[(size_t)e * nv + k];
+  for (int k = 0; k < 6; k++, f++) if (ctrl) r[f] = (T)ctrl[(size_t)e * 6 + k];
+  for (int k = 0; k < nv; k++, f++) if (warm) r[f] = (T)warm[(size_t)e * nv + k];
+  for (int k = 0; k < LCR_NAUX; k++, f++) if (aux) r[f] = (T)aux[(size_t)e * LCR_NAUX + k];
+  if (ints) for (int k = 0; k < LCR_NINT; k++) s.ib[(size_t)e * LCR_IB_WORDS + k] = ints[(size_t)e * LCR_NINT + k];
 }
 template <typename T>
-__global__ void k_init_state(const DevModel<T>* dm, DevState<T> s, int nq, int nv) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x, n = s.n;
-  if (e >= n) return;
-  const int nf = nq + 2 * nv + LCR_NARM + LCR_NAUX;
-  for (int f = 0; f < nf; f++) s.st[(size_t)f * n + e] = 0;
+__global__ void k_init_state(const DevModel<T>* dm, DevState<T> s) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= s.n) return;
+  T* r = s.st + (size_t)e * s.nfp;
+  for (int f = 0; f < s.nfp; f++) r[f] = 0;
   for (int c = 0; c < dm->ncube; c++) {
-    for (int k = 0; k < 3; k++) s.st[(size_t)(6 + 7 * c + k) * n + e] = dm->cube_qpos0[c][k];
-    s.st[(size_t)(6 + 7 * c + 3) * n + e] = 1;
+    for (int k = 0; k < 3; k++) r[6 + 7 * c + k] = dm->cube_qpos0[c][k];
+    r[6 + 7 * c + 3] = 1;
   }
-  for (int k = 0; k < LCR_NINT; k++) s.ints[(size_t)k * n + e] = 0;
-  for (int k = 0; k < LCR_NDIAG; k++) s.diag[(size_t)k * n + e] = 0;
-  s.rng[(size_t)0 * n + e] = 0; s.rng[(size_t)1 * n + e] = 1; s.rng[(size_t)2 * n + e] = 0; s.rng[(size_t)3 * n + e] = 1;
+  int32_t* ib = s.ib + (size_t)e * LCR_IB_WORDS;
+  for (int k = 0; k < LCR_IB_WORDS; k++) ib[k] = 0;
+  ib[8 + 2] = 1;  // rng[1] (state_lo) = 1
+  ib[8 + 6] = 1;  // rng[3] (inc_lo) = 1
+}
+template <typename T>
+__global__ void k_get_diag(DevState<T> s, int32_t* out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= s.n) return;
+  for (int k = 0; k < LCR_NDIAG; k++) out[(size_t)e * LCR_NDIAG + k] = s.ib[(size_t)e * LCR_IB_WORDS + LCR_NINT + k];
+}
+template <typename T>
+__global__ void k_seed(DevState<T> s, const unsigned long long* st) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= s.n) return;
+  unsigned long long* rng = reinterpret_cast<unsigned long long*>(s.ib + (size_t)e * LCR_IB_WORDS + 8);
+  for (int k = 0; k < 4; k++) rng[k] = st[4 * (size_t)e + k];
 }
 
 // ---------------------------------------------------------------- launchers
@@ -1236,6 +1258,7 @@ template <typename T, int NC> static void set_smem_attr() {
   cudaFuncSetAttribute(k_reset<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_substeps<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_ik<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_debug_contacts<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 template <typename T>
@@ -1281,7 +1304,16 @@ void Launch<T>::set_state(int ncube, DevState<T> s, const double* qpos, const do
 }
 template <typename T>
 void Launch<T>::init_state(int ncube, const DevModel<T>* dm, DevState<T> s, cudaStream_t st) {
-  k_init_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(dm, s, 6 + 7 * ncube, 6 + 6 * ncube);
+  k_init_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(dm, s);
 }
+
+template <typename T>
+void Launch<T>::debug_contacts(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, double* out, int32_t* ncon, cudaStream_t st) {
+  LCR_LAUNCH(k_debug_contacts, dm, verts, s, out, ncon);
+}
+template <typename T>
+void Launch<T>::get_diag(DevState<T> s, int32_t* out, cudaStream_t st) { k_get_diag<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, out); }
+template <typename T>
+void Launch<T>::seed(DevState<T> s, const unsigned long long* d_state, cudaStream_t st) { k_seed<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, d_state); }
 
 }  // namespace lcr

@@ -201,6 +201,14 @@ class BatchedLowCostRobotEnv:
             capi.check(self._L.lcr_get_diag(self._h, _ptr(d), self._stream()))
         return dict(zip(("ncon", "nefc", "niter", "max_nefc", "overflow", "nan_resets"), d.unbind(1)))
 
+    def debug_contacts(self):
+        """(contacts [n, MAXCON, 12] float64, ncon [n]) of ``mj_forward`` on the current state (state untouched)."""
+        c = torch.zeros(self.num_envs, model.MAXCON, 12, dtype=torch.float64, device=self.device)
+        k = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            capi.check(self._L.lcr_debug_contacts(self._h, _ptr(c), _ptr(k), self._stream()))
+        return c, k
+
     @property
     def kernel_launches(self):
         return int(self._L.lcr_kernel_launches(self._h))

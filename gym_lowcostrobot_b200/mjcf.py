@@ -124,15 +124,31 @@ def quat_to_mat(q):
     ])
 
 
-def load_stl_vertices(path):
-    """Unique vertices of a binary STL (80-byte header, uint32 count, 50-byte records)."""
+def load_stl_triangles(path):
+    """Triangles [n,3,3] of a binary STL (80-byte header, uint32 count, 50-byte records)."""
     raw = open(path, "rb").read()
     (n,) = struct.unpack("<I", raw[80:84])
     if len(raw) < 84 + 50 * n:
         raise ValueError(f"{path}: not a binary STL")
     rec = np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")])
     tri = np.frombuffer(raw, dtype=rec, count=n, offset=84)
-    return np.unique(tri["v"].reshape(-1, 3).astype(np.float64), axis=0)
+    return tri["v"].astype(np.float64)
+
+
+def load_stl_vertices(path):
+    """Unique vertices of a binary STL."""
+    return np.unique(load_stl_triangles(path).reshape(-1, 3), axis=0)
+
+
+def mesh_volume_centroid(tri):
+    """Centroid of the volume enclosed by a triangle mesh (signed tetrahedra against the vertex mean)."""
+    ref = tri.reshape(-1, 3).mean(0)
+    a, b, c = tri[:, 0] - ref, tri[:, 1] - ref, tri[:, 2] - ref
+    vol = np.einsum("ij,ij->i", a, np.cross(b, c)) / 6.0
+    cen = (a + b + c) / 4.0
+    if abs(vol.sum()) < 1e-18:
+        return ref
+    return ref + (vol[:, None] * cen).sum(0) / vol.sum()
 
 
 def convex_hull_vertices(points):
@@ -304,8 +320,9 @@ def compile_model(assets_dir, task):
     hull_cache = {}
     for m in meshes:
         if m["mesh"] not in hull_cache:
-            hull_cache[m["mesh"]] = convex_hull_vertices(load_stl_vertices(mesh_files[m["mesh"]]))
-        hv = hull_cache[m["mesh"]]
+            tri = load_stl_triangles(mesh_files[m["mesh"]])
+            hull_cache[m["mesh"]] = (convex_hull_vertices(np.unique(tri.reshape(-1, 3), axis=0)), mesh_volume_centroid(tri))
+        hv, m["com"] = hull_cache[m["mesh"]]
         vertadr.append(sum(vertnum))
         vertnum.append(len(hv))
         verts.append(hv)
@@ -361,7 +378,7 @@ def compile_model(assets_dir, task):
         verts=verts, mesh_vertadr=np.array(vertadr, np.int32), mesh_vertnum=np.array(vertnum, np.int32),
         mesh_body=np.array([m["body"] for m in meshes], np.int32),
         mesh_center=np.stack([m["center"] for m in meshes]), mesh_half=np.stack([m["half"] for m in meshes]),
-        mesh_rbound=np.array([m["rbound"] for m in meshes]),
+        mesh_rbound=np.array([m["rbound"] for m in meshes]), mesh_com=np.stack([m["com"] for m in meshes]),
         pair_g1=np.array([p[0] for p in pairs], np.int32), pair_g2=np.array([p[1] for p in pairs], np.int32),
         mesh_names=np.array([m["mesh"] for m in meshes]),
     )

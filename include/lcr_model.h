@@ -32,8 +32,8 @@
 #define LCR_MAXNQ (LCR_NARM + 7 * LCR_MAXCUBE)
 /* per-env caps of the contact list and of the constraint rows; contacts past a cap are dropped in
  * generation order (limits, floor-cube, cube-cube, cube-mesh, floor-mesh, mesh-mesh) and counted */
-#define LCR_MAXCON 40
-#define LCR_MAXEFC 128
+#define LCR_MAXCON 32
+#define LCR_MAXEFC 96
 
 enum { LCR_TASK_REACH = 0, LCR_TASK_PUSH = 1, LCR_TASK_LIFT = 2, LCR_TASK_PICK_PLACE = 3, LCR_TASK_STACK = 4 };
 
@@ -64,6 +64,8 @@ typedef struct LcrModel {
    * body-frame bounding box (centre, half extents) and bounding-sphere radius about that centre */
   int32_t mesh_body[LCR_MAXMESH], mesh_vertadr[LCR_MAXMESH], mesh_vertnum[LCR_MAXMESH];
   double mesh_center[LCR_MAXMESH][3], mesh_half[LCR_MAXMESH][3], mesh_rbound[LCR_MAXMESH];
+  /* geom centre MuJoCo gives a mesh geom = volume centroid of the mesh (body frame); interior point of MPR */
+  double mesh_com[LCR_MAXMESH][3];
   /* candidate arm self-collision mesh pairs after the body-pair filter */
   int32_t pair_g1[LCR_MAXPAIR], pair_g2[LCR_MAXPAIR];
 } LcrModel;

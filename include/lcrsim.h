@@ -90,6 +90,11 @@ int lcr_ik(LcrSim* sim, const float* d_ee_target, float* d_q_out, void* stream);
 #define LCR_NDIAG 6
 int lcr_get_diag(LcrSim* sim, int32_t* d_diag, void* stream);
 
+/* Test hook: run mj_forward on the current state WITHOUT writing it back and dump the contact list:
+ * d_contacts [n][LCR_MAXCON][12] float64 = pos[3], normal[3], dist, body1, body2, dim, mu, first row;
+ * d_ncon [n] int32.  Lets the parity tests compare collision geometry with the oracle directly. */
+int lcr_debug_contacts(LcrSim* sim, double* d_contacts, int32_t* d_ncon, void* stream);
+
 int lcr_n_envs(const LcrSim* sim);
 int lcr_kernel_launches(const LcrSim* sim); /* kernels launched by this handle so far */
 const char* lcr_last_error(void);

@@ -20,6 +20,7 @@
  * Plain C99, one environment per OrcSim, scalar double arithmetic.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -85,7 +86,8 @@ static void quat_to_mat(double *m, const double *q) {
 static void quat_normalize(double *q) {
   double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   if (n < MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
-  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+  double inv = 1 / n;
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
 }
 static void mat_vec(double *r, const double *m, const double *v) { /* r = m v, row-major 3x3 */
   double x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
@@ -317,8 +319,8 @@ static void make_frame(double *f) { /* f[0:3] = unit normal; builds the two tang
   if (f[1] < 0.5 && f[1] > -0.5) y[1] = 1; else y[2] = 1;
   double d = dot3(f, y);
   for (int k = 0; k < 3; k++) y[k] -= d * f[k];
-  double n = norm3(y);
-  for (int k = 0; k < 3; k++) f[3 + k] = y[k] / n;
+  double inv = 1 / sqrt(dot3(y, y));
+  for (int k = 0; k < 3; k++) f[3 + k] = y[k] * inv;
   cross3(f + 6, f, f + 3);
 }
 

@@ -71,3 +71,125 @@ def test_f32_reach_rollout_close_to_oracle():
     err_cube = np.abs(st["qpos"][:, 6:9] - ref_q[:, 6:9]).max(1)
     assert np.median(err_arm) < 2e-3 and np.median(err_cube) < 1e-3, (err_arm, err_cube)
     assert (err_arm < 2e-3).mean() > 0.9
+
+
+def random_states(task, n, rng, nq, nv):
+    """Contact-rich random states: arm anywhere in its range, cube(s) near the arm / floor, random velocities."""
+    lo = np.array([-3.14159, -1.5708, -1.48353, -1.91986, -2.96706, -1.74533])
+    hi = np.array([3.14159, 1.22173, 1.74533, 1.91986, 2.96706, 0.0523599])
+    qpos = np.zeros((n, nq))
+    qpos[:, :6] = rng.uniform(lo, hi, size=(n, 6))
+    ncube = (nq - 6) // 7
+    for c in range(ncube):
+        p = qpos[:, 6 + 7 * c:13 + 7 * c]
+        p[:, 0] = rng.uniform(-0.15, 0.15, n)
+        p[:, 1] = rng.uniform(0.0, 0.3, n)
+        p[:, 2] = rng.uniform(0.0, 0.08, n)
+        q = rng.normal(size=(n, 4))
+        p[:, 3:] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    # a third of the envs: first cube within 3 cm of a random arm link origin (cube-mesh contacts)
+    from gym_lowcostrobot_b200 import mjcf, model
+    m = model.load_compiled(task)
+    for i in range(0, n, 3):
+        xpos, _, _ = mjcf.arm_kinematics(m, qpos[i, :6])
+        qpos[i, 6:9] = xpos[rng.integers(1, 7)] + rng.uniform(-0.03, 0.03, 3)
+    if ncube == 2:  # half of the envs: blue cube on / inside the red one
+        k = n // 2
+        qpos[:k, 13:16] = qpos[:k, 6:9] + rng.uniform(-0.02, 0.02, size=(k, 3)) + np.array([0, 0, 0.02])
+    qvel = rng.normal(scale=0.5, size=(n, nv))
+    ctrl = rng.uniform(lo, hi, size=(n, 6))
+    return qpos, qvel, ctrl
+
+
+def _contact_lists(task, precision, mask, n=192, seed=7):
+    """Contact lists of mj_forward from identical contact-rich random states: CUDA (C-ABI test hook) and oracle."""
+    env = glr.make(IDS[task], num_envs=n, precision=precision, collision_mask=mask)
+    rng = np.random.default_rng(seed)
+    qpos, qvel, ctrl = random_states(task, n, rng, env.nq, env.nv)
+    env.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, warm=np.zeros((n, env.nv)))
+    con, ncon = env.debug_contacts()
+    con, ncon = con.cpu().numpy(), ncon.cpu().numpy()
+    env.close()
+    ref = []
+    for i in range(n):
+        o = Oracle(task, collision_mask=mask)
+        o.set_state(qpos=qpos[i], qvel=qvel[i], ctrl=ctrl[i], warm=np.zeros(len(qvel[i])))
+        o.forward()
+        ref.append(o.get("contacts").reshape(-1, 27))
+    return con, ncon, ref
+
+
+def _contact_err(g, oc):
+    if len(oc) == 0:
+        return 0.0
+    return max(np.abs(oc[:, 0:3] - g[:, 0:3]).max(), np.abs(oc[:, 3:6] - g[:, 3:6]).max(), np.abs(oc[:, 12] - g[:, 6]).max())
+
+
+# (task, collision mask, minimum fraction of envs whose whole contact list must agree to 1e-9)
+# floor-cube / cube-cube / cube-mesh are exact.  Hull-vs-plane and hull-vs-hull pick support vertices among
+# hundreds of nearly coplanar hull vertices, so a last-bit difference (CUDA sincos vs glibc) can flip a vertex in
+# deeply interpenetrating random poses: those envs are counted, not compared.
+@pytest.mark.parametrize("task,mask,min_exact", [("push", 1, 1.0), ("stack", 8, 1.0), ("push", 4, 0.98), ("push", 2, 0.97),
+                                                 ("push", 16, 0.9), ("stack", 31, 0.85)])
+def test_f64_contact_geometry_matches_oracle(task, mask, min_exact):
+    con, ncon, ref = _contact_lists(task, "float64", mask)
+    n = len(ref)
+    exact = sum(len(ref[i]) == ncon[i] and _contact_err(con[i, :ncon[i]], ref[i]) < 1e-9 for i in range(n))
+    total = sum(len(r) for r in ref)
+    assert total > n // 4, "states should produce contacts of this class"
+    assert exact >= min_exact * n, f"only {exact} of {n} envs have identical contact lists"
+
+
+@pytest.mark.parametrize("task", ["push", "lift", "stack"])
+def test_f64_one_substep_map_from_random_states(task):
+    """Single mj_step from identical contact-rich states (all collision types active), CUDA float64 vs oracle.
+    Envs whose contact lists agree must agree in the resulting state to 1e-7 (qpos) / 1e-4 (qvel: accelerations
+    reach 1e4 rad/s^2 in these deeply penetrating poses and the Newton solver stops at a 1e-8 relative tolerance)."""
+    n = 192
+    con, ncon, ref_con = _contact_lists(task, "float64", 31, n=n)
+    env = glr.make(IDS[task], num_envs=n, precision="float64")
+    rng = np.random.default_rng(7)
+    qpos, qvel, ctrl = random_states(task, n, rng, env.nq, env.nv)
+    env.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, warm=np.zeros((n, env.nv)))
+    env.substeps(1)
+    st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
+    compared, bad = 0, 0
+    for i in range(n):
+        if len(ref_con[i]) != ncon[i] or _contact_err(con[i, :ncon[i]], ref_con[i]) > 1e-9:
+            continue
+        o = Oracle(task)
+        o.set_state(qpos=qpos[i], qvel=qvel[i], ctrl=ctrl[i], warm=np.zeros(env.nv))
+        o.substep(1)
+        ref = o.get_state()
+        compared += 1
+        bad += np.abs(st["qpos"][i] - ref["qpos"]).max() > 1e-7 or np.abs(st["qvel"][i] - ref["qvel"]).max() > 1e-4
+    assert compared >= 0.8 * n
+    assert bad == 0, f"{bad} of {compared} envs differ"
+    env.close()
+
+
+def test_f32_one_substep_map_from_random_states():
+    """float32 product path on the same contact-rich states: report-style thresholds.  Contact counts equal for
+    >= 90% of envs; for those, velocity after one mj_step within 5% of (1 + max|qvel|) for >= 90%."""
+    task, n = "lift", 256
+    env = glr.make(IDS[task], num_envs=n, precision="float32")
+    rng = np.random.default_rng(11)
+    qpos, qvel, ctrl = random_states(task, n, rng, env.nq, env.nv)
+    env.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, warm=np.zeros((n, env.nv)))
+    env.substeps(1)
+    st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
+    diag = {k: v.cpu().numpy() for k, v in env.diagnostics().items()}
+    same_con, close = 0, 0
+    for i in range(n):
+        o = Oracle(task)
+        o.set_state(qpos=qpos[i], qvel=qvel[i], ctrl=ctrl[i], warm=np.zeros(env.nv))
+        o.substep(1)
+        ref = o.get_state()
+        if o.diag()["ncon"] != diag["ncon"][i]:
+            continue
+        same_con += 1
+        scale = 1.0 + np.abs(ref["qvel"]).max()
+        close += np.abs(st["qvel"][i] - ref["qvel"]).max() / scale < 5e-2
+    print("f32 substep map: same contact count", same_con, "of", n, "; close", close)
+    assert same_con >= 0.9 * n and close >= 0.9 * same_con, (same_con, close)
+    env.close()
