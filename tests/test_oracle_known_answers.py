@@ -1,0 +1,247 @@
+"""Analytic / independent known-answer tests that pin the float64 oracle.
+
+The reference ships no numeric tests (tests/test_env.py:8-13 is gymnasium check_env only) and MuJoCo is not
+installable here, so the oracle is pinned by closed-form results and by an independent numpy restatement of
+the kinematics / dynamics (gym_lowcostrobot_b200.mjcf.arm_kinematics / arm_mass_matrix, Jacobian-sum form vs
+the oracle's recursive forms).
+"""
+import numpy as np
+import pytest
+
+from gym_lowcostrobot_b200 import mjcf, model
+from oracle.oracle import Oracle
+
+H = 0.002
+
+
+def test_pcg64_stream_is_numpy_bit_exact():
+    o = Oracle("reach")
+    for seed in (0, 1, 12345, 2**40 + 7):
+        o.seed(seed)
+        ref = np.random.default_rng(seed).random(16)
+        got = np.array([o.rng_double() for _ in range(16)])
+        assert np.array_equal(ref, got)
+
+
+@pytest.mark.parametrize("task", ["reach", "push", "pick_place", "stack"])
+def test_reset_draws_match_numpy_generator(task):
+    # reference reset: np_random.uniform(low, high) for cube(s), then target (push_cube_env.py:312-320,
+    # stack_two_cubes_env.py:312-315); gymnasium seeds np_random = default_rng(seed)
+    o = Oracle(task)
+    for seed in (0, 3, 99):
+        obs = o.reset(seed=seed)
+        g = np.random.default_rng(seed)
+        lo, hi = np.array(o.cfg.cube_low[:]), np.array(o.cfg.cube_high[:])
+        st = o.get_state()
+        ncube = 2 if task == "stack" else 1
+        for c in range(ncube):
+            np.testing.assert_array_equal(st["qpos"][6 + 7 * c:9 + 7 * c], g.uniform(lo, hi))
+            np.testing.assert_array_equal(st["qpos"][9 + 7 * c:13 + 7 * c], [1, 0, 0, 0])
+        if task in ("push", "pick_place"):
+            tgt = g.uniform(np.array(o.cfg.target_low[:]), np.array(o.cfg.target_high[:])).astype(np.float32)
+            np.testing.assert_array_equal(obs[12:15], tgt)
+        # second reset without seed continues the same stream
+        o.reset()
+        np.testing.assert_array_equal(o.get_state()["qpos"][6:9], g.uniform(lo, hi))
+        assert np.all(st["qpos"][:6] == 0)
+
+
+def test_fk_at_zero_pose():
+    o = Oracle("reach")
+    o.set_state(qpos=np.r_[np.zeros(6), 0, 0.2, 0.5, 1, 0, 0, 0])
+    o.forward()
+    np.testing.assert_allclose(o.get("site_xpos"), [0.002017, 0.212570, 0.168400], atol=5e-7)
+    xpos = o.get("xpos").reshape(9, 3)
+    ref = [[0, -0.012, 0.0409], [-0.0209, -0.012, 0.0563], [-0.0144, 0.0028, 0.1646], [-0.01435, 0.10328, 0.1673]]
+    np.testing.assert_allclose(xpos[1:5], ref, atol=2e-5)
+    axis = o.get("axis").reshape(6, 3)
+    np.testing.assert_allclose(axis, [[0, 0, -1], [1, 0, 0], [-1, 0, 0], [1, 0, 0], [0, -1, 0], [0, 0, -1]], atol=1e-3)
+
+
+def test_kinematics_and_mass_matrix_match_numpy_restatement():
+    m = model.load_compiled("reach")
+    rng = np.random.default_rng(0)
+    o = Oracle("reach")
+    for _ in range(10):
+        q = rng.uniform(-1.5, 1.5, 6)
+        o.set_state(qpos=np.r_[q, 0, 0.2, 0.5, 1, 0, 0, 0], qvel=np.zeros(12))
+        o.forward()
+        xpos, xmat, axis = mjcf.arm_kinematics(m, q)
+        np.testing.assert_allclose(o.get("xpos").reshape(9, 3)[:7], xpos, atol=1e-13)
+        np.testing.assert_allclose(o.get("xmat").reshape(9, 3, 3)[:7], xmat, atol=1e-13)
+        M, _ = mjcf.arm_mass_matrix(m, q)
+        np.testing.assert_allclose(o.get("M").reshape(12, 12)[:6, :6], M, atol=1e-13)
+    M0, _ = mjcf.arm_mass_matrix(m, np.zeros(6), armature=False)
+    np.testing.assert_allclose(np.diag(M0), [2.229e-3, 4.037e-3, 1.776e-3, 2.34e-4, 6e-6, 1.1e-5], rtol=2e-2, atol=6e-7)
+    np.testing.assert_allclose(m["dof_invweight0"], [9.78192, 9.61595, 9.82961, 9.97732, 9.99935, 9.99895], rtol=1e-5)
+    assert abs(m["body_mass"][1:].sum() - 0.226020) < 1e-6
+
+
+def _numeric_bias(m, q, v, g=np.array([0, 0, -9.81])):
+    """C(q, v) v + g(q) from the mass matrix by finite differences (independent of the oracle's RNE)."""
+    eps = 1e-6
+    n = 6
+    dM = np.zeros((n, n, n))
+    for k in range(n):
+        dq = np.zeros(n)
+        dq[k] = eps
+        dM[:, :, k] = (mjcf.arm_mass_matrix(m, q + dq, False)[0] - mjcf.arm_mass_matrix(m, q - dq, False)[0]) / (2 * eps)
+    c = np.einsum("ijk,j,k->i", dM, v, v) - 0.5 * np.einsum("jki,j,k->i", dM, v, v)
+
+    def pot(qq):
+        xpos, xmat, _ = mjcf.arm_kinematics(m, qq)
+        return -sum(m["body_mass"][b] * g @ (xpos[b] + xmat[b] @ m["body_ipos"][b]) for b in range(1, 7))
+
+    grav = np.array([(pot(q + eps * np.eye(n)[k]) - pot(q - eps * np.eye(n)[k])) / (2 * eps) for k in range(n)])
+    return c + grav
+
+
+def test_bias_forces_match_lagrangian_finite_differences():
+    m = model.load_compiled("reach")
+    rng = np.random.default_rng(1)
+    o = Oracle("reach")
+    o.set_state(qpos=np.r_[np.zeros(6), 0, 0.2, 0.5, 1, 0, 0, 0], qvel=np.zeros(12))
+    o.forward()
+    np.testing.assert_allclose(o.get("bias")[:6], [0, 0.147385, -0.129713, 0.034035, 0.000725, 0], atol=2e-6)
+    for _ in range(5):
+        q, v = rng.uniform(-1.2, 1.2, 6), rng.uniform(-3, 3, 6)
+        o.set_state(qpos=np.r_[q, 0, 0.2, 0.5, 1, 0, 0, 0], qvel=np.r_[v, np.zeros(6)])
+        o.forward()
+        np.testing.assert_allclose(o.get("bias")[:6], _numeric_bias(m, q, v), atol=2e-8)
+    np.testing.assert_allclose(o.get("bias")[6:9], [0, 0, 0.1 * 9.81])
+
+
+def test_free_fall_is_semi_implicit_euler():
+    # z_k = z0 - 1/2 g h^2 k (k + 1) exactly until contact
+    o = Oracle("reach")
+    z0 = 0.5
+    o.set_state(qpos=np.r_[np.zeros(6), 0.1, 0.2, z0, 1, 0, 0, 0], qvel=np.zeros(12), ctrl=np.zeros(6))
+    for k in range(1, 60):
+        o.substep()
+        z = o.get_state()["qpos"][8]
+        assert abs(z - (z0 - 0.5 * 9.81 * H * H * k * (k + 1))) < 1e-12
+        assert o.diag()["ncon"] == 0 or k > 1
+
+
+@pytest.mark.parametrize("task", ["reach", "pick_place"])  # cube mass 0.1 and 10
+def test_cube_rest_height_is_mass_independent(task):
+    o = Oracle(task)
+    o.set_state(qpos=np.r_[np.zeros(6), 0.1, 0.2, 0.0149, 1, 0, 0, 0], qvel=np.zeros(12), ctrl=np.zeros(6))
+    o.substep(1500)
+    z = o.get_state()["qpos"][8]
+    assert abs(z - 0.0148922) < 2e-6, z
+    assert o.diag()["ncon"] == 4 and o.diag()["nefc"] == 16
+    con = o.get("contacts").reshape(-1, 27)
+    assert np.all(con[:, 13] == 4) and np.allclose(con[:, 17], 0.5)  # condim 4, cube friction wins by priority
+    np.testing.assert_allclose(con[:, 12], z - 0.015, atol=1e-9)
+
+
+def test_contact_parameter_classes():
+    o = Oracle("lift")
+    # gripper finger (link_6_collision, geom 19) pressed into the floor
+    q = np.array([0, 1.2, 1.0, 1.0, 0, 0.0])
+    o.set_state(qpos=np.r_[q, 0.3, 0.3, 0.0149, 1, 0, 0, 0], qvel=np.zeros(12))
+    o.forward()
+    con = o.get("contacts").reshape(-1, 27)
+    geoms = {(int(c[14]), int(c[15])): c for c in con}
+    finger = [c for (g1, g2), c in geoms.items() if g2 in (17, 19)]
+    other = [c for (g1, g2), c in geoms.items() if g1 == 20 and g2 < 17]
+    if finger:
+        c = finger[0]
+        assert c[13] == 6 and np.isclose(c[17], 1.5) and np.isclose(c[22], 0.015) and np.isclose(c[24], 0.036)
+    for c in other:
+        assert c[13] == 3 and np.isclose(c[17], 1.0)
+    # default K, B of solref (0.02, 1) with dmax 0.95
+    assert np.isclose(1 / (0.95**2 * 0.02**2), 2770.083, rtol=1e-6) and np.isclose(2 / (0.95 * 0.02), 105.2632, rtol=1e-6)
+
+
+def test_servo_step_matches_closed_form_on_joint_1():
+    # joint_1 has a vertical axis: no gravity torque; M11 + armature + h (damping + kv) in the implicit update
+    o = Oracle("reach")
+    m = model.load_compiled("reach")
+    o.set_state(qpos=np.r_[np.zeros(6), 0.3, 0.3, 0.0149, 1, 0, 0, 0], qvel=np.zeros(12), ctrl=np.r_[1.0, np.zeros(5)])
+    o.forward()
+    assert np.isclose(o.get("actuator")[0], 10.0)  # 1000 * 1 rad clamps at +10 N m
+    M = o.get("M").reshape(12, 12)[:6, :6]
+    smooth = o.get("actuator")[:6] + o.get("passive")[:6] - o.get("bias")[:6]
+    qacc = np.linalg.solve(M, smooth)
+    a = np.linalg.solve(M + H * np.diag(m["jnt_damping"] + m["act_kv"]), M @ qacc)
+    o.set_state(qpos=np.r_[np.zeros(6), 0.3, 0.3, 0.0149, 1, 0, 0, 0], qvel=np.zeros(12), ctrl=np.r_[1.0, np.zeros(5)])
+    o.substep()
+    st = o.get_state()
+    np.testing.assert_allclose(st["qvel"][:6], H * a, atol=1e-10)
+    np.testing.assert_allclose(st["qpos"][:6], H * H * a, atol=1e-12)
+    assert 60 < a[0] < 100  # |qdd| ~ 10 / (0.1 + M11 + 0.022)
+
+
+def test_joint_action_map_and_limits():
+    o = Oracle("lift")
+    o.reset(seed=0)
+    a = np.array([2.0, -2.0, 0.5, 0.25, -0.75, 1.0], np.float32)  # clipped to [-1, 1] first
+    o.step(a)
+    lo = np.array([-3.14159, -1.5708, -1.48353, -1.91986, -2.96706, -1.74533])
+    hi = np.array([3.14159, 1.22173, 1.74533, 1.91986, 2.96706, 0.0523599])
+    np.testing.assert_allclose(o.get_state()["ctrl"], np.clip(np.clip(a, -1, 1), lo, hi), atol=1e-12)
+    r = Oracle("reach")
+    r.reset(seed=0)
+    r.step(np.ones(5, np.float32))
+    assert r.get_state()["ctrl"][5] == 0.0  # blocked gripper (reach_cube_env.py:255)
+
+
+def test_ik_properties():
+    o = Oracle("reach", action_mode="ee")
+    o.reset(seed=0)
+    site = o.get_state()["aux"][4:7]
+    q0 = o.get_state()["qpos"][:6].copy()
+    q = o.ik(site + np.array([0.004, 0, 0]))  # within tolerance 0.01: zero iterations
+    np.testing.assert_allclose(q, q0, atol=1e-7)
+    q = o.ik(site + np.array([0.0, -0.05, 0.03]))
+    assert np.abs(q - q0).max() <= 10 * 0.5 + 1e-6 and q[5] == q0[5]  # gripper column of the Jacobian is zero
+    np.testing.assert_allclose(o.get_state()["qpos"][:6], q0)  # lcr_ik-style call leaves the state untouched
+    # in-step IK teleports the arm (reach_cube_env.py:185): qpos jumps by more than one substep could move it
+    o.step(np.array([0.0, -1.0, 1.0], np.float32))
+    assert np.abs(o.get_state()["ctrl"][:5] - q0[:5]).max() > 0.05
+
+
+def test_time_limit_and_termination():
+    o = Oracle("lift")
+    o.reset(seed=1)
+    for k in range(50):
+        obs, r, te, tr, su = o.step(np.zeros(6, np.float32))
+        assert te is False and tr == (k == 49)
+    p = Oracle("push", distance_threshold=10.0)
+    p.reset(seed=1)
+    obs, r, te, tr, su = p.step(np.zeros(5, np.float32))
+    assert te and su and r == 0.0
+    d = Oracle("push", reward_type="dense")
+    d.reset(seed=1)
+    obs, r, te, tr, su = d.step(np.zeros(5, np.float32))
+    assert np.isclose(-r, np.linalg.norm(obs[15:18].astype(np.float64) - obs[12:15]), atol=2e-3)
+
+
+def test_box_box_stack_is_stable():
+    o = Oracle("stack")
+    qpos = np.r_[np.zeros(6), 0.1, 0.2, 0.0149, 1, 0, 0, 0, 0.1, 0.2, 0.0448, 1, 0, 0, 0]
+    o.set_state(qpos=qpos, qvel=np.zeros(18), ctrl=np.zeros(6))
+    o.substep(1000)
+    st = o.get_state()
+    assert abs(st["qpos"][15] - 0.0447) < 3e-4 and abs(st["qpos"][8] - 0.01489) < 1e-4
+    assert np.abs(st["qvel"][6:]).max() < 1e-6
+    assert o.diag()["ncon"] == 8
+
+
+def test_mpr_box_mesh_and_self_collision_contacts_are_sane():
+    o = Oracle("push")
+    # cube pushed 5 mm into the side of link_5 (site is on link_5)
+    o.set_state(qpos=np.r_[np.zeros(6), 0.0, 0.2, 0.5, 1, 0, 0, 0])
+    o.forward()
+    site = o.get("site_xpos")
+    o.set_state(qpos=np.r_[np.zeros(6), site[0], site[1] + 0.012, site[2], 1, 0, 0, 0])
+    o.forward()
+    con = o.get("contacts").reshape(-1, 27)
+    cm = con[con[:, 14] == 21]
+    assert len(cm) >= 1
+    for c in cm:
+        assert -0.03 < c[12] < 0 and abs(np.linalg.norm(c[3:6]) - 1) < 1e-9
+        assert c[4] < -0.5  # normal from the cube (geom1) towards the mesh (geom2): -y here
+    assert o.diag()["overflow"] == 0

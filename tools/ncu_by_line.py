@@ -6,6 +6,7 @@ Joins `ncu --page source --csv` (per SASS instruction: samples, executed) with `
 info by instruction order inside the kernel's .text section.
 """
 import csv
+import os
 import re
 import subprocess
 import sys
@@ -25,7 +26,7 @@ for ln in sass:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', ln)
     if m:
-        cur = int(m.group(2))
+        cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
     if re.match(r"^\s+/\*[0-9a-f]{4,}\*/", ln):
         lines.append(cur)
@@ -35,15 +36,16 @@ hdr = rows[hi]
 body = rows[hi + 1:]
 ci = {h: i for i, h in enumerate(hdr)}
 print("sass rows", len(body), "disasm instrs", len(lines))
-src = open("/root/repo/gym_lowcostrobot_b200/csrc/lcr_kernels.cuh").read().splitlines()
-# function of each source line
-func_of, curf = {}, "?"
-for i, l in enumerate(src, 1):
-    m = re.match(r"^(?:__device__|DI|template|__global__).*?\b(\w+)\s*\(", l)
-    m2 = re.match(r"^(?:__device__ __noinline__|DI|__global__)\s+\S+\s+(\w+)\(", l) or re.match(r"^DI\s+\S+\s+(\w+)\(", l) or re.match(r"^\w[\w<>:, \*&]*\s+(\w+)\(.*\)\s*\{?$", l)
-    if m2 and not l.startswith(" "):
-        curf = m2.group(1)
-    func_of[i] = curf
+srcs, func_of = {}, {}
+for fn in ("lcr_kernels.cuh", "lcr_convex.cuh", "lcr_device.cuh"):
+    src = open("/root/repo/gym_lowcostrobot_b200/csrc/" + fn).read().splitlines()
+    srcs[fn] = src
+    curf = "?"
+    for i, l in enumerate(src, 1):
+        m2 = re.match(r"^(?:template <typename T> )?(?:__device__ __noinline__|DI|__global__)\s+.*?(\w+)\((?!.*;\s*$)", l) or re.match(r"^\w[\w<>:, \*&]*\s+(\w+)\(.*\)\s*\{?$", l)
+        if m2 and not l.startswith(" "):
+            curf = m2.group(1)
+        func_of[(fn, i)] = curf
 by_line = defaultdict(lambda: [0, 0])
 tot_s = tot_e = 0
 n = min(len(body), len(lines))
@@ -65,4 +67,5 @@ for f, (s, e) in sorted(by_func.items(), key=lambda x: -x[1][0])[:25]:
     print(f"{f:28s} {100*s/tot_s:6.2f}% {100*e/tot_e:6.2f}%")
 print("== by line")
 for l, (s, e) in sorted(by_line.items(), key=lambda x: -x[1][0])[:top]:
-    print(f"{l:5d} {100*s/tot_s:6.2f}% {100*e/tot_e:6.2f}%  {src[l-1].strip()[:110] if l else ''}")
+    txt = srcs.get(l[0], [""] * 100000)[l[1] - 1].strip()[:100] if l else ""
+    print(f"{l[0][4:12] if l else '':8s}{l[1] if l else 0:5d} {100*s/tot_s:6.2f}% {100*e/tot_e:6.2f}%  {txt}")
