@@ -168,28 +168,35 @@ def test_f64_one_substep_map_from_random_states(task):
     env.close()
 
 
-def test_f32_one_substep_map_from_random_states():
-    """float32 product path on the same contact-rich states: report-style thresholds.  Contact counts equal for
-    >= 90% of envs; for those, velocity after one mj_step within 5% of (1 + max|qvel|) for >= 90%."""
-    task, n = "lift", 256
+def test_f32_one_substep_map_from_rollout_states():
+    """float32 product path: one mj_step from states harvested out of random-action oracle rollouts (the regime the
+    simulator runs in: shallow penetrations).  Contact counts equal for >= 95% of envs; for those the new qvel is
+    within 2e-3 * (1 + max|qvel|) of the float64 oracle for >= 95%."""
+    task, n = "lift", 96
+    rng = np.random.default_rng(5)
+    oracles = []
+    for i in range(n):
+        o = Oracle(task)
+        o.reset(seed=1000 + i)
+        for _ in range(int(rng.integers(2, 9))):
+            o.step(rng.uniform(-1, 1, o.na).astype(np.float32))
+        oracles.append(o)
+    st0 = [o.get_state() for o in oracles]
     env = glr.make(IDS[task], num_envs=n, precision="float32")
-    rng = np.random.default_rng(11)
-    qpos, qvel, ctrl = random_states(task, n, rng, env.nq, env.nv)
-    env.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, warm=np.zeros((n, env.nv)))
+    env.set_state(**{k: np.stack([s[k] for s in st0]) for k in ("qpos", "qvel", "ctrl", "warm", "aux")})
     env.substeps(1)
     st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
     diag = {k: v.cpu().numpy() for k, v in env.diagnostics().items()}
-    same_con, close = 0, 0
-    for i in range(n):
-        o = Oracle(task)
-        o.set_state(qpos=qpos[i], qvel=qvel[i], ctrl=ctrl[i], warm=np.zeros(env.nv))
+    same_con, close, errs = 0, 0, []
+    for i, o in enumerate(oracles):
         o.substep(1)
         ref = o.get_state()
         if o.diag()["ncon"] != diag["ncon"][i]:
             continue
         same_con += 1
-        scale = 1.0 + np.abs(ref["qvel"]).max()
-        close += np.abs(st["qvel"][i] - ref["qvel"]).max() / scale < 5e-2
-    print("f32 substep map: same contact count", same_con, "of", n, "; close", close)
-    assert same_con >= 0.9 * n and close >= 0.9 * same_con, (same_con, close)
+        e = np.abs(st["qvel"][i] - ref["qvel"]).max() / (1.0 + np.abs(ref["qvel"]).max())
+        errs.append(e)
+        close += e < 2e-3
+    print("f32 substep map: same contact count", same_con, "of", n, "; close", close, "; median rel err", np.median(errs))
+    assert same_con >= 0.95 * n and close >= 0.95 * same_con, (same_con, close, np.sort(errs)[-5:])
     env.close()
