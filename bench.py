@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--action-mode", dest="action_mode", default="joint", choices=["joint", "ee"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exec-mode", dest="exec_mode", default="fused", choices=["fused", "phased"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -178,7 +179,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_local, n_total = args.envs, args.envs * world
     env = glr.make(IDS[args.task], num_envs=n_local, device=f"cuda:{local_rank}", action_mode=args.action_mode,
-                   autoreset=True, env_offset=rank * n_local)
+                   autoreset=True, env_offset=rank * n_local, exec_mode=args.exec_mode)
     env.reset(seed=0)
     sh = ShardedEnv(env, n_total, world, rank) if world > 1 else None
     K, W, A = args.steps, args.warmup, env.action_dim
@@ -271,7 +272,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"{IDS[args.task]} {n_local} envs/GPU, state obs, {args.action_mode} action, 20 substeps, "
                                    "random U(-1,1) actions, next-step autoreset (TimeLimit 50)",
-                       "envs_per_gpu": n_local, "envs_total": n_total, "action_mode": args.action_mode,
+                       "envs_per_gpu": n_local, "envs_total": n_total, "action_mode": args.action_mode, "exec_mode": args.exec_mode,
                        "l2": "256 MiB memset between timed steps (outside the per-step event pairs)",
                        "parallelism": f"env-index shard x{world}" + (", 1 NCCL all-gather of the output batch per step" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n_local * A * 4, "d2h_bytes_per_step": n_local * (O + 4) * 4},

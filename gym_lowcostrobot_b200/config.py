@@ -22,7 +22,7 @@ MAX_EPISODE_STEPS = 50
 
 def make_cfg(task, action_mode="joint", reward_type="sparse", block_gripper=None, distance_threshold=0.05,
              height_threshold=0.1, cube_xy_range=0.3, target_xy_range=0.3, goal_z_range=0.1, n_substeps=20,
-             max_episode_steps=MAX_EPISODE_STEPS, autoreset=False, collision_mask=COLLIDE_ALL):
+             max_episode_steps=MAX_EPISODE_STEPS, autoreset=False, collision_mask=COLLIDE_ALL, exec_mode=0):
     if action_mode not in ("joint", "ee"):
         raise ValueError("Invalid action mode, must be 'ee' or 'joint'")  # reach_cube_env.py:270
     if reward_type not in ("sparse", "dense"):
@@ -37,6 +37,7 @@ def make_cfg(task, action_mode="joint", reward_type="sparse", block_gripper=None
     cfg.max_episode_steps = int(max_episode_steps) if max_episode_steps else 0
     cfg.autoreset = int(bool(autoreset))
     cfg.collision_mask = int(collision_mask)
+    cfg.exec_mode = int(exec_mode)
     cfg.distance_threshold = float(distance_threshold)
     cfg.height_threshold = float(height_threshold)
     # sampling boxes (reach_cube_env.py:134-139): xy range centred, then y shifted

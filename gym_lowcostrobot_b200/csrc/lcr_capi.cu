@@ -143,6 +143,7 @@ struct Impl {
   DevModel<T>* dm = nullptr;
   T* verts = nullptr;
   DevState<T> s{};
+  void* gws = nullptr;  // per-env workspaces for the phased execution mode
   int nf = 0;
 
   int create(const LcrModel& m, const double* hv, const LcrEnvCfg& c, int n) {
@@ -159,6 +160,7 @@ struct Impl {
     s.nfp = (nf + 3) & ~3;
     CUDA_OK(cudaMalloc(&s.st, sizeof(T) * (size_t)s.nfp * n));
     CUDA_OK(cudaMalloc(&s.ib, sizeof(int32_t) * LCR_IB_WORDS * (size_t)n));
+    if (c.exec_mode == 1) CUDA_OK(cudaMalloc(&gws, lcr::Launch<T>::smem_bytes(m.ncube) * (size_t)n));
     lcr::Launch<T>::prepare(m.ncube);
     lcr::Launch<T>::init_state(m.ncube, dm, s, 0);
     CUDA_OK(cudaGetLastError());
@@ -166,7 +168,7 @@ struct Impl {
     return 0;
   }
   void destroy() {
-    cudaFree(dm); cudaFree(verts); cudaFree(s.st); cudaFree(s.ib);
+    cudaFree(dm); cudaFree(verts); cudaFree(s.st); cudaFree(s.ib); cudaFree(gws);
   }
 };
 
@@ -245,11 +247,20 @@ int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward,
              uint8_t* d_success, void* stream) {
   WITH_DEVICE(sim);
   if (!d_actions || !d_obs || !d_reward || !d_terminated || !d_truncated || !d_success) return fail("lcr_step: null buffer");
-  if (sim->precision == LCR_F32)
-    lcr::Launch<float>::step(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
-  else
-    lcr::Launch<double>::step(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
-  sim->launches++;
+  if (sim->cfg.exec_mode == 1) {
+    if (sim->precision == LCR_F32)
+      sim->launches += lcr::Launch<float>::step_phased(sim->ncube, sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, d_actions, d_obs,
+                                                       d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
+    else
+      sim->launches += lcr::Launch<double>::step_phased(sim->ncube, sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, d_actions, d_obs,
+                                                        d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
+  } else {
+    if (sim->precision == LCR_F32)
+      lcr::Launch<float>::step(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
+    else
+      lcr::Launch<double>::step(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
+    sim->launches++;
+  }
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -50,6 +50,7 @@ __device__ __noinline__ void shape_support(const Ws<T, NC>& w, const T* __restri
   } else {
     T bv = (T)-1e30;
     int bi = 0x7fffffff;
+#pragma unroll 4
     for (int i = LANE; i < sh.num; i += 32) {
       const T* v = verts + 4 * (size_t)(sh.adr + i);
       const T s = v[0] * dl[0] + v[1] * dl[1] + v[2] * dl[2];
@@ -141,9 +142,10 @@ template <typename T> DI void find_pos(const SPoint<T>* P, T* pos) {
   }
 }
 
-// returns true and fills depth / pdir / pos if the shapes penetrate (warp-uniform)
+// returns 1 and fills depth / pdir / pos if the shapes penetrate; 0 if a separating direction was found (returned
+// in pdir: max over A-B of x.pdir <= 0); -1 if separated without a usable direction (warp-uniform)
 template <typename T, int NC>
-__device__ __noinline__ bool mpr_penetration(const Ws<T, NC>& w, const T* __restrict__ verts, const Shape<T>& A, const Shape<T>& B, T& depth,
+__device__ __noinline__ int mpr_penetration(const Ws<T, NC>& w, const T* __restrict__ verts, const Shape<T>& A, const Shape<T>& B, T& depth,
                                              T* pdir, T* pos) {
   const T tol = (T)1e-6;
   SPoint<T> P[4], v4;
@@ -156,21 +158,21 @@ __device__ __noinline__ bool mpr_penetration(const Ws<T, NC>& w, const T* __rest
   normalize3(dir);
   md_support(w, verts, A, B, dir, P[1]);
   d = dot3(P[1].v, dir);
-  if (is_zero(d) || d < 0) return false;
+  if (is_zero(d) || d < 0) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; return 0; }
   cross3(dir, P[0].v, P[1].v);
   if (is_zero(dot3(dir, dir))) {
 #pragma unroll
     for (int k = 0; k < 3; k++) pos[k] = (T)0.5 * (P[1].v1[k] + P[1].v2[k]);
-    if (vec_is_origin(P[1].v)) { depth = 0; pdir[0] = pdir[1] = pdir[2] = 0; return true; }
+    if (vec_is_origin(P[1].v)) { depth = 0; pdir[0] = pdir[1] = pdir[2] = 0; return 1; }
     depth = sqrt(dot3(P[1].v, P[1].v));
     pdir[0] = P[1].v[0]; pdir[1] = P[1].v[1]; pdir[2] = P[1].v[2];
     normalize3(pdir);
-    return true;
+    return 1;
   }
   normalize3(dir);
   md_support(w, verts, A, B, dir, P[2]);
   d = dot3(P[2].v, dir);
-  if (is_zero(d) || d < 0) return false;
+  if (is_zero(d) || d < 0) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; return 0; }
 #pragma unroll
   for (int k = 0; k < 3; k++) { va[k] = P[1].v[k] - P[0].v[k]; vb[k] = P[2].v[k] - P[0].v[k]; }
   cross3(dir, va, vb);
@@ -181,10 +183,10 @@ __device__ __noinline__ bool mpr_penetration(const Ws<T, NC>& w, const T* __rest
   }
 #pragma unroll 1
   for (int guard = 0;; guard++) {
-    if (guard > 100) return false;
+    if (guard > 100) return -1;
     md_support(w, verts, A, B, dir, P[3]);
     d = dot3(P[3].v, dir);
-    if (is_zero(d) || d < 0) return false;
+    if (is_zero(d) || d < 0) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; return 0; }
     bool cont = false;
     cross3(va, P[1].v, P[3].v); d = dot3(va, P[0].v);
     if (d < 0 && !is_zero(d)) { P[2] = P[3]; cont = true; }
@@ -200,13 +202,14 @@ __device__ __noinline__ bool mpr_penetration(const Ws<T, NC>& w, const T* __rest
   }
 #pragma unroll 1
   for (int guard = 0;; guard++) {
-    if (guard > 100) return false;
+    if (guard > 100) return -1;
     portal_dir(P, dir);
     d = dot3(dir, P[1].v);
     if (is_zero(d) || d > 0) break;
     md_support(w, verts, A, B, dir, v4);
     d = dot3(v4.v, dir);
-    if (!(is_zero(d) || d > 0) || reach_tolerance(P, v4, dir, tol)) return false;
+    if (!(is_zero(d) || d > 0)) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; return 0; }
+    if (reach_tolerance(P, v4, dir, tol)) return -1;
     expand_portal(P, v4);
   }
 #pragma unroll 1
@@ -220,7 +223,7 @@ __device__ __noinline__ bool mpr_penetration(const Ws<T, NC>& w, const T* __rest
       else { pdir[0] = wit[0]; pdir[1] = wit[1]; pdir[2] = wit[2]; }
       normalize3(pdir);
       find_pos(P, pos);
-      return true;
+      return 1;
     }
     expand_portal(P, v4);
   }
@@ -418,6 +421,38 @@ __device__ __noinline__ void collide_cube_cube(Ws<T, NC>& w, const DevModel<T>& 
   }
 }
 
+// ---------------------------------------------------------------- separating-axis cache (performance only)
+// A pair that was separated along direction d in the previous substep is first tested along d again; if
+// max over A-B of x.d < -tol the pair is still disjoint and MPR is skipped (2 support evaluations instead of ~12).
+// Entries live for one API call; round-robin replacement.  The oracle keeps the identical cache.
+template <typename T, int NC> DI void sa_clear(Ws<T, NC>& w) {
+  if (LANE < LCR_NSA) w.sa_key[LANE] = -1;
+  if (LANE == 0) w.sa_next = 0;
+  __syncwarp();
+}
+template <typename T, int NC>
+__device__ __noinline__ bool cached_mpr(Ws<T, NC>& w, const T* __restrict__ verts, int key, const Shape<T>& A, const Shape<T>& B, T& depth,
+                                        T* dir, T* pos) {
+  const unsigned hit = __ballot_sync(FULLMASK, LANE < LCR_NSA && w.sa_key[LANE] == key);
+  int slot = hit ? __ffs(hit) - 1 : -1;
+  if (slot >= 0) {
+    T d[3] = {w.sa_dir[slot][0], w.sa_dir[slot][1], w.sa_dir[slot][2]};
+    SPoint<T> p;
+    md_support(w, verts, A, B, d, p);
+    if (dot3(p.v, d) < (T)-1e-6) return false;
+  }
+  const int r = mpr_penetration(w, verts, A, B, depth, dir, pos);
+  __syncwarp();
+  if (r == 0) {
+    if (slot < 0) { slot = w.sa_next; __syncwarp(); if (LANE == 0) w.sa_next = (slot + 1) % LCR_NSA; }
+    if (LANE == 0) { w.sa_key[slot] = (short)key; w.sa_dir[slot][0] = dir[0]; w.sa_dir[slot][1] = dir[1]; w.sa_dir[slot][2] = dir[2]; }
+  } else if (slot >= 0) {
+    if (LANE == 0) w.sa_key[slot] = -1;
+  }
+  __syncwarp();
+  return r == 1;
+}
+
 // ---------------------------------------------------------------- pair drivers
 template <typename T, int NC>
 __device__ __noinline__ void collide_cube_meshes(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc, int c) {
@@ -437,7 +472,7 @@ __device__ __noinline__ void collide_cube_meshes(Ws<T, NC>& w, const DevModel<T>
     cube_shape(w, m, c, A);
     mesh_shape(w, m, g, B);
     T depth, dir[3], pos[3];
-    if (!mpr_penetration(w, verts, A, B, depth, dir, pos)) continue;
+    if (!cached_mpr(w, verts, 200 + LCR_MAXMESH * c + g, A, B, depth, dir, pos)) continue;
     if (dir[0] == 0 && dir[1] == 0 && dir[2] == 0) continue;
     add_contact(w, ncon, nefc, &m.par_cube_mesh[c][g], bc, m.mesh_body[g], pos, dir, -depth);
   }
@@ -465,7 +500,7 @@ __device__ __noinline__ void collide_mesh_meshes(Ws<T, NC>& w, const DevModel<T>
       mesh_shape(w, m, g1, A);
       mesh_shape(w, m, g2, B);
       T depth, dir[3], pos[3];
-      if (!mpr_penetration(w, verts, A, B, depth, dir, pos)) continue;
+      if (!cached_mpr(w, verts, pp, A, B, depth, dir, pos)) continue;
       if (dir[0] == 0 && dir[1] == 0 && dir[2] == 0) continue;
       add_contact(w, ncon, nefc, &m.par_mesh_mesh[pp], m.mesh_body[g1], m.mesh_body[g2], pos, dir, -depth);
     }

@@ -10,6 +10,7 @@
 // with lanes <-> rows/columns and warp shuffles; there is no tensor-core work on this path.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/lcr_model.h"
@@ -88,12 +89,17 @@ struct Ws {  // per-warp shared-memory workspace
   short c_efc[LCR_MAXCON];
   signed char c_b1[LCR_MAXCON], c_b2[LCR_MAXCON];
   // constraint rows
-  T J[LCR_MAXEFC][JS];
   T e_pos[LCR_MAXEFC], e_D[LCR_MAXEFC], e_aref[LCR_MAXEFC], e_jar[LCR_MAXEFC], e_jv[LCR_MAXEFC], e_force[LCR_MAXEFC];
   T e_w[LCR_MAXEFC], e_g[LCR_MAXEFC], e_p[LCR_MAXEFC];  // Hessian pieces, see contact_eval
   short e_unit[LCR_MAXEFC];  // >= 0: contact index; < 0: limit row of joint -1-e_unit
   signed char e_r[LCR_MAXEFC];  // row index within its contact
   int ncon, nefc, nlim;
+  short sa_key[LCR_NSA];   // separating-axis cache of the convex narrowphase (see lcr_convex.cuh)
+  int sa_next;
+  T sa_dir[LCR_NSA][3];
+  int skip;          // phased execution: this env was auto-reset by the current step, substep kernels pass
+  int redo_forward;  // phased execution: state was reset after a bad qacc, re-run mj_forward before integrating
+  alignas(16) T J[LCR_MAXEFC][JS];  // last member: only the first nefc rows are live (and staged)
 
   __device__ T* qpos() { return st; }
   __device__ T* qvel() { return st + NQ; }
@@ -114,6 +120,8 @@ struct Launch {
   static void reset(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const uint8_t* mask, float* obs, cudaStream_t st);
   static void step(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
                    uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st);
+  static int step_phased(int ncube, int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, const float* actions,
+                         float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st);
   static void substeps(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, int n, cudaStream_t st);
   static void ik(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* target, float* q_out, cudaStream_t st);
   static void get_state(int ncube, DevState<T> s, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,

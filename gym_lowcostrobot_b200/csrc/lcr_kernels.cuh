@@ -899,19 +899,30 @@ template <typename T, int NC> DI void reset_data(Ws<T, NC>& w, const DevModel<T>
 
 template <typename T> DI bool bad_val(T x) { return !(x == x) || x > (T)1e10 || x < (T)-1e10; }
 
-template <typename T, int NC>
-__device__ __noinline__ void substep(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts) {
+// mj_checkPos / mj_checkVel: reset the env (mj_resetData) on NaN / huge values
+template <typename T, int NC> DI void check_state(Ws<T, NC>& w, const DevModel<T>& m) {
   constexpr int NVV = Ws<T, NC>::NVV, NQ = Ws<T, NC>::NQ;
+  const int lane = LANE;
+  const bool bad = (lane < NQ && bad_val(w.qpos()[lane])) || (lane < NVV && bad_val(w.qvel()[lane]));
+  if (__any_sync(FULLMASK, bad)) { reset_data(w, m); if (lane == 0) w.diag[5]++; }
+}
+// mj_checkAcc: returns true if qacc was bad and the env has been reset (caller must redo mj_forward)
+template <typename T, int NC> DI bool check_acc(Ws<T, NC>& w, const DevModel<T>& m) {
+  const int lane = LANE;
+  const bool bad = lane < Ws<T, NC>::NVV && bad_val(w.qacc[lane]);
+  if (__any_sync(FULLMASK, bad)) { reset_data(w, m); if (lane == 0) w.diag[5]++; return true; }
+  return false;
+}
+
+// implicitfast velocity update + semi-implicit position update (mj_implicit + mj_advance)
+template <typename T, int NC>
+__device__ __noinline__ void integrate(Ws<T, NC>& w, const DevModel<T>& m) {
+  constexpr int NVV = Ws<T, NC>::NVV;
   const int lane = LANE;
   T* qpos = w.qpos();
   T* qvel = w.qvel();
-  bool bad = (lane < NQ && bad_val(qpos[lane])) || (lane < NVV && bad_val(qvel[lane]));
-  if (__any_sync(FULLMASK, bad)) { reset_data(w, m); if (lane == 0) w.diag[5]++; }
-  forward(w, m, verts);
-  bad = lane < NVV && bad_val(w.qacc[lane]);
-  if (__any_sync(FULLMASK, bad)) { reset_data(w, m); if (lane == 0) w.diag[5]++; forward(w, m, verts); }
   const T h = m.timestep;
-  // implicitfast: (M + h diag(damping + kv)) a = M qacc on the arm block; cubes keep qacc
+  // (M + h diag(damping + kv)) a = M qacc on the arm block; cubes keep qacc
   T rhs = mul_M(w, m, w.qacc);
   if (lane < LCR_NARM) {
     for (int j = 0; j < LCR_NARM; j++) w.Lm[lane][j] = w.M[lane][j];
@@ -945,6 +956,14 @@ __device__ __noinline__ void substep(Ws<T, NC>& w, const DevModel<T>& m, const T
   }
   if (lane == 0) w.aux()[0] += h;
   __syncwarp();
+}
+
+template <typename T, int NC>
+__device__ __noinline__ void substep(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts) {
+  check_state(w, m);
+  forward(w, m, verts);
+  if (check_acc(w, m)) forward(w, m, verts);
+  integrate(w, m);
 }
 
 // ---------------------------------------------------------------- env glue
@@ -1031,14 +1050,17 @@ __device__ const double kTargetLow[6] = {-3.14159, -1.5708, -1.48353, -1.91986, 
 __device__ const double kTargetHigh[6] = {3.14159, 1.22173, 1.74533, 1.91986, 2.96706, 0.0523599};
 
 template <typename T, int NC>
-__device__ __noinline__ void env_step(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const float* action, float* obs,
-                                      float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ) {
+__device__ __noinline__ bool env_step_begin(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const float* action, float* obs,
+                                            float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ) {
+  // returns false if the env was auto-reset instead of stepped (outputs already written)
   const int lane = LANE, task = m.task;
+  sa_clear(w);
   if (m.autoreset && w.ints[1]) {
     env_reset(w, m, verts);
     write_obs(w, m, obs);
     if (lane == 0) { *reward = 0; *term = 0; *trunc = 0; *succ = 0; }
-    return;
+    __syncwarp();
+    return false;
   }
   if (lane == 0) w.diag[3] = 0;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
@@ -1068,8 +1090,13 @@ __device__ __noinline__ void env_step(Ws<T, NC>& w, const DevModel<T>& m, const 
   }
   if (lane < 6) w.ctrl()[lane] = tq;
   __syncwarp();
-#pragma unroll 1
-  for (int k = 0; k < m.n_substeps; k++) substep(w, m, verts);
+  return true;
+}
+
+template <typename T, int NC>
+__device__ __noinline__ void env_step_end(Ws<T, NC>& w, const DevModel<T>& m, float* obs, float* reward, uint8_t* term, uint8_t* trunc,
+                                          uint8_t* succ) {
+  const int lane = LANE, task = m.task;
   write_obs(w, m, obs);
   if (lane == 0) {
     T pa[3], pb[3];
@@ -1094,6 +1121,15 @@ __device__ __noinline__ void env_step(Ws<T, NC>& w, const DevModel<T>& m, const 
     *reward = r; *term = te; *trunc = tr; *succ = su;
   }
   __syncwarp();
+}
+
+template <typename T, int NC>
+DI void env_step(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const float* action, float* obs, float* reward,
+                 uint8_t* term, uint8_t* trunc, uint8_t* succ) {
+  if (!env_step_begin(w, m, verts, action, obs, reward, term, trunc, succ)) return;
+#pragma unroll 1
+  for (int k = 0; k < m.n_substeps; k++) substep(w, m, verts);
+  env_step_end(w, m, obs, reward, term, trunc, succ);
 }
 
 // ---------------------------------------------------------------- state staging HBM <-> shared
@@ -1143,6 +1179,7 @@ __global__ void __launch_bounds__(32, 16) k_reset(const DevModel<T>* __restrict_
   const int env = blockIdx.x;
   if (mask != nullptr && !mask[env]) return;
   load_state(w, s, env);
+  sa_clear(w);
   const DevModel<T>& m = *dm;
   const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
   env_reset(w, m, verts);
@@ -1155,6 +1192,7 @@ __global__ void __launch_bounds__(32, 16) k_substeps(const DevModel<T>* __restri
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = blockIdx.x;
   load_state(w, s, env);
+  sa_clear(w);
   if (LANE == 0) w.diag[3] = 0;
   if (nsub == 0) forward(w, *dm, verts);
   for (int k = 0; k < nsub; k++) substep(w, *dm, verts);
@@ -1175,6 +1213,110 @@ __global__ void __launch_bounds__(32) k_ik(const DevModel<T>* __restrict__ dm, c
   // state is not written back: lcr_ik leaves the simulation untouched
 }
 
+// ---------------------------------------------------------------- phased execution
+// The same device functions as k_step, but one small kernel per phase of mj_step with the per-env workspace
+// parked in HBM/L2 between launches.  Every launch has a small, homogeneous instruction footprint (the fused
+// kernel is instruction-fetch bound: ~200 KB of code per substep against a 32 KB L1.5 I-cache) and variable-cost
+// phases (collision, Newton solve) no longer hold the uniform ones back.  Staging is coalesced 128-bit copies.
+template <typename T, int NC>
+DI void load_ws(Ws<T, NC>& w, const Ws<T, NC>* g, int env, bool with_J) {
+  typedef Ws<T, NC> WsT;
+  constexpr int HEAD = (int)(offsetof(WsT, J) / 16), JROW = WsT::JS * (int)sizeof(T);
+  const uint4* src = reinterpret_cast<const uint4*>(g + env);
+  uint4* dst = reinterpret_cast<uint4*>(&w);
+  for (int i = LANE; i < HEAD; i += 32) dst[i] = src[i];
+  __syncwarp();
+  if (with_J) {
+    const int n4 = (w.nefc * JROW + 15) / 16;
+    for (int i = LANE; i < n4; i += 32) dst[HEAD + i] = src[HEAD + i];
+    __syncwarp();
+  }
+}
+template <typename T, int NC>
+DI void store_ws(const Ws<T, NC>& w, Ws<T, NC>* g, int env, bool with_J) {
+  typedef Ws<T, NC> WsT;
+  constexpr int HEAD = (int)(offsetof(WsT, J) / 16), JROW = WsT::JS * (int)sizeof(T);
+  __syncwarp();
+  uint4* dst = reinterpret_cast<uint4*>(g + env);
+  const uint4* src = reinterpret_cast<const uint4*>(&w);
+  for (int i = LANE; i < HEAD; i += 32) dst[i] = src[i];
+  if (with_J) {
+    const int n4 = (w.nefc * JROW + 15) / 16;
+    for (int i = LANE; i < n4; i += 32) dst[HEAD + i] = src[HEAD + i];
+  }
+}
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(32, 16) k_ph_begin(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                                     Ws<T, NC>* __restrict__ gws, const float* __restrict__ actions, float* __restrict__ obs,
+                                                     float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
+                                                     uint8_t* __restrict__ succ) {
+  Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env = blockIdx.x;
+  load_state(w, s, env);
+  const DevModel<T>& m = *dm;
+  const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
+  const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+  const bool go = env_step_begin(w, m, verts, actions + (size_t)env * na, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
+  if (LANE == 0) { w.skip = go ? 0 : 1; w.redo_forward = 0; w.nefc = 0; w.ncon = 0; w.nlim = 0; }
+  if (!go) store_state(w, s, env);
+  store_ws(w, gws, env, false);
+}
+
+// [integrate the previous substep] -> checks -> kinematics -> inertia / bias -> smooth forces
+template <typename T, int NC>
+__global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int first) {
+  Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env = blockIdx.x;
+  if (gws[env].skip) return;
+  load_ws(w, gws, env, false);
+  const DevModel<T>& m = *dm;
+  if (!first) {
+    if (w.redo_forward) { forward(w, m, verts); if (LANE == 0) w.redo_forward = 0; __syncwarp(); }
+    integrate(w, m);
+  }
+  check_state(w, m);
+  kinematics(w, m);
+  inertia_and_bias(w, m);
+  smooth_forces(w, m);
+  store_ws(w, gws, env, false);
+}
+template <typename T, int NC>
+__global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws) {
+  Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env = blockIdx.x;
+  if (gws[env].skip) return;
+  load_ws(w, gws, env, false);
+  make_constraints(w, *dm, verts);
+  store_ws(w, gws, env, true);
+}
+template <typename T, int NC>
+__global__ void __launch_bounds__(32, 16) k_ph_sol(const DevModel<T>* __restrict__ dm, Ws<T, NC>* __restrict__ gws) {
+  Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env = blockIdx.x;
+  if (gws[env].skip) return;
+  load_ws(w, gws, env, true);
+  const DevModel<T>& m = *dm;
+  solve_constraints(w, m, solver_tol<T>(m));
+  if (check_acc(w, m)) { if (LANE == 0) w.redo_forward = 1; }
+  store_ws(w, gws, env, false);
+}
+template <typename T, int NC>
+__global__ void __launch_bounds__(32, 16) k_ph_end(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                                   Ws<T, NC>* __restrict__ gws, float* __restrict__ obs, float* __restrict__ reward,
+                                                   uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ) {
+  Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env = blockIdx.x;
+  if (gws[env].skip) return;
+  load_ws(w, gws, env, false);
+  const DevModel<T>& m = *dm;
+  const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+  if (w.redo_forward) forward(w, m, verts);
+  integrate(w, m);
+  env_step_end(w, m, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
+  store_state(w, s, env);
+}
+
 // debug / test hook: mj_forward on the current state (not written back) and dump of the contact list
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_debug_contacts(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
@@ -1182,6 +1324,7 @@ __global__ void __launch_bounds__(32, 16) k_debug_contacts(const DevModel<T>* __
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = blockIdx.x;
   load_state(w, s, env);
+  sa_clear(w);
   forward(w, *dm, verts);
   const int ncon = w.ncon;
   if (LANE == 0) ncon_out[env] = ncon;
@@ -1259,6 +1402,11 @@ template <typename T, int NC> static void set_smem_attr() {
   cudaFuncSetAttribute(k_substeps<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_ik<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_debug_contacts<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_ph_begin<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_ph_dyn<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_ph_col<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_ph_sol<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_ph_end<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 template <typename T>
@@ -1283,6 +1431,35 @@ template <typename T>
 void Launch<T>::step(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
                      uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st) {
   LCR_LAUNCH(k_step, dm, verts, s, actions, obs, reward, term, trunc, succ);
+}
+template <typename T>
+int Launch<T>::step_phased(int ncube, int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws_, const float* actions,
+                           float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st) {
+  const int grid = s.n;
+  if (ncube == 1) {
+    typedef Ws<T, 1> W;
+    W* gws = reinterpret_cast<W*>(gws_);
+    const size_t sm = sizeof(W);
+    k_ph_begin<T, 1><<<grid, 32, sm, st>>>(dm, verts, s, gws, actions, obs, reward, term, trunc, succ);
+    for (int k = 0; k < n_substeps; k++) {
+      k_ph_dyn<T, 1><<<grid, 32, sm, st>>>(dm, verts, gws, k == 0);
+      k_ph_col<T, 1><<<grid, 32, sm, st>>>(dm, verts, gws);
+      k_ph_sol<T, 1><<<grid, 32, sm, st>>>(dm, gws);
+    }
+    k_ph_end<T, 1><<<grid, 32, sm, st>>>(dm, verts, s, gws, obs, reward, term, trunc, succ);
+  } else {
+    typedef Ws<T, 2> W;
+    W* gws = reinterpret_cast<W*>(gws_);
+    const size_t sm = sizeof(W);
+    k_ph_begin<T, 2><<<grid, 32, sm, st>>>(dm, verts, s, gws, actions, obs, reward, term, trunc, succ);
+    for (int k = 0; k < n_substeps; k++) {
+      k_ph_dyn<T, 2><<<grid, 32, sm, st>>>(dm, verts, gws, k == 0);
+      k_ph_col<T, 2><<<grid, 32, sm, st>>>(dm, verts, gws);
+      k_ph_sol<T, 2><<<grid, 32, sm, st>>>(dm, gws);
+    }
+    k_ph_end<T, 2><<<grid, 32, sm, st>>>(dm, verts, s, gws, obs, reward, term, trunc, succ);
+  }
+  return 2 + 3 * n_substeps;
 }
 template <typename T>
 void Launch<T>::substeps(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, int n, cudaStream_t st) {

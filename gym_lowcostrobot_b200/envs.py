@@ -52,7 +52,7 @@ class BatchedLowCostRobotEnv:
                  block_gripper=None, distance_threshold=0.05, height_threshold=0.1, cube_xy_range=0.3,
                  target_xy_range=0.3, goal_z_range=0.1, n_substeps=20, render_mode=None, max_episode_steps=50,
                  autoreset=False, precision="float32", assets_path=None, collision_mask=model.COLLIDE_ALL,
-                 env_offset=0):
+                 env_offset=0, exec_mode="fused"):
         if observation_mode != "state":
             raise NotImplementedError("only observation_mode='state' is implemented (image rendering is out of scope)")
         if render_mode is not None:
@@ -66,7 +66,7 @@ class BatchedLowCostRobotEnv:
                                    distance_threshold=distance_threshold, height_threshold=height_threshold,
                                    cube_xy_range=cube_xy_range, target_xy_range=target_xy_range, goal_z_range=goal_z_range,
                                    n_substeps=n_substeps, max_episode_steps=max_episode_steps, autoreset=autoreset,
-                                   collision_mask=collision_mask)
+                                   collision_mask=collision_mask, exec_mode={"fused": 0, "phased": 1}[exec_mode])
         self.block_gripper = bool(self.cfg.block_gripper)
         self.compiled = model.load_compiled(self.task, assets_path)
         self.cmodel, self.verts = model.pack_model(self.compiled)

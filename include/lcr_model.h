@@ -34,6 +34,8 @@
  * generation order (limits, floor-cube, cube-cube, cube-mesh, floor-mesh, mesh-mesh) and counted */
 #define LCR_MAXCON 32
 #define LCR_MAXEFC 96
+/* entries of the per-env separating-axis cache of the convex narrowphase (performance only) */
+#define LCR_NSA 16
 
 enum { LCR_TASK_REACH = 0, LCR_TASK_PUSH = 1, LCR_TASK_LIFT = 2, LCR_TASK_PICK_PLACE = 3, LCR_TASK_STACK = 4 };
 
@@ -82,7 +84,7 @@ typedef struct LcrEnvCfg {
   int32_t max_episode_steps;/* 50; <= 0 disables truncation */
   int32_t autoreset;        /* 0 = never (caller resets), 1 = next-step autoreset of done envs */
   int32_t collision_mask;   /* bit0 floor-cube, bit1 floor-mesh, bit2 cube-mesh, bit3 cube-cube, bit4 mesh-mesh */
-  int32_t pad0;
+  int32_t exec_mode;        /* 0 = one fused kernel per step, 1 = phased (one small kernel per mj_step phase) */
   double distance_threshold;/* 0.05 */
   double height_threshold;  /* 0.1 (Lift) */
   double cube_low[3], cube_high[3];     /* reset sampling box of the cube(s) */

@@ -56,6 +56,8 @@ typedef struct OrcSim {
   double bias[NV], passive[NV], actuator[NV], smooth[NV], qacc_smooth[NV], qacc[NV], qfrc_constraint[NV];
   Contact con[LCR_MAXCON];
   int ncon, nefc, niter, overflow, nan_resets, max_nefc;
+  int sa_key[LCR_NSA], sa_next; /* separating-axis cache, see lcr_oracle_convex.inc */
+  double sa_dir[LCR_NSA][3];
   int efc_type[LCR_MAXEFC]; /* 0 limit, 1 first row of a contact, 2 following row of a contact */
   int efc_con[LCR_MAXEFC];
   double J[LCR_MAXEFC][NV], efc_pos[LCR_MAXEFC], efc_vel[LCR_MAXEFC], efc_diag[LCR_MAXEFC];
@@ -454,7 +456,7 @@ static void collision(OrcSim *s) {
     for (int g = 0; g < m->nmesh; g++)
       if (m->mesh_body[g] != 0) collide_floor_mesh(s, g);
   if (mask & LCR_COLLIDE_MESH_MESH)
-    for (int p = 0; p < m->npair; p++) collide_mesh_mesh(s, m->pair_g1[p], m->pair_g2[p]);
+    for (int p = 0; p < m->npair; p++) collide_mesh_mesh(s, m->pair_g1[p], m->pair_g2[p], p);
 }
 
 /* ------------------------------------------------------------------ constraints (mj_makeConstraint, mj_makeImpedance, mj_referenceConstraint) */
@@ -758,7 +760,9 @@ static void solve_constraints(OrcSim *s) {
 /* ------------------------------------------------------------------ mj_forward / mj_step */
 static void reset_data(OrcSim *s);
 
-void orc_forward(OrcSim *s) {
+static void sa_clear(OrcSim *s) { for (int k = 0; k < LCR_NSA; k++) s->sa_key[k] = -1; s->sa_next = 0; }
+
+static void forward_(OrcSim *s) {
   kinematics(s);
   mass_matrix(s);
   bias_forces(s);
@@ -769,14 +773,14 @@ void orc_forward(OrcSim *s) {
 
 static int bad(double x) { return !(x == x) || x > MAXVAL || x < -MAXVAL; }
 
-void orc_substep(OrcSim *s) {
+static void substep_(OrcSim *s) {
   const LcrModel *m = &s->m;
   int nv = m->nv;
   double h = m->timestep;
   for (int i = 0; i < m->nq; i++) if (bad(s->qpos[i])) { reset_data(s); s->nan_resets++; break; }
   for (int i = 0; i < nv; i++) if (bad(s->qvel[i])) { reset_data(s); s->nan_resets++; break; }
-  orc_forward(s);
-  for (int i = 0; i < nv; i++) if (bad(s->qacc[i])) { reset_data(s); s->nan_resets++; orc_forward(s); break; }
+  forward_(s);
+  for (int i = 0; i < nv; i++) if (bad(s->qacc[i])) { reset_data(s); s->nan_resets++; forward_(s); break; }
   /* implicitfast: (M - h dF/dv) a = M qacc, dF/dv = -(damping + kv) on the arm dofs */
   double rhs[NV], a[NV];
   double A[NV][NV], L[NV][NV];
@@ -804,6 +808,11 @@ void orc_substep(OrcSim *s) {
   }
   s->time += h;
 }
+
+/* API entry points: the separating-axis cache lives for one call */
+void orc_forward(OrcSim *s) { sa_clear(s); forward_(s); }
+void orc_substeps(OrcSim *s, int n) { sa_clear(s); s->max_nefc = 0; for (int k = 0; k < n; k++) substep_(s); }
+void orc_substep(OrcSim *s) { orc_substeps(s, 1); }
 
 static void reset_data(OrcSim *s) { /* mj_resetData: qpos0, everything else zero */
   const LcrModel *m = &s->m;
@@ -837,7 +846,7 @@ static void write_obs(const OrcSim *s, float *obs) {
 /* Env.reset (reach_cube_env.py:297-311, push_cube_env.py:308-328, lift_cube_env.py:306-320,
  * pick_place_cube_env.py:316-336, stack_two_cubes_env.py:307-324).  qvel/ctrl/warmstart/time are
  * deliberately NOT reset (the reference never calls mj_resetData). */
-void orc_reset(OrcSim *s, float *obs) {
+static void reset_(OrcSim *s, float *obs) {
   const LcrModel *m = &s->m;
   double p[3];
   for (int j = 0; j < 6; j++) s->qpos[j] = 0;
@@ -850,11 +859,12 @@ void orc_reset(OrcSim *s, float *obs) {
     draw_uniform3(s->rng, s->cfg.target_low, s->cfg.target_high, p);
     for (int k = 0; k < 3; k++) s->target[k] = (double)(float)p[k]; /* .astype(np.float32), push_cube_env.py:320 */
   }
-  orc_forward(s);
+  forward_(s);
   s->elapsed = 0;
   s->needs_reset = 0;
   if (obs) write_obs(s, obs);
 }
+void orc_reset(OrcSim *s, float *obs) { sa_clear(s); reset_(s, obs); }
 
 /* inverse_kinematics + check_joint_limits (reach_cube_env.py:141-221).  Faithful to the reference:
  * each iterate is written to data.qpos and mj_forward is run on it, and the arm is left there. */
@@ -865,7 +875,7 @@ static void inverse_kinematics(OrcSim *s, const double *target, double *q_out, i
   memcpy(save, s->qpos, sizeof save);
   for (int it = 0; it < 10; it++) {
     memcpy(s->qpos, q, sizeof q);
-    if (teleport) orc_forward(s); else kinematics(s);
+    if (teleport) forward_(s); else kinematics(s);
     double err[3], en;
     sub3(err, target, s->site_xpos);
     en = norm3(err);
@@ -935,7 +945,7 @@ static void apply_action(OrcSim *s, const float *action_in) {
     else tq[5] = clampd(a[na - 1] + s->qpos[5], TARGET_LOW[5], TARGET_HIGH[5]); /* action[-1], lift_cube_env.py:264 */
   }
   memcpy(s->ctrl, tq, sizeof tq);
-  for (int k = 0; k < cfg->n_substeps; k++) orc_substep(s);
+  for (int k = 0; k < cfg->n_substeps; k++) substep_(s);
 }
 
 /* Env.step (reach_cube_env.py:313-348, push_cube_env.py:330-361, lift_cube_env.py:322-346,
@@ -943,8 +953,9 @@ static void apply_action(OrcSim *s, const float *action_in) {
 void orc_step(OrcSim *s, const float *action, float *obs, float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *success) {
   const LcrEnvCfg *cfg = &s->cfg;
   int task = s->m.task;
+  sa_clear(s);
   if (cfg->autoreset && s->needs_reset) {
-    orc_reset(s, obs);
+    reset_(s, obs);
     *reward = 0; *terminated = 0; *truncated = 0; *success = 0;
     return;
   }
@@ -977,6 +988,7 @@ OrcSim *orc_create(const LcrModel *m, const double *verts, const LcrEnvCfg *cfg)
   s->verts = (double *)malloc(sizeof(double) * 3 * m->nvert);
   memcpy(s->verts, verts, sizeof(double) * 3 * m->nvert);
   reset_data(s);
+  sa_clear(s);
   s->rng[1] = 1; s->rng[3] = 1;
   return s;
 }

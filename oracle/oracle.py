@@ -36,6 +36,7 @@ def lib():
         L.orc_rng_double.restype = C.c_double
         for f in ("orc_destroy", "orc_forward", "orc_substep"):
             getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_substeps.argtypes = [C.c_void_p, C.c_int]
         assert L.orc_sizeof_model() == C.sizeof(_model.LcrModel), "LcrModel layout mismatch"
         assert L.orc_sizeof_cfg() == C.sizeof(_model.LcrEnvCfg), "LcrEnvCfg layout mismatch"
         _LIB = L
@@ -96,8 +97,7 @@ class Oracle:
         self.L.orc_forward(self.h)
 
     def substep(self, n=1):
-        for _ in range(n):
-            self.L.orc_substep(self.h)
+        self.L.orc_substeps(self.h, int(n))
 
     def ik(self, target):
         t = np.ascontiguousarray(target, np.float32)
