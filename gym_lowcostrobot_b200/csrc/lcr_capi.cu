@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -176,6 +177,11 @@ struct Impl {
 
 struct LcrSim {
   int precision, device, n, ncube, task, launches;
+  // phased mode: the env range is cut into groups, each with its own stream, so that the tail of one group's
+  // variable-cost kernels (collision, solver) overlaps the other groups' work
+  int ngroups = 0;
+  cudaStream_t gstream[16];
+  cudaEvent_t ev_begin, ev_done[16];
   LcrModel model;
   LcrEnvCfg cfg;
   Impl<float> f;
@@ -207,6 +213,19 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
   int rc = precision == LCR_F32 ? s->f.create(*model, hull_verts, *cfg, n_envs) : s->d.create(*model, hull_verts, *cfg, n_envs);
   if (rc) { delete s; return rc; }
   s->launches = 1;
+  if (cfg->exec_mode == 1) {
+    const char* e = getenv("LCR_GROUPS");
+    int g = e ? atoi(e) : 8;
+    g = std::max(1, std::min(16, std::min(g, n_envs)));
+    s->ngroups = g;
+    for (int k = 0; k < g; k++) {
+      if (cudaStreamCreateWithFlags(&s->gstream[k], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_done[k], cudaEventDisableTiming) != cudaSuccess) {
+        fail("lcr_create: stream/event creation failed");
+        return 1;
+      }
+    }
+    cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming);
+  }
   *out = s;
   return 0;
 }
@@ -215,6 +234,8 @@ int lcr_destroy(LcrSim* sim) {
   if (!sim) return 0;
   cudaSetDevice(sim->device);
   if (sim->precision == LCR_F32) sim->f.destroy(); else sim->d.destroy();
+  for (int k = 0; k < sim->ngroups; k++) { cudaStreamDestroy(sim->gstream[k]); cudaEventDestroy(sim->ev_done[k]); }
+  if (sim->ngroups) cudaEventDestroy(sim->ev_begin);
   delete sim;
   return 0;
 }
@@ -248,12 +269,22 @@ int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward,
   WITH_DEVICE(sim);
   if (!d_actions || !d_obs || !d_reward || !d_terminated || !d_truncated || !d_success) return fail("lcr_step: null buffer");
   if (sim->cfg.exec_mode == 1) {
-    if (sim->precision == LCR_F32)
-      sim->launches += lcr::Launch<float>::step_phased(sim->ncube, sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, d_actions, d_obs,
-                                                       d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
-    else
-      sim->launches += lcr::Launch<double>::step_phased(sim->ncube, sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, d_actions, d_obs,
-                                                        d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int G = sim->ngroups, per = (sim->n + G - 1) / G;
+    CUDA_OK(cudaEventRecord(sim->ev_begin, st));
+    for (int g = 0; g < G; g++) {
+      const int env0 = g * per, cnt = std::min(per, sim->n - env0);
+      if (cnt <= 0) break;
+      CUDA_OK(cudaStreamWaitEvent(sim->gstream[g], sim->ev_begin, 0));
+      if (sim->precision == LCR_F32)
+        sim->launches += lcr::Launch<float>::step_phased(sim->ncube, sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, d_actions, d_obs,
+                                                         d_reward, d_terminated, d_truncated, d_success, env0, cnt, sim->gstream[g]);
+      else
+        sim->launches += lcr::Launch<double>::step_phased(sim->ncube, sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, d_actions, d_obs,
+                                                          d_reward, d_terminated, d_truncated, d_success, env0, cnt, sim->gstream[g]);
+      CUDA_OK(cudaEventRecord(sim->ev_done[g], sim->gstream[g]));
+      CUDA_OK(cudaStreamWaitEvent(st, sim->ev_done[g], 0));
+    }
   } else {
     if (sim->precision == LCR_F32)
       lcr::Launch<float>::step(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);

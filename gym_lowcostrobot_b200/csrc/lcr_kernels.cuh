@@ -714,19 +714,36 @@ __device__ __noinline__ Eval3<T> contact_eval(Ws<T, NC>& w, int ci, T alpha, boo
   return Eval3<T>{cost, d1, d2};
 }
 
-// cost at qacc: fills e_jar, Ma; if FULL also e_force, grad and the Hessian pieces (e_w, e_g, e_p, c_c1, c_c2)
+// (M x)_dof with M = blockdiag(M_arm, cube diagonals); x read from shared memory
+template <typename T, int NC> DI T mul_M_dof(const Ws<T, NC>& w, const DevModel<T>& m, const T* x, int dof) {
+  T a = 0;
+  if (dof < LCR_NARM) {
+#pragma unroll
+    for (int d = 0; d < LCR_NARM; d++) a += w.M[dof][d] * x[d];
+  } else if (dof < Ws<T, NC>::NVV) {
+    const int d = dof - LCR_NARM, c = d / 6;
+    a = ((d % 6) < 3 ? m.cube_mass[c] : m.cube_inertia[c]) * x[dof];
+  }
+  return a;
+}
+
+// cost at qacc over the dof island [d0, NVV): fills e_jar, Ma; if FULL also e_force, grad and the Hessian pieces
+// (e_w, e_g, e_p, c_c1, c_c2).  Lane l owns dof d0 + l.
 template <typename T, int NC>
-__device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T* qacc, bool FULL) {
+__device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T* qacc, bool FULL, int d0) {
   constexpr int NVV = Ws<T, NC>::NVV;
-  const int lane = LANE, nefc = w.nefc, ncon = w.ncon, nlim = w.nlim;
+  const int lane = LANE, nefc = w.nefc, ncon = w.ncon, nlim = w.nlim, dof = d0 + lane;
   for (int i = lane; i < nefc; i += 32) {
     T a = -w.e_aref[i];
-#pragma unroll
-    for (int d = 0; d < NVV; d++) a += w.J[i][d] * qacc[d];
+    for (int d = d0; d < NVV; d++) a += w.J[i][d] * qacc[d];
     w.e_jar[i] = a;
   }
-  T ma = mul_M(w, m, qacc), cost = 0;
-  if (lane < NVV) { w.Ma[lane] = ma; cost = (T)0.5 * (ma - w.smooth[lane]) * (qacc[lane] - w.qacc_smooth[lane]); }
+  T cost = 0;
+  if (dof < NVV) {
+    const T ma = mul_M_dof(w, m, qacc, dof);
+    w.Ma[dof] = ma;
+    cost = (T)0.5 * (ma - w.smooth[dof]) * (qacc[dof] - w.qacc_smooth[dof]);
+  }
   __syncwarp();
   if (lane < nlim) {
     const T x = w.e_jar[lane];
@@ -734,25 +751,26 @@ __device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T
     if (x < 0) { cost += (T)0.5 * w.e_D[lane] * x * x; f = -w.e_D[lane] * x; ww = w.e_D[lane]; }
     if (FULL) { w.e_force[lane] = f; w.e_w[lane] = ww; }
   }
-  for (int ci = lane; ci < ncon; ci += 32) {
-    cost += contact_eval<T, NC>(w, ci, (T)0, false, FULL).cost;
-  }
+  for (int ci = lane; ci < ncon; ci += 32) cost += contact_eval<T, NC>(w, ci, (T)0, false, FULL).cost;
   cost = warp_sum(cost);
   if (FULL) {
     __syncwarp();
-    if (lane < NVV) {
-      T g = w.Ma[lane] - w.smooth[lane];
+    if (dof < NVV) {
+      T g = w.Ma[dof] - w.smooth[dof];
       for (int i = 0; i < nefc; i++) {
         const T f = w.e_force[i];
-        if (f != 0) g -= w.J[i][lane] * f;
+        if (f != 0) g -= w.J[i][dof] * f;
       }
-      w.grad[lane] = g;
+      w.grad[dof] = g;
     }
   }
   __syncwarp();
   return cost;
 }
 
+// Primal Newton solve.  If no constraint row touches an arm dof (no limit rows, no contact on links 1..6) the arm
+// block of the problem is decoupled: qacc_arm = qacc_smooth_arm exactly and the solve runs on the cube dofs only
+// (island [6, NVV): 6x6 or 12x12 Hessian instead of 12x12 / 18x18).
 template <typename T, int NC>
 __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& m, T tol) {
   constexpr int NVV = Ws<T, NC>::NVV;
@@ -765,18 +783,24 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
     __syncwarp();
     return;
   }
-  const T cw = total_cost<T, NC>(w, m, warm, false);
-  const T cs = total_cost<T, NC>(w, m, w.qacc_smooth, false);
-  if (lane < NVV) w.qacc[lane] = cw < cs ? warm[lane] : w.qacc_smooth[lane];
+  bool arm = nlim > 0;
+  for (int ci = lane; ci < ncon; ci += 32) arm |= (w.c_b1[ci] > 0 && w.c_b1[ci] < LCR_NABODY) || (w.c_b2[ci] > 0 && w.c_b2[ci] < LCR_NABODY);
+  const int d0 = __any_sync(FULLMASK, arm) ? 0 : LCR_NARM, n = NVV - d0, dof = d0 + lane;
+  const int nent = n * (n + 1) / 2;
+  if (lane < d0) warm[lane] = w.qacc_smooth[lane];  // decoupled dofs take no warm start
+  __syncwarp();
+  const T cw = total_cost<T, NC>(w, m, warm, false, d0);
+  const T cs = total_cost<T, NC>(w, m, w.qacc_smooth, false, d0);
+  if (lane < NVV) w.qacc[lane] = (cw < cs && lane >= d0) ? warm[lane] : w.qacc_smooth[lane];
   __syncwarp();
   const T scale = 1 / (m.meaninertia * (T)NVV);
-  T cost = total_cost<T, NC>(w, m, w.qacc, true);
-  // lower-triangle entries owned by this lane
+  T cost = total_cost<T, NC>(w, m, w.qacc, true, d0);
+  // lower-triangle entries (island-local indices) owned by this lane
   int ea[EPL], eb[EPL];
 #pragma unroll
   for (int k = 0; k < EPL; k++) {
     int e = lane + 32 * k, a = 0;
-    if (e >= NENT) e = 0;
+    if (e >= nent) e = 0;
     while (e > a) { e -= a + 1; a++; }
     ea[k] = a; eb[k] = e;
   }
@@ -786,7 +810,7 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
     T h[EPL];
 #pragma unroll
     for (int k = 0; k < EPL; k++) {
-      const int a = ea[k], b = eb[k];
+      const int a = d0 + ea[k], b = d0 + eb[k];
       T v = 0;
       if (a < LCR_NARM) v = w.M[a][b];
       else if (a == b) { const int d = a - LCR_NARM, c = d / 6; v = (d % 6) < 3 ? m.cube_mass[c] : m.cube_inertia[c]; }
@@ -796,7 +820,7 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
       const T ww = w.e_w[i];
       if (ww == 0) continue;  // warp-uniform
 #pragma unroll
-      for (int k = 0; k < EPL; k++) h[k] += ww * w.J[i][ea[k]] * w.J[i][eb[k]];
+      for (int k = 0; k < EPL; k++) h[k] += ww * w.J[i][d0 + ea[k]] * w.J[i][d0 + eb[k]];
     }
     for (int ci = 0; ci < ncon; ci++) {
       const T c1 = w.c_c1[ci];
@@ -804,8 +828,8 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
       const T c2 = w.c_c2[ci];
       const int i0 = w.c_efc[ci], dim = w.c_par[ci]->dim;
       T G = 0, P = 0;
-      if (lane < NVV)
-        for (int k = 0; k < dim; k++) { const T jk = w.J[i0 + k][lane]; G += w.e_g[i0 + k] * jk; P += w.e_p[i0 + k] * jk; }
+      if (dof < NVV)
+        for (int k = 0; k < dim; k++) { const T jk = w.J[i0 + k][dof]; G += w.e_g[i0 + k] * jk; P += w.e_p[i0 + k] * jk; }
 #pragma unroll
       for (int k = 0; k < EPL; k++) {
         const T Ga = __shfl_sync(FULLMASK, G, ea[k]), Gb = __shfl_sync(FULLMASK, G, eb[k]);
@@ -815,25 +839,24 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
     }
 #pragma unroll
     for (int k = 0; k < EPL; k++)
-      if (lane + 32 * k < NENT) w.H[ea[k]][eb[k]] = h[k];
+      if (lane + 32 * k < nent) w.H[ea[k]][eb[k]] = h[k];
     __syncwarp();
-    warp_cholesky(&w.H[0][0], NVV + 1, NVV);
-    T s = -warp_chol_solve(&w.H[0][0], NVV + 1, NVV, lane < NVV ? w.grad[lane] : (T)0);
-    if (lane < NVV) w.search[lane] = s;
-    const T snorm = sqrt(warp_sum(lane < NVV ? s * s : (T)0));
+    warp_cholesky(&w.H[0][0], NVV + 1, n);
+    T s = -warp_chol_solve(&w.H[0][0], NVV + 1, n, lane < n ? w.grad[dof] : (T)0);
+    if (lane < n) w.search[dof] = s;
+    const T snorm = sqrt(warp_sum(lane < n ? s * s : (T)0));
     __syncwarp();
     if (snorm < c_minval<T>()) break;
     // ---- exact line search (safeguarded Newton on alpha)
-    T mv = mul_M(w, m, w.search);
-    if (lane < NVV) w.Mv[lane] = mv;
+    T mv = 0;
+    if (lane < n) { mv = mul_M_dof(w, m, w.search, dof); w.Mv[dof] = mv; }
     for (int i = lane; i < nefc; i += 32) {
       T a = 0;
-#pragma unroll
-      for (int d = 0; d < NVV; d++) a += w.J[i][d] * w.search[d];
+      for (int d = d0; d < NVV; d++) a += w.J[i][d] * w.search[d];
       w.e_jv[i] = a;
     }
     T g1 = 0, g2 = 0;
-    if (lane < NVV) { g1 = s * (w.Ma[lane] - w.smooth[lane]); g2 = s * mv; }
+    if (lane < n) { g1 = s * (w.Ma[dof] - w.smooth[dof]); g2 = s * mv; }
     g1 = warp_sum(g1);
     g2 = warp_sum(g2);
     __syncwarp();
@@ -859,12 +882,12 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
       alpha = an;
     }
     if (!(alpha > 0)) break;
-    if (lane < NVV) w.qacc[lane] += alpha * s;
+    if (lane < n) w.qacc[dof] += alpha * s;
     __syncwarp();
     const T old = cost;
-    cost = total_cost<T, NC>(w, m, w.qacc, true);
+    cost = total_cost<T, NC>(w, m, w.qacc, true, d0);
     niter = iter + 1;
-    const T gn = sqrt(warp_sum(lane < NVV ? w.grad[lane] * w.grad[lane] : (T)0));
+    const T gn = sqrt(warp_sum(lane < n ? w.grad[dof] * w.grad[dof] : (T)0));
     if (scale * (old - cost) < tol || scale * gn < tol) break;
   }
   if (lane < NVV) warm[lane] = w.qacc[lane];
@@ -1250,9 +1273,9 @@ template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_begin(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
                                                      Ws<T, NC>* __restrict__ gws, const float* __restrict__ actions, float* __restrict__ obs,
                                                      float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
-                                                     uint8_t* __restrict__ succ) {
+                                                     uint8_t* __restrict__ succ, int env0) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = blockIdx.x;
+  const int env = env0 + blockIdx.x;
   load_state(w, s, env);
   const DevModel<T>& m = *dm;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
@@ -1265,9 +1288,9 @@ __global__ void __launch_bounds__(32, 16) k_ph_begin(const DevModel<T>* __restri
 
 // [integrate the previous substep] -> checks -> kinematics -> inertia / bias -> smooth forces
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int first) {
+__global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int first, int env0) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = blockIdx.x;
+  const int env = env0 + blockIdx.x;
   if (gws[env].skip) return;
   load_ws(w, gws, env, false);
   const DevModel<T>& m = *dm;
@@ -1282,18 +1305,18 @@ __global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict
   store_ws(w, gws, env, false);
 }
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws) {
+__global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = blockIdx.x;
+  const int env = env0 + blockIdx.x;
   if (gws[env].skip) return;
   load_ws(w, gws, env, false);
   make_constraints(w, *dm, verts);
   store_ws(w, gws, env, true);
 }
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_ph_sol(const DevModel<T>* __restrict__ dm, Ws<T, NC>* __restrict__ gws) {
+__global__ void __launch_bounds__(32, 16) k_ph_sol(const DevModel<T>* __restrict__ dm, Ws<T, NC>* __restrict__ gws, int env0) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = blockIdx.x;
+  const int env = env0 + blockIdx.x;
   if (gws[env].skip) return;
   load_ws(w, gws, env, true);
   const DevModel<T>& m = *dm;
@@ -1304,9 +1327,9 @@ __global__ void __launch_bounds__(32, 16) k_ph_sol(const DevModel<T>* __restrict
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_end(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
                                                    Ws<T, NC>* __restrict__ gws, float* __restrict__ obs, float* __restrict__ reward,
-                                                   uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ) {
+                                                   uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ, int env0) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = blockIdx.x;
+  const int env = env0 + blockIdx.x;
   if (gws[env].skip) return;
   load_ws(w, gws, env, false);
   const DevModel<T>& m = *dm;
@@ -1432,33 +1455,26 @@ void Launch<T>::step(int ncube, const DevModel<T>* dm, const T* verts, DevState<
                      uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st) {
   LCR_LAUNCH(k_step, dm, verts, s, actions, obs, reward, term, trunc, succ);
 }
-template <typename T>
-int Launch<T>::step_phased(int ncube, int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws_, const float* actions,
-                           float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st) {
-  const int grid = s.n;
-  if (ncube == 1) {
-    typedef Ws<T, 1> W;
-    W* gws = reinterpret_cast<W*>(gws_);
-    const size_t sm = sizeof(W);
-    k_ph_begin<T, 1><<<grid, 32, sm, st>>>(dm, verts, s, gws, actions, obs, reward, term, trunc, succ);
-    for (int k = 0; k < n_substeps; k++) {
-      k_ph_dyn<T, 1><<<grid, 32, sm, st>>>(dm, verts, gws, k == 0);
-      k_ph_col<T, 1><<<grid, 32, sm, st>>>(dm, verts, gws);
-      k_ph_sol<T, 1><<<grid, 32, sm, st>>>(dm, gws);
-    }
-    k_ph_end<T, 1><<<grid, 32, sm, st>>>(dm, verts, s, gws, obs, reward, term, trunc, succ);
-  } else {
-    typedef Ws<T, 2> W;
-    W* gws = reinterpret_cast<W*>(gws_);
-    const size_t sm = sizeof(W);
-    k_ph_begin<T, 2><<<grid, 32, sm, st>>>(dm, verts, s, gws, actions, obs, reward, term, trunc, succ);
-    for (int k = 0; k < n_substeps; k++) {
-      k_ph_dyn<T, 2><<<grid, 32, sm, st>>>(dm, verts, gws, k == 0);
-      k_ph_col<T, 2><<<grid, 32, sm, st>>>(dm, verts, gws);
-      k_ph_sol<T, 2><<<grid, 32, sm, st>>>(dm, gws);
-    }
-    k_ph_end<T, 2><<<grid, 32, sm, st>>>(dm, verts, s, gws, obs, reward, term, trunc, succ);
+// one chain of 2 + 3*n_substeps launches over the env range [env0, env0 + cnt) on stream st
+template <typename T, int NC>
+static void phased_chain(int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws_, const float* actions, float* obs,
+                         float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, cudaStream_t st) {
+  typedef Ws<T, NC> W;
+  W* gws = reinterpret_cast<W*>(gws_);
+  const size_t sm = sizeof(W);
+  k_ph_begin<T, NC><<<cnt, 32, sm, st>>>(dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0);
+  for (int k = 0; k < n_substeps; k++) {
+    k_ph_dyn<T, NC><<<cnt, 32, sm, st>>>(dm, verts, gws, k == 0, env0);
+    k_ph_col<T, NC><<<cnt, 32, sm, st>>>(dm, verts, gws, env0);
+    k_ph_sol<T, NC><<<cnt, 32, sm, st>>>(dm, gws, env0);
   }
+  k_ph_end<T, NC><<<cnt, 32, sm, st>>>(dm, verts, s, gws, obs, reward, term, trunc, succ, env0);
+}
+template <typename T>
+int Launch<T>::step_phased(int ncube, int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, const float* actions,
+                           float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, cudaStream_t st) {
+  if (ncube == 1) phased_chain<T, 1>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, st);
+  else phased_chain<T, 2>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, st);
   return 2 + 3 * n_substeps;
 }
 template <typename T>

@@ -683,6 +683,14 @@ static void solve_constraints(OrcSim *s) {
   double jar[LCR_MAXEFC], Ma[NV], grad[NV], search[NV], Mv[NV], jv[LCR_MAXEFC];
   double H[NV][NV], L[NV][NV];
   double *force = s->efc_force, *qacc = s->qacc;
+  /* if no constraint row touches an arm dof (no limit rows, no contact on links 1..6) the arm block is decoupled:
+   * those dofs take no warm start, so they stay at qacc_smooth (the optimum) through the monolithic iterations */
+  {
+    int arm = 0;
+    for (int i = 0; i < nefc; i++) if (s->efc_type[i] == 0) arm = 1;
+    for (int c = 0; c < s->ncon; c++) if ((s->con[c].b1 > 0 && s->con[c].b1 < LCR_NABODY) || (s->con[c].b2 > 0 && s->con[c].b2 < LCR_NABODY)) arm = 1;
+    if (!arm) memcpy(s->warm, s->qacc_smooth, sizeof(double) * LCR_NARM);
+  }
   /* warm start: the better of qacc_warmstart and qacc_smooth */
   double cw = total_cost(s, s->warm, jar, Ma, NULL, NULL);
   double cs = total_cost(s, s->qacc_smooth, jar, Ma, NULL, NULL);
