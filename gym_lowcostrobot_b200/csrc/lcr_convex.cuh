@@ -430,81 +430,153 @@ template <typename T, int NC> DI void sa_clear(Ws<T, NC>& w) {
   if (LANE == 0) w.sa_next = 0;
   __syncwarp();
 }
+// ---------------------------------------------------------------- convex pairs: candidates -> jobs -> contacts
+// The narrowphase of the box-mesh and mesh-mesh pairs is organised as three steps so that it can run either inline
+// (fused kernel) or as its own launch with one warp per (env, slot) (phased mode: MPR calls are the most
+// unevenly distributed work of mj_step -- a folded arm yields nine penetrating hull pairs -- and a per-env warp
+// would hold its whole launch back):
+//   1. collect_candidates : sphere + oriented-box broadphase, candidate keys in canonical (contact generation) order
+//   2. narrowphase_job    : cached separating-axis test or full MPR for ONE candidate; reads the workspace only
+//   3. consume_candidates : separating-axis cache updates and add_contact, in candidate order
+// key: mesh-mesh pair p -> p; cube c vs mesh g -> LCR_KEY_CUBE + LCR_MAXMESH * c + g
+#define LCR_KEY_CUBE 200
+
+template <typename T, int NC> DI T (*cand_res(Ws<T, NC>& w))[8] { return reinterpret_cast<T(*)[8]>(w.e_w); }
+
 template <typename T, int NC>
-__device__ __noinline__ bool cached_mpr(Ws<T, NC>& w, const T* __restrict__ verts, int key, const Shape<T>& A, const Shape<T>& B, T& depth,
-                                        T* dir, T* pos) {
+__device__ __noinline__ void collect_candidates(Ws<T, NC>& w, const DevModel<T>& m) {
+  const int lane = LANE, cmask = m.collision_mask;
+  if (lane < m.nmesh) {  // world centres of the mesh bounding spheres / boxes
+    const int b = m.mesh_body[lane];
+    T c[3] = {m.mesh_center[lane][0], m.mesh_center[lane][1], m.mesh_center[lane][2]}, t[3];
+    mat_vec(t, w.xmat[b], c);
+    w.gc[lane][0] = w.xpos[b][0] + t[0]; w.gc[lane][1] = w.xpos[b][1] + t[1]; w.gc[lane][2] = w.xpos[b][2] + t[2];
+  }
+  __syncwarp();
+  int n = 0;
+  if (cmask & LCR_COLLIDE_CUBE_MESH)
+    for (int c = 0; c < NC; c++) {
+      const int bc = LCR_NABODY + c;
+      bool cand = false;
+      if (lane < m.nmesh) {
+        T hc[3] = {m.cube_size[c][0], m.cube_size[c][1], m.cube_size[c][2]};
+        const T r = m.mesh_rbound[lane] + sqrt(dot3(hc, hc));
+        T d[3] = {w.gc[lane][0] - w.xpos[bc][0], w.gc[lane][1] - w.xpos[bc][1], w.gc[lane][2] - w.xpos[bc][2]};
+        cand = !(dot3(d, d) > r * r);
+      }
+      const unsigned mask = __ballot_sync(FULLMASK, cand);
+      if (cand) {
+        const int k = n + __popc(mask & ((1u << lane) - 1));
+        if (k < LCR_MAXCAND) w.cand_key[k] = (short)(LCR_KEY_CUBE + LCR_MAXMESH * c + lane);
+      }
+      n += __popc(mask);
+    }
+  if (cmask & LCR_COLLIDE_MESH_MESH)
+    for (int base = 0; base < m.npair; base += 32) {
+      const int p = base + lane;
+      bool cand = false;
+      if (p < m.npair) {
+        const int g1 = m.pair_g1[p], g2 = m.pair_g2[p];
+        const T r = m.mesh_rbound[g1] + m.mesh_rbound[g2];
+        T d[3] = {w.gc[g1][0] - w.gc[g2][0], w.gc[g1][1] - w.gc[g2][1], w.gc[g1][2] - w.gc[g2][2]};
+        cand = !(dot3(d, d) > r * r);
+        if (cand) cand = !obb_apart(w, m, g1, g2);
+      }
+      const unsigned mask = __ballot_sync(FULLMASK, cand);
+      if (cand) {
+        const int k = n + __popc(mask & ((1u << lane) - 1));
+        if (k < LCR_MAXCAND) w.cand_key[k] = (short)p;
+      }
+      n += __popc(mask);
+    }
+  if (lane == 0) w.ncand = n;  // n > LCR_MAXCAND: the tail is recomputed inline by consume_candidates (rare)
+  __syncwarp();
+}
+
+template <typename T, int NC> DI void key_shapes(const Ws<T, NC>& w, const DevModel<T>& m, int key, Shape<T>& A, Shape<T>& B) {
+  if (key >= LCR_KEY_CUBE) {
+    const int c = (key - LCR_KEY_CUBE) / LCR_MAXMESH, g = (key - LCR_KEY_CUBE) % LCR_MAXMESH;
+    cube_shape(w, m, c, A);
+    mesh_shape(w, m, g, B);
+  } else {
+    mesh_shape(w, m, m.pair_g1[key], A);
+    mesh_shape(w, m, m.pair_g2[key], B);
+  }
+}
+
+// One candidate.  res = {code, depth, dir[3], pos[3]}; code 2: still separated along the cached axis, 1: penetrating,
+// 0: separated, new axis in dir, -1: separated without a usable axis.  `w` is only read (it may live in HBM).
+template <typename T, int NC>
+__device__ __noinline__ void narrowphase_job(const Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int key, T* res) {
+  Shape<T> A, B;
+  key_shapes(w, m, key, A, B);
   const unsigned hit = __ballot_sync(FULLMASK, LANE < LCR_NSA && w.sa_key[LANE] == key);
-  int slot = hit ? __ffs(hit) - 1 : -1;
-  if (slot >= 0) {
+  if (hit) {
+    const int slot = __ffs(hit) - 1;
     T d[3] = {w.sa_dir[slot][0], w.sa_dir[slot][1], w.sa_dir[slot][2]};
     SPoint<T> p;
     md_support(w, verts, A, B, d, p);
-    if (dot3(p.v, d) < (T)-1e-6) return false;
+    if (dot3(p.v, d) < (T)-1e-6) { res[0] = 2; return; }
   }
+  T depth = 0, dir[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
   const int r = mpr_penetration(w, verts, A, B, depth, dir, pos);
+  res[0] = (T)r; res[1] = depth;
+  res[2] = dir[0]; res[3] = dir[1]; res[4] = dir[2];
+  res[5] = pos[0]; res[6] = pos[1]; res[7] = pos[2];
+}
+
+template <typename T, int NC>
+__device__ __noinline__ void run_jobs_inline(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts) {
+  const int n = w.ncand < LCR_MAXCAND ? w.ncand : LCR_MAXCAND;
+  T (*res)[8] = cand_res(w);
+  for (int k = 0; k < n; k++) {
+    T r[8];
+    narrowphase_job(w, m, verts, w.cand_key[k], r);
+    __syncwarp();
+    if (LANE < 8) res[k][LANE] = r[LANE];
+    __syncwarp();
+  }
+}
+
+template <typename T, int NC>
+DI void apply_result(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, int key, const T* r) {
+  const int code = (int)r[0];
+  if (code == 2) return;
+  const unsigned hit = __ballot_sync(FULLMASK, LANE < LCR_NSA && w.sa_key[LANE] == key);
+  int slot = hit ? __ffs(hit) - 1 : -1;
   __syncwarp();
-  if (r == 0) {
+  if (code == 0) {
     if (slot < 0) { slot = w.sa_next; __syncwarp(); if (LANE == 0) w.sa_next = (slot + 1) % LCR_NSA; }
-    if (LANE == 0) { w.sa_key[slot] = (short)key; w.sa_dir[slot][0] = dir[0]; w.sa_dir[slot][1] = dir[1]; w.sa_dir[slot][2] = dir[2]; }
+    if (LANE == 0) { w.sa_key[slot] = (short)key; w.sa_dir[slot][0] = r[2]; w.sa_dir[slot][1] = r[3]; w.sa_dir[slot][2] = r[4]; }
   } else if (slot >= 0) {
     if (LANE == 0) w.sa_key[slot] = -1;
   }
   __syncwarp();
-  return r == 1;
-}
-
-// ---------------------------------------------------------------- pair drivers
-template <typename T, int NC>
-__device__ __noinline__ void collide_cube_meshes(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc, int c) {
-  const int lane = LANE, bc = LCR_NABODY + c;
-  bool cand = false;
-  if (lane < m.nmesh) {
-    T hc[3] = {m.cube_size[c][0], m.cube_size[c][1], m.cube_size[c][2]};
-    const T r = m.mesh_rbound[lane] + sqrt(dot3(hc, hc));
-    T d[3] = {w.gc[lane][0] - w.xpos[bc][0], w.gc[lane][1] - w.xpos[bc][1], w.gc[lane][2] - w.xpos[bc][2]};
-    cand = !(dot3(d, d) > r * r);
-  }
-  unsigned mask = __ballot_sync(FULLMASK, cand);
-  while (mask) {
-    const int g = __ffs(mask) - 1;
-    mask &= mask - 1;
-    Shape<T> A, B;
-    cube_shape(w, m, c, A);
-    mesh_shape(w, m, g, B);
-    T depth, dir[3], pos[3];
-    if (!cached_mpr(w, verts, 200 + LCR_MAXMESH * c + g, A, B, depth, dir, pos)) continue;
-    if (dir[0] == 0 && dir[1] == 0 && dir[2] == 0) continue;
-    add_contact(w, ncon, nefc, &m.par_cube_mesh[c][g], bc, m.mesh_body[g], pos, dir, -depth);
+  if (code != 1 || (r[2] == 0 && r[3] == 0 && r[4] == 0)) return;
+  T dir[3] = {r[2], r[3], r[4]}, pos[3] = {r[5], r[6], r[7]};
+  if (key >= LCR_KEY_CUBE) {
+    const int c = (key - LCR_KEY_CUBE) / LCR_MAXMESH, g = (key - LCR_KEY_CUBE) % LCR_MAXMESH;
+    add_contact(w, ncon, nefc, &m.par_cube_mesh[c][g], LCR_NABODY + c, m.mesh_body[g], pos, dir, -r[1]);
+  } else {
+    add_contact(w, ncon, nefc, &m.par_mesh_mesh[key], m.mesh_body[m.pair_g1[key]], m.mesh_body[m.pair_g2[key]], pos, dir, -r[1]);
   }
 }
 
+// contacts of the candidates [k0, k1) whose keys satisfy cube == (key >= LCR_KEY_CUBE); candidates past LCR_MAXCAND
+// have no stored key / result and are not processed (counted as overflow)
 template <typename T, int NC>
-__device__ __noinline__ void collide_mesh_meshes(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc) {
-  const int lane = LANE;
-  for (int base = 0; base < m.npair; base += 32) {
-    const int p = base + lane;
-    bool cand = false;
-    if (p < m.npair) {
-      const int g1 = m.pair_g1[p], g2 = m.pair_g2[p];
-      const T r = m.mesh_rbound[g1] + m.mesh_rbound[g2];
-      T d[3] = {w.gc[g1][0] - w.gc[g2][0], w.gc[g1][1] - w.gc[g2][1], w.gc[g1][2] - w.gc[g2][2]};
-      cand = !(dot3(d, d) > r * r);
-      if (cand) cand = !obb_apart(w, m, g1, g2);
-    }
-    unsigned mask = __ballot_sync(FULLMASK, cand);
-    while (mask) {
-      const int pp = base + __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int g1 = m.pair_g1[pp], g2 = m.pair_g2[pp];
-      Shape<T> A, B;
-      mesh_shape(w, m, g1, A);
-      mesh_shape(w, m, g2, B);
-      T depth, dir[3], pos[3];
-      if (!cached_mpr(w, verts, pp, A, B, depth, dir, pos)) continue;
-      if (dir[0] == 0 && dir[1] == 0 && dir[2] == 0) continue;
-      add_contact(w, ncon, nefc, &m.par_mesh_mesh[pp], m.mesh_body[g1], m.mesh_body[g2], pos, dir, -depth);
-    }
+__device__ __noinline__ void consume_candidates(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, bool cube) {
+  const int n = w.ncand < LCR_MAXCAND ? w.ncand : LCR_MAXCAND;
+  T (*res)[8] = cand_res(w);
+  for (int k = 0; k < n; k++) {
+    const int key = w.cand_key[k];
+    if ((key >= LCR_KEY_CUBE) != cube) continue;
+    T r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = res[k][j];
+    apply_result(w, m, ncon, nefc, key, r);
   }
+  if (!cube && w.ncand > LCR_MAXCAND && LANE == 0) w.diag[4] += w.ncand - LCR_MAXCAND;
 }
 
 }  // namespace lcr

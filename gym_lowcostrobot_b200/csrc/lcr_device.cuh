@@ -18,6 +18,7 @@
 
 #define LCR_WPB 1          // warps (= envs) per CTA: every env is an independent 32-thread CTA
 #define FULLMASK 0xffffffffu
+#define LCR_MAXCAND (3 * LCR_MAXEFC / 8)  // candidate results (8 words each) live in the e_w / e_g / e_p rows
 
 // contact parameter classes, precomputed on the host by the MuJoCo mixing rule
 template <typename T>
@@ -97,6 +98,8 @@ struct Ws {  // per-warp shared-memory workspace
   short sa_key[LCR_NSA];   // separating-axis cache of the convex narrowphase (see lcr_convex.cuh)
   int sa_next;
   T sa_dir[LCR_NSA][3];
+  short cand_key[LCR_MAXCAND];  // convex-pair candidates of this substep (results alias e_w / e_g / e_p)
+  int ncand;
   int skip;          // phased execution: this env was auto-reset by the current step, substep kernels pass
   int redo_forward;  // phased execution: state was reset after a bad qacc, re-run mj_forward before integrating
   alignas(16) T J[LCR_MAXEFC][JS];  // last member: only the first nefc rows are live (and staged)

@@ -478,7 +478,7 @@ DI void fill_jac_row(Ws<T, NC>& w, int i, int b1, int b2, const T* pos, const T*
 }
 
 template <typename T, int NC>
-__device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts) {
+__device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, bool precomputed) {
   constexpr int NVV = Ws<T, NC>::NVV;
   const int lane = LANE;
   const T* qpos = w.qpos();
@@ -507,21 +507,17 @@ __device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m
   }
   __syncwarp();
   const int cmask = m.collision_mask;
-  if (lane < m.nmesh) {  // world centres of the mesh bounding spheres / boxes
-    const int b = m.mesh_body[lane];
-    T c[3] = {m.mesh_center[lane][0], m.mesh_center[lane][1], m.mesh_center[lane][2]}, t[3];
-    mat_vec(t, w.xmat[b], c);
-    w.gc[lane][0] = w.xpos[b][0] + t[0]; w.gc[lane][1] = w.xpos[b][1] + t[1]; w.gc[lane][2] = w.xpos[b][2] + t[2];
+  if (!precomputed) {  // fused path: broadphase and narrowphase jobs inline
+    collect_candidates(w, m);
+    run_jobs_inline(w, m, verts);
   }
-  __syncwarp();
   // generation order (= drop order at the caps): floor-cube, cube-cube, cube-mesh, floor-mesh, mesh-mesh
   if (cmask & LCR_COLLIDE_FLOOR_CUBE)
     for (int c = 0; c < NC; c++) collide_floor_cube(w, m, ncon, nefc, c);
   if (NC == 2 && (cmask & LCR_COLLIDE_CUBE_CUBE)) collide_cube_cube(w, m, ncon, nefc);
-  if (cmask & LCR_COLLIDE_CUBE_MESH)
-    for (int c = 0; c < NC; c++) collide_cube_meshes(w, m, verts, ncon, nefc, c);
+  if (cmask & LCR_COLLIDE_CUBE_MESH) consume_candidates(w, m, ncon, nefc, true);
   if (cmask & LCR_COLLIDE_FLOOR_MESH) collide_floor_meshes(w, m, verts, ncon, nefc);
-  if (cmask & LCR_COLLIDE_MESH_MESH) collide_mesh_meshes(w, m, verts, ncon, nefc);
+  if (cmask & LCR_COLLIDE_MESH_MESH) consume_candidates(w, m, ncon, nefc, false);
   if (lane == 0) { w.ncon = ncon; w.nefc = nefc; w.nlim = nlim; }
   __syncwarp();
   // contact rows: lane <-> row
@@ -904,7 +900,7 @@ template <typename T, int NC>
 __device__ __noinline__ void forward(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts) {
   kinematics(w, m);
   inertia_and_bias(w, m);
-  make_constraints(w, m, verts);
+  make_constraints(w, m, verts, false);
   smooth_forces(w, m);
   solve_constraints(w, m, solver_tol<T>(m));
 }
@@ -1302,15 +1298,33 @@ __global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict
   kinematics(w, m);
   inertia_and_bias(w, m);
   smooth_forces(w, m);
+  collect_candidates(w, m);
   store_ws(w, gws, env, false);
 }
+// narrowphase jobs: one warp per (env, slot); the workspace stays in HBM/L2 and is only read, results go to the
+// candidate result rows.  No shared memory, so the hull vertices stay L1 resident.
+#define LCR_NSLOT 4
+template <typename T, int NC>
+__global__ void __launch_bounds__(32, 16) k_ph_job(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0) {
+  const int env = env0 + blockIdx.x / LCR_NSLOT, slot = blockIdx.x % LCR_NSLOT;
+  Ws<T, NC>& w = gws[env];
+  if (w.skip) return;
+  const int n = w.ncand < LCR_MAXCAND ? w.ncand : LCR_MAXCAND;
+  T (*res)[8] = cand_res(w);
+  for (int k = slot; k < n; k += LCR_NSLOT) {
+    T r[8];
+    narrowphase_job(w, *dm, verts, w.cand_key[k], r);
+    if (LANE < 8) res[k][LANE] = r[LANE];
+  }
+}
+
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = env0 + blockIdx.x;
   if (gws[env].skip) return;
   load_ws(w, gws, env, false);
-  make_constraints(w, *dm, verts);
+  make_constraints(w, *dm, verts, true);
   store_ws(w, gws, env, true);
 }
 template <typename T, int NC>
@@ -1465,6 +1479,7 @@ static void phased_chain(int n_substeps, const DevModel<T>* dm, const T* verts, 
   k_ph_begin<T, NC><<<cnt, 32, sm, st>>>(dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0);
   for (int k = 0; k < n_substeps; k++) {
     k_ph_dyn<T, NC><<<cnt, 32, sm, st>>>(dm, verts, gws, k == 0, env0);
+    k_ph_job<T, NC><<<cnt * LCR_NSLOT, 32, 0, st>>>(dm, verts, gws, env0);
     k_ph_col<T, NC><<<cnt, 32, sm, st>>>(dm, verts, gws, env0);
     k_ph_sol<T, NC><<<cnt, 32, sm, st>>>(dm, gws, env0);
   }
@@ -1475,7 +1490,7 @@ int Launch<T>::step_phased(int ncube, int n_substeps, const DevModel<T>* dm, con
                            float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, cudaStream_t st) {
   if (ncube == 1) phased_chain<T, 1>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, st);
   else phased_chain<T, 2>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, st);
-  return 2 + 3 * n_substeps;
+  return 2 + 4 * n_substeps;
 }
 template <typename T>
 void Launch<T>::substeps(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, int n, cudaStream_t st) {
