@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--action-mode", dest="action_mode", default="joint", choices=["joint", "ee"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exec-mode", dest="exec_mode", default="phased", choices=["fused", "phased"])
+    ap.add_argument("--exec-mode", dest="exec_mode", default="phased", choices=["fused", "phased", "lockstep"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -11,7 +11,7 @@ import os
 from . import model as _model
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblcrsim.so")
+LIB_PATH = os.environ.get("LCR_LIB") or os.path.join(_HERE, "liblcrsim.so")  # LCR_LIB: alternative build (experiments)
 F32, F64 = 0, 1
 
 # every symbol declared in include/lcrsim.h

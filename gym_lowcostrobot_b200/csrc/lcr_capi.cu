@@ -180,6 +180,7 @@ struct LcrSim {
   // phased mode: the env range is cut into groups, each with its own stream, so that the tail of one group's
   // variable-cost kernels (collision, solver) overlaps the other groups' work
   int ngroups = 0;
+  int ls_warps = 0, ls_flags = 0;  // lockstep mode: envs per CTA (0 = as many as fit one SM) and LCR_LS_* barrier flags
   cudaStream_t gstream[16];
   cudaEvent_t ev_begin, ev_done[16];
   LcrModel model;
@@ -225,6 +226,12 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
       }
     }
     cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming);
+  }
+  if (cfg->exec_mode == 2) {  // tuning overrides for experiments; the defaults are the measured best
+    const char* e = getenv("LCR_LS_WARPS");
+    s->ls_warps = e ? atoi(e) : 0;
+    e = getenv("LCR_LS_FLAGS");
+    s->ls_flags = e ? atoi(e) : 23;
   }
   *out = s;
   return 0;
@@ -285,6 +292,14 @@ int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward,
       CUDA_OK(cudaEventRecord(sim->ev_done[g], sim->gstream[g]));
       CUDA_OK(cudaStreamWaitEvent(st, sim->ev_done[g], 0));
     }
+  } else if (sim->cfg.exec_mode == 2) {
+    if (sim->precision == LCR_F32)
+      lcr::Launch<float>::step_lockstep(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success,
+                                        sim->ls_warps, sim->ls_flags, (cudaStream_t)stream);
+    else
+      lcr::Launch<double>::step_lockstep(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success,
+                                         sim->ls_warps, sim->ls_flags, (cudaStream_t)stream);
+    sim->launches++;
   } else {
     if (sim->precision == LCR_F32)
       lcr::Launch<float>::step(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);

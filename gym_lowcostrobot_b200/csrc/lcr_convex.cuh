@@ -38,6 +38,16 @@ struct Shape {  // warp-uniform descriptor
 };
 template <typename T> struct SPoint { T v[3], v1[3], v2[3]; };
 
+// hull vertex i as one (float) or two (double) 128-bit read-only loads; verts is [nvert][4], 16-byte aligned
+DI void load_vert(const float* __restrict__ verts, int i, float& x, float& y, float& z) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(verts) + i);
+  x = v.x; y = v.y; z = v.z;
+}
+DI void load_vert(const double* __restrict__ verts, int i, double& x, double& y, double& z) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(verts) + 2 * (size_t)i);
+  x = a.x; y = a.y; z = __ldg(verts + 4 * (size_t)i + 2);
+}
+
 // support point of one shape along world direction d (all lanes get the same result)
 template <typename T, int NC>
 __device__ __noinline__ void shape_support(const Ws<T, NC>& w, const T* __restrict__ verts, const Shape<T>& sh, const T* d, T* out) {
@@ -52,13 +62,13 @@ __device__ __noinline__ void shape_support(const Ws<T, NC>& w, const T* __restri
     int bi = 0x7fffffff;
 #pragma unroll 4
     for (int i = LANE; i < sh.num; i += 32) {
-      const T* v = verts + 4 * (size_t)(sh.adr + i);
-      const T s = v[0] * dl[0] + v[1] * dl[1] + v[2] * dl[2];
+      T vx, vy, vz;
+      load_vert(verts, sh.adr + i, vx, vy, vz);
+      const T s = vx * dl[0] + vy * dl[1] + vz * dl[2];
       if (s > bv) { bv = s; bi = i; }
     }
     warp_argmax(bv, bi);
-    const T* v = verts + 4 * (size_t)(sh.adr + bi);
-    p[0] = v[0]; p[1] = v[1]; p[2] = v[2];
+    load_vert(verts, sh.adr + bi, p[0], p[1], p[2]);
   }
   mat_vec(out, R, p);
 #pragma unroll

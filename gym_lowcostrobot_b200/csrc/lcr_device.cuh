@@ -77,10 +77,9 @@ struct Ws {  // per-warp shared-memory workspace
   int diag[LCR_NDIAG];
   unsigned long long rng[4];
   // kinematics
-  T xpos[NB][3], xquat[NB][4], xmat[NB][9], xipos[LCR_NABODY][3], ximat[LCR_NABODY][9], axis[LCR_NARM][3];
+  T xpos[NB][3], xquat[NB][4], xmat[NB][9], xipos[LCR_NABODY][3], axis[LCR_NARM][3];
   T Iw[LCR_NABODY][6];
   T gc[LCR_MAXMESH][3];  // world centres of the mesh bounding spheres / boxes
-  T rw[LCR_NABODY][3], ral[LCR_NABODY][3], ra[LCR_NABODY][3], F[LCR_NABODY][3], Nn[LCR_NABODY][3];
   T M[LCR_NARM][LCR_NARM], Lm[LCR_NARM][LCR_NARM + 1];
   T bias[NVV], smooth[NVV], qacc_smooth[NVV], qacc[NVV], Ma[NVV], grad[NVV], search[NVV], Mv[NVV];
   T H[NVV][NVV + 1];
@@ -90,7 +89,11 @@ struct Ws {  // per-warp shared-memory workspace
   short c_efc[LCR_MAXCON];
   signed char c_b1[LCR_MAXCON], c_b2[LCR_MAXCON];
   // constraint rows
-  T e_pos[LCR_MAXEFC], e_D[LCR_MAXEFC], e_aref[LCR_MAXEFC], e_jar[LCR_MAXEFC], e_jv[LCR_MAXEFC], e_force[LCR_MAXEFC];
+  T e_pos[LCR_MAXEFC], e_D[LCR_MAXEFC], e_aref[LCR_MAXEFC], e_jar[LCR_MAXEFC];
+  union {  // solver rows / RNE temporaries of inertia_and_bias (dead before the constraint rows are built)
+    struct { T e_jv[LCR_MAXEFC], e_force[LCR_MAXEFC]; };
+    struct { T rw[LCR_NABODY][3], ral[LCR_NABODY][3], ra[LCR_NABODY][3], F[LCR_NABODY][3], Nn[LCR_NABODY][3]; };
+  };
   T e_w[LCR_MAXEFC], e_g[LCR_MAXEFC], e_p[LCR_MAXEFC];  // Hessian pieces, see contact_eval
   short e_unit[LCR_MAXEFC];  // >= 0: contact index; < 0: limit row of joint -1-e_unit
   signed char e_r[LCR_MAXEFC];  // row index within its contact
@@ -123,6 +126,9 @@ struct Launch {
   static void reset(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const uint8_t* mask, float* obs, cudaStream_t st);
   static void step(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
                    uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st);
+  static int lockstep_warps(int ncube, int warps);
+  static void step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
+                            uint8_t* term, uint8_t* trunc, uint8_t* succ, int warps, int flags, cudaStream_t st);
   static int step_phased(int ncube, int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, const float* actions,
                          float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, cudaStream_t st);
   static void substeps(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, int n, cudaStream_t st);

@@ -10,10 +10,13 @@
 // Around it: apply_action incl. the damped-least-squares IK (reach_cube_env.py:148-279),
 // get_observation (:281-295), reward / success (:313-348), reset (:297-311), TimeLimit(50).
 #pragma once
+#include <algorithm>
+
 #include "lcr_device.cuh"
 
 namespace lcr {
 
+#define LCR_LS_MAXSMEM (227 * 1024 - 64)  // dynamic shared memory of one lockstep CTA (the static part is one int)
 #define LANE (threadIdx.x & 31)
 #define DI __device__ __forceinline__
 
@@ -165,8 +168,6 @@ __device__ __noinline__ void kinematics(Ws<T, NC>& w, const DevModel<T>& m) {
     quat_mul(qi, qq, iq);
     T Ri[9];
     quat_to_mat(Ri, qi);
-#pragma unroll
-    for (int k = 0; k < 9; k++) w.ximat[b][k] = Ri[k];
     // world inertia Iw = Ri diag(I) Ri^T, symmetric storage xx xy xz yy yz zz
     T I0 = m.body_inertia[b][0], I1 = m.body_inertia[b][1], I2 = m.body_inertia[b][2];
     w.Iw[b][0] = Ri[0] * I0 * Ri[0] + Ri[1] * I1 * Ri[1] + Ri[2] * I2 * Ri[2];
@@ -368,8 +369,8 @@ DI void mesh_support4(const Ws<T, NC>& w, const DevModel<T>& m, const T* __restr
 #pragma unroll
   for (int t = 0; t < 4; t++) { matT_vec(dl[t], w.xmat[b], dirs[t]); bv[t] = (T)-1e30; bi[t] = 0x7fffffff; }
   for (int i = lane; i < num; i += 32) {
-    const T* v = verts + 4 * (size_t)(adr + i);
-    T vx = v[0], vy = v[1], vz = v[2];
+    T vx, vy, vz;
+    load_vert(verts, adr + i, vx, vy, vz);
 #pragma unroll
     for (int t = 0; t < 4; t++) {
       T s = vx * dl[t][0] + vy * dl[t][1] + vz * dl[t][2];
@@ -380,8 +381,8 @@ DI void mesh_support4(const Ws<T, NC>& w, const DevModel<T>& m, const T* __restr
   for (int t = 0; t < 4; t++) {
     warp_argmax(bv[t], bi[t]);
     idx[t] = bi[t];
-    const T* v = verts + 4 * (size_t)(adr + bi[t]);
-    T vl[3] = {v[0], v[1], v[2]};
+    T vl[3];
+    load_vert(verts, adr + bi[t], vl[0], vl[1], vl[2]);
     mat_vec(pts[t], w.xmat[b], vl);
 #pragma unroll
     for (int k = 0; k < 3; k++) pts[t][k] += w.xpos[b][k];
@@ -634,8 +635,8 @@ template <typename T, int NC> DI T mul_M(const Ws<T, NC>& w, const DevModel<T>& 
 // (bottom zone: wrow = D, c1 = c2 = 0;  middle zone: wrow_0 = 0, wrow_k = c2 f_k^2,
 //  g = dNT/djar, p_k = f_k u_k / T, c1 = Dm, c2 = -mu NT Dm / T >= 0).
 template <typename T> struct Eval3 { T cost, d1, d2; };
-template <typename T, int NC>
-__device__ __noinline__ Eval3<T> contact_eval(Ws<T, NC>& w, int ci, T alpha, bool with_jv, bool FULL) {
+template <typename T, int NC, bool with_jv, bool FULL>
+__device__ __noinline__ Eval3<T> contact_eval(Ws<T, NC>& w, int ci, T alpha) {
   T cost, d1, d2;
   const CPar<T>* par = w.c_par[ci];
   const int dim = par->dim, i0 = w.c_efc[ci];
@@ -725,8 +726,8 @@ template <typename T, int NC> DI T mul_M_dof(const Ws<T, NC>& w, const DevModel<
 
 // cost at qacc over the dof island [d0, NVV): fills e_jar, Ma; if FULL also e_force, grad and the Hessian pieces
 // (e_w, e_g, e_p, c_c1, c_c2).  Lane l owns dof d0 + l.
-template <typename T, int NC>
-__device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T* qacc, bool FULL, int d0) {
+template <typename T, int NC, bool FULL>
+__device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T* qacc, int d0) {
   constexpr int NVV = Ws<T, NC>::NVV;
   const int lane = LANE, nefc = w.nefc, ncon = w.ncon, nlim = w.nlim, dof = d0 + lane;
   for (int i = lane; i < nefc; i += 32) {
@@ -747,7 +748,7 @@ __device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T
     if (x < 0) { cost += (T)0.5 * w.e_D[lane] * x * x; f = -w.e_D[lane] * x; ww = w.e_D[lane]; }
     if (FULL) { w.e_force[lane] = f; w.e_w[lane] = ww; }
   }
-  for (int ci = lane; ci < ncon; ci += 32) cost += contact_eval<T, NC>(w, ci, (T)0, false, FULL).cost;
+  for (int ci = lane; ci < ncon; ci += 32) cost += contact_eval<T, NC, false, FULL>(w, ci, (T)0).cost;
   cost = warp_sum(cost);
   if (FULL) {
     __syncwarp();
@@ -767,128 +768,150 @@ __device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T
 // Primal Newton solve.  If no constraint row touches an arm dof (no limit rows, no contact on links 1..6) the arm
 // block of the problem is decoupled: qacc_arm = qacc_smooth_arm exactly and the solve runs on the cube dofs only
 // (island [6, NVV): 6x6 or 12x12 Hessian instead of 12x12 / 18x18).
-template <typename T, int NC>
-__device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& m, T tol) {
+// CTA_SYNC (lockstep kernel): every warp of the CTA calls this together (`active` false for warps without work)
+// and the Newton iterations are separated by CTA barriers, so that the warps of a CTA walk the same code at the
+// same time and share its instruction-cache lines; the arithmetic per env is unchanged.
+template <typename T, int NC, bool CTA_SYNC>
+__device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& m, T tol, bool active = true) {
   constexpr int NVV = Ws<T, NC>::NVV;
   constexpr int NENT = NVV * (NVV + 1) / 2, EPL = (NENT + 31) / 32;
-  const int lane = LANE, nefc = w.nefc, ncon = w.ncon, nlim = w.nlim;
+  const int lane = LANE, nefc = active ? w.nefc : 0, ncon = w.ncon, nlim = w.nlim;
   T* warm = w.warm();
-  if (nefc == 0) {
+  bool done = !active;
+  if (active && nefc == 0) {
     if (lane < NVV) { T a = w.qacc_smooth[lane]; w.qacc[lane] = a; warm[lane] = a; }
     if (lane == 0) w.diag[2] = 0;
     __syncwarp();
-    return;
+    done = true;
+    if (!CTA_SYNC) return;
   }
-  bool arm = nlim > 0;
-  for (int ci = lane; ci < ncon; ci += 32) arm |= (w.c_b1[ci] > 0 && w.c_b1[ci] < LCR_NABODY) || (w.c_b2[ci] > 0 && w.c_b2[ci] < LCR_NABODY);
-  const int d0 = __any_sync(FULLMASK, arm) ? 0 : LCR_NARM, n = NVV - d0, dof = d0 + lane;
-  const int nent = n * (n + 1) / 2;
-  if (lane < d0) warm[lane] = w.qacc_smooth[lane];  // decoupled dofs take no warm start
-  __syncwarp();
-  const T cw = total_cost<T, NC>(w, m, warm, false, d0);
-  const T cs = total_cost<T, NC>(w, m, w.qacc_smooth, false, d0);
-  if (lane < NVV) w.qacc[lane] = (cw < cs && lane >= d0) ? warm[lane] : w.qacc_smooth[lane];
-  __syncwarp();
-  const T scale = 1 / (m.meaninertia * (T)NVV);
-  T cost = total_cost<T, NC>(w, m, w.qacc, true, d0);
-  // lower-triangle entries (island-local indices) owned by this lane
+  int d0 = 0, n = NVV, dof = lane, nent = 0, niter = 0;
+  T scale = 0, cost = 0;
   int ea[EPL], eb[EPL];
 #pragma unroll
-  for (int k = 0; k < EPL; k++) {
-    int e = lane + 32 * k, a = 0;
-    if (e >= nent) e = 0;
-    while (e > a) { e -= a + 1; a++; }
-    ea[k] = a; eb[k] = e;
-  }
-  int niter = 0;
-  for (int iter = 0; iter < m.iterations; iter++) {
-    // ---- Hessian H = M + sum_rows w_i J_i J_i^T + sum_cone-contacts (c1 G G^T - c2 P P^T)
-    T h[EPL];
+  for (int k = 0; k < EPL; k++) { ea[k] = 0; eb[k] = 0; }
+  if (!done) {
+    bool arm = nlim > 0;
+    for (int ci = lane; ci < ncon; ci += 32) arm |= (w.c_b1[ci] > 0 && w.c_b1[ci] < LCR_NABODY) || (w.c_b2[ci] > 0 && w.c_b2[ci] < LCR_NABODY);
+    d0 = __any_sync(FULLMASK, arm) ? 0 : LCR_NARM; n = NVV - d0; dof = d0 + lane;
+    nent = n * (n + 1) / 2;
+    if (lane < d0) warm[lane] = w.qacc_smooth[lane];  // decoupled dofs take no warm start
+    __syncwarp();
+    // start from the warm start if it is cheaper than qacc_smooth; the FULL evaluation at the warm start is kept
+    // when it wins (the common case for persistent contacts), so the chosen point is evaluated only once
+    const T cs = total_cost<T, NC, false>(w, m, w.qacc_smooth, d0);
+    const T cw = total_cost<T, NC, true>(w, m, warm, d0);
+    const bool use_warm = cw < cs;
+    if (lane < NVV) w.qacc[lane] = (use_warm && lane >= d0) ? warm[lane] : w.qacc_smooth[lane];
+    __syncwarp();
+    scale = 1 / (m.meaninertia * (T)NVV);
+    cost = use_warm ? cw : total_cost<T, NC, true>(w, m, w.qacc, d0);
+    // lower-triangle entries (island-local indices) owned by this lane
 #pragma unroll
     for (int k = 0; k < EPL; k++) {
-      const int a = d0 + ea[k], b = d0 + eb[k];
-      T v = 0;
-      if (a < LCR_NARM) v = w.M[a][b];
-      else if (a == b) { const int d = a - LCR_NARM, c = d / 6; v = (d % 6) < 3 ? m.cube_mass[c] : m.cube_inertia[c]; }
-      h[k] = v;
+      int e = lane + 32 * k, a = 0;
+      if (e >= nent) e = 0;
+      while (e > a) { e -= a + 1; a++; }
+      ea[k] = a; eb[k] = e;
     }
-    for (int i = 0; i < nefc; i++) {
-      const T ww = w.e_w[i];
-      if (ww == 0) continue;  // warp-uniform
-#pragma unroll
-      for (int k = 0; k < EPL; k++) h[k] += ww * w.J[i][d0 + ea[k]] * w.J[i][d0 + eb[k]];
-    }
-    for (int ci = 0; ci < ncon; ci++) {
-      const T c1 = w.c_c1[ci];
-      if (c1 == 0) continue;  // warp-uniform
-      const T c2 = w.c_c2[ci];
-      const int i0 = w.c_efc[ci], dim = w.c_par[ci]->dim;
-      T G = 0, P = 0;
-      if (dof < NVV)
-        for (int k = 0; k < dim; k++) { const T jk = w.J[i0 + k][dof]; G += w.e_g[i0 + k] * jk; P += w.e_p[i0 + k] * jk; }
+  }
+  for (int iter = 0; iter < m.iterations; iter++) {
+    if (CTA_SYNC) { if (!__syncthreads_or(!done)) break; }
+    else if (done) break;
+    if (done) continue;
+    done = true;  // every `break` below ends this env's solve; cleared again at the bottom if it goes on
+    do {
+      // ---- Hessian H = M + sum_rows w_i J_i J_i^T + sum_cone-contacts (c1 G G^T - c2 P P^T)
+      T h[EPL];
 #pragma unroll
       for (int k = 0; k < EPL; k++) {
-        const T Ga = __shfl_sync(FULLMASK, G, ea[k]), Gb = __shfl_sync(FULLMASK, G, eb[k]);
-        const T Pa = __shfl_sync(FULLMASK, P, ea[k]), Pb = __shfl_sync(FULLMASK, P, eb[k]);
-        h[k] += c1 * Ga * Gb - c2 * Pa * Pb;
+        const int a = d0 + ea[k], b = d0 + eb[k];
+        T v = 0;
+        if (a < LCR_NARM) v = w.M[a][b];
+        else if (a == b) { const int d = a - LCR_NARM, c = d / 6; v = (d % 6) < 3 ? m.cube_mass[c] : m.cube_inertia[c]; }
+        h[k] = v;
       }
-    }
+      for (int i = 0; i < nefc; i++) {
+        const T ww = w.e_w[i];
+        if (ww == 0) continue;  // warp-uniform
 #pragma unroll
-    for (int k = 0; k < EPL; k++)
-      if (lane + 32 * k < nent) w.H[ea[k]][eb[k]] = h[k];
-    __syncwarp();
-    warp_cholesky(&w.H[0][0], NVV + 1, n);
-    T s = -warp_chol_solve(&w.H[0][0], NVV + 1, n, lane < n ? w.grad[dof] : (T)0);
-    if (lane < n) w.search[dof] = s;
-    const T snorm = sqrt(warp_sum(lane < n ? s * s : (T)0));
-    __syncwarp();
-    if (snorm < c_minval<T>()) break;
-    // ---- exact line search (safeguarded Newton on alpha)
-    T mv = 0;
-    if (lane < n) { mv = mul_M_dof(w, m, w.search, dof); w.Mv[dof] = mv; }
-    for (int i = lane; i < nefc; i += 32) {
-      T a = 0;
-      for (int d = d0; d < NVV; d++) a += w.J[i][d] * w.search[d];
-      w.e_jv[i] = a;
-    }
-    T g1 = 0, g2 = 0;
-    if (lane < n) { g1 = s * (w.Ma[dof] - w.smooth[dof]); g2 = s * mv; }
-    g1 = warp_sum(g1);
-    g2 = warp_sum(g2);
-    __syncwarp();
-    const T gtol = tol * m.ls_tolerance * snorm / scale;
-    T alpha = 0, lo = 0, hi = -1;
-    for (int ls = 0; ls <= m.ls_iterations; ls++) {
-      T d1 = 0, d2 = 0;
-      if (lane < nlim) {
-        const T jv = w.e_jv[lane], x = w.e_jar[lane] + alpha * jv;
-        if (x < 0) { d1 = w.e_D[lane] * x * jv; d2 = w.e_D[lane] * jv * jv; }
+        for (int k = 0; k < EPL; k++) h[k] += ww * w.J[i][d0 + ea[k]] * w.J[i][d0 + eb[k]];
       }
-      for (int ci = lane; ci < ncon; ci += 32) {
-        const Eval3<T> ev = contact_eval<T, NC>(w, ci, alpha, true, false);
-        d1 += ev.d1; d2 += ev.d2;
+      for (int ci = 0; ci < ncon; ci++) {
+        const T c1 = w.c_c1[ci];
+        if (c1 == 0) continue;  // warp-uniform
+        const T c2 = w.c_c2[ci];
+        const int i0 = w.c_efc[ci], dim = w.c_par[ci]->dim;
+        T G = 0, P = 0;
+        if (dof < NVV)
+          for (int k = 0; k < dim; k++) { const T jk = w.J[i0 + k][dof]; G += w.e_g[i0 + k] * jk; P += w.e_p[i0 + k] * jk; }
+#pragma unroll
+        for (int k = 0; k < EPL; k++) {
+          const T Ga = __shfl_sync(FULLMASK, G, ea[k]), Gb = __shfl_sync(FULLMASK, G, eb[k]);
+          const T Pa = __shfl_sync(FULLMASK, P, ea[k]), Pb = __shfl_sync(FULLMASK, P, eb[k]);
+          h[k] += c1 * Ga * Gb - c2 * Pa * Pb;
+        }
       }
-      d1 = warp_sum(d1) + g1 + alpha * g2;
-      d2 = warp_sum(d2) + g2;
-      if (fabs(d1) < gtol || ls == m.ls_iterations) break;
-      if (d1 < 0) lo = alpha; else hi = alpha;
-      T an = alpha - d1 / d2;
-      if (hi >= 0 && (an <= lo || an >= hi)) an = (T)0.5 * (lo + hi);
-      if (an == alpha) break;
-      alpha = an;
-    }
-    if (!(alpha > 0)) break;
-    if (lane < n) w.qacc[dof] += alpha * s;
-    __syncwarp();
-    const T old = cost;
-    cost = total_cost<T, NC>(w, m, w.qacc, true, d0);
-    niter = iter + 1;
-    const T gn = sqrt(warp_sum(lane < n ? w.grad[dof] * w.grad[dof] : (T)0));
-    if (scale * (old - cost) < tol || scale * gn < tol) break;
+#pragma unroll
+      for (int k = 0; k < EPL; k++)
+        if (lane + 32 * k < nent) w.H[ea[k]][eb[k]] = h[k];
+      __syncwarp();
+      warp_cholesky(&w.H[0][0], NVV + 1, n);
+      T s = -warp_chol_solve(&w.H[0][0], NVV + 1, n, lane < n ? w.grad[dof] : (T)0);
+      if (lane < n) w.search[dof] = s;
+      const T snorm = sqrt(warp_sum(lane < n ? s * s : (T)0));
+      __syncwarp();
+      if (snorm < c_minval<T>()) break;
+      // ---- exact line search (safeguarded Newton on alpha)
+      T mv = 0;
+      if (lane < n) { mv = mul_M_dof(w, m, w.search, dof); w.Mv[dof] = mv; }
+      for (int i = lane; i < nefc; i += 32) {
+        T a = 0;
+        for (int d = d0; d < NVV; d++) a += w.J[i][d] * w.search[d];
+        w.e_jv[i] = a;
+      }
+      T g1 = 0, g2 = 0;
+      if (lane < n) { g1 = s * (w.Ma[dof] - w.smooth[dof]); g2 = s * mv; }
+      g1 = warp_sum(g1);
+      g2 = warp_sum(g2);
+      __syncwarp();
+      const T gtol = tol * m.ls_tolerance * snorm / scale;
+      T alpha = 0, lo = 0, hi = -1;
+      for (int ls = 0; ls <= m.ls_iterations; ls++) {
+        T d1 = 0, d2 = 0;
+        if (lane < nlim) {
+          const T jv = w.e_jv[lane], x = w.e_jar[lane] + alpha * jv;
+          if (x < 0) { d1 = w.e_D[lane] * x * jv; d2 = w.e_D[lane] * jv * jv; }
+        }
+        for (int ci = lane; ci < ncon; ci += 32) {
+          const Eval3<T> ev = contact_eval<T, NC, true, false>(w, ci, alpha);
+          d1 += ev.d1; d2 += ev.d2;
+        }
+        d1 = warp_sum(d1) + g1 + alpha * g2;
+        d2 = warp_sum(d2) + g2;
+        if (fabs(d1) < gtol || ls == m.ls_iterations) break;
+        if (d1 < 0) lo = alpha; else hi = alpha;
+        T an = alpha - d1 / d2;
+        if (hi >= 0 && (an <= lo || an >= hi)) an = (T)0.5 * (lo + hi);
+        if (an == alpha) break;
+        alpha = an;
+      }
+      if (!(alpha > 0)) break;
+      if (lane < n) w.qacc[dof] += alpha * s;
+      __syncwarp();
+      const T old = cost;
+      cost = total_cost<T, NC, true>(w, m, w.qacc, d0);
+      niter = iter + 1;
+      const T gn = sqrt(warp_sum(lane < n ? w.grad[dof] * w.grad[dof] : (T)0));
+      if (scale * (old - cost) < tol || scale * gn < tol) break;
+      done = false;
+    } while (0);
   }
-  if (lane < NVV) warm[lane] = w.qacc[lane];
-  if (lane == 0) w.diag[2] = niter;
-  __syncwarp();
+  if (active && nefc > 0) {
+    if (lane < NVV) warm[lane] = w.qacc[lane];
+    if (lane == 0) w.diag[2] = niter;
+    __syncwarp();
+  }
 }
 
 // ---------------------------------------------------------------- mj_forward / mj_step
@@ -902,7 +925,7 @@ __device__ __noinline__ void forward(Ws<T, NC>& w, const DevModel<T>& m, const T
   inertia_and_bias(w, m);
   make_constraints(w, m, verts, false);
   smooth_forces(w, m);
-  solve_constraints(w, m, solver_tol<T>(m));
+  solve_constraints<T, NC, false>(w, m, solver_tol<T>(m));
 }
 
 template <typename T, int NC> DI void reset_data(Ws<T, NC>& w, const DevModel<T>& m) {  // mj_resetData
@@ -1088,8 +1111,7 @@ __device__ __noinline__ bool env_step_begin(Ws<T, NC>& w, const DevModel<T>& m, 
   T a = lane < na ? clampT((T)action[lane], (T)-1, (T)1) : (T)0;
   T tq = 0;
   if (m.action_mode == 1) {
-    __shared__ T ik_scratch[8];
-    T* sc = ik_scratch;
+    T* sc = w.search;  // free before the first and after the last mj_forward of the IK loop
     const T* site = w.site_xpos();
     if (lane < 3) { T t = site[lane] + a * (T)0.05; if (lane == 2 && t < 0) t = 0; sc[lane] = t; }
     __syncwarp();
@@ -1222,7 +1244,7 @@ template <typename T, int NC>
 __global__ void __launch_bounds__(32) k_ik(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
                                            const float* __restrict__ target, float* __restrict__ q_out) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  __shared__ T outq[8];
+  T* outq = w.search;
   const int env = blockIdx.x, lane = LANE;
   load_state(w, s, env);
   T tgt[3] = {(T)target[3 * (size_t)env], (T)target[3 * (size_t)env + 1], (T)target[3 * (size_t)env + 2]};
@@ -1230,6 +1252,92 @@ __global__ void __launch_bounds__(32) k_ik(const DevModel<T>* __restrict__ dm, c
   __syncwarp();
   if (lane < 6) q_out[6 * (size_t)env + lane] = (float)outq[lane];
   // state is not written back: lcr_ik leaves the simulation untouched
+}
+
+// ---------------------------------------------------------------- lockstep execution
+// One CTA = W warps = W envs that walk mj_step phase by phase TOGETHER.  The fused one-warp-per-CTA kernel is
+// instruction-fetch bound (ncu: `no_instruction` = 17 of the 24 cycles between two issues of a warp): a substep
+// is ~110 KB of SASS against a 32 KB L1.5 instruction cache, and 14 independent warps per SM each sit in a
+// different place of it.  Here the warps of a CTA are re-aligned by CTA barriers at the phase boundaries (and
+// optionally between Newton iterations), so a cache line fetched for one warp is hit by the others; the
+// narrowphase jobs of all W envs go into one CTA-wide pool that any warp drains (the workspaces are in shared
+// memory, so a warp can run another env's MPR), which evens out the most unevenly distributed work of the step.
+// Per-env arithmetic is identical to k_step (bitwise identical state and outputs).
+#define LCR_LS_BAR_TOP 1      // barrier at the top of every substep
+#define LCR_LS_BAR_CON 2      // barrier before the constraint build (implied by the job pool)
+#define LCR_LS_BAR_SOL 4      // barrier before the solver
+#define LCR_LS_SYNC_NEWTON 8  // barriers between Newton iterations
+#define LCR_LS_JOB_POOL 16    // CTA-wide narrowphase job pool
+
+template <typename T, int NC>
+DI void cta_jobs(Ws<T, NC>* wsa, int W, const DevModel<T>& m, const T* __restrict__ verts, int* next) {
+  int tot = 0;
+  for (int e = 0; e < W; e++) { const int c = wsa[e].ncand; tot += c < LCR_MAXCAND ? c : LCR_MAXCAND; }
+  for (;;) {
+    int j = 0;
+    if (LANE == 0) j = atomicAdd(next, 1);
+    j = __shfl_sync(FULLMASK, j, 0);
+    if (j >= tot) break;
+    int e = 0;
+    for (;; e++) {
+      int c = wsa[e].ncand;
+      c = c < LCR_MAXCAND ? c : LCR_MAXCAND;
+      if (j < c) break;
+      j -= c;
+    }
+    Ws<T, NC>& we = wsa[e];
+    T r[8];
+    narrowphase_job(we, m, verts, we.cand_key[j], r);
+    __syncwarp();
+    if (LANE < 8) cand_res(we)[j][LANE] = r[LANE];
+  }
+}
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                                    const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
+                                                    uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ, int flags) {
+  Ws<T, NC>* wsa = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  __shared__ int job_next;
+  const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, env = blockIdx.x * W + warp;
+  const bool valid = env < s.n;
+  Ws<T, NC>& w = wsa[warp];
+  const DevModel<T>& m = *dm;
+  const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
+  const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+  bool go = false;
+  if (valid) {
+    load_state(w, s, env);
+    go = env_step_begin(w, m, verts, actions + (size_t)env * na, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
+  }
+  if (!go) { if (LANE == 0) w.ncand = 0; __syncwarp(); }
+  const T tol = solver_tol<T>(m);
+#pragma unroll 1
+  for (int k = 0; k < m.n_substeps; k++) {
+    if (flags & LCR_LS_BAR_TOP) __syncthreads();
+    if (go) { check_state(w, m); kinematics(w, m); inertia_and_bias(w, m); }
+    if (flags & LCR_LS_JOB_POOL) {
+      if (go) collect_candidates(w, m);
+      if (threadIdx.x == 0) job_next = 0;
+      __syncthreads();
+      cta_jobs(wsa, W, m, verts, &job_next);
+      __syncthreads();
+      if (go) make_constraints(w, m, verts, true);
+    } else {
+      if (flags & LCR_LS_BAR_CON) __syncthreads();
+      if (go) make_constraints(w, m, verts, false);
+    }
+    if (go) smooth_forces(w, m);
+    if (flags & LCR_LS_BAR_SOL) __syncthreads();
+    if (flags & LCR_LS_SYNC_NEWTON) solve_constraints<T, NC, true>(w, m, tol, go);
+    else if (go) solve_constraints<T, NC, false>(w, m, tol);
+    if (go) {
+      if (check_acc(w, m)) forward(w, m, verts);
+      integrate(w, m);
+    }
+  }
+  if (go) env_step_end(w, m, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
+  if (valid) store_state(w, s, env);
 }
 
 // ---------------------------------------------------------------- phased execution
@@ -1334,7 +1442,7 @@ __global__ void __launch_bounds__(32, 16) k_ph_sol(const DevModel<T>* __restrict
   if (gws[env].skip) return;
   load_ws(w, gws, env, true);
   const DevModel<T>& m = *dm;
-  solve_constraints(w, m, solver_tol<T>(m));
+  solve_constraints<T, NC, false>(w, m, solver_tol<T>(m));
   if (check_acc(w, m)) { if (LANE == 0) w.redo_forward = 1; }
   store_ws(w, gws, env, false);
 }
@@ -1444,6 +1552,7 @@ template <typename T, int NC> static void set_smem_attr() {
   cudaFuncSetAttribute(k_ph_col<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_ph_sol<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_ph_end<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_step_ls<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
 }
 
 template <typename T>
@@ -1468,6 +1577,20 @@ template <typename T>
 void Launch<T>::step(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
                      uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st) {
   LCR_LAUNCH(k_step, dm, verts, s, actions, obs, reward, term, trunc, succ);
+}
+// lockstep kernel: CTAs of `warps` envs; warps <= 0 picks the largest CTA that fits one SM
+template <typename T>
+int Launch<T>::lockstep_warps(int ncube, int warps) {
+  const int fit = (int)(LCR_LS_MAXSMEM / smem_bytes(ncube));
+  if (warps <= 0) warps = fit;
+  return std::max(1, std::min(std::min(warps, fit), 16));
+}
+template <typename T>
+void Launch<T>::step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
+                              uint8_t* term, uint8_t* trunc, uint8_t* succ, int warps, int flags, cudaStream_t st) {
+  const int W = lockstep_warps(ncube, warps), grid = (s.n + W - 1) / W;
+  if (ncube == 1) k_step_ls<T, 1><<<grid, 32 * W, sizeof(Ws<T, 1>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags);
+  else k_step_ls<T, 2><<<grid, 32 * W, sizeof(Ws<T, 2>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags);
 }
 // one chain of 2 + 3*n_substeps launches over the env range [env0, env0 + cnt) on stream st
 template <typename T, int NC>

@@ -84,7 +84,8 @@ typedef struct LcrEnvCfg {
   int32_t max_episode_steps;/* 50; <= 0 disables truncation */
   int32_t autoreset;        /* 0 = never (caller resets), 1 = next-step autoreset of done envs */
   int32_t collision_mask;   /* bit0 floor-cube, bit1 floor-mesh, bit2 cube-mesh, bit3 cube-cube, bit4 mesh-mesh */
-  int32_t exec_mode;        /* 0 = one fused kernel per step, 1 = phased (one small kernel per mj_step phase) */
+  int32_t exec_mode;        /* 0 = one fused kernel per step (one warp per CTA), 1 = phased (one small kernel per mj_step phase),
+                             * 2 = lockstep (one kernel per step, CTAs of several envs aligned at the phase boundaries) */
   double distance_threshold;/* 0.05 */
   double height_threshold;  /* 0.1 (Lift) */
   double cube_low[3], cube_high[3];     /* reset sampling box of the cube(s) */

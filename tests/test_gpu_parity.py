@@ -225,3 +225,32 @@ def test_phased_execution_is_bitwise_identical_to_fused(task, mode):
         assert torch.equal(sa[k], sb[k]), k
     for e in envs:
         e.close()
+
+
+@pytest.mark.parametrize("task,mode,warps,flags", [("reach", "joint", 0, 31), ("stack", "joint", 0, 31), ("pick_place", "ee", 4, 31),
+                                                   ("push", "joint", 8, 7), ("lift", "joint", 3, 24), ("stack", "joint", 5, 0)])
+def test_lockstep_execution_is_bitwise_identical_to_fused(task, mode, warps, flags, monkeypatch):
+    """exec_mode="lockstep" (CTAs of several envs re-aligned by barriers at the phase boundaries / Newton iterations, CTA-wide
+    narrowphase job pool) runs the same per-env arithmetic as the fused kernel: float32 results must be bit-identical for every
+    CTA width and barrier configuration, with an env count that is not a multiple of the CTA width, autoreset included."""
+    n = 67
+    monkeypatch.setenv("LCR_LS_WARPS", str(warps))
+    monkeypatch.setenv("LCR_LS_FLAGS", str(flags))
+    envs = [glr.make(IDS[task], num_envs=n, action_mode=mode, autoreset=True, max_episode_steps=5, exec_mode=em) for em in ("fused", "lockstep")]
+    for e in envs:
+        e.reset(seed=3)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(8):
+        a = torch.rand(n, envs[0].action_dim, generator=gen, device="cuda") * 2 - 1
+        outs = [e.step(a) for e in envs]
+        for x, y in zip(outs[0][:4], outs[1][:4]):
+            if isinstance(x, dict):
+                for k in x:
+                    assert torch.equal(x[k], y[k]), (t, k)
+            else:
+                assert torch.equal(x, y), t
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    for e in envs:
+        e.close()
