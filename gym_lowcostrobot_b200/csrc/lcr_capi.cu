@@ -180,6 +180,7 @@ struct LcrSim {
   // phased mode: the env range is cut into groups, each with its own stream, so that the tail of one group's
   // variable-cost kernels (collision, solver) overlaps the other groups' work
   int ngroups = 0;
+  int* perm = nullptr;  // lockstep mode: work-aware env order of the current step (device, int[n])
   int ls_warps = 0, ls_flags = 0;  // lockstep mode: envs per CTA (0 = as many as fit one SM) and LCR_LS_* barrier flags
   cudaStream_t gstream[16];
   cudaEvent_t ev_begin, ev_done[16];
@@ -232,6 +233,10 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
     s->ls_warps = e ? atoi(e) : 0;
     e = getenv("LCR_LS_FLAGS");
     s->ls_flags = e ? atoi(e) : 23;
+    e = getenv("LCR_LS_SORT");
+    if (!e || atoi(e) != 0) {
+      if (cudaMalloc(&s->perm, sizeof(int) * (size_t)n_envs) != cudaSuccess) { fail("lcr_create: cudaMalloc(perm) failed"); return 1; }
+    }
   }
   *out = s;
   return 0;
@@ -243,6 +248,7 @@ int lcr_destroy(LcrSim* sim) {
   if (sim->precision == LCR_F32) sim->f.destroy(); else sim->d.destroy();
   for (int k = 0; k < sim->ngroups; k++) { cudaStreamDestroy(sim->gstream[k]); cudaEventDestroy(sim->ev_done[k]); }
   if (sim->ngroups) cudaEventDestroy(sim->ev_begin);
+  cudaFree(sim->perm);
   delete sim;
   return 0;
 }
@@ -295,11 +301,11 @@ int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward,
   } else if (sim->cfg.exec_mode == 2) {
     if (sim->precision == LCR_F32)
       lcr::Launch<float>::step_lockstep(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success,
-                                        sim->ls_warps, sim->ls_flags, (cudaStream_t)stream);
+                                        sim->ls_warps, sim->ls_flags, sim->perm, (cudaStream_t)stream);
     else
       lcr::Launch<double>::step_lockstep(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success,
-                                         sim->ls_warps, sim->ls_flags, (cudaStream_t)stream);
-    sim->launches++;
+                                         sim->ls_warps, sim->ls_flags, sim->perm, (cudaStream_t)stream);
+    sim->launches += sim->perm ? 2 : 1;
   } else {
     if (sim->precision == LCR_F32)
       lcr::Launch<float>::step(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);

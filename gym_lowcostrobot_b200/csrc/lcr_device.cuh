@@ -80,7 +80,7 @@ struct Ws {  // per-warp shared-memory workspace
   T xpos[NB][3], xquat[NB][4], xmat[NB][9], xipos[LCR_NABODY][3], axis[LCR_NARM][3];
   T Iw[LCR_NABODY][6];
   T gc[LCR_MAXMESH][3];  // world centres of the mesh bounding spheres / boxes
-  T M[LCR_NARM][LCR_NARM], Lm[LCR_NARM][LCR_NARM + 1];
+  T M[LCR_NARM][LCR_NARM];
   T bias[NVV], smooth[NVV], qacc_smooth[NVV], qacc[NVV], Ma[NVV], grad[NVV], search[NVV], Mv[NVV];
   T H[NVV][NVV + 1];
   // contacts
@@ -128,7 +128,7 @@ struct Launch {
                    uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st);
   static int lockstep_warps(int ncube, int warps);
   static void step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
-                            uint8_t* term, uint8_t* trunc, uint8_t* succ, int warps, int flags, cudaStream_t st);
+                            uint8_t* term, uint8_t* trunc, uint8_t* succ, int warps, int flags, int* perm, cudaStream_t st);
   static int step_phased(int ncube, int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, const float* actions,
                          float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, cudaStream_t st);
   static void substeps(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, int n, cudaStream_t st);

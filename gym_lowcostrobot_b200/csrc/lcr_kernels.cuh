@@ -124,6 +124,54 @@ template <typename T> __device__ __noinline__ T warp_chol_solve(const T* L, int 
   return y;
 }
 
+// Register version for a compile-time size: lane i holds row i of the SPD matrix (a[0..i] = A[i][0..i], zeros in lanes >= N).
+// On return a[k] = L[i][k] (k <= i) and c[j] = L[j][i] (j > i): lane i also holds column i of L, which is what the
+// back substitution needs.  Same operations in the same order as warp_cholesky / warp_chol_solve, but the factor
+// never touches shared memory and the loops are fully unrolled (a few shuffles and FMAs per column).
+template <typename T, int N> DI void chol_reg(T (&a)[N], T (&c)[N]) {
+  const int i = LANE;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    T akk = __shfl_sync(FULLMASK, a[k], k);
+    if (akk < c_minval<T>()) akk = c_minval<T>();
+    const T piv = sqrt(akk);
+    const T lik = (i > k) ? a[k] / piv : (T)0;
+    a[k] = (i == k) ? piv : lik;
+#pragma unroll
+    for (int j = k + 1; j < N; j++) {
+      const T ljk = __shfl_sync(FULLMASK, lik, j);
+      if (i >= j) a[j] -= lik * ljk;
+      if (i == k) c[j] = ljk;
+    }
+  }
+}
+template <typename T, int N> DI T chol_reg_solve(const T (&a)[N], const T (&c)[N], T b) {
+  const int i = LANE;
+  T y = (i < N) ? b : (T)0;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const T yk = __shfl_sync(FULLMASK, y, k) / __shfl_sync(FULLMASK, a[k], k);
+    if (i == k) y = yk;
+    else if (i > k && i < N) y -= a[k] * yk;
+  }
+#pragma unroll
+  for (int k = N - 1; k >= 0; k--) {
+    const T xk = __shfl_sync(FULLMASK, y, k) / __shfl_sync(FULLMASK, a[k], k);
+    if (i == k) y = xk;
+    else if (i < k) y -= c[k] * xk;
+  }
+  return y;
+}
+// x = A^-1 b for the N x N SPD matrix stored row-major (stride ld) in shared memory; lane i passes b_i, gets x_i
+template <typename T, int N> DI T chol_reg_factor_solve(const T* A, int ld, T b) {
+  const int i = LANE;
+  T a[N], c[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) { a[k] = (i < N && k <= i) ? A[i * ld + k] : (T)0; c[k] = 0; }
+  chol_reg<T, N>(a, c);
+  return chol_reg_solve<T, N>(a, c, b);
+}
+
 // ---------------------------------------------------------------- kinematics
 template <typename T, int NC>
 __device__ __noinline__ void kinematics(Ws<T, NC>& w, const DevModel<T>& m) {
@@ -598,12 +646,9 @@ __device__ __noinline__ void smooth_forces(Ws<T, NC>& w, const DevModel<T>& m) {
     sm = -m.jnt_damping[j] * qvel[j] - w.bias[j] + f;
   } else if (lane < NVV) sm = -w.bias[lane];
   if (lane < NVV) w.smooth[lane] = sm;
-  // factor the arm block once per substep: Lm = chol(M_arm)
-  if (lane < LCR_NARM)
-    for (int j = 0; j < LCR_NARM; j++) w.Lm[lane][j] = w.M[lane][j];
+  // qacc_smooth of the arm block: M_arm x = smooth (Cholesky in registers)
   __syncwarp();
-  warp_cholesky(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM);
-  T x = warp_chol_solve(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM, sm);
+  T x = chol_reg_factor_solve<T, LCR_NARM>(&w.M[0][0], LCR_NARM, sm);
   if (lane >= LCR_NARM && lane < NVV) {
     const int d = lane - LCR_NARM, c = d / 6;
     x = sm / ((d % 6) < 3 ? m.cube_mass[c] : m.cube_inertia[c]);
@@ -856,8 +901,13 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
       for (int k = 0; k < EPL; k++)
         if (lane + 32 * k < nent) w.H[ea[k]][eb[k]] = h[k];
       __syncwarp();
-      warp_cholesky(&w.H[0][0], NVV + 1, n);
-      T s = -warp_chol_solve(&w.H[0][0], NVV + 1, n, lane < n ? w.grad[dof] : (T)0);
+      T s;
+      {
+        const T gi = lane < n ? w.grad[dof] : (T)0;
+        if (n == 6) s = -chol_reg_factor_solve<T, 6>(&w.H[0][0], NVV + 1, gi);
+        else if (n == 12) s = -chol_reg_factor_solve<T, 12>(&w.H[0][0], NVV + 1, gi);
+        else { warp_cholesky(&w.H[0][0], NVV + 1, n); s = -warp_chol_solve(&w.H[0][0], NVV + 1, n, gi); }
+      }
       if (lane < n) w.search[dof] = s;
       const T snorm = sqrt(warp_sum(lane < n ? s * s : (T)0));
       __syncwarp();
@@ -966,13 +1016,19 @@ __device__ __noinline__ void integrate(Ws<T, NC>& w, const DevModel<T>& m) {
   const T h = m.timestep;
   // (M + h diag(damping + kv)) a = M qacc on the arm block; cubes keep qacc
   T rhs = mul_M(w, m, w.qacc);
-  if (lane < LCR_NARM) {
-    for (int j = 0; j < LCR_NARM; j++) w.Lm[lane][j] = w.M[lane][j];
-    w.Lm[lane][lane] += h * (m.jnt_damping[lane] + m.act_kv[lane]);
+  T a;
+  {
+    T ar[LCR_NARM], cr[LCR_NARM];
+#pragma unroll
+    for (int k = 0; k < LCR_NARM; k++) { ar[k] = (lane < LCR_NARM && k <= lane) ? w.M[lane][k] : (T)0; cr[k] = 0; }
+    if (lane < LCR_NARM) {
+      const T dd = h * (m.jnt_damping[lane] + m.act_kv[lane]);
+#pragma unroll
+      for (int k = 0; k < LCR_NARM; k++) if (k == lane) ar[k] += dd;
+    }
+    chol_reg<T, LCR_NARM>(ar, cr);
+    a = chol_reg_solve<T, LCR_NARM>(ar, cr, rhs);
   }
-  __syncwarp();
-  warp_cholesky(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM);
-  T a = warp_chol_solve(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM, rhs);
   if (lane >= LCR_NARM && lane < NVV) a = w.qacc[lane];
   if (lane < NVV) qvel[lane] += h * a;
   __syncwarp();
@@ -1068,13 +1124,15 @@ __device__ __noinline__ void inverse_kinematics(Ws<T, NC>& w, const DevModel<T>&
       cross3(col, w.axis[lane], r);
     }
     T rhs = dot3(col, err);
+    T ar[LCR_NARM], cr[LCR_NARM];
+#pragma unroll
     for (int b = 0; b < 6; b++) {
       T cb[3] = {__shfl_sync(FULLMASK, col[0], b), __shfl_sync(FULLMASK, col[1], b), __shfl_sync(FULLMASK, col[2], b)};
-      if (lane < 6) w.Lm[lane][b] = dot3(col, cb) + (lane == b ? (T)0.15 : (T)0);
+      ar[b] = (lane < 6 && b <= lane) ? dot3(col, cb) + (lane == b ? (T)0.15 : (T)0) : (T)0;
+      cr[b] = 0;
     }
-    __syncwarp();
-    warp_cholesky(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM);
-    T qd = warp_chol_solve(&w.Lm[0][0], LCR_NARM + 1, LCR_NARM, rhs);
+    chol_reg<T, LCR_NARM>(ar, cr);
+    T qd = chol_reg_solve<T, LCR_NARM>(ar, cr, rhs);
     const T n = sqrt(warp_sum(lane < 6 ? qd * qd : (T)0));
     if (n > 1) qd /= n;
     if (lane < 6) q = clampT(q + (T)0.5 * qd, m.jnt_range[lane][0], m.jnt_range[lane][1]);
@@ -1293,14 +1351,47 @@ DI void cta_jobs(Ws<T, NC>* wsa, int W, const DevModel<T>& m, const T* __restric
   }
 }
 
+// Work-aware env order for the lockstep kernel: envs are bucketed by the constraint count they reached in their
+// previous step (diag[3] = max nefc; contacts persist, so it predicts the cost of the next step; envs that will only
+// be auto-reset are the cheapest) and processed heaviest first.  CTAs then hold envs of similar cost -- the barrier
+// wait of a CTA is set by its slowest env -- and the grid tail is made of the cheapest CTAs.  One CTA, two passes
+// over the 64-byte int records; the order inside a bucket is arbitrary and does not affect any result.
+#define LCR_NBUCKET 16
+template <typename T>
+__global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__ perm) {
+  __shared__ int hist[LCR_NBUCKET], start[LCR_NBUCKET];
+  if (threadIdx.x < LCR_NBUCKET) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int e = threadIdx.x; e < s.n; e += blockDim.x) {
+    const int32_t* ib = s.ib + (size_t)e * LCR_IB_WORDS;
+    int key = ib[1] ? 0 : 1 + ib[LCR_NINT + 3] / 8;
+    key = key < LCR_NBUCKET ? key : LCR_NBUCKET - 1;
+    atomicAdd(&hist[key], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = LCR_NBUCKET - 1; k >= 0; k--) { start[k] = acc; acc += hist[k]; }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < s.n; e += blockDim.x) {
+    const int32_t* ib = s.ib + (size_t)e * LCR_IB_WORDS;
+    int key = ib[1] ? 0 : 1 + ib[LCR_NINT + 3] / 8;
+    key = key < LCR_NBUCKET ? key : LCR_NBUCKET - 1;
+    perm[atomicAdd(&start[key], 1)] = e;
+  }
+}
+
 template <typename T, int NC>
 __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
                                                     const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
-                                                    uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ, int flags) {
+                                                    uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ, int flags,
+                                                    const int* __restrict__ perm) {
   Ws<T, NC>* wsa = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   __shared__ int job_next;
-  const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, env = blockIdx.x * W + warp;
-  const bool valid = env < s.n;
+  const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, slot = blockIdx.x * W + warp;
+  const bool valid = slot < s.n;
+  const int env = (valid && perm != nullptr) ? perm[slot] : slot;
   Ws<T, NC>& w = wsa[warp];
   const DevModel<T>& m = *dm;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
@@ -1553,6 +1644,9 @@ template <typename T, int NC> static void set_smem_attr() {
   cudaFuncSetAttribute(k_ph_sol<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_ph_end<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_step_ls<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
+  // all of the SM's L1/shared array as shared memory: several CTAs of a few workspaces each must fit one SM
+  cudaFuncSetAttribute(k_step_ls<T, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_step<T, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 template <typename T>
@@ -1587,10 +1681,11 @@ int Launch<T>::lockstep_warps(int ncube, int warps) {
 }
 template <typename T>
 void Launch<T>::step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
-                              uint8_t* term, uint8_t* trunc, uint8_t* succ, int warps, int flags, cudaStream_t st) {
+                              uint8_t* term, uint8_t* trunc, uint8_t* succ, int warps, int flags, int* perm, cudaStream_t st) {
   const int W = lockstep_warps(ncube, warps), grid = (s.n + W - 1) / W;
-  if (ncube == 1) k_step_ls<T, 1><<<grid, 32 * W, sizeof(Ws<T, 1>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags);
-  else k_step_ls<T, 2><<<grid, 32 * W, sizeof(Ws<T, 2>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags);
+  if (perm != nullptr) k_sched<T><<<1, 1024, 0, st>>>(s, perm);
+  if (ncube == 1) k_step_ls<T, 1><<<grid, 32 * W, sizeof(Ws<T, 1>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm);
+  else k_step_ls<T, 2><<<grid, 32 * W, sizeof(Ws<T, 2>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm);
 }
 // one chain of 2 + 3*n_substeps launches over the env range [env0, env0 + cnt) on stream st
 template <typename T, int NC>

@@ -227,15 +227,17 @@ def test_phased_execution_is_bitwise_identical_to_fused(task, mode):
         e.close()
 
 
-@pytest.mark.parametrize("task,mode,warps,flags", [("reach", "joint", 0, 31), ("stack", "joint", 0, 31), ("pick_place", "ee", 4, 31),
-                                                   ("push", "joint", 8, 7), ("lift", "joint", 3, 24), ("stack", "joint", 5, 0)])
-def test_lockstep_execution_is_bitwise_identical_to_fused(task, mode, warps, flags, monkeypatch):
+@pytest.mark.parametrize("task,mode,warps,flags,sort", [("reach", "joint", 0, 31, 1), ("stack", "joint", 0, 31, 1), ("pick_place", "ee", 4, 31, 1),
+                                                        ("push", "joint", 8, 7, 0), ("lift", "joint", 3, 24, 1), ("stack", "joint", 5, 0, 0),
+                                                        ("reach", "joint", 4, 23, 1), ("stack", "joint", 6, 23, 1)])
+def test_lockstep_execution_is_bitwise_identical_to_fused(task, mode, warps, flags, sort, monkeypatch):
     """exec_mode="lockstep" (CTAs of several envs re-aligned by barriers at the phase boundaries / Newton iterations, CTA-wide
-    narrowphase job pool) runs the same per-env arithmetic as the fused kernel: float32 results must be bit-identical for every
+    narrowphase job pool, envs processed in a work-aware order) runs the same per-env arithmetic as the fused kernel: float32 results must be bit-identical for every
     CTA width and barrier configuration, with an env count that is not a multiple of the CTA width, autoreset included."""
     n = 67
     monkeypatch.setenv("LCR_LS_WARPS", str(warps))
     monkeypatch.setenv("LCR_LS_FLAGS", str(flags))
+    monkeypatch.setenv("LCR_LS_SORT", str(sort))  # work-aware env order on / off
     envs = [glr.make(IDS[task], num_envs=n, action_mode=mode, autoreset=True, max_episode_steps=5, exec_mode=em) for em in ("fused", "lockstep")]
     for e in envs:
         e.reset(seed=3)
