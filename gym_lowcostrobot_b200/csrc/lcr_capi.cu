@@ -235,7 +235,7 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
     s->ls_flags = e ? atoi(e) : 23;
     e = getenv("LCR_LS_SORT");
     if (!e || atoi(e) != 0) {
-      if (cudaMalloc(&s->perm, sizeof(int) * (size_t)n_envs) != cudaSuccess) { fail("lcr_create: cudaMalloc(perm) failed"); return 1; }
+      if (cudaMalloc(&s->perm, sizeof(int) * ((size_t)n_envs + 16)) != cudaSuccess) { fail("lcr_create: cudaMalloc(perm) failed"); return 1; }
     }
   }
   *out = s;

@@ -12,6 +12,11 @@
 
 namespace lcr {
 
+#ifndef LCR_SCAN_UNROLL
+#define LCR_SCAN_UNROLL 4
+#endif
+constexpr int kScanUnroll = LCR_SCAN_UNROLL;  // hull-scan loads in flight per lane
+
 template <typename T> DI T ccd_eps();
 template <> DI float ccd_eps<float>() { return 1.1920929e-07f; }
 template <> DI double ccd_eps<double>() { return 2.220446049250313e-16; }
@@ -60,7 +65,7 @@ __device__ __noinline__ void shape_support(const Ws<T, NC>& w, const T* __restri
   } else {
     T bv = (T)-1e30;
     int bi = 0x7fffffff;
-#pragma unroll 4
+#pragma unroll kScanUnroll
     for (int i = LANE; i < sh.num; i += 32) {
       T vx, vy, vz;
       load_vert(verts, sh.adr + i, vx, vy, vz);

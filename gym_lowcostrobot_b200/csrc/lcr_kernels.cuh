@@ -11,6 +11,7 @@
 // get_observation (:281-295), reward / success (:313-348), reset (:297-311), TimeLimit(50).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "lcr_device.cuh"
 
@@ -904,9 +905,12 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
       T s;
       {
         const T gi = lane < n ? w.grad[dof] : (T)0;
+#ifndef LCR_NO_CHOL_REG
         if (n == 6) s = -chol_reg_factor_solve<T, 6>(&w.H[0][0], NVV + 1, gi);
         else if (n == 12) s = -chol_reg_factor_solve<T, 12>(&w.H[0][0], NVV + 1, gi);
-        else { warp_cholesky(&w.H[0][0], NVV + 1, n); s = -warp_chol_solve(&w.H[0][0], NVV + 1, n, gi); }
+        else
+#endif
+        { warp_cholesky(&w.H[0][0], NVV + 1, n); s = -warp_chol_solve(&w.H[0][0], NVV + 1, n, gi); }
       }
       if (lane < n) w.search[dof] = s;
       const T snorm = sqrt(warp_sum(lane < n ? s * s : (T)0));
@@ -1351,16 +1355,20 @@ DI void cta_jobs(Ws<T, NC>* wsa, int W, const DevModel<T>& m, const T* __restric
   }
 }
 
-// Work-aware env order for the lockstep kernel: envs are bucketed by the constraint count they reached in their
+// Work-aware env order for the lockstep kernel.  Envs are ranked by the constraint count they reached in their
 // previous step (diag[3] = max nefc; contacts persist, so it predicts the cost of the next step; envs that will only
-// be auto-reset are the cheapest) and processed heaviest first.  CTAs then hold envs of similar cost -- the barrier
-// wait of a CTA is set by its slowest env -- and the grid tail is made of the cheapest CTAs.  One CTA, two passes
-// over the 64-byte int records; the order inside a bucket is arbitrary and does not affect any result.
+// be auto-reset are the cheapest) and dealt out like cards: rank r goes to CTA r % nCTA, seat r / nCTA.  Every CTA
+// gets one env of each cost stratum -- a heavy env sits with light ones whose warps drain its narrowphase jobs --
+// and CTAs are ordered by their heaviest member, so the longest CTAs start first (the grid tail is made of cheap
+// ones).  One CTA, two passes over the 64-byte int records; the order inside a bucket is arbitrary and does not
+// affect any result.  Empty seats (n not a multiple of W) hold -1.
 #define LCR_NBUCKET 16
 template <typename T>
-__global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__ perm) {
+__global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__ perm, int W) {
   __shared__ int hist[LCR_NBUCKET], start[LCR_NBUCKET];
+  const int ncta = (s.n + W - 1) / W;
   if (threadIdx.x < LCR_NBUCKET) hist[threadIdx.x] = 0;
+  for (int k = s.n + threadIdx.x; k < ncta * W; k += blockDim.x) perm[((k % ncta) * W) + k / ncta] = -1;
   __syncthreads();
   for (int e = threadIdx.x; e < s.n; e += blockDim.x) {
     const int32_t* ib = s.ib + (size_t)e * LCR_IB_WORDS;
@@ -1378,7 +1386,8 @@ __global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__
     const int32_t* ib = s.ib + (size_t)e * LCR_IB_WORDS;
     int key = ib[1] ? 0 : 1 + ib[LCR_NINT + 3] / 8;
     key = key < LCR_NBUCKET ? key : LCR_NBUCKET - 1;
-    perm[atomicAdd(&start[key], 1)] = e;
+    const int r = atomicAdd(&start[key], 1);
+    perm[(r % ncta) * W + r / ncta] = e;
   }
 }
 
@@ -1390,8 +1399,8 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
   Ws<T, NC>* wsa = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   __shared__ int job_next;
   const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, slot = blockIdx.x * W + warp;
-  const bool valid = slot < s.n;
-  const int env = (valid && perm != nullptr) ? perm[slot] : slot;
+  const int env = perm != nullptr ? perm[slot] : slot;  // perm has gridDim.x * W seats, -1 = empty
+  const bool valid = env >= 0 && env < s.n;
   Ws<T, NC>& w = wsa[warp];
   const DevModel<T>& m = *dm;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
@@ -1645,7 +1654,8 @@ template <typename T, int NC> static void set_smem_attr() {
   cudaFuncSetAttribute(k_ph_end<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_step_ls<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
   // all of the SM's L1/shared array as shared memory: several CTAs of a few workspaces each must fit one SM
-  cudaFuncSetAttribute(k_step_ls<T, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  const char* cv = getenv("LCR_LS_CARVEOUT");  // experiment: percent of the L1/shared array used as shared memory
+  cudaFuncSetAttribute(k_step_ls<T, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_step<T, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
@@ -1683,7 +1693,7 @@ template <typename T>
 void Launch<T>::step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
                               uint8_t* term, uint8_t* trunc, uint8_t* succ, int warps, int flags, int* perm, cudaStream_t st) {
   const int W = lockstep_warps(ncube, warps), grid = (s.n + W - 1) / W;
-  if (perm != nullptr) k_sched<T><<<1, 1024, 0, st>>>(s, perm);
+  if (perm != nullptr) k_sched<T><<<1, 1024, 0, st>>>(s, perm, W);
   if (ncube == 1) k_step_ls<T, 1><<<grid, 32 * W, sizeof(Ws<T, 1>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm);
   else k_step_ls<T, 2><<<grid, 32 * W, sizeof(Ws<T, 2>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm);
 }
