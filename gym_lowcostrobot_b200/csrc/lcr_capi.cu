@@ -161,6 +161,7 @@ struct Impl {
     s.nfp = (nf + 3) & ~3;
     CUDA_OK(cudaMalloc(&s.st, sizeof(T) * (size_t)s.nfp * n));
     CUDA_OK(cudaMalloc(&s.ib, sizeof(int32_t) * LCR_IB_WORDS * (size_t)n));
+    CUDA_OK(cudaMalloc(&s.sa, (size_t)Ws<T, 1>::SA_BYTES * n));
     if (c.exec_mode == 1) CUDA_OK(cudaMalloc(&gws, lcr::Launch<T>::smem_bytes(m.ncube) * (size_t)n));
     lcr::Launch<T>::prepare(m.ncube);
     lcr::Launch<T>::init_state(m.ncube, dm, s, 0);
@@ -169,7 +170,7 @@ struct Impl {
     return 0;
   }
   void destroy() {
-    cudaFree(dm); cudaFree(verts); cudaFree(s.st); cudaFree(s.ib); cudaFree(gws);
+    cudaFree(dm); cudaFree(verts); cudaFree(s.st); cudaFree(s.ib); cudaFree(s.sa); cudaFree(gws);
   }
 };
 

@@ -13,7 +13,7 @@
 namespace lcr {
 
 #ifndef LCR_SCAN_UNROLL
-#define LCR_SCAN_UNROLL 4
+#define LCR_SCAN_UNROLL 8
 #endif
 constexpr int kScanUnroll = LCR_SCAN_UNROLL;  // hull-scan loads in flight per lane
 
@@ -65,12 +65,22 @@ __device__ __noinline__ void shape_support(const Ws<T, NC>& w, const T* __restri
   } else {
     T bv = (T)-1e30;
     int bi = 0x7fffffff;
-#pragma unroll kScanUnroll
-    for (int i = LANE; i < sh.num; i += 32) {
-      T vx, vy, vz;
-      load_vert(verts, sh.adr + i, vx, vy, vz);
-      const T s = vx * dl[0] + vy * dl[1] + vz * dl[2];
-      if (s > bv) { bv = s; bi = i; }
+    // chunks of kScanUnroll vertices per lane: all loads of a chunk are issued before the first use (the vertex pool is
+    // served by L2 -- with the whole L1 carved out as shared memory -- so a scan costs one L2 round trip per chunk
+    // instead of one per vertex); out-of-range slots re-read the last vertex and are ignored
+    for (int base = LANE; base < sh.num; base += 32 * kScanUnroll) {
+      T vx[kScanUnroll], vy[kScanUnroll], vz[kScanUnroll];
+#pragma unroll
+      for (int u = 0; u < kScanUnroll; u++) {
+        const int i = base + 32 * u;
+        load_vert(verts, sh.adr + (i < sh.num ? i : sh.num - 1), vx[u], vy[u], vz[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kScanUnroll; u++) {
+        const int i = base + 32 * u;
+        const T s = vx[u] * dl[0] + vy[u] * dl[1] + vz[u] * dl[2];
+        if (i < sh.num && s > bv) { bv = s; bi = i; }
+      }
     }
     warp_argmax(bv, bi);
     load_vert(verts, sh.adr + bi, p[0], p[1], p[2]);
@@ -529,9 +539,24 @@ __device__ __noinline__ void narrowphase_job(const Ws<T, NC>& w, const DevModel<
   if (hit) {
     const int slot = __ffs(hit) - 1;
     T d[3] = {w.sa_dir[slot][0], w.sa_dir[slot][1], w.sa_dir[slot][2]};
-    SPoint<T> p;
-    md_support(w, verts, A, B, d, p);
-    if (dot3(p.v, d) < (T)-1e-6) { res[0] = 2; return; }
+    if (key < LCR_KEY_CUBE && A.body == 0) {
+      // A sits on the world-fixed base: its support value along the cached axis is constant and was stored with the
+      // axis, so only B is needed -- first the bound from B's oriented box, then B's exact support
+      const int g2 = m.pair_g2[key];
+      const T* R = w.xmat[B.body];
+      const T sa = w.sa_val[slot];
+      T ext = 0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) ext += fabs(R[k] * d[0] + R[3 + k] * d[1] + R[6 + k] * d[2]) * (m.mesh_half[g2][k] + (T)1e-6);
+      if (sa - ((w.gc[g2][0] * d[0] + w.gc[g2][1] * d[1] + w.gc[g2][2] * d[2]) - ext) < (T)-1e-6) { res[0] = 2; return; }
+      T nd[3] = {-d[0], -d[1], -d[2]}, v2[3];
+      shape_support(w, verts, B, nd, v2);
+      if (sa - dot3(v2, d) < (T)-1e-6) { res[0] = 2; return; }
+    } else {
+      SPoint<T> p;
+      md_support(w, verts, A, B, d, p);
+      if (dot3(p.v, d) < (T)-1e-6) { res[0] = 2; return; }
+    }
   }
   T depth = 0, dir[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
   const int r = mpr_penetration(w, verts, A, B, depth, dir, pos);
@@ -554,7 +579,7 @@ __device__ __noinline__ void run_jobs_inline(Ws<T, NC>& w, const DevModel<T>& m,
 }
 
 template <typename T, int NC>
-DI void apply_result(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, int key, const T* r) {
+DI void apply_result(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc, int key, const T* r) {
   const int code = (int)r[0];
   if (code == 2) return;
   const unsigned hit = __ballot_sync(FULLMASK, LANE < LCR_NSA && w.sa_key[LANE] == key);
@@ -563,6 +588,13 @@ DI void apply_result(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, i
   if (code == 0) {
     if (slot < 0) { slot = w.sa_next; __syncwarp(); if (LANE == 0) w.sa_next = (slot + 1) % LCR_NSA; }
     if (LANE == 0) { w.sa_key[slot] = (short)key; w.sa_dir[slot][0] = r[2]; w.sa_dir[slot][1] = r[3]; w.sa_dir[slot][2] = r[4]; }
+    if (key < LCR_KEY_CUBE && m.mesh_body[m.pair_g1[key]] == 0) {  // world-fixed first hull: keep its support value
+      Shape<T> A;
+      mesh_shape(w, m, m.pair_g1[key], A);
+      T dd[3] = {r[2], r[3], r[4]}, v1[3];
+      shape_support(w, verts, A, dd, v1);
+      if (LANE == 0) w.sa_val[slot] = dot3(v1, dd);
+    }
   } else if (slot >= 0) {
     if (LANE == 0) w.sa_key[slot] = -1;
   }
@@ -580,7 +612,7 @@ DI void apply_result(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, i
 // contacts of the candidates [k0, k1) whose keys satisfy cube == (key >= LCR_KEY_CUBE); candidates past LCR_MAXCAND
 // have no stored key / result and are not processed (counted as overflow)
 template <typename T, int NC>
-__device__ __noinline__ void consume_candidates(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, bool cube) {
+__device__ __noinline__ void consume_candidates(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc, bool cube) {
   const int n = w.ncand < LCR_MAXCAND ? w.ncand : LCR_MAXCAND;
   T (*res)[8] = cand_res(w);
   for (int k = 0; k < n; k++) {
@@ -589,7 +621,7 @@ __device__ __noinline__ void consume_candidates(Ws<T, NC>& w, const DevModel<T>&
     T r[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) r[j] = res[k][j];
-    apply_result(w, m, ncon, nefc, key, r);
+    apply_result(w, m, verts, ncon, nefc, key, r);
   }
   if (!cube && w.ncand > LCR_MAXCAND && LANE == 0) w.diag[4] += w.ncand - LCR_MAXCAND;
 }

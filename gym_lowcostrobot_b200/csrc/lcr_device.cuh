@@ -58,11 +58,13 @@ struct DevModel {
 // Global (HBM) state: one record per env.  `st` [n][NFP] of T, fields qpos[nq] | qvel[nv] | ctrl[6] |
 // warm[nv] | aux[LCR_NAUX] (time, target[3], site_xpos[3], cube_xpos[6]) | pad to a multiple of 16 B.
 // `ib` [n][16] int32: elapsed, needs_reset | diag[6] | PCG64 state_hi, state_lo, inc_hi, inc_lo (4 x u64).
+// `sa` [n][SA_BYTES]: separating-axis cache dir[16][3], val[16] of T | key[16] int16 | next | pad.
 #define LCR_IB_WORDS 16
 template <typename T>
 struct DevState {
   T* st;
   int32_t* ib;
+  unsigned char* sa;  // [n][Ws::SA_BYTES] separating-axis cache (performance only; emptied by init / set_state)
   int n, nfp;
 };
 
@@ -98,9 +100,14 @@ struct Ws {  // per-warp shared-memory workspace
   short e_unit[LCR_MAXEFC];  // >= 0: contact index; < 0: limit row of joint -1-e_unit
   signed char e_r[LCR_MAXEFC];  // row index within its contact
   int ncon, nefc, nlim;
-  short sa_key[LCR_NSA];   // separating-axis cache of the convex narrowphase (see lcr_convex.cuh)
+  // separating-axis cache of the convex narrowphase (see lcr_convex.cuh): one contiguous 16-byte aligned block
+  // that travels with the env record (DevState::sa)
+  alignas(16) T sa_dir[LCR_NSA][3];
+  T sa_val[LCR_NSA];  // support value of a world-fixed (body 0) first hull along its cached axis
+  short sa_key[LCR_NSA];
   int sa_next;
-  T sa_dir[LCR_NSA][3];
+  int sa_pad[3];
+  static constexpr int SA_BYTES = LCR_NSA * 4 * (int)sizeof(T) + LCR_NSA * 2 + 16;
   short cand_key[LCR_MAXCAND];  // convex-pair candidates of this substep (results alias e_w / e_g / e_p)
   int ncand;
   int skip;          // phased execution: this env was auto-reset by the current step, substep kernels pass

@@ -39,6 +39,16 @@ template <typename T> DI void warp_argmax(T& v, int& idx) {
   }
 }
 
+// float: two hardware warp reductions (REDUX) on an order-preserving integer key instead of five dependent shuffle
+// rounds; same result (largest value, ties to the smaller index; -0 and +0 compare equal like the float compare)
+template <> DI void warp_argmax<float>(float& v, int& idx) {
+  const unsigned u = __float_as_uint(v + 0.0f);
+  const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  const unsigned kmax = __reduce_max_sync(FULLMASK, key);
+  idx = (int)__reduce_min_sync(FULLMASK, key == kmax ? (unsigned)idx : 0xffffffffu);
+  v = __uint_as_float((kmax & 0x80000000u) ? (kmax & 0x7fffffffu) : ~kmax);
+}
+
 // ---------------------------------------------------------------- small math
 template <typename T> DI T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 template <typename T> DI void cross3(T* r, const T* a, const T* b) {
@@ -417,13 +427,21 @@ DI void mesh_support4(const Ws<T, NC>& w, const DevModel<T>& m, const T* __restr
   int bi[4];
 #pragma unroll
   for (int t = 0; t < 4; t++) { matT_vec(dl[t], w.xmat[b], dirs[t]); bv[t] = (T)-1e30; bi[t] = 0x7fffffff; }
-  for (int i = lane; i < num; i += 32) {
-    T vx, vy, vz;
-    load_vert(verts, adr + i, vx, vy, vz);
+  for (int base = lane; base < num; base += 32 * kScanUnroll) {  // batched loads, see shape_support
+    T vx[kScanUnroll], vy[kScanUnroll], vz[kScanUnroll];
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-      T s = vx * dl[t][0] + vy * dl[t][1] + vz * dl[t][2];
-      if (s > bv[t]) { bv[t] = s; bi[t] = i; }
+    for (int u = 0; u < kScanUnroll; u++) {
+      const int i = base + 32 * u;
+      load_vert(verts, adr + (i < num ? i : num - 1), vx[u], vy[u], vz[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kScanUnroll; u++) {
+      const int i = base + 32 * u;
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        T s = vx[u] * dl[t][0] + vy[u] * dl[t][1] + vz[u] * dl[t][2];
+        if (i < num && s > bv[t]) { bv[t] = s; bi[t] = i; }
+      }
     }
   }
 #pragma unroll
@@ -565,9 +583,9 @@ __device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m
   if (cmask & LCR_COLLIDE_FLOOR_CUBE)
     for (int c = 0; c < NC; c++) collide_floor_cube(w, m, ncon, nefc, c);
   if (NC == 2 && (cmask & LCR_COLLIDE_CUBE_CUBE)) collide_cube_cube(w, m, ncon, nefc);
-  if (cmask & LCR_COLLIDE_CUBE_MESH) consume_candidates(w, m, ncon, nefc, true);
+  if (cmask & LCR_COLLIDE_CUBE_MESH) consume_candidates(w, m, verts, ncon, nefc, true);
   if (cmask & LCR_COLLIDE_FLOOR_MESH) collide_floor_meshes(w, m, verts, ncon, nefc);
-  if (cmask & LCR_COLLIDE_MESH_MESH) consume_candidates(w, m, ncon, nefc, false);
+  if (cmask & LCR_COLLIDE_MESH_MESH) consume_candidates(w, m, verts, ncon, nefc, false);
   if (lane == 0) { w.ncon = ncon; w.nefc = nefc; w.nlim = nlim; }
   __syncwarp();
   // contact rows: lane <-> row
@@ -1158,7 +1176,6 @@ __device__ __noinline__ bool env_step_begin(Ws<T, NC>& w, const DevModel<T>& m, 
                                             float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ) {
   // returns false if the env was auto-reset instead of stepped (outputs already written)
   const int lane = LANE, task = m.task;
-  sa_clear(w);
   if (m.autoreset && w.ints[1]) {
     env_reset(w, m, verts);
     write_obs(w, m, obs);
@@ -1245,6 +1262,10 @@ DI void load_state(Ws<T, NC>& w, const DevState<T>& s, int env) {
   for (int i = LANE; i < NV4; i += 32) dst[i] = src[i];
   if (LANE < LCR_IB_WORDS / 4)
     reinterpret_cast<uint4*>(w.ints)[LANE] = reinterpret_cast<const uint4*>(s.ib + (size_t)env * LCR_IB_WORDS)[LANE];
+  constexpr int NSA4 = Ws<T, NC>::SA_BYTES / 16;
+  const uint4* sas = reinterpret_cast<const uint4*>(s.sa + (size_t)env * Ws<T, NC>::SA_BYTES);
+  uint4* sad = reinterpret_cast<uint4*>(w.sa_dir);
+  for (int i = LANE; i < NSA4; i += 32) sad[i] = sas[i];
   __syncwarp();
 }
 template <typename T, int NC>
@@ -1256,6 +1277,10 @@ DI void store_state(Ws<T, NC>& w, const DevState<T>& s, int env) {
   for (int i = LANE; i < NV4; i += 32) dst[i] = src[i];
   if (LANE < LCR_IB_WORDS / 4)
     reinterpret_cast<uint4*>(s.ib + (size_t)env * LCR_IB_WORDS)[LANE] = reinterpret_cast<const uint4*>(w.ints)[LANE];
+  constexpr int NSA4 = Ws<T, NC>::SA_BYTES / 16;
+  uint4* sad = reinterpret_cast<uint4*>(s.sa + (size_t)env * Ws<T, NC>::SA_BYTES);
+  const uint4* sas = reinterpret_cast<const uint4*>(w.sa_dir);
+  for (int i = LANE; i < NSA4; i += 32) sad[i] = sas[i];
 }
 
 // ---------------------------------------------------------------- kernels (grid = n_envs CTAs of one warp)
@@ -1282,7 +1307,6 @@ __global__ void __launch_bounds__(32, 16) k_reset(const DevModel<T>* __restrict_
   const int env = blockIdx.x;
   if (mask != nullptr && !mask[env]) return;
   load_state(w, s, env);
-  sa_clear(w);
   const DevModel<T>& m = *dm;
   const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
   env_reset(w, m, verts);
@@ -1295,7 +1319,6 @@ __global__ void __launch_bounds__(32, 16) k_substeps(const DevModel<T>* __restri
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = blockIdx.x;
   load_state(w, s, env);
-  sa_clear(w);
   if (LANE == 0) w.diag[3] = 0;
   if (nsub == 0) forward(w, *dm, verts);
   for (int k = 0; k < nsub; k++) substep(w, *dm, verts);
@@ -1569,7 +1592,6 @@ __global__ void __launch_bounds__(32, 16) k_debug_contacts(const DevModel<T>* __
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = blockIdx.x;
   load_state(w, s, env);
-  sa_clear(w);
   forward(w, *dm, verts);
   const int ncon = w.ncon;
   if (LANE == 0) ncon_out[env] = ncon;
@@ -1580,6 +1602,14 @@ __global__ void __launch_bounds__(32, 16) k_debug_contacts(const DevModel<T>* __
   }
 }
 
+// empty separating-axis cache of env e in HBM: keys -1, next 0 (the block layout does not depend on NC)
+template <typename T> DI void sa_empty(DevState<T> s, int e) {
+  unsigned char* blk = s.sa + (size_t)e * Ws<T, 1>::SA_BYTES;
+  short* key = reinterpret_cast<short*>(blk + LCR_NSA * 4 * sizeof(T));
+  for (int k = 0; k < LCR_NSA; k++) key[k] = -1;
+  int* next = reinterpret_cast<int*>(blk + LCR_NSA * 4 * sizeof(T) + LCR_NSA * 2);
+  for (int k = 0; k < 4; k++) next[k] = 0;
+}
 // row-major float64 <-> per-env records of T
 template <typename T>
 __global__ void k_get_state(DevState<T> s, int nq, int nv, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints) {
@@ -1607,6 +1637,7 @@ __global__ void k_set_state(DevState<T> s, int nq, int nv, const double* qpos, c
   for (int k = 0; k < nv; k++, f++) if (warm) r[f] = (T)warm[(size_t)e * nv + k];
   for (int k = 0; k < LCR_NAUX; k++, f++) if (aux) r[f] = (T)aux[(size_t)e * LCR_NAUX + k];
   if (ints) for (int k = 0; k < LCR_NINT; k++) s.ib[(size_t)e * LCR_IB_WORDS + k] = ints[(size_t)e * LCR_NINT + k];
+  sa_empty<T>(s, e);  // the separating-axis cache is not part of the checkpointed state
 }
 template <typename T>
 __global__ void k_init_state(const DevModel<T>* dm, DevState<T> s) {
@@ -1622,6 +1653,7 @@ __global__ void k_init_state(const DevModel<T>* dm, DevState<T> s) {
   for (int k = 0; k < LCR_IB_WORDS; k++) ib[k] = 0;
   ib[8 + 2] = 1;  // rng[1] (state_lo) = 1
   ib[8 + 6] = 1;  // rng[3] (inc_lo) = 1
+  sa_empty<T>(s, e);
 }
 template <typename T>
 __global__ void k_get_diag(DevState<T> s, int32_t* out) {

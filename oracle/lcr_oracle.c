@@ -57,7 +57,7 @@ typedef struct OrcSim {
   Contact con[LCR_MAXCON];
   int ncon, nefc, niter, overflow, nan_resets, max_nefc;
   int sa_key[LCR_NSA], sa_next; /* separating-axis cache, see lcr_oracle_convex.inc */
-  double sa_dir[LCR_NSA][3];
+  double sa_dir[LCR_NSA][3], sa_val[LCR_NSA];
   int efc_type[LCR_MAXEFC]; /* 0 limit, 1 first row of a contact, 2 following row of a contact */
   int efc_con[LCR_MAXEFC];
   double J[LCR_MAXEFC][NV], efc_pos[LCR_MAXEFC], efc_vel[LCR_MAXEFC], efc_diag[LCR_MAXEFC];
@@ -818,8 +818,8 @@ static void substep_(OrcSim *s) {
 }
 
 /* API entry points: the separating-axis cache lives for one call */
-void orc_forward(OrcSim *s) { sa_clear(s); forward_(s); }
-void orc_substeps(OrcSim *s, int n) { sa_clear(s); s->max_nefc = 0; for (int k = 0; k < n; k++) substep_(s); }
+void orc_forward(OrcSim *s) { forward_(s); }
+void orc_substeps(OrcSim *s, int n) { s->max_nefc = 0; for (int k = 0; k < n; k++) substep_(s); }
 void orc_substep(OrcSim *s) { orc_substeps(s, 1); }
 
 static void reset_data(OrcSim *s) { /* mj_resetData: qpos0, everything else zero */
@@ -872,7 +872,7 @@ static void reset_(OrcSim *s, float *obs) {
   s->needs_reset = 0;
   if (obs) write_obs(s, obs);
 }
-void orc_reset(OrcSim *s, float *obs) { sa_clear(s); reset_(s, obs); }
+void orc_reset(OrcSim *s, float *obs) { reset_(s, obs); }
 
 /* inverse_kinematics + check_joint_limits (reach_cube_env.py:141-221).  Faithful to the reference:
  * each iterate is written to data.qpos and mj_forward is run on it, and the arm is left there. */
@@ -961,7 +961,6 @@ static void apply_action(OrcSim *s, const float *action_in) {
 void orc_step(OrcSim *s, const float *action, float *obs, float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *success) {
   const LcrEnvCfg *cfg = &s->cfg;
   int task = s->m.task;
-  sa_clear(s);
   if (cfg->autoreset && s->needs_reset) {
     reset_(s, obs);
     *reward = 0; *terminated = 0; *truncated = 0; *success = 0;
@@ -1026,6 +1025,7 @@ void orc_set_state(OrcSim *s, const double *qpos, const double *qvel, const doub
     memcpy(s->cube_xpos, aux + 7, 48);
   }
   if (ints) { s->elapsed = ints[0]; s->needs_reset = ints[1]; }
+  sa_clear(s); /* the separating-axis cache is not part of the checkpointed state */
 }
 void orc_get_diag(const OrcSim *s, int32_t *d) {
   d[0] = s->ncon; d[1] = s->nefc; d[2] = s->niter; d[3] = s->max_nefc; d[4] = s->overflow; d[5] = s->nan_resets;
