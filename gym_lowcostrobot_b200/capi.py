@@ -17,7 +17,7 @@ F32, F64 = 0, 1
 # every symbol declared in include/lcrsim.h
 SYMBOLS = (
     "lcr_obs_dim", "lcr_action_dim", "lcr_create", "lcr_destroy", "lcr_seed", "lcr_reset", "lcr_step",
-    "lcr_get_state", "lcr_set_state", "lcr_substeps", "lcr_ik", "lcr_get_diag", "lcr_debug_contacts", "lcr_n_envs",
+    "lcr_get_state", "lcr_set_state", "lcr_substeps", "lcr_ik", "lcr_get_diag", "lcr_debug_contacts", "lcr_debug_phase_clocks", "lcr_n_envs",
     "lcr_kernel_launches", "lcr_last_error", "lcr_version", "lcr_sizeof_model", "lcr_sizeof_cfg",
 )
 
@@ -47,6 +47,7 @@ def lib():
         L.lcr_ik.argtypes = [vp, vp, vp, vp]
         L.lcr_get_diag.argtypes = [vp, vp, vp]
         L.lcr_debug_contacts.argtypes = [vp, vp, vp, vp]
+        L.lcr_debug_phase_clocks.argtypes = [vp, vp]
         L.lcr_n_envs.argtypes = [vp]
         L.lcr_kernel_launches.argtypes = [vp]
         L.lcr_action_dim.argtypes = [vp]

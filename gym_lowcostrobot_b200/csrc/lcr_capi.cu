@@ -181,6 +181,7 @@ struct LcrSim {
   // phased mode: the env range is cut into groups, each with its own stream, so that the tail of one group's
   // variable-cost kernels (collision, solver) overlaps the other groups' work
   int ngroups = 0;
+  long long* prof = nullptr;  // debug: per-env phase clocks of the last lockstep step, see lcr_debug_phase_clocks
   int* perm = nullptr;  // lockstep mode: work-aware env order of the current step (device, int[n])
   int ls_warps = 0, ls_flags = 0;  // lockstep mode: envs per CTA (0 = as many as fit one SM) and LCR_LS_* barrier flags
   cudaStream_t gstream[16];
@@ -302,10 +303,10 @@ int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward,
   } else if (sim->cfg.exec_mode == 2) {
     if (sim->precision == LCR_F32)
       lcr::Launch<float>::step_lockstep(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success,
-                                        sim->ls_warps, sim->ls_flags, sim->perm, (cudaStream_t)stream);
+                                        sim->ls_warps, sim->ls_flags, sim->perm, sim->prof, (cudaStream_t)stream);
     else
       lcr::Launch<double>::step_lockstep(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success,
-                                         sim->ls_warps, sim->ls_flags, sim->perm, (cudaStream_t)stream);
+                                         sim->ls_warps, sim->ls_flags, sim->perm, sim->prof, (cudaStream_t)stream);
     sim->launches += sim->perm ? 2 : 1;
   } else {
     if (sim->precision == LCR_F32)
@@ -373,6 +374,13 @@ int lcr_debug_contacts(LcrSim* sim, double* d_contacts, int32_t* d_ncon, void* s
   else lcr::Launch<double>::debug_contacts(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_contacts, d_ncon, (cudaStream_t)stream);
   sim->launches++;
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_debug_phase_clocks(LcrSim* sim, long long* d_clocks) {
+  if (!sim) return fail("null handle");
+  if (sim->cfg.exec_mode != 2) return fail("lcr_debug_phase_clocks: lockstep mode only");
+  sim->prof = d_clocks;
   return 0;
 }
 

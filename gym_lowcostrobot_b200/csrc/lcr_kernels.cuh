@@ -1418,7 +1418,7 @@ template <typename T, int NC>
 __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
                                                     const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
                                                     uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ, int flags,
-                                                    const int* __restrict__ perm) {
+                                                    const int* __restrict__ perm, long long* __restrict__ prof) {
   Ws<T, NC>* wsa = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   __shared__ int job_next;
   const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, slot = blockIdx.x * W + warp;
@@ -1428,6 +1428,10 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
   const DevModel<T>& m = *dm;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
   const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+  // optional per-env phase timing (debug hook, prof == nullptr in production): clock64 deltas summed over the substeps
+  long long tp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0;
+#define LCR_TICK(k) do { if (prof) { const long long t1_ = clock64(); tp[k] += t1_ - t0; t0 = t1_; } } while (0)
+  if (prof) t0 = clock64();
   bool go = false;
   if (valid) {
     load_state(w, s, env);
@@ -1435,32 +1439,47 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
   }
   if (!go) { if (LANE == 0) w.ncand = 0; __syncwarp(); }
   const T tol = solver_tol<T>(m);
+  LCR_TICK(0);
 #pragma unroll 1
   for (int k = 0; k < m.n_substeps; k++) {
     if (flags & LCR_LS_BAR_TOP) __syncthreads();
+    LCR_TICK(1);  // wait at the top of the substep
     if (go) { check_state(w, m); kinematics(w, m); inertia_and_bias(w, m); }
     if (flags & LCR_LS_JOB_POOL) {
       if (go) collect_candidates(w, m);
       if (threadIdx.x == 0) job_next = 0;
+      LCR_TICK(2);  // kinematics, inertia, broadphase
       __syncthreads();
+      LCR_TICK(3);  // wait before the job pool
       cta_jobs(wsa, W, m, verts, &job_next);
+      LCR_TICK(4);  // narrowphase jobs
       __syncthreads();
+      LCR_TICK(5);  // wait after the job pool
       if (go) make_constraints(w, m, verts, true);
     } else {
       if (flags & LCR_LS_BAR_CON) __syncthreads();
       if (go) make_constraints(w, m, verts, false);
     }
     if (go) smooth_forces(w, m);
+    LCR_TICK(6);  // constraint rows, smooth forces
     if (flags & LCR_LS_BAR_SOL) __syncthreads();
+    LCR_TICK(7);  // wait before the solver
     if (flags & LCR_LS_SYNC_NEWTON) solve_constraints<T, NC, true>(w, m, tol, go);
     else if (go) solve_constraints<T, NC, false>(w, m, tol);
+    LCR_TICK(8);  // Newton solve
     if (go) {
       if (check_acc(w, m)) forward(w, m, verts);
       integrate(w, m);
     }
+    LCR_TICK(9);  // integrate
   }
   if (go) env_step_end(w, m, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
   if (valid) store_state(w, s, env);
+  if (prof && valid && LANE == 0) {
+    LCR_TICK(0);
+    for (int k = 0; k < 10; k++) prof[(size_t)env * 10 + k] = tp[k];
+  }
+#undef LCR_TICK
 }
 
 // ---------------------------------------------------------------- phased execution
@@ -1723,11 +1742,11 @@ int Launch<T>::lockstep_warps(int ncube, int warps) {
 }
 template <typename T>
 void Launch<T>::step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
-                              uint8_t* term, uint8_t* trunc, uint8_t* succ, int warps, int flags, int* perm, cudaStream_t st) {
+                              uint8_t* term, uint8_t* trunc, uint8_t* succ, int warps, int flags, int* perm, long long* prof, cudaStream_t st) {
   const int W = lockstep_warps(ncube, warps), grid = (s.n + W - 1) / W;
   if (perm != nullptr) k_sched<T><<<1, 1024, 0, st>>>(s, perm, W);
-  if (ncube == 1) k_step_ls<T, 1><<<grid, 32 * W, sizeof(Ws<T, 1>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm);
-  else k_step_ls<T, 2><<<grid, 32 * W, sizeof(Ws<T, 2>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm);
+  if (ncube == 1) k_step_ls<T, 1><<<grid, 32 * W, sizeof(Ws<T, 1>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm, prof);
+  else k_step_ls<T, 2><<<grid, 32 * W, sizeof(Ws<T, 2>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm, prof);
 }
 // one chain of 2 + 3*n_substeps launches over the env range [env0, env0 + cnt) on stream st
 template <typename T, int NC>

@@ -95,6 +95,11 @@ int lcr_get_diag(LcrSim* sim, int32_t* d_diag, void* stream);
  * d_ncon [n] int32.  Lets the parity tests compare collision geometry with the oracle directly. */
 int lcr_debug_contacts(LcrSim* sim, double* d_contacts, int32_t* d_ncon, void* stream);
 
+/* Debug hook (lockstep mode): from the next lcr_step on, every env writes the SM clock cycles it spent in each phase
+ * of the step to d_clocks [n][10] int64 = begin/end, wait top, dynamics+broadphase, wait, narrowphase jobs, wait,
+ * constraint rows, wait, Newton solve, integrate (sums over the substeps).  NULL switches it off again. */
+int lcr_debug_phase_clocks(LcrSim* sim, long long* d_clocks);
+
 int lcr_n_envs(const LcrSim* sim);
 int lcr_kernel_launches(const LcrSim* sim); /* kernels launched by this handle so far */
 const char* lcr_last_error(void);
