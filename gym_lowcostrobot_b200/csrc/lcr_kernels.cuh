@@ -49,6 +49,14 @@ template <> DI void warp_argmax<float>(float& v, int& idx) {
   v = __uint_as_float((kmax & 0x80000000u) ? (kmax & 0x7fffffffu) : ~kmax);
 }
 
+// row a and column b (a >= b) of entry e of a row-major packed lower triangle: e = a (a + 1) / 2 + b
+DI void tri_index(int e, int& a, int& b) {
+  a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+  if (a * (a + 1) / 2 > e) a--;
+  else if ((a + 1) * (a + 2) / 2 <= e) a++;
+  b = e - a * (a + 1) / 2;
+}
+
 // ---------------------------------------------------------------- small math
 template <typename T> DI T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 template <typename T> DI void cross3(T* r, const T* a, const T* b) {
@@ -264,9 +272,8 @@ __device__ __noinline__ void inertia_and_bias(Ws<T, NC>& w, const DevModel<T>& m
   const int lane = LANE;
   // M: lane e < 21 -> lower-triangle entry (i, j), i >= j
   if (lane < 21) {
-    int i = 0, e = lane;
-    while (e > i) { e -= i + 1; i++; }
-    const int j = e;
+    int i, j;
+    tri_index(lane, i, j);
     T zi[3] = {w.axis[i][0], w.axis[i][1], w.axis[i][2]}, zj[3] = {w.axis[j][0], w.axis[j][1], w.axis[j][2]};
     T acc = 0;
     for (int b = i + 1; b < LCR_NABODY; b++) {
@@ -818,10 +825,8 @@ __device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T
     __syncwarp();
     if (dof < NVV) {
       T g = w.Ma[dof] - w.smooth[dof];
-      for (int i = 0; i < nefc; i++) {
-        const T f = w.e_force[i];
-        if (f != 0) g -= w.J[i][dof] * f;
-      }
+#pragma unroll 4
+      for (int i = 0; i < nefc; i++) g -= w.J[i][dof] * w.e_force[i];
       w.grad[dof] = g;
     }
   }
@@ -873,10 +878,9 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
     // lower-triangle entries (island-local indices) owned by this lane
 #pragma unroll
     for (int k = 0; k < EPL; k++) {
-      int e = lane + 32 * k, a = 0;
+      int e = lane + 32 * k;
       if (e >= nent) e = 0;
-      while (e > a) { e -= a + 1; a++; }
-      ea[k] = a; eb[k] = e;
+      tri_index(e, ea[k], eb[k]);
     }
   }
   for (int iter = 0; iter < m.iterations; iter++) {
@@ -895,9 +899,9 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
         else if (a == b) { const int d = a - LCR_NARM, c = d / 6; v = (d % 6) < 3 ? m.cube_mass[c] : m.cube_inertia[c]; }
         h[k] = v;
       }
-      for (int i = 0; i < nefc; i++) {
+#pragma unroll 4
+      for (int i = 0; i < nefc; i++) {  // no skip of zero-weight rows: the loads of several rows stay in flight
         const T ww = w.e_w[i];
-        if (ww == 0) continue;  // warp-uniform
 #pragma unroll
         for (int k = 0; k < EPL; k++) h[k] += ww * w.J[i][d0 + ea[k]] * w.J[i][d0 + eb[k]];
       }
@@ -1378,20 +1382,24 @@ DI void cta_jobs(Ws<T, NC>* wsa, int W, const DevModel<T>& m, const T* __restric
   }
 }
 
-// Work-aware env order for the lockstep kernel.  Envs are ranked by the constraint count they reached in their
+// Work-aware env order for the lockstep kernels.  Envs are ranked by the constraint count they reached in their
 // previous step (diag[3] = max nefc; contacts persist, so it predicts the cost of the next step; envs that will only
-// be auto-reset are the cheapest) and dealt out like cards: rank r goes to CTA r % nCTA, seat r / nCTA.  Every CTA
-// gets one env of each cost stratum -- a heavy env sits with light ones whose warps drain its narrowphase jobs --
-// and CTAs are ordered by their heaviest member, so the longest CTAs start first (the grid tail is made of cheap
-// ones).  One CTA, two passes over the 64-byte int records; the order inside a bucket is arbitrary and does not
-// affect any result.  Empty seats (n not a multiple of W) hold -1.
+// be auto-reset are the cheapest).
+//  * HEAVY envs -- buckets above the most populated one (arm in contact: 12x12 Newton systems, dozens of rows, many
+//    penetrating hull pairs), at most `cap` of them -- get a CTA of their own with helper warps for their narrowphase
+//    jobs (launched first, on a second stream), so that their long solves stall nobody.
+//  * the others are dealt out like cards over the CTAs of the main launch: rank r goes to CTA r % nCTA, seat r / nCTA,
+//    so every CTA gets the same mix and CTAs are ordered by their most expensive member.
+// One CTA, two passes over the 64-byte int records; the order inside a bucket is arbitrary and does not affect any
+// result.  Empty seats hold -1 (a CTA without any env exits at once).
 #define LCR_NBUCKET 16
 template <typename T>
-__global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__ perm, int W) {
-  __shared__ int hist[LCR_NBUCKET], start[LCR_NBUCKET];
-  const int ncta = (s.n + W - 1) / W;
+__global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__ perm, int W, int* __restrict__ heavy, int cap) {
+  __shared__ int hist[LCR_NBUCKET], start[LCR_NBUCKET], sh_K, sh_ncta, sh_hcount;
+  const int nseat = ((s.n + W - 1) / W) * W;
   if (threadIdx.x < LCR_NBUCKET) hist[threadIdx.x] = 0;
-  for (int k = s.n + threadIdx.x; k < ncta * W; k += blockDim.x) perm[((k % ncta) * W) + k / ncta] = -1;
+  for (int k = threadIdx.x; k < nseat; k += blockDim.x) perm[k] = -1;
+  for (int k = threadIdx.x; k < cap; k += blockDim.x) heavy[k] = -1;
   __syncthreads();
   for (int e = threadIdx.x; e < s.n; e += blockDim.x) {
     const int32_t* ib = s.ib + (size_t)e * LCR_IB_WORDS;
@@ -1401,16 +1409,29 @@ __global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    int mode = 0;
+    for (int k = 1; k < LCR_NBUCKET; k++) if (hist[k] > hist[mode]) mode = k;
+    int K = mode + 1, cnt = 0;
+    for (int k = K; k < LCR_NBUCKET; k++) cnt += hist[k];
+    while (K < LCR_NBUCKET && cnt > cap) { cnt -= hist[K]; K++; }
+    if (cap <= 0) { K = LCR_NBUCKET; cnt = 0; }
+    const int nlight = s.n - cnt;
+    sh_K = K; sh_hcount = 0;
+    sh_ncta = nlight > 0 ? (nlight + W - 1) / W : 1;
     int acc = 0;
-    for (int k = LCR_NBUCKET - 1; k >= 0; k--) { start[k] = acc; acc += hist[k]; }
+    for (int k = K - 1; k >= 0; k--) { start[k] = acc; acc += hist[k]; }
   }
   __syncthreads();
+  const int K = sh_K, ncta = sh_ncta;
   for (int e = threadIdx.x; e < s.n; e += blockDim.x) {
     const int32_t* ib = s.ib + (size_t)e * LCR_IB_WORDS;
     int key = ib[1] ? 0 : 1 + ib[LCR_NINT + 3] / 8;
     key = key < LCR_NBUCKET ? key : LCR_NBUCKET - 1;
-    const int r = atomicAdd(&start[key], 1);
-    perm[(r % ncta) * W + r / ncta] = e;
+    if (key >= K) heavy[atomicAdd(&sh_hcount, 1)] = e;
+    else {
+      const int r = atomicAdd(&start[key], 1);
+      perm[(r % ncta) * W + r / ncta] = e;
+    }
   }
 }
 
@@ -1418,13 +1439,17 @@ template <typename T, int NC>
 __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
                                                     const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
                                                     uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ, int flags,
-                                                    const int* __restrict__ perm, long long* __restrict__ prof) {
+                                                    const int* __restrict__ perm, int epc, long long* __restrict__ prof) {
+  // blockDim.x / 32 warps, the first `epc` of them own an env (seat blockIdx.x * epc + warp), the others only help
+  // with narrowphase jobs; shared memory holds epc workspaces
   Ws<T, NC>* wsa = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   __shared__ int job_next;
-  const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, slot = blockIdx.x * W + warp;
-  const int env = perm != nullptr ? perm[slot] : slot;  // perm has gridDim.x * W seats, -1 = empty
+  const int W = epc, warp = threadIdx.x >> 5, slot = blockIdx.x * epc + warp;
+  const bool owner = warp < epc;
+  const int env = owner ? (perm != nullptr ? perm[slot] : slot) : -1;  // -1 = empty seat
   const bool valid = env >= 0 && env < s.n;
-  Ws<T, NC>& w = wsa[warp];
+  if (!__syncthreads_or(valid)) return;
+  Ws<T, NC>& w = wsa[owner ? warp : 0];
   const DevModel<T>& m = *dm;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
   const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
@@ -1437,7 +1462,7 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
     load_state(w, s, env);
     go = env_step_begin(w, m, verts, actions + (size_t)env * na, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
   }
-  if (!go) { if (LANE == 0) w.ncand = 0; __syncwarp(); }
+  if (!go && owner) { if (LANE == 0) w.ncand = 0; __syncwarp(); }
   const T tol = solver_tol<T>(m);
   LCR_TICK(0);
 #pragma unroll 1
@@ -1741,12 +1766,14 @@ int Launch<T>::lockstep_warps(int ncube, int warps) {
   return std::max(1, std::min(std::min(warps, fit), 16));
 }
 template <typename T>
+void Launch<T>::sched(DevState<T> s, int* perm, int W, int* heavy, int cap, cudaStream_t st) { k_sched<T><<<1, 1024, 0, st>>>(s, perm, W, heavy, cap); }
+// `grid` CTAs of `warps` warps, the first `epc` of which own an env (seats from perm, or env = seat if perm is null)
+template <typename T>
 void Launch<T>::step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
-                              uint8_t* term, uint8_t* trunc, uint8_t* succ, int warps, int flags, int* perm, long long* prof, cudaStream_t st) {
-  const int W = lockstep_warps(ncube, warps), grid = (s.n + W - 1) / W;
-  if (perm != nullptr) k_sched<T><<<1, 1024, 0, st>>>(s, perm, W);
-  if (ncube == 1) k_step_ls<T, 1><<<grid, 32 * W, sizeof(Ws<T, 1>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm, prof);
-  else k_step_ls<T, 2><<<grid, 32 * W, sizeof(Ws<T, 2>) * W, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm, prof);
+                              uint8_t* term, uint8_t* trunc, uint8_t* succ, int grid, int warps, int epc, int flags, const int* perm, long long* prof,
+                              cudaStream_t st) {
+  if (ncube == 1) k_step_ls<T, 1><<<grid, 32 * warps, sizeof(Ws<T, 1>) * epc, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm, epc, prof);
+  else k_step_ls<T, 2><<<grid, 32 * warps, sizeof(Ws<T, 2>) * epc, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm, epc, prof);
 }
 // one chain of 2 + 3*n_substeps launches over the env range [env0, env0 + cnt) on stream st
 template <typename T, int NC>
