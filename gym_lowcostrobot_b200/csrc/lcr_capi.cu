@@ -183,10 +183,7 @@ struct LcrSim {
   int ngroups = 0;
   long long* prof = nullptr;  // debug: per-env phase clocks of the last lockstep step, see lcr_debug_phase_clocks
   int* perm = nullptr;  // lockstep mode: work-aware env order of the current step (device, int[n])
-  int* heavy = nullptr;  // lockstep mode: envs that get a CTA of their own this step (device, int[heavy_cap], -1 = empty)
-  int heavy_cap = 0, heavy_warps = 4;
-  cudaStream_t hstream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int ls_striped = 1;  // seat order of the lockstep scheduler, see k_sched
   int ls_warps = 0, ls_flags = 0;  // lockstep mode: envs per CTA (0 = as many as fit one SM) and LCR_LS_* barrier flags
   cudaStream_t gstream[16];
   cudaEvent_t ev_begin, ev_done[16];
@@ -242,17 +239,8 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
     e = getenv("LCR_LS_SORT");
     if (!e || atoi(e) != 0) {
       if (cudaMalloc(&s->perm, sizeof(int) * ((size_t)n_envs + 16)) != cudaSuccess) { fail("lcr_create: cudaMalloc(perm) failed"); return 1; }
-      e = getenv("LCR_LS_HEAVY");  // 0 disables the separate launch for heavy envs
-      s->heavy_cap = (e && atoi(e) == 0) ? 0 : std::max(1, n_envs / 8);
-      e = getenv("LCR_LS_HEAVY_WARPS");
-      s->heavy_warps = e ? std::max(1, std::min(16, atoi(e))) : 4;
-      if (cudaMalloc(&s->heavy, sizeof(int) * (size_t)std::max(1, s->heavy_cap)) != cudaSuccess ||
-          cudaStreamCreateWithPriority(&s->hstream, cudaStreamNonBlocking, -1) != cudaSuccess ||  // ahead of the main launch
-          cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-        fail("lcr_create: lockstep scheduler resources");
-        return 1;
-      }
+      // striped seats while the step time is set by the most expensive env, sorted seats once there are many waves
+      s->ls_striped = atoi(e ? e : "0") == 2 ? 0 : (atoi(e ? e : "0") == 1 ? 1 : (n_envs < 12288 ? 1 : 0));
     }
   }
   *out = s;
@@ -265,10 +253,7 @@ int lcr_destroy(LcrSim* sim) {
   if (sim->precision == LCR_F32) sim->f.destroy(); else sim->d.destroy();
   for (int k = 0; k < sim->ngroups; k++) { cudaStreamDestroy(sim->gstream[k]); cudaEventDestroy(sim->ev_done[k]); }
   if (sim->ngroups) cudaEventDestroy(sim->ev_begin);
-  cudaFree(sim->perm); cudaFree(sim->heavy);
-  if (sim->hstream) cudaStreamDestroy(sim->hstream);
-  if (sim->ev_fork) cudaEventDestroy(sim->ev_fork);
-  if (sim->ev_join) cudaEventDestroy(sim->ev_join);
+  cudaFree(sim->perm);
   delete sim;
   return 0;
 }
@@ -332,18 +317,11 @@ int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward,
     sim->launches++;                                                                                                                           \
   } while (0)
     if (sim->perm) {
-      if (f32) lcr::Launch<float>::sched(sim->f.s, sim->perm, W, sim->heavy, sim->heavy_cap, st);
-      else lcr::Launch<double>::sched(sim->d.s, sim->perm, W, sim->heavy, sim->heavy_cap, st);
+      if (f32) lcr::Launch<float>::sched(sim->f.s, sim->perm, W, sim->ls_striped, st);
+      else lcr::Launch<double>::sched(sim->d.s, sim->perm, W, sim->ls_striped, st);
       sim->launches++;
-      if (sim->heavy_cap > 0) {  // heavy envs first, one per CTA with helper warps, concurrently with the main launch
-        CUDA_OK(cudaEventRecord(sim->ev_fork, st));
-        CUDA_OK(cudaStreamWaitEvent(sim->hstream, sim->ev_fork, 0));
-        LCR_LS_LAUNCH(sim->heavy_cap, sim->heavy_warps, 1, sim->heavy, sim->hstream);
-        CUDA_OK(cudaEventRecord(sim->ev_join, sim->hstream));
-      }
     }
     LCR_LS_LAUNCH(grid, W, W, sim->perm, st);
-    if (sim->perm && sim->heavy_cap > 0) CUDA_OK(cudaStreamWaitEvent(st, sim->ev_join, 0));
 #undef LCR_LS_LAUNCH
   } else {
     if (sim->precision == LCR_F32)

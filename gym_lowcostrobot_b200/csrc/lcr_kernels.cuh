@@ -1382,24 +1382,24 @@ DI void cta_jobs(Ws<T, NC>* wsa, int W, const DevModel<T>& m, const T* __restric
   }
 }
 
-// Work-aware env order for the lockstep kernels.  Envs are ranked by the constraint count they reached in their
+// Work-aware env order for the lockstep kernel.  Envs are ranked by the constraint count they reached in their
 // previous step (diag[3] = max nefc; contacts persist, so it predicts the cost of the next step; envs that will only
-// be auto-reset are the cheapest).
-//  * HEAVY envs -- buckets above the most populated one (arm in contact: 12x12 Newton systems, dozens of rows, many
-//    penetrating hull pairs), at most `cap` of them -- get a CTA of their own with helper warps for their narrowphase
-//    jobs (launched first, on a second stream), so that their long solves stall nobody.
-//  * the others are dealt out like cards over the CTAs of the main launch: rank r goes to CTA r % nCTA, seat r / nCTA,
-//    so every CTA gets the same mix and CTAs are ordered by their most expensive member.
+// be auto-reset are the cheapest), most expensive first, and seated in one of two ways:
+//  * STRIPED (few envs per SM: the step time is the chain of the most expensive env): rank r goes to CTA r % nCTA,
+//    seat r / nCTA -- every CTA gets one env of each cost stratum, so an expensive env sits with cheap ones whose
+//    warps drain its narrowphase jobs, and CTAs are ordered by their most expensive member (the grid tail is cheap);
+//  * SORTED (many waves of CTAs: the step time is the total work): rank r takes seat r -- CTAs hold envs of equal
+//    cost, so nobody waits at the phase barriers for a much slower neighbour, and the few all-expensive CTAs start
+//    first and overlap the cheap ones.
 // One CTA, two passes over the 64-byte int records; the order inside a bucket is arbitrary and does not affect any
-// result.  Empty seats hold -1 (a CTA without any env exits at once).
+// result.  Empty seats (n not a multiple of W) hold -1.
 #define LCR_NBUCKET 16
 template <typename T>
-__global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__ perm, int W, int* __restrict__ heavy, int cap) {
-  __shared__ int hist[LCR_NBUCKET], start[LCR_NBUCKET], sh_K, sh_ncta, sh_hcount;
-  const int nseat = ((s.n + W - 1) / W) * W;
+__global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__ perm, int W, int striped) {
+  __shared__ int hist[LCR_NBUCKET], start[LCR_NBUCKET];
+  const int ncta = (s.n + W - 1) / W;
   if (threadIdx.x < LCR_NBUCKET) hist[threadIdx.x] = 0;
-  for (int k = threadIdx.x; k < nseat; k += blockDim.x) perm[k] = -1;
-  for (int k = threadIdx.x; k < cap; k += blockDim.x) heavy[k] = -1;
+  for (int k = s.n + threadIdx.x; k < ncta * W; k += blockDim.x) perm[striped ? ((k % ncta) * W) + k / ncta : k] = -1;
   __syncthreads();
   for (int e = threadIdx.x; e < s.n; e += blockDim.x) {
     const int32_t* ib = s.ib + (size_t)e * LCR_IB_WORDS;
@@ -1409,29 +1409,16 @@ __global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int mode = 0;
-    for (int k = 1; k < LCR_NBUCKET; k++) if (hist[k] > hist[mode]) mode = k;
-    int K = mode + 1, cnt = 0;
-    for (int k = K; k < LCR_NBUCKET; k++) cnt += hist[k];
-    while (K < LCR_NBUCKET && cnt > cap) { cnt -= hist[K]; K++; }
-    if (cap <= 0) { K = LCR_NBUCKET; cnt = 0; }
-    const int nlight = s.n - cnt;
-    sh_K = K; sh_hcount = 0;
-    sh_ncta = nlight > 0 ? (nlight + W - 1) / W : 1;
     int acc = 0;
-    for (int k = K - 1; k >= 0; k--) { start[k] = acc; acc += hist[k]; }
+    for (int k = LCR_NBUCKET - 1; k >= 0; k--) { start[k] = acc; acc += hist[k]; }
   }
   __syncthreads();
-  const int K = sh_K, ncta = sh_ncta;
   for (int e = threadIdx.x; e < s.n; e += blockDim.x) {
     const int32_t* ib = s.ib + (size_t)e * LCR_IB_WORDS;
     int key = ib[1] ? 0 : 1 + ib[LCR_NINT + 3] / 8;
     key = key < LCR_NBUCKET ? key : LCR_NBUCKET - 1;
-    if (key >= K) heavy[atomicAdd(&sh_hcount, 1)] = e;
-    else {
-      const int r = atomicAdd(&start[key], 1);
-      perm[(r % ncta) * W + r / ncta] = e;
-    }
+    const int r = atomicAdd(&start[key], 1);
+    perm[striped ? (r % ncta) * W + r / ncta : r] = e;
   }
 }
 
@@ -1455,7 +1442,8 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
   const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
   // optional per-env phase timing (debug hook, prof == nullptr in production): clock64 deltas summed over the substeps
   long long tp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0;
-#define LCR_TICK(k) do { if (prof) { const long long t1_ = clock64(); tp[k] += t1_ - t0; t0 = t1_; } } while (0)
+#define LCR_TICK(k) do { if (prof) { (void)*(volatile int*)&job_next; /* BAR.SYNC defers blocking to the next memory access */ \
+    const long long t1_ = clock64(); tp[k] += t1_ - t0; t0 = t1_; } } while (0)
   if (prof) t0 = clock64();
   bool go = false;
   if (valid) {
@@ -1766,7 +1754,7 @@ int Launch<T>::lockstep_warps(int ncube, int warps) {
   return std::max(1, std::min(std::min(warps, fit), 16));
 }
 template <typename T>
-void Launch<T>::sched(DevState<T> s, int* perm, int W, int* heavy, int cap, cudaStream_t st) { k_sched<T><<<1, 1024, 0, st>>>(s, perm, W, heavy, cap); }
+void Launch<T>::sched(DevState<T> s, int* perm, int W, int striped, cudaStream_t st) { k_sched<T><<<1, 1024, 0, st>>>(s, perm, W, striped); }
 // `grid` CTAs of `warps` warps, the first `epc` of which own an env (seats from perm, or env = seat if perm is null)
 template <typename T>
 void Launch<T>::step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
