@@ -63,7 +63,7 @@ __device__ __noinline__ void shape_support(const Ws<T, NC>& w, const T* __restri
 #pragma unroll
     for (int k = 0; k < 3; k++) p[k] = dl[k] >= 0 ? sh.half[k] : -sh.half[k];
   } else {
-    T bv = (T)-1e30;
+    T bv = (T)-1e30, bx = 0, by = 0, bz = 0;
     int bi = 0x7fffffff;
     // chunks of kScanUnroll vertices per lane: all loads of a chunk are issued before the first use (the vertex pool is
     // served by L2 -- with the whole L1 carved out as shared memory -- so a scan costs one L2 round trip per chunk
@@ -79,11 +79,12 @@ __device__ __noinline__ void shape_support(const Ws<T, NC>& w, const T* __restri
       for (int u = 0; u < kScanUnroll; u++) {
         const int i = base + 32 * u;
         const T s = vx[u] * dl[0] + vy[u] * dl[1] + vz[u] * dl[2];
-        if (i < sh.num && s > bv) { bv = s; bi = i; }
+        if (i < sh.num && s > bv) { bv = s; bi = i; bx = vx[u]; by = vy[u]; bz = vz[u]; }
       }
     }
     warp_argmax(bv, bi);
-    load_vert(verts, sh.adr + bi, p[0], p[1], p[2]);
+    // vertex i lives in lane i % 32: fetch the winner from that lane's registers instead of another trip to L2
+    p[0] = __shfl_sync(FULLMASK, bx, bi & 31); p[1] = __shfl_sync(FULLMASK, by, bi & 31); p[2] = __shfl_sync(FULLMASK, bz, bi & 31);
   }
   mat_vec(out, R, p);
 #pragma unroll
@@ -372,7 +373,7 @@ __device__ __noinline__ void collide_cube_cube(Ws<T, NC>& w, const DevModel<T>& 
     sa = clampT(sa, -hA[ia], hA[ia]); sb = clampT(sb, -hB[ib], hB[ib]);
     T pos[3];
     for (int k = 0; k < 3; k++) pos[k] = (T)0.5 * (ea[k] + sa * ua[k] + eb[k] + sb * ub[k]);
-    add_contact(w, ncon, nefc, par, bA, bB, pos, bestn, -(best / (T)1.05));
+    add_contact(w, m, ncon, nefc, par, bA, bB, pos, bestn, -(best / (T)1.05));
     return;
   }
   const bool refA = code < 3;
@@ -442,7 +443,7 @@ __device__ __noinline__ void collide_cube_cube(Ws<T, NC>& w, const DevModel<T>& 
     const T depth = hR[ir] - dot3(rp, nr);
     if (depth <= 0) continue;
     T pos[3] = {poly[v][0] + (T)0.5 * depth * nr[0], poly[v][1] + (T)0.5 * depth * nr[1], poly[v][2] + (T)0.5 * depth * nr[2]};
-    if (add_contact(w, ncon, nefc, par, bA, bB, pos, bestn, -depth)) cnt++;
+    if (add_contact(w, m, ncon, nefc, par, bA, bB, pos, bestn, -depth)) cnt++;
   }
 }
 
@@ -529,40 +530,68 @@ template <typename T, int NC> DI void key_shapes(const Ws<T, NC>& w, const DevMo
   }
 }
 
-// One candidate.  res = {code, depth, dir[3], pos[3]}; code 2: still separated along the cached axis, 1: penetrating,
-// 0: separated, new axis in dir, -1: separated without a usable axis.  `w` is only read (it may live in HBM).
+// Upper bound of max over the hull of mesh g of x . dw (dw a world direction, slot/side = its cache entry) WITHOUT touching
+// the vertices: with c the world centre of the hull's bounding sphere, r its radius, S the exact support value about c
+// along the body-frame direction u0 recorded at the last exact evaluation, and u1 = R^T dw the direction now,
+//     max x . dw  =  c . dw + max y . u1  <=  c . dw + S + |u1 - u0| r        (y = body-frame vertex - centre, |y| <= r).
+// Translation is followed exactly, only the relative rotation since the last exact evaluation costs slack.
+template <typename T, int NC>
+DI T hull_support_bound(const Ws<T, NC>& w, const DevModel<T>& m, int g, const T* dw, int slot, int side) {
+  const T* R = w.xmat[m.mesh_body[g]];
+  T u1[3], e2 = 0;
+  matT_vec(u1, R, dw);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { const T e = u1[k] - w.sa_u[slot][side][k]; e2 += e * e; }
+  return w.gc[g][0] * dw[0] + w.gc[g][1] * dw[1] + w.gc[g][2] * dw[2] + w.sa_S[slot][side] + sqrt(e2) * m.mesh_rbound[g];
+}
+
+// One candidate.  res = {code, SA, dir[3], SB | depth, dir[3], pos[3]}; code 1: penetrating (depth, dir, pos);
+// 0: separated, new axis in dir; 2: still separated along the cached axis; 3: same, and the exact supports were
+// re-evaluated; -1: separated without a usable axis.  For codes 0 and 3, SA = res[1] and SB = res[5] are the support
+// values of the two shapes about their bounding-sphere centres along +dir / -dir (meshes only), which the cache keeps
+// for hull_support_bound.  `w` is only read (it may live in HBM, or belong to another warp of the CTA).
 template <typename T, int NC>
 __device__ __noinline__ void narrowphase_job(const Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int key, T* res) {
   Shape<T> A, B;
   key_shapes(w, m, key, A, B);
+  const bool cube = key >= LCR_KEY_CUBE;
+  const int gA = cube ? -1 : m.pair_g1[key], gB = cube ? (key - LCR_KEY_CUBE) % LCR_MAXMESH : m.pair_g2[key];
   const unsigned hit = __ballot_sync(FULLMASK, LANE < LCR_NSA && w.sa_key[LANE] == key);
+  T d[3] = {0, 0, 0};
+  SPoint<T> p;
+  int code = -2;
   if (hit) {
     const int slot = __ffs(hit) - 1;
-    T d[3] = {w.sa_dir[slot][0], w.sa_dir[slot][1], w.sa_dir[slot][2]};
-    if (key < LCR_KEY_CUBE && A.body == 0) {
-      // A sits on the world-fixed base: its support value along the cached axis is constant and was stored with the
-      // axis, so only B is needed -- first the bound from B's oriented box, then B's exact support
-      const int g2 = m.pair_g2[key];
-      const T* R = w.xmat[B.body];
-      const T sa = w.sa_val[slot];
-      T ext = 0;
-#pragma unroll
-      for (int k = 0; k < 3; k++) ext += fabs(R[k] * d[0] + R[3 + k] * d[1] + R[6 + k] * d[2]) * (m.mesh_half[g2][k] + (T)1e-6);
-      if (sa - ((w.gc[g2][0] * d[0] + w.gc[g2][1] * d[1] + w.gc[g2][2] * d[2]) - ext) < (T)-1e-6) { res[0] = 2; return; }
-      T nd[3] = {-d[0], -d[1], -d[2]}, v2[3];
-      shape_support(w, verts, B, nd, v2);
-      if (sa - dot3(v2, d) < (T)-1e-6) { res[0] = 2; return; }
-    } else {
-      SPoint<T> p;
-      md_support(w, verts, A, B, d, p);
-      if (dot3(p.v, d) < (T)-1e-6) { res[0] = 2; return; }
-    }
+    d[0] = w.sa_dir[slot][0]; d[1] = w.sa_dir[slot][1]; d[2] = w.sa_dir[slot][2];
+    const T nd[3] = {-d[0], -d[1], -d[2]};
+    // cheap proof first: exact support of the box, conservative bounds for the hulls (no vertex is read)
+    T supA;
+    if (cube) { T pa[3]; shape_support(w, verts, A, d, pa); supA = dot3(pa, d); }
+    else supA = hull_support_bound(w, m, gA, d, slot, 0);
+    const T supB = hull_support_bound(w, m, gB, nd, slot, 1);
+    if (supA + supB < (T)-2e-6) { res[0] = 2; return; }
+    md_support(w, verts, A, B, d, p);  // exact test: two hull scans
+    if (dot3(p.v, d) < (T)-1e-6) code = 3;
   }
-  T depth = 0, dir[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
-  const int r = mpr_penetration(w, verts, A, B, depth, dir, pos);
-  res[0] = (T)r; res[1] = depth;
-  res[2] = dir[0]; res[3] = dir[1]; res[4] = dir[2];
-  res[5] = pos[0]; res[6] = pos[1]; res[7] = pos[2];
+  if (code == -2) {
+    T depth = 0, pos[3] = {0, 0, 0};
+    code = mpr_penetration(w, verts, A, B, depth, d, pos);
+    if (code != 0) {
+      res[0] = (T)code; res[1] = depth;
+      res[2] = d[0]; res[3] = d[1]; res[4] = d[2];
+      res[5] = pos[0]; res[6] = pos[1]; res[7] = pos[2];
+      return;
+    }
+    md_support(w, verts, A, B, d, p);  // supports along the new axis, kept with it
+  }
+  // code 0 or 3: report the axis and the centred support values
+  res[0] = (T)code;
+  res[2] = d[0]; res[3] = d[1]; res[4] = d[2];
+  T sA = 0;
+  if (!cube) sA = (p.v1[0] - w.gc[gA][0]) * d[0] + (p.v1[1] - w.gc[gA][1]) * d[1] + (p.v1[2] - w.gc[gA][2]) * d[2];
+  res[1] = sA;
+  res[5] = -((p.v2[0] - w.gc[gB][0]) * d[0] + (p.v2[1] - w.gc[gB][1]) * d[1] + (p.v2[2] - w.gc[gB][2]) * d[2]);
+  res[6] = 0; res[7] = 0;
 }
 
 template <typename T, int NC>
@@ -579,21 +608,23 @@ __device__ __noinline__ void run_jobs_inline(Ws<T, NC>& w, const DevModel<T>& m,
 }
 
 template <typename T, int NC>
-DI void apply_result(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc, int key, const T* r) {
+DI void apply_result(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, int key, const T* r) {
   const int code = (int)r[0];
   if (code == 2) return;
   const unsigned hit = __ballot_sync(FULLMASK, LANE < LCR_NSA && w.sa_key[LANE] == key);
   int slot = hit ? __ffs(hit) - 1 : -1;
   __syncwarp();
-  if (code == 0) {
-    if (slot < 0) { slot = w.sa_next; __syncwarp(); if (LANE == 0) w.sa_next = (slot + 1) % LCR_NSA; }
-    if (LANE == 0) { w.sa_key[slot] = (short)key; w.sa_dir[slot][0] = r[2]; w.sa_dir[slot][1] = r[3]; w.sa_dir[slot][2] = r[4]; }
-    if (key < LCR_KEY_CUBE && m.mesh_body[m.pair_g1[key]] == 0) {  // world-fixed first hull: keep its support value
-      Shape<T> A;
-      mesh_shape(w, m, m.pair_g1[key], A);
-      T dd[3] = {r[2], r[3], r[4]}, v1[3];
-      shape_support(w, verts, A, dd, v1);
-      if (LANE == 0) w.sa_val[slot] = dot3(v1, dd);
+  if (code == 0 || code == 3) {
+    if (code == 0 && slot < 0) { slot = w.sa_next; __syncwarp(); if (LANE == 0) w.sa_next = (slot + 1) % LCR_NSA; }
+    if (slot >= 0 && LANE == 0) {  // (code 3 without an entry cannot happen: the job found the entry it refreshed)
+      const bool cube = key >= LCR_KEY_CUBE;
+      const int gB = cube ? (key - LCR_KEY_CUBE) % LCR_MAXMESH : m.pair_g2[key];
+      const T d[3] = {r[2], r[3], r[4]}, nd[3] = {-r[2], -r[3], -r[4]};
+      w.sa_key[slot] = (short)key;
+      w.sa_dir[slot][0] = d[0]; w.sa_dir[slot][1] = d[1]; w.sa_dir[slot][2] = d[2];
+      w.sa_S[slot][0] = r[1]; w.sa_S[slot][1] = r[5];
+      if (!cube) matT_vec(w.sa_u[slot][0], w.xmat[m.mesh_body[m.pair_g1[key]]], d);
+      matT_vec(w.sa_u[slot][1], w.xmat[m.mesh_body[gB]], nd);
     }
   } else if (slot >= 0) {
     if (LANE == 0) w.sa_key[slot] = -1;
@@ -603,16 +634,16 @@ DI void apply_result(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ v
   T dir[3] = {r[2], r[3], r[4]}, pos[3] = {r[5], r[6], r[7]};
   if (key >= LCR_KEY_CUBE) {
     const int c = (key - LCR_KEY_CUBE) / LCR_MAXMESH, g = (key - LCR_KEY_CUBE) % LCR_MAXMESH;
-    add_contact(w, ncon, nefc, &m.par_cube_mesh[c][g], LCR_NABODY + c, m.mesh_body[g], pos, dir, -r[1]);
+    add_contact(w, m, ncon, nefc, &m.par_cube_mesh[c][g], LCR_NABODY + c, m.mesh_body[g], pos, dir, -r[1]);
   } else {
-    add_contact(w, ncon, nefc, &m.par_mesh_mesh[key], m.mesh_body[m.pair_g1[key]], m.mesh_body[m.pair_g2[key]], pos, dir, -r[1]);
+    add_contact(w, m, ncon, nefc, &m.par_mesh_mesh[key], m.mesh_body[m.pair_g1[key]], m.mesh_body[m.pair_g2[key]], pos, dir, -r[1]);
   }
 }
 
 // contacts of the candidates [k0, k1) whose keys satisfy cube == (key >= LCR_KEY_CUBE); candidates past LCR_MAXCAND
 // have no stored key / result and are not processed (counted as overflow)
 template <typename T, int NC>
-__device__ __noinline__ void consume_candidates(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int& ncon, int& nefc, bool cube) {
+__device__ __noinline__ void consume_candidates(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, bool cube) {
   const int n = w.ncand < LCR_MAXCAND ? w.ncand : LCR_MAXCAND;
   T (*res)[8] = cand_res(w);
   for (int k = 0; k < n; k++) {
@@ -621,7 +652,7 @@ __device__ __noinline__ void consume_candidates(Ws<T, NC>& w, const DevModel<T>&
     T r[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) r[j] = res[k][j];
-    apply_result(w, m, verts, ncon, nefc, key, r);
+    apply_result(w, m, ncon, nefc, key, r);
   }
   if (!cube && w.ncand > LCR_MAXCAND && LANE == 0) w.diag[4] += w.ncand - LCR_MAXCAND;
 }

@@ -42,7 +42,7 @@ struct DevModel {
   int mesh_body[LCR_MAXMESH], mesh_vertadr[LCR_MAXMESH], mesh_vertnum[LCR_MAXMESH];
   T mesh_center[LCR_MAXMESH][3], mesh_half[LCR_MAXMESH][3], mesh_rbound[LCR_MAXMESH], mesh_com[LCR_MAXMESH][3];
   int pair_g1[LCR_MAXPAIR], pair_g2[LCR_MAXPAIR];
-  // contact parameter classes
+  // contact parameter classes (one contiguous table: Ws::c_par stores indices relative to par_limit)
   CPar<T> par_limit[LCR_NARM];
   CPar<T> par_floor_cube[LCR_MAXCUBE];
   CPar<T> par_cube_cube;
@@ -53,12 +53,14 @@ struct DevModel {
   int action_mode, block_gripper, reward_type, n_substeps, max_episode_steps, autoreset, collision_mask;
   T distance_threshold, height_threshold;
   double cube_low[3], cube_high[3], target_low[3], target_high[3];  // reset draws are float64 like numpy
+  __host__ __device__ const CPar<T>* par(int idx) const { return par_limit + idx; }
+  __host__ __device__ int par_index(const CPar<T>* p) const { return (int)(p - par_limit); }
 };
 
 // Global (HBM) state: one record per env.  `st` [n][NFP] of T, fields qpos[nq] | qvel[nv] | ctrl[6] |
 // warm[nv] | aux[LCR_NAUX] (time, target[3], site_xpos[3], cube_xpos[6]) | pad to a multiple of 16 B.
 // `ib` [n][16] int32: elapsed, needs_reset | diag[6] | PCG64 state_hi, state_lo, inc_hi, inc_lo (4 x u64).
-// `sa` [n][SA_BYTES]: separating-axis cache dir[16][3], val[16] of T | key[16] int16 | next | pad.
+// `sa` [n][SA_BYTES]: separating-axis cache dir[16][3], S[16][2], u[16][2][3] of T | key[16] int16 | next | pad.
 #define LCR_IB_WORDS 16
 template <typename T>
 struct DevState {
@@ -87,7 +89,7 @@ struct Ws {  // per-warp shared-memory workspace
   T H[NVV][NVV + 1];
   // contacts
   T c_pos[LCR_MAXCON][3], c_frame[LCR_MAXCON][9], c_dist[LCR_MAXCON], c_mu[LCR_MAXCON], c_c1[LCR_MAXCON], c_c2[LCR_MAXCON];
-  const CPar<T>* c_par[LCR_MAXCON];
+  short c_par[LCR_MAXCON];  // index into the contiguous CPar tables of DevModel, see DevModel::par()
   short c_efc[LCR_MAXCON];
   signed char c_b1[LCR_MAXCON], c_b2[LCR_MAXCON];
   // constraint rows
@@ -103,11 +105,13 @@ struct Ws {  // per-warp shared-memory workspace
   // separating-axis cache of the convex narrowphase (see lcr_convex.cuh): one contiguous 16-byte aligned block
   // that travels with the env record (DevState::sa)
   alignas(16) T sa_dir[LCR_NSA][3];
-  T sa_val[LCR_NSA];  // support value of a world-fixed (body 0) first hull along its cached axis
+  T sa_S[LCR_NSA][2];     // per hull of the pair: support value about the hull's bounding-sphere centre, along +-axis ...
+  T sa_u[LCR_NSA][2][3];  // ... and that direction in the hull's body frame, both at the last exact evaluation
   short sa_key[LCR_NSA];
   int sa_next;
   int sa_pad[3];
-  static constexpr int SA_BYTES = LCR_NSA * 4 * (int)sizeof(T) + LCR_NSA * 2 + 16;
+  static constexpr int SA_WORDS = LCR_NSA * 11;  // dir, S, u
+  static constexpr int SA_BYTES = SA_WORDS * (int)sizeof(T) + LCR_NSA * 2 + 16;
   short cand_key[LCR_MAXCAND];  // convex-pair candidates of this substep (results alias e_w / e_g / e_p)
   int ncand;
   int skip;          // phased execution: this env was auto-reset by the current step, substep kernels pass

@@ -373,7 +373,7 @@ template <typename T> DI void make_frame(T* f) {
 // Append one contact (warp-uniform arguments; lane 0 writes).  ncon / nefc are warp-uniform
 // registers owned by make_constraints.  Returns true if stored.
 template <typename T, int NC>
-DI bool add_contact(Ws<T, NC>& w, int& ncon, int& nefc, const CPar<T>* par, int b1, int b2, const T* pos, const T* normal, T dist) {
+DI bool add_contact(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, const CPar<T>* par, int b1, int b2, const T* pos, const T* normal, T dist) {
   const int dim = par->dim;
   if (ncon >= LCR_MAXCON || nefc + dim > LCR_MAXEFC) {
     if (LANE == 0) w.diag[4]++;
@@ -389,7 +389,7 @@ DI bool add_contact(Ws<T, NC>& w, int& ncon, int& nefc, const CPar<T>* par, int 
 #pragma unroll
     for (int k = 0; k < 9; k++) w.c_frame[ci][k] = f[k];
     w.c_dist[ci] = dist;
-    w.c_par[ci] = par;
+    w.c_par[ci] = (short)m.par_index(par);
     w.c_b1[ci] = (signed char)b1;
     w.c_b2[ci] = (signed char)b2;
     w.c_efc[ci] = (short)nefc;
@@ -417,7 +417,7 @@ DI void collide_floor_cube(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& n
     pos[0] = w.xpos[b][0] + __shfl_sync(FULLMASK, wv[0], src);
     pos[1] = w.xpos[b][1] + __shfl_sync(FULLMASK, wv[1], src);
     pos[2] = w.xpos[b][2] + __shfl_sync(FULLMASK, wv[2], src) - (T)0.5 * dd;
-    if (add_contact(w, ncon, nefc, &m.par_floor_cube[c], -1, b, pos, n, dd)) cnt++;
+    if (add_contact(w, m, ncon, nefc, &m.par_floor_cube[c], -1, b, pos, n, dd)) cnt++;
   }
 }
 
@@ -456,7 +456,7 @@ DI void mesh_support4(const Ws<T, NC>& w, const DevModel<T>& m, const T* __restr
     warp_argmax(bv[t], bi[t]);
     idx[t] = bi[t];
     T vl[3];
-    load_vert(verts, adr + bi[t], vl[0], vl[1], vl[2]);
+    load_vert(verts, adr + bi[t], vl[0], vl[1], vl[2]);  // (cold path: four winners, one reload each)
     mat_vec(pts[t], w.xmat[b], vl);
 #pragma unroll
     for (int k = 0; k < 3; k++) pts[t][k] += w.xpos[b][k];
@@ -487,7 +487,7 @@ __device__ __noinline__ void collide_floor_meshes(Ws<T, NC>& w, const DevModel<T
       for (int k = 0; k < cnt; k++) dup |= (used[k] == idx[t]);
       if (dup) continue;
       T pos[3] = {pts[t][0], pts[t][1], pts[t][2] - (T)0.5 * d};
-      if (add_contact(w, ncon, nefc, &m.par_floor_mesh[g], -1, m.mesh_body[g], pos, n, d)) used[cnt++] = idx[t];
+      if (add_contact(w, m, ncon, nefc, &m.par_floor_mesh[g], -1, m.mesh_body[g], pos, n, d)) used[cnt++] = idx[t];
     }
   }
 }
@@ -590,14 +590,14 @@ __device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m
   if (cmask & LCR_COLLIDE_FLOOR_CUBE)
     for (int c = 0; c < NC; c++) collide_floor_cube(w, m, ncon, nefc, c);
   if (NC == 2 && (cmask & LCR_COLLIDE_CUBE_CUBE)) collide_cube_cube(w, m, ncon, nefc);
-  if (cmask & LCR_COLLIDE_CUBE_MESH) consume_candidates(w, m, verts, ncon, nefc, true);
+  if (cmask & LCR_COLLIDE_CUBE_MESH) consume_candidates(w, m, ncon, nefc, true);
   if (cmask & LCR_COLLIDE_FLOOR_MESH) collide_floor_meshes(w, m, verts, ncon, nefc);
-  if (cmask & LCR_COLLIDE_MESH_MESH) consume_candidates(w, m, verts, ncon, nefc, false);
+  if (cmask & LCR_COLLIDE_MESH_MESH) consume_candidates(w, m, ncon, nefc, false);
   if (lane == 0) { w.ncon = ncon; w.nefc = nefc; w.nlim = nlim; }
   __syncwarp();
   // contact rows: lane <-> row
   for (int ci = lane; ci < ncon; ci += 32) {
-    const int dim = w.c_par[ci]->dim, e0 = w.c_efc[ci];
+    const int dim = m.par(w.c_par[ci])->dim, e0 = w.c_efc[ci];
     for (int r = 0; r < dim; r++) { w.e_unit[e0 + r] = (short)ci; w.e_r[e0 + r] = (signed char)r; }
   }
   __syncwarp();
@@ -619,7 +619,7 @@ __device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m
     T diagA;
     if (u < 0) { par = &m.par_limit[-1 - u]; diagA = m.dof_invweight0[-1 - u]; }
     else {
-      par = w.c_par[u];
+      par = m.par(w.c_par[u]);
       const int rot = w.e_r[i] >= 3;
       diagA = body_invweight<T, NC>(m, w.c_b1[u], rot) + body_invweight<T, NC>(m, w.c_b2[u], rot);
     }
@@ -637,7 +637,7 @@ __device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m
     T Rnew = 0;
     if (act) {
       const int u = w.e_unit[i], r = w.e_r[i];
-      const CPar<T>* par = w.c_par[u];
+      const CPar<T>* par = m.par(w.c_par[u]);
       const T R0 = w.e_D[w.c_efc[u]];
       T ir = m.impratio < c_minval<T>() ? c_minval<T>() : m.impratio;
       const T R1 = R0 / ir;
@@ -707,9 +707,9 @@ template <typename T, int NC> DI T mul_M(const Ws<T, NC>& w, const DevModel<T>& 
 //  g = dNT/djar, p_k = f_k u_k / T, c1 = Dm, c2 = -mu NT Dm / T >= 0).
 template <typename T> struct Eval3 { T cost, d1, d2; };
 template <typename T, int NC, bool with_jv, bool FULL>
-__device__ __noinline__ Eval3<T> contact_eval(Ws<T, NC>& w, int ci, T alpha) {
+__device__ __noinline__ Eval3<T> contact_eval(Ws<T, NC>& w, const DevModel<T>& m, int ci, T alpha) {
   T cost, d1, d2;
-  const CPar<T>* par = w.c_par[ci];
+  const CPar<T>* par = m.par(w.c_par[ci]);
   const int dim = par->dim, i0 = w.c_efc[ci];
   const T mu = w.c_mu[ci];
   T x[6], u[6], fri[6], jv[6];
@@ -819,7 +819,7 @@ __device__ __noinline__ T total_cost(Ws<T, NC>& w, const DevModel<T>& m, const T
     if (x < 0) { cost += (T)0.5 * w.e_D[lane] * x * x; f = -w.e_D[lane] * x; ww = w.e_D[lane]; }
     if (FULL) { w.e_force[lane] = f; w.e_w[lane] = ww; }
   }
-  for (int ci = lane; ci < ncon; ci += 32) cost += contact_eval<T, NC, false, FULL>(w, ci, (T)0).cost;
+  for (int ci = lane; ci < ncon; ci += 32) cost += contact_eval<T, NC, false, FULL>(w, m, ci, (T)0).cost;
   cost = warp_sum(cost);
   if (FULL) {
     __syncwarp();
@@ -909,7 +909,7 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
         const T c1 = w.c_c1[ci];
         if (c1 == 0) continue;  // warp-uniform
         const T c2 = w.c_c2[ci];
-        const int i0 = w.c_efc[ci], dim = w.c_par[ci]->dim;
+        const int i0 = w.c_efc[ci], dim = m.par(w.c_par[ci])->dim;
         T G = 0, P = 0;
         if (dof < NVV)
           for (int k = 0; k < dim; k++) { const T jk = w.J[i0 + k][dof]; G += w.e_g[i0 + k] * jk; P += w.e_p[i0 + k] * jk; }
@@ -960,7 +960,7 @@ __device__ __noinline__ void solve_constraints(Ws<T, NC>& w, const DevModel<T>& 
           if (x < 0) { d1 = w.e_D[lane] * x * jv; d2 = w.e_D[lane] * jv * jv; }
         }
         for (int ci = lane; ci < ncon; ci += 32) {
-          const Eval3<T> ev = contact_eval<T, NC, true, false>(w, ci, alpha);
+          const Eval3<T> ev = contact_eval<T, NC, true, false>(w, m, ci, alpha);
           d1 += ev.d1; d2 += ev.d2;
         }
         d1 = warp_sum(d1) + g1 + alpha * g2;
@@ -1422,7 +1422,7 @@ __global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__
   }
 }
 
-template <typename T, int NC>
+template <typename T, int NC, bool PROF>
 __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
                                                     const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
                                                     uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ, int flags,
@@ -1441,10 +1441,10 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
   const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
   // optional per-env phase timing (debug hook, prof == nullptr in production): clock64 deltas summed over the substeps
-  long long tp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0;
-#define LCR_TICK(k) do { if (prof) { (void)*(volatile int*)&job_next; /* BAR.SYNC defers blocking to the next memory access */ \
+  long long tp[PROF ? 10 : 1] = {0}, t0 = 0;
+#define LCR_TICK(k) do { if (PROF) { (void)*(volatile int*)&job_next; /* BAR.SYNC defers blocking to the next memory access */ \
     const long long t1_ = clock64(); tp[k] += t1_ - t0; t0 = t1_; } } while (0)
-  if (prof) t0 = clock64();
+  if (PROF) t0 = clock64();
   bool go = false;
   if (valid) {
     load_state(w, s, env);
@@ -1488,7 +1488,7 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
   }
   if (go) env_step_end(w, m, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
   if (valid) store_state(w, s, env);
-  if (prof && valid && LANE == 0) {
+  if (PROF && valid && LANE == 0) {
     LCR_TICK(0);
     for (int k = 0; k < 10; k++) prof[(size_t)env * 10 + k] = tp[k];
   }
@@ -1630,16 +1630,16 @@ __global__ void __launch_bounds__(32, 16) k_debug_contacts(const DevModel<T>* __
   for (int ci = LANE; ci < ncon; ci += 32) {
     double* o = out + ((size_t)env * LCR_MAXCON + ci) * 12;
     for (int k = 0; k < 3; k++) { o[k] = (double)w.c_pos[ci][k]; o[3 + k] = (double)w.c_frame[ci][k]; }
-    o[6] = (double)w.c_dist[ci]; o[7] = w.c_b1[ci]; o[8] = w.c_b2[ci]; o[9] = w.c_par[ci]->dim; o[10] = (double)w.c_mu[ci]; o[11] = w.c_efc[ci];
+    o[6] = (double)w.c_dist[ci]; o[7] = w.c_b1[ci]; o[8] = w.c_b2[ci]; o[9] = dm->par(w.c_par[ci])->dim; o[10] = (double)w.c_mu[ci]; o[11] = w.c_efc[ci];
   }
 }
 
 // empty separating-axis cache of env e in HBM: keys -1, next 0 (the block layout does not depend on NC)
 template <typename T> DI void sa_empty(DevState<T> s, int e) {
   unsigned char* blk = s.sa + (size_t)e * Ws<T, 1>::SA_BYTES;
-  short* key = reinterpret_cast<short*>(blk + LCR_NSA * 4 * sizeof(T));
+  short* key = reinterpret_cast<short*>(blk + Ws<T, 1>::SA_WORDS * sizeof(T));
   for (int k = 0; k < LCR_NSA; k++) key[k] = -1;
-  int* next = reinterpret_cast<int*>(blk + LCR_NSA * 4 * sizeof(T) + LCR_NSA * 2);
+  int* next = reinterpret_cast<int*>(blk + Ws<T, 1>::SA_WORDS * sizeof(T) + LCR_NSA * 2);
   for (int k = 0; k < 4; k++) next[k] = 0;
 }
 // row-major float64 <-> per-env records of T
@@ -1716,10 +1716,12 @@ template <typename T, int NC> static void set_smem_attr() {
   cudaFuncSetAttribute(k_ph_col<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_ph_sol<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_ph_end<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_step_ls<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
+  cudaFuncSetAttribute(k_step_ls<T, NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
+  cudaFuncSetAttribute(k_step_ls<T, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
   // all of the SM's L1/shared array as shared memory: several CTAs of a few workspaces each must fit one SM
   const char* cv = getenv("LCR_LS_CARVEOUT");  // experiment: percent of the L1/shared array used as shared memory
-  cudaFuncSetAttribute(k_step_ls<T, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_step_ls<T, NC, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_step_ls<T, NC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_step<T, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
@@ -1760,8 +1762,10 @@ template <typename T>
 void Launch<T>::step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
                               uint8_t* term, uint8_t* trunc, uint8_t* succ, int grid, int warps, int epc, int flags, const int* perm, long long* prof,
                               cudaStream_t st) {
-  if (ncube == 1) k_step_ls<T, 1><<<grid, 32 * warps, sizeof(Ws<T, 1>) * epc, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm, epc, prof);
-  else k_step_ls<T, 2><<<grid, 32 * warps, sizeof(Ws<T, 2>) * epc, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm, epc, prof);
+#define LCR_LS_GO(NCV, PROFV) k_step_ls<T, NCV, PROFV><<<grid, 32 * warps, sizeof(Ws<T, NCV>) * epc, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm, epc, prof)
+  if (ncube == 1) { if (prof) LCR_LS_GO(1, true); else LCR_LS_GO(1, false); }
+  else { if (prof) LCR_LS_GO(2, true); else LCR_LS_GO(2, false); }
+#undef LCR_LS_GO
 }
 // one chain of 2 + 3*n_substeps launches over the env range [env0, env0 + cnt) on stream st
 template <typename T, int NC>
