@@ -533,16 +533,18 @@ template <typename T, int NC> DI void key_shapes(const Ws<T, NC>& w, const DevMo
 // Upper bound of max over the hull of mesh g of x . dw (dw a world direction, slot/side = its cache entry) WITHOUT touching
 // the vertices: with c the world centre of the hull's bounding sphere, r its radius, S the exact support value about c
 // along the body-frame direction u0 recorded at the last exact evaluation, and u1 = R^T dw the direction now,
-//     max x . dw  =  c . dw + max y . u1  <=  c . dw + S + |u1 - u0| r        (y = body-frame vertex - centre, |y| <= r).
+//     max x . dw  =  c . dw + max y . u1  <=  c . dw + S + min(|u1 - u0| r, sum_k |u1 - u0|_k half_k)
+// (y = body-frame vertex - centre lies in the bounding sphere and in the bounding box, which share the centre).
 // Translation is followed exactly, only the relative rotation since the last exact evaluation costs slack.
 template <typename T, int NC>
 DI T hull_support_bound(const Ws<T, NC>& w, const DevModel<T>& m, int g, const T* dw, int slot, int side) {
   const T* R = w.xmat[m.mesh_body[g]];
-  T u1[3], e2 = 0;
+  T u1[3], e2 = 0, eb = 0;
   matT_vec(u1, R, dw);
 #pragma unroll
-  for (int k = 0; k < 3; k++) { const T e = u1[k] - w.sa_u[slot][side][k]; e2 += e * e; }
-  return w.gc[g][0] * dw[0] + w.gc[g][1] * dw[1] + w.gc[g][2] * dw[2] + w.sa_S[slot][side] + sqrt(e2) * m.mesh_rbound[g];
+  for (int k = 0; k < 3; k++) { const T e = u1[k] - w.sa_u[slot][side][k]; e2 += e * e; eb += fabs(e) * m.mesh_half[g][k]; }
+  const T es = sqrt(e2) * m.mesh_rbound[g];  // y lies in the bounding sphere and in the bounding box: use the smaller slack
+  return w.gc[g][0] * dw[0] + w.gc[g][1] * dw[1] + w.gc[g][2] * dw[2] + w.sa_S[slot][side] + (eb < es ? eb : es);
 }
 
 // One candidate.  res = {code, SA, dir[3], SB | depth, dir[3], pos[3]}; code 1: penetrating (depth, dir, pos);
@@ -584,7 +586,42 @@ __device__ __noinline__ void narrowphase_job(const Ws<T, NC>& w, const DevModel<
     }
     md_support(w, verts, A, B, d, p);  // supports along the new axis, kept with it
   }
-  // code 0 or 3: report the axis and the centred support values
+  // code 0 or 3: MPR stops at the first direction that separates, usually a grazing one.  The parts of this arm are
+  // box-like and face each other across millimetre gaps, so the widest gap is (nearly) along a face normal of one of
+  // the two oriented bounding boxes: take the normal whose box-vs-box gap estimate is largest, evaluate it exactly
+  // (one more support pair) and keep it if it separates better -- the axis then survives many substeps of relative
+  // rotation before hull_support_bound needs the vertices again.
+  {
+    const T* RA = w.xmat[A.body];
+    const T* RB = w.xmat[B.body];
+    T cA[3], cB[3], hA[3], hB[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      cA[k] = cube ? w.xpos[A.body][k] : w.gc[gA][k]; hA[k] = cube ? A.half[k] : m.mesh_half[gA][k];
+      cB[k] = w.gc[gB][k]; hB[k] = m.mesh_half[gB][k];
+    }
+    const T t[3] = {cB[0] - cA[0], cB[1] - cA[1], cB[2] - cA[2]};
+    T best = (T)-1e30, dn[3] = {0, 0, 0};
+#pragma unroll 1
+    for (int c = 0; c < 6; c++) {
+      const T* R = c < 3 ? RA : RB;
+      const int k = c % 3;
+      T ax[3] = {R[k], R[3 + k], R[6 + k]};
+      const T sg = dot3(t, ax) < 0 ? (T)-1 : (T)1;
+      ax[0] *= sg; ax[1] *= sg; ax[2] *= sg;
+      T eA = 0, eB = 0;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        eA += fabs(RA[j] * ax[0] + RA[3 + j] * ax[1] + RA[6 + j] * ax[2]) * hA[j];
+        eB += fabs(RB[j] * ax[0] + RB[3 + j] * ax[1] + RB[6 + j] * ax[2]) * hB[j];
+      }
+      const T est = dot3(t, ax) - eA - eB;
+      if (est > best) { best = est; dn[0] = ax[0]; dn[1] = ax[1]; dn[2] = ax[2]; }
+    }
+    SPoint<T> q;
+    md_support(w, verts, A, B, dn, q);
+    if (-dot3(q.v, dn) > -dot3(p.v, d)) { p = q; d[0] = dn[0]; d[1] = dn[1]; d[2] = dn[2]; }
+  }
   res[0] = (T)code;
   res[2] = d[0]; res[3] = d[1]; res[4] = d[2];
   T sA = 0;

@@ -57,7 +57,7 @@ typedef struct OrcSim {
   Contact con[LCR_MAXCON];
   int ncon, nefc, niter, overflow, nan_resets, max_nefc;
   int sa_key[LCR_NSA], sa_next; /* separating-axis cache, see lcr_oracle_convex.inc */
-  double sa_dir[LCR_NSA][3];
+  double sa_dir[LCR_NSA][3], sa_S[LCR_NSA][2], sa_u[LCR_NSA][2][3];
   int efc_type[LCR_MAXEFC]; /* 0 limit, 1 first row of a contact, 2 following row of a contact */
   int efc_con[LCR_MAXEFC];
   double J[LCR_MAXEFC][NV], efc_pos[LCR_MAXEFC], efc_vel[LCR_MAXEFC], efc_diag[LCR_MAXEFC];
