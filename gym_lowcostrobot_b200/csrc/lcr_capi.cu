@@ -392,6 +392,16 @@ int lcr_debug_contacts(LcrSim* sim, double* d_contacts, int32_t* d_ncon, void* s
   return 0;
 }
 
+int lcr_pack_outputs(LcrSim* sim, const float* d_obs, const float* d_reward, const uint8_t* d_terminated, const uint8_t* d_truncated,
+                     const uint8_t* d_success, float* d_record, void* stream) {
+  WITH_DEVICE(sim);
+  if (!d_obs || !d_reward || !d_terminated || !d_truncated || !d_success || !d_record) return fail("lcr_pack_outputs: null buffer");
+  lcr::Launch<float>::pack(d_obs, d_reward, d_terminated, d_truncated, d_success, d_record, sim->n, lcr_obs_dim(sim->task), (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int lcr_debug_phase_clocks(LcrSim* sim, long long* d_clocks) {
   if (!sim) return fail("null handle");
   if (sim->cfg.exec_mode != 2) return fail("lcr_debug_phase_clocks: lockstep mode only");

@@ -139,6 +139,8 @@ struct Launch {
                    uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st);
   static int lockstep_warps(int ncube, int warps);
   static void sched(DevState<T> s, int* perm, int W, int striped, cudaStream_t st);
+  static void pack(const float* obs, const float* reward, const uint8_t* term, const uint8_t* trunc, const uint8_t* succ, float* rec, int n, int od,
+                   cudaStream_t st);
   static void step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
                             uint8_t* term, uint8_t* trunc, uint8_t* succ, int grid, int warps, int epc, int flags, const int* perm, long long* prof,
                             cudaStream_t st);

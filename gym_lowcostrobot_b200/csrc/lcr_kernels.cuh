@@ -1701,6 +1701,23 @@ __global__ void k_seed(DevState<T> s, const unsigned long long* st) {
   for (int k = 0; k < 4; k++) rng[k] = st[4 * (size_t)e + k];
 }
 
+// obs | reward | terminated | truncated | success as one float32 record per env (the send buffer of the one all-gather
+// per step, and the single device->host copy of the host-facing path)
+static __global__ void k_pack(const float* __restrict__ obs, const float* __restrict__ reward, const uint8_t* __restrict__ term,
+                       const uint8_t* __restrict__ trunc, const uint8_t* __restrict__ succ, float* __restrict__ rec, int n, int od) {
+  const int w = od + 4, total = n * w;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i / w, c = i - e * w;
+    float v;
+    if (c < od) v = obs[(size_t)e * od + c];
+    else if (c == od) v = reward[e];
+    else if (c == od + 1) v = (float)term[e];
+    else if (c == od + 2) v = (float)trunc[e];
+    else v = (float)succ[e];
+    rec[i] = v;
+  }
+}
+
 // ---------------------------------------------------------------- launchers
 template <typename T, int NC> static void set_smem_attr() {
   static bool done = false;  // per process; attributes are per device but identical
@@ -1754,6 +1771,12 @@ int Launch<T>::lockstep_warps(int ncube, int warps) {
   const int fit = (int)(LCR_LS_MAXSMEM / smem_bytes(ncube));
   if (warps <= 0) warps = fit;
   return std::max(1, std::min(std::min(warps, fit), 16));
+}
+template <typename T>
+void Launch<T>::pack(const float* obs, const float* reward, const uint8_t* term, const uint8_t* trunc, const uint8_t* succ, float* rec, int n, int od,
+                     cudaStream_t st) {
+  const int total = n * (od + 4), blocks = std::min((total + 255) / 256, 148 * 8);
+  k_pack<<<blocks, 256, 0, st>>>(obs, reward, term, trunc, succ, rec, n, od);
 }
 template <typename T>
 void Launch<T>::sched(DevState<T> s, int* perm, int W, int striped, cudaStream_t st) { k_sched<T><<<1, 1024, 0, st>>>(s, perm, W, striped); }

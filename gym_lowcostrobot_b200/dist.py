@@ -55,8 +55,10 @@ class ShardedEnv:
         """actions_full: [n_total, A] (every rank holds the full action batch, e.g. from a replicated
         policy).  Returns the gathered (obs, reward, terminated, truncated, success) of all envs."""
         a = actions_full[self.lo:self.hi]
-        obs, reward, te, tr, su = self.env.step_flat(a)
-        self._local = pack_record(obs, reward, te, tr, su, out=self._local)
+        if hasattr(self.env, "step_packed"):  # CUDA env: one fused pack kernel writes the send buffer
+            self._local = self.env.step_packed(a)
+        else:
+            self._local = pack_record(*self.env.step_flat(a), out=self._local)
         if self.world_size == 1:
             return unpack_record(self._local)
         if self._full is None:

@@ -52,7 +52,7 @@ class BatchedLowCostRobotEnv:
                  block_gripper=None, distance_threshold=0.05, height_threshold=0.1, cube_xy_range=0.3,
                  target_xy_range=0.3, goal_z_range=0.1, n_substeps=20, render_mode=None, max_episode_steps=50,
                  autoreset=False, precision="float32", assets_path=None, collision_mask=model.COLLIDE_ALL,
-                 env_offset=0, exec_mode="fused"):
+                 env_offset=0, exec_mode="auto"):
         if observation_mode != "state":
             raise NotImplementedError("only observation_mode='state' is implemented (image rendering is out of scope)")
         if render_mode is not None:
@@ -66,7 +66,7 @@ class BatchedLowCostRobotEnv:
                                    distance_threshold=distance_threshold, height_threshold=height_threshold,
                                    cube_xy_range=cube_xy_range, target_xy_range=target_xy_range, goal_z_range=goal_z_range,
                                    n_substeps=n_substeps, max_episode_steps=max_episode_steps, autoreset=autoreset,
-                                   collision_mask=collision_mask, exec_mode={"fused": 0, "phased": 1, "lockstep": 2}[exec_mode])
+                                   collision_mask=collision_mask, exec_mode={"fused": 0, "phased": 1, "lockstep": 2}[self._pick_exec_mode(exec_mode, int(num_envs))])
         self.block_gripper = bool(self.cfg.block_gripper)
         self.compiled = model.load_compiled(self.task, assets_path)
         self.cmodel, self.verts = model.pack_model(self.compiled)
@@ -83,6 +83,7 @@ class BatchedLowCostRobotEnv:
         self._obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, device=dev)
         self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
         self._flags = torch.zeros(3, n, dtype=torch.uint8, device=dev)
+        self._record = None
         self.single_action_space = spaces.Box(-1.0, 1.0, (self.action_dim,), np.float32)
         sub = {"arm_qpos": spaces.Box(-np.pi, np.pi, (6,)), "arm_qvel": spaces.Box(-10.0, 10.0, (6,))}
         for key, width in _OBS_LAYOUT[self.task][2:]:
@@ -91,6 +92,15 @@ class BatchedLowCostRobotEnv:
         self.action_space = spaces.batch_space(self.single_action_space, n)
         self.observation_space = spaces.batch_space(self.single_observation_space, n)
         self.seed(0)
+
+    @classmethod
+    def _pick_exec_mode(cls, exec_mode, num_envs):
+        """"auto": the lockstep kernel (one launch per step), except for big two-cube batches where the phased chain
+        (one small kernel per mj_step phase) is faster on B200 -- its 17.8 KB workspaces leave the lockstep CTAs only
+        13 warps per SM.  All three modes give bit-identical results (tests/test_gpu_parity.py)."""
+        if exec_mode != "auto":
+            return exec_mode
+        return "phased" if (cls.task == "stack" and num_envs >= 8192) else "lockstep"
 
     # -- helpers ---------------------------------------------------------------------------
     def _stream(self):
@@ -135,6 +145,18 @@ class BatchedLowCostRobotEnv:
             capi.check(self._L.lcr_step(self._h, _ptr(a), _ptr(self._obs), _ptr(self._reward), _ptr(f[0]), _ptr(f[1]),
                                         _ptr(f[2]), self._stream()))
         return self._obs, self._reward, f[0], f[1], f[2]
+
+    def step_packed(self, actions, out=None):
+        """One control step, outputs as one float32 record per env ``[num_envs, obs_dim + 4]`` = obs | reward |
+        terminated | truncated | success (one fused pack kernel): the all-gather / device->host unit of ``dist.ShardedEnv``."""
+        obs, reward, te, tr, su = self.step_flat(actions)
+        if out is None:
+            if self._record is None:
+                self._record = torch.empty(self.num_envs, self.obs_dim + 4, dtype=torch.float32, device=self.device)
+            out = self._record
+        with torch.cuda.device(self.device):
+            capi.check(self._L.lcr_pack_outputs(self._h, _ptr(obs), _ptr(reward), _ptr(te), _ptr(tr), _ptr(su), _ptr(out), self._stream()))
+        return out
 
     def step(self, actions):
         obs, reward, te, tr, su = self.step_flat(actions)

@@ -63,6 +63,13 @@ int lcr_reset(LcrSim* sim, const uint8_t* d_mask, float* d_obs, void* stream);
 int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated,
              uint8_t* d_truncated, uint8_t* d_success, void* stream);
 
+/* Packs the outputs of lcr_step into one float32 record per env, d_record [n_envs][obs_dim + 4] =
+ * obs | reward | terminated | truncated | success (what the reference's step() returns as a 5-tuple,
+ * reach_cube_env.py:333).  It is the send buffer of the one all-gather per step of the sharded multi-GPU path
+ * and the single device->host copy of a host-facing caller. */
+int lcr_pack_outputs(LcrSim* sim, const float* d_obs, const float* d_reward, const uint8_t* d_terminated,
+                     const uint8_t* d_truncated, const uint8_t* d_success, float* d_record, void* stream);
+
 /* Replaces direct reads/writes of MjData the reference performs (data.qpos / data.qvel / data.ctrl,
  * reach_cube_env.py:182,185,252,273,285-294,305-306) and provides checkpoint/resume.  Row-major
  * DEVICE arrays of float64 regardless of precision: qpos [n][nq], qvel [n][nv], ctrl [n][6],

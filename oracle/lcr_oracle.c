@@ -446,17 +446,24 @@ static void collision(OrcSim *s) {
   const LcrModel *m = &s->m;
   int mask = s->cfg.collision_mask;
   s->ncon = 0;
+  /* convex pairs: candidates -> jobs (against the cache of the substep start) -> consume, as in the CUDA kernels */
+  int keys[LCR_MAXCAND];
+  CandRes res[LCR_MAXCAND];
+  const int ncand_all = collect_candidates(s, keys), ncand = ncand_all < LCR_MAXCAND ? ncand_all : LCR_MAXCAND;
+  for (int k = 0; k < ncand; k++) cand_job(s, keys[k], &res[k]);
+  /* generation order (= drop order at the caps): floor-cube, cube-cube, cube-mesh, floor-mesh, mesh-mesh */
   if (mask & LCR_COLLIDE_FLOOR_CUBE)
     for (int c = 0; c < m->ncube; c++) collide_floor_cube(s, c);
   if ((mask & LCR_COLLIDE_CUBE_CUBE) && m->ncube == 2) collide_cube_cube(s);
   if (mask & LCR_COLLIDE_CUBE_MESH)
-    for (int c = 0; c < m->ncube; c++)
-      for (int g = 0; g < m->nmesh; g++) collide_cube_mesh(s, c, g);
+    for (int k = 0; k < ncand; k++) if (keys[k] >= 200) cand_apply(s, &res[k]);
   if (mask & LCR_COLLIDE_FLOOR_MESH)
     for (int g = 0; g < m->nmesh; g++)
       if (m->mesh_body[g] != 0) collide_floor_mesh(s, g);
-  if (mask & LCR_COLLIDE_MESH_MESH)
-    for (int p = 0; p < m->npair; p++) collide_mesh_mesh(s, m->pair_g1[p], m->pair_g2[p], p);
+  if (mask & LCR_COLLIDE_MESH_MESH) {
+    for (int k = 0; k < ncand; k++) if (keys[k] < 200) cand_apply(s, &res[k]);
+    if (ncand_all > LCR_MAXCAND) s->overflow += ncand_all - LCR_MAXCAND; /* candidates past the cap are not processed */
+  }
 }
 
 /* ------------------------------------------------------------------ constraints (mj_makeConstraint, mj_makeImpedance, mj_referenceConstraint) */

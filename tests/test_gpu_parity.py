@@ -256,3 +256,20 @@ def test_lockstep_execution_is_bitwise_identical_to_fused(task, mode, warps, fla
         assert torch.equal(sa[k], sb[k]), k
     for e in envs:
         e.close()
+
+
+def test_step_packed_matches_the_separate_outputs():
+    """lcr_pack_outputs (the all-gather / device->host record) holds exactly obs | reward | terminated | truncated | success."""
+    from gym_lowcostrobot_b200.dist import pack_record
+    n = 33
+    a_env, b_env = (glr.make("PushCube-v0", num_envs=n, autoreset=True, max_episode_steps=4) for _ in range(2))
+    a_env.reset(seed=5)
+    b_env.reset(seed=5)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(6):
+        a = torch.rand(n, a_env.action_dim, generator=gen, device="cuda") * 2 - 1
+        rec = a_env.step_packed(a)
+        ref = pack_record(*b_env.step_flat(a))
+        assert rec.shape == (n, a_env.obs_dim + 4) and torch.equal(rec, ref), t
+    a_env.close()
+    b_env.close()
