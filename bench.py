@@ -79,40 +79,39 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_rollout(task, action_mode, n_envs, n_steps, n_threads, seed0=0):
-    """Oracle port timed on the host cores: n_envs envs x n_steps steps split over n_threads threads.
-    Returns (env_steps_per_s, seconds)."""
-    import ctypes as C
+class CpuRollout:
+    """Oracle port timed on the host cores: n_envs envs split over n_threads threads (the C rollout releases the GIL)."""
 
-    from oracle.oracle import Oracle, lib
+    def __init__(self, task, action_mode, n_envs, n_threads, seed0=0):
+        import ctypes as C
 
-    L = lib()
-    sims = [Oracle(task, action_mode=action_mode, autoreset=True) for _ in range(n_envs)]
-    for i, s in enumerate(sims):
-        s.reset(seed=seed0 + i)
-    na = sims[0].na
-    rng = np.random.default_rng(1234)
-    chunks = np.array_split(np.arange(n_envs), n_threads)
-    jobs = []
-    for ch in chunks:
-        if len(ch) == 0:
-            continue
-        acts = rng.uniform(-1, 1, size=(n_steps, len(ch), na)).astype(np.float32)
-        handles = (C.c_void_p * len(ch))(*[sims[i].h for i in ch])
-        jobs.append((handles, len(ch), acts))
+        from oracle.oracle import Oracle, lib
 
-    def work(job):
-        handles, n, acts = job
-        L.orc_rollout(handles, n, n_steps, acts.ctypes.data_as(C.c_void_p), None, None)
+        self.C, self.L = C, lib()
+        self.sims = [Oracle(task, action_mode=action_mode, autoreset=True) for _ in range(n_envs)]
+        for i, s in enumerate(self.sims):
+            s.reset(seed=seed0 + i)
+        self.na, self.n_envs = self.sims[0].na, n_envs
+        self.rng = np.random.default_rng(1234)
+        self.chunks = [ch for ch in np.array_split(np.arange(n_envs), n_threads) if len(ch)]
+        self.handles = [(C.c_void_p * len(ch))(*[self.sims[i].h for i in ch]) for ch in self.chunks]
 
-    threads = [threading.Thread(target=work, args=(j,)) for j in jobs]
-    t0 = time.perf_counter()
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    dt = time.perf_counter() - t0
-    return n_envs * n_steps / dt, dt
+    def run(self, n_steps):
+        """n_steps env.steps of every env with fresh U(-1,1) actions; returns (env_steps_per_s, seconds)"""
+        C, L = self.C, self.L
+        acts = [self.rng.uniform(-1, 1, size=(n_steps, len(ch), self.na)).astype(np.float32) for ch in self.chunks]
+
+        def work(k):
+            L.orc_rollout(self.handles[k], len(self.chunks[k]), n_steps, acts[k].ctypes.data_as(C.c_void_p), None, None)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(self.chunks))]
+        t0 = time.perf_counter()
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        dt = time.perf_counter() - t0
+        return self.n_envs * n_steps / dt, dt
 
 
 def run_reference(args, rank, world):
@@ -126,10 +125,11 @@ def run_reference(args, rank, world):
     from oracle.oracle import build
 
     build()
-    # bounded sample: each "step" = one env.step of min(envs, 64*cores) envs, scaled to the full batch
+    # bounded sample: each "step" = 10 env.steps of min(envs, 64*cores) envs on all cores, scaled to the full batch
     sample = min(n_envs, 64 * cores)
+    cpu = CpuRollout(args.task, args.action_mode, sample, cores)
     for k in range(args.warmup + args.steps):
-        rate, dt = cpu_rollout(args.task, args.action_mode, sample, 1, cores, seed0=k * sample)
+        rate, dt = cpu.run(10)
         if k >= args.warmup:
             per_step.append(rate)
     value = float(np.mean(per_step))
@@ -140,7 +140,7 @@ def run_reference(args, rank, world):
         "config": {"workload": f"{IDS[args.task]} {n_envs} envs, state obs, {args.action_mode} action, 20 substeps (CPU)",
                    "envs": n_envs, "action_mode": args.action_mode},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} envs x 1 env.step per timed step on {cores} threads, scaled to {n_envs} envs; "
+                         "sample": f"{sample} envs x 10 env.steps per timed step on {cores} threads, scaled to {n_envs} envs; "
                                    "MuJoCo itself is not installable in this image, the port is oracle/lcr_oracle.c"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--action-mode", dest="action_mode", default="joint", choices=["joint", "ee"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exec-mode", dest="exec_mode", default="phased", choices=["fused", "phased", "lockstep"])
+    ap.add_argument("--exec-mode", dest="exec_mode", default="auto", choices=["auto", "fused", "phased", "lockstep"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -187,19 +187,19 @@ def main():
     actions = torch.rand(W + K, n_local, A, generator=gen, device=dev) * 2 - 1  # resident in HBM
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    from gym_lowcostrobot_b200.dist import pack_record
+    exec_mode = env.exec_mode  # what "auto" resolved to
 
-    def gather(out):
-        """multi-GPU tail of a step: pack the local outputs and all-gather the batch over NCCL"""
-        sh._local = pack_record(*out, out=sh._local)
+    def gather(rec):
+        """multi-GPU tail of a step: all-gather the packed output records of all ranks over NCCL"""
         if sh._full is None:
-            sh._full = torch.empty(n_total, sh._local.shape[1], dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(sh._full, sh._local)
+            sh._full = torch.empty(n_total, rec.shape[1], dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(sh._full, rec)
         return sh._full
 
     def one_step(t):
-        out = env.step_flat(actions[t])
-        return gather(out) if sh is not None else out
+        if sh is None:
+            return env.step_flat(actions[t])
+        return gather(env.step_packed(actions[t]))
 
     for t in range(W):
         one_step(t)
@@ -217,10 +217,13 @@ def main():
         flush.zero_()  # L2 flush between timed iterations (outside the event pairs)
         ev[t][0].record()
         kev[t][0].record()
-        out = env.step_flat(actions[W + t])
-        kev[t][1].record()
-        if sh is not None:
-            gather(out)
+        if sh is None:
+            env.step_flat(actions[W + t])
+            kev[t][1].record()
+        else:
+            rec = env.step_packed(actions[W + t])
+            kev[t][1].record()
+            gather(rec)
         ev[t][1].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -248,8 +251,7 @@ def main():
     e0.record()
     for t in range(K):
         a = h_act[t].to(dev, non_blocking=True)
-        out = env.step_flat(a)
-        pack_record(*out, out=d_rec)
+        env.step_packed(a, out=d_rec)
         h_out.copy_(d_rec, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the result every step
     e1.record()
@@ -272,22 +274,25 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"{IDS[args.task]} {n_local} envs/GPU, state obs, {args.action_mode} action, 20 substeps, "
                                    "random U(-1,1) actions, next-step autoreset (TimeLimit 50)",
-                       "envs_per_gpu": n_local, "envs_total": n_total, "action_mode": args.action_mode, "exec_mode": args.exec_mode,
+                       "envs_per_gpu": n_local, "envs_total": n_total, "action_mode": args.action_mode, "exec_mode": exec_mode,
                        "l2": "256 MiB memset between timed steps (outside the per-step event pairs)",
                        "parallelism": f"env-index shard x{world}" + (", 1 NCCL all-gather of the output batch per step" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n_local * A * 4, "d2h_bytes_per_step": n_local * (O + 4) * 4},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "k_step", "kernel_ms": kern_ms,
-                         "note": "the step kernel is FP32-ALU/latency bound (20 substeps of small dense algebra per 446 B of state); see DESIGN.md"},
+                         "peak_source": peak_src, "kernel": {"lockstep": "k_step_ls (+ k_sched)", "fused": "k_step", "phased": "k_ph_* chain (2 + 4 x 20 launches per env group)"}[exec_mode],
+                         "kernel_ms": kern_ms,
+                         "note": "per-step device time of the step kernel(s); the path is latency bound (one warp walks 20 substeps of small dense algebra and "
+                                 "collision per ~0.45 KB of state), not HBM bound; see DESIGN.md 4"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = min(n_local, 64 * cores)
-            rate, dt = cpu_rollout(args.task, args.action_mode, sample, 4, cores)
+            rate, dt = CpuRollout(args.task, args.action_mode, sample, cores).run(300)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"{sample} envs x 4 env.steps on {cores} threads ({dt:.1f} s); float64 oracle port, MuJoCo not installable here"}
+                                    "sample": f"{sample} envs x 300 env.steps (episodes of 50, autoreset) on {cores} threads ({dt:.1f} s); float64 oracle port, "
+                                              "MuJoCo not installable here"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -67,6 +67,7 @@ class BatchedLowCostRobotEnv:
                                    cube_xy_range=cube_xy_range, target_xy_range=target_xy_range, goal_z_range=goal_z_range,
                                    n_substeps=n_substeps, max_episode_steps=max_episode_steps, autoreset=autoreset,
                                    collision_mask=collision_mask, exec_mode={"fused": 0, "phased": 1, "lockstep": 2}[self._pick_exec_mode(exec_mode, int(num_envs))])
+        self.exec_mode = {0: "fused", 1: "phased", 2: "lockstep"}[self.cfg.exec_mode]
         self.block_gripper = bool(self.cfg.block_gripper)
         self.compiled = model.load_compiled(self.task, assets_path)
         self.cmodel, self.verts = model.pack_model(self.compiled)
