@@ -93,9 +93,11 @@ __device__ __noinline__ void shape_support(const Ws<T, NC>& w, const T* __restri
 
 template <typename T, int NC>
 DI void md_support(const Ws<T, NC>& w, const T* __restrict__ verts, const Shape<T>& A, const Shape<T>& B, const T* dir, SPoint<T>& p) {
-  T nd[3] = {-dir[0], -dir[1], -dir[2]};
-  shape_support(w, verts, A, dir, p.v1);
-  shape_support(w, verts, B, nd, p.v2);
+  // (both directions are private copies: `dir` may point into a caller array that the optimiser also uses as an output)
+  const T dx = dir[0], dy = dir[1], dz = dir[2];
+  T da[3] = {dx, dy, dz}, db[3] = {-dx, -dy, -dz};
+  shape_support(w, verts, A, da, p.v1);
+  shape_support(w, verts, B, db, p.v2);
 #pragma unroll
   for (int k = 0; k < 3; k++) p.v[k] = p.v1[k] - p.v2[k];
 }

@@ -11,6 +11,7 @@
 // get_observation (:281-295), reward / success (:313-348), reset (:297-311), TimeLimit(50).
 #pragma once
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "lcr_device.cuh"
