@@ -220,7 +220,7 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
   s->launches = 1;
   if (cfg->exec_mode == 1) {
     const char* e = getenv("LCR_GROUPS");
-    int g = e ? atoi(e) : 8;
+    int g = e ? atoi(e) : 4;
     g = std::max(1, std::min(16, std::min(g, n_envs)));
     s->ngroups = g;
     for (int k = 0; k < g; k++) {

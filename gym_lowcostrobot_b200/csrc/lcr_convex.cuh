@@ -471,6 +471,53 @@ template <typename T, int NC> DI void sa_clear(Ws<T, NC>& w) {
 
 template <typename T, int NC> DI T (*cand_res(Ws<T, NC>& w))[8] { return reinterpret_cast<T(*)[8]>(w.e_w); }
 
+// Upper bound of max over the hull of mesh g of x . dw (dw a world direction, slot/side = its cache entry) WITHOUT touching
+// the vertices: with c the world centre of the hull's bounding sphere, r its radius, S the exact support value about c
+// along the body-frame direction u0 recorded at the last exact evaluation, and u1 = R^T dw the direction now,
+//     max x . dw  =  c . dw + max y . u1  <=  c . dw + S + min(|u1 - u0| r, sum_k |u1 - u0|_k half_k)
+// (y = body-frame vertex - centre lies in the bounding sphere and in the bounding box, which share the centre).
+// Translation is followed exactly, only the relative rotation since the last exact evaluation costs slack.
+template <typename T, int NC>
+DI T hull_support_bound(const Ws<T, NC>& w, const DevModel<T>& m, int g, const T* dw, int slot, int side) {
+  const T* R = w.xmat[m.mesh_body[g]];
+  T u1[3], e2 = 0, eb = 0;
+  matT_vec(u1, R, dw);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { const T e = u1[k] - w.sa_u[slot][side][k]; e2 += e * e; eb += fabs(e) * m.mesh_half[g][k]; }
+  const T es = sqrt(e2) * m.mesh_rbound[g];  // y lies in the bounding sphere and in the bounding box: use the smaller slack
+  return w.gc[g][0] * dw[0] + w.gc[g][1] * dw[1] + w.gc[g][2] * dw[2] + w.sa_S[slot][side] + (eb < es ? eb : es);
+}
+
+// Broadphase use of the cache (lane-local, no warp cooperation): true if the pair `key` has a cached axis that provably
+// still separates it -- exact support of the box for cube pairs, hull_support_bound for hulls.  Such a pair produces no
+// candidate at all, so a resting or slowly moving arm costs no narrowphase work.
+template <typename T, int NC>
+DI bool cached_axis_separates(const Ws<T, NC>& w, const DevModel<T>& m, int key) {
+  int slot = -1;
+#pragma unroll
+  for (int k = 0; k < LCR_NSA; k++) if (w.sa_key[k] == key) slot = k;  // at most one entry per key
+  if (slot < 0) return false;
+  const T d[3] = {w.sa_dir[slot][0], w.sa_dir[slot][1], w.sa_dir[slot][2]}, nd[3] = {-d[0], -d[1], -d[2]};
+  T supA;
+  int gB;
+  if (key >= LCR_KEY_CUBE) {
+    const int c = (key - LCR_KEY_CUBE) / LCR_MAXMESH, b = LCR_NABODY + c;
+    gB = (key - LCR_KEY_CUBE) % LCR_MAXMESH;
+    T dl[3], pl[3], pw[3];
+    matT_vec(dl, w.xmat[b], d);
+#pragma unroll
+    for (int k = 0; k < 3; k++) pl[k] = dl[k] >= 0 ? m.cube_size[c][k] : -m.cube_size[c][k];
+    mat_vec(pw, w.xmat[b], pl);
+#pragma unroll
+    for (int k = 0; k < 3; k++) pw[k] += w.xpos[b][k];
+    supA = dot3(pw, d);
+  } else {
+    supA = hull_support_bound(w, m, m.pair_g1[key], d, slot, 0);
+    gB = m.pair_g2[key];
+  }
+  return supA + hull_support_bound(w, m, gB, nd, slot, 1) < (T)-2e-6;
+}
+
 template <typename T, int NC>
 __device__ __noinline__ void collect_candidates(Ws<T, NC>& w, const DevModel<T>& m) {
   const int lane = LANE, cmask = m.collision_mask;
@@ -491,6 +538,7 @@ __device__ __noinline__ void collect_candidates(Ws<T, NC>& w, const DevModel<T>&
         const T r = m.mesh_rbound[lane] + sqrt(dot3(hc, hc));
         T d[3] = {w.gc[lane][0] - w.xpos[bc][0], w.gc[lane][1] - w.xpos[bc][1], w.gc[lane][2] - w.xpos[bc][2]};
         cand = !(dot3(d, d) > r * r);
+        if (cand) cand = !cached_axis_separates(w, m, LCR_KEY_CUBE + LCR_MAXMESH * c + lane);
       }
       const unsigned mask = __ballot_sync(FULLMASK, cand);
       if (cand) {
@@ -509,6 +557,7 @@ __device__ __noinline__ void collect_candidates(Ws<T, NC>& w, const DevModel<T>&
         T d[3] = {w.gc[g1][0] - w.gc[g2][0], w.gc[g1][1] - w.gc[g2][1], w.gc[g1][2] - w.gc[g2][2]};
         cand = !(dot3(d, d) > r * r);
         if (cand) cand = !obb_apart(w, m, g1, g2);
+        if (cand) cand = !cached_axis_separates(w, m, p);
       }
       const unsigned mask = __ballot_sync(FULLMASK, cand);
       if (cand) {
@@ -532,26 +581,9 @@ template <typename T, int NC> DI void key_shapes(const Ws<T, NC>& w, const DevMo
   }
 }
 
-// Upper bound of max over the hull of mesh g of x . dw (dw a world direction, slot/side = its cache entry) WITHOUT touching
-// the vertices: with c the world centre of the hull's bounding sphere, r its radius, S the exact support value about c
-// along the body-frame direction u0 recorded at the last exact evaluation, and u1 = R^T dw the direction now,
-//     max x . dw  =  c . dw + max y . u1  <=  c . dw + S + min(|u1 - u0| r, sum_k |u1 - u0|_k half_k)
-// (y = body-frame vertex - centre lies in the bounding sphere and in the bounding box, which share the centre).
-// Translation is followed exactly, only the relative rotation since the last exact evaluation costs slack.
-template <typename T, int NC>
-DI T hull_support_bound(const Ws<T, NC>& w, const DevModel<T>& m, int g, const T* dw, int slot, int side) {
-  const T* R = w.xmat[m.mesh_body[g]];
-  T u1[3], e2 = 0, eb = 0;
-  matT_vec(u1, R, dw);
-#pragma unroll
-  for (int k = 0; k < 3; k++) { const T e = u1[k] - w.sa_u[slot][side][k]; e2 += e * e; eb += fabs(e) * m.mesh_half[g][k]; }
-  const T es = sqrt(e2) * m.mesh_rbound[g];  // y lies in the bounding sphere and in the bounding box: use the smaller slack
-  return w.gc[g][0] * dw[0] + w.gc[g][1] * dw[1] + w.gc[g][2] * dw[2] + w.sa_S[slot][side] + (eb < es ? eb : es);
-}
-
 // One candidate.  res = {code, SA, dir[3], SB | depth, dir[3], pos[3]}; code 1: penetrating (depth, dir, pos);
-// 0: separated, new axis in dir; 2: still separated along the cached axis; 3: same, and the exact supports were
-// re-evaluated; -1: separated without a usable axis.  For codes 0 and 3, SA = res[1] and SB = res[5] are the support
+// 0: separated, new axis in dir; 3: still separated along the cached axis by the exact test, axis and supports
+// refreshed; -1: separated without a usable axis.  For codes 0 and 3, SA = res[1] and SB = res[5] are the support
 // values of the two shapes about their bounding-sphere centres along +dir / -dir (meshes only), which the cache keeps
 // for hull_support_bound.  `w` is only read (it may live in HBM, or belong to another warp of the CTA).
 template <typename T, int NC>
@@ -567,13 +599,7 @@ __device__ __noinline__ void narrowphase_job(const Ws<T, NC>& w, const DevModel<
   if (hit) {
     const int slot = __ffs(hit) - 1;
     d[0] = w.sa_dir[slot][0]; d[1] = w.sa_dir[slot][1]; d[2] = w.sa_dir[slot][2];
-    const T nd[3] = {-d[0], -d[1], -d[2]};
-    // cheap proof first: exact support of the box, conservative bounds for the hulls (no vertex is read)
-    T supA;
-    if (cube) { T pa[3]; shape_support(w, verts, A, d, pa); supA = dot3(pa, d); }
-    else supA = hull_support_bound(w, m, gA, d, slot, 0);
-    const T supB = hull_support_bound(w, m, gB, nd, slot, 1);
-    if (supA + supB < (T)-2e-6) { res[0] = 2; return; }
+    // (the vertex-free bound along this axis already failed in the broadphase, see cached_axis_separates)
     md_support(w, verts, A, B, d, p);  // exact test: two hull scans
     if (dot3(p.v, d) < (T)-1e-6) code = 3;
   }
