@@ -105,15 +105,18 @@ def test_facade_and_recorder_on_the_simulator():
     obs = v.reset(seed=0)
     assert obs.shape == (64, 18) and obs.is_cuda
     g = torch.Generator(device="cuda").manual_seed(0)
+    age = torch.zeros(64, dtype=torch.long, device="cuda")
     for t in range(13):
         a = torch.rand(64, env.action_dim, generator=g, device="cuda") * 2 - 1
         obs, rew, done, info = v.step(a)
+        age += 1
+        assert done[age >= 6].all()  # TimeLimit(6); success may end an episode earlier
+        assert torch.equal(info["TimeLimit.truncated"] | info["is_success"], done)
         step_obs = obs.clone()
         if done.any():
             step_obs[info["done_index"]] = info["terminal_observation"]
+            assert torch.all(obs[done][:, 0:6] == 0)  # freshly reset arms (reference reset: qpos[:6] = 0)
         rec.record(step_obs, a, done)
-        if t in (5, 11):
-            assert done.all() and info["TimeLimit.truncated"].sum() >= 1  # TimeLimit(6)
-            assert torch.all(obs[:, 0:6] == 0)  # freshly reset arms (reference reset: qpos[:6] = 0)
+        age[done] = 0
     assert rec.n_finished >= 128 and all(len(ep["action"]) <= 6 for ep in rec.episodes)
     v.close()
