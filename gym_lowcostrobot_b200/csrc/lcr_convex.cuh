@@ -91,13 +91,57 @@ __device__ __noinline__ void shape_support(const Ws<T, NC>& w, const T* __restri
   for (int k = 0; k < 3; k++) out[k] += w.xpos[sh.body][k];
 }
 
+// Supports of two hulls at once (same result as two shape_support calls): the vertex loads of both scans are issued
+// together, so a support pair costs the L2 round trips of the longer scan instead of the sum.
+template <typename T, int NC>
+__device__ __noinline__ void dual_mesh_support(const Ws<T, NC>& w, const T* __restrict__ verts, const Shape<T>& A, const Shape<T>& B, const T* da,
+                                               const T* db, T* outA, T* outB) {
+  const T* RA = w.xmat[A.body];
+  const T* RB = w.xmat[B.body];
+  T la[3], lb[3];
+  matT_vec(la, RA, da);
+  matT_vec(lb, RB, db);
+  T va = (T)-1e30, vb = (T)-1e30, ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0;
+  int ia = 0x7fffffff, ib = 0x7fffffff;
+  constexpr int U = kScanUnroll;  // U vertices of each hull per lane and round, all 2U loads in flight together
+  const int nmax = A.num > B.num ? A.num : B.num;
+  for (int base = LANE; base < nmax; base += 32 * U) {
+    T xa[U], ya[U], za[U], xb[U], yb[U], zb[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int i = base + 32 * u;
+      load_vert(verts, A.adr + (i < A.num ? i : A.num - 1), xa[u], ya[u], za[u]);
+      load_vert(verts, B.adr + (i < B.num ? i : B.num - 1), xb[u], yb[u], zb[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int i = base + 32 * u;
+      const T sa = xa[u] * la[0] + ya[u] * la[1] + za[u] * la[2];
+      const T sb = xb[u] * lb[0] + yb[u] * lb[1] + zb[u] * lb[2];
+      if (i < A.num && sa > va) { va = sa; ia = i; ax = xa[u]; ay = ya[u]; az = za[u]; }
+      if (i < B.num && sb > vb) { vb = sb; ib = i; bx = xb[u]; by = yb[u]; bz = zb[u]; }
+    }
+  }
+  warp_argmax(va, ia);
+  warp_argmax(vb, ib);
+  T pa[3] = {__shfl_sync(FULLMASK, ax, ia & 31), __shfl_sync(FULLMASK, ay, ia & 31), __shfl_sync(FULLMASK, az, ia & 31)};
+  T pb[3] = {__shfl_sync(FULLMASK, bx, ib & 31), __shfl_sync(FULLMASK, by, ib & 31), __shfl_sync(FULLMASK, bz, ib & 31)};
+  mat_vec(outA, RA, pa);
+  mat_vec(outB, RB, pb);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { outA[k] += w.xpos[A.body][k]; outB[k] += w.xpos[B.body][k]; }
+}
+
 template <typename T, int NC>
 DI void md_support(const Ws<T, NC>& w, const T* __restrict__ verts, const Shape<T>& A, const Shape<T>& B, const T* dir, SPoint<T>& p) {
   // (both directions are private copies: `dir` may point into a caller array that the optimiser also uses as an output)
   const T dx = dir[0], dy = dir[1], dz = dir[2];
   T da[3] = {dx, dy, dz}, db[3] = {-dx, -dy, -dz};
-  shape_support(w, verts, A, da, p.v1);
-  shape_support(w, verts, B, db, p.v2);
+  if (A.kind == 1 && B.kind == 1) dual_mesh_support(w, verts, A, B, da, db, p.v1, p.v2);
+  else {
+    shape_support(w, verts, A, da, p.v1);
+    shape_support(w, verts, B, db, p.v2);
+  }
 #pragma unroll
   for (int k = 0; k < 3; k++) p.v[k] = p.v1[k] - p.v2[k];
 }
@@ -547,16 +591,31 @@ __device__ __noinline__ void collect_candidates(Ws<T, NC>& w, const DevModel<T>&
       }
       n += __popc(mask);
     }
-  if (cmask & LCR_COLLIDE_MESH_MESH)
+  if (cmask & LCR_COLLIDE_MESH_MESH) {
+    // pass 1: bounding spheres over all pairs, survivors compacted (in pair order) into scratch that is dead here
+    // (the solver's e_jv row / the RNE temporaries); pass 2: oriented boxes and the cached-axis bound on the short list
+    short* list = reinterpret_cast<short*>(w.e_jv);
+    int n1 = 0;
     for (int base = 0; base < m.npair; base += 32) {
       const int p = base + lane;
-      bool cand = false;
+      bool pass = false;
       if (p < m.npair) {
         const int g1 = m.pair_g1[p], g2 = m.pair_g2[p];
         const T r = m.mesh_rbound[g1] + m.mesh_rbound[g2];
         T d[3] = {w.gc[g1][0] - w.gc[g2][0], w.gc[g1][1] - w.gc[g2][1], w.gc[g1][2] - w.gc[g2][2]};
-        cand = !(dot3(d, d) > r * r);
-        if (cand) cand = !obb_apart(w, m, g1, g2);
+        pass = !(dot3(d, d) > r * r);
+      }
+      const unsigned mask = __ballot_sync(FULLMASK, pass);
+      if (pass) list[n1 + __popc(mask & ((1u << lane) - 1))] = (short)p;
+      n1 += __popc(mask);
+    }
+    __syncwarp();
+    for (int base = 0; base < n1; base += 32) {
+      bool cand = false;
+      int p = 0;
+      if (base + lane < n1) {
+        p = list[base + lane];
+        cand = !obb_apart(w, m, m.pair_g1[p], m.pair_g2[p]);
         if (cand) cand = !cached_axis_separates(w, m, p);
       }
       const unsigned mask = __ballot_sync(FULLMASK, cand);
@@ -566,6 +625,7 @@ __device__ __noinline__ void collect_candidates(Ws<T, NC>& w, const DevModel<T>&
       }
       n += __popc(mask);
     }
+  }
   if (lane == 0) w.ncand = n;  // n > LCR_MAXCAND: the tail is recomputed inline by consume_candidates (rare)
   __syncwarp();
 }
