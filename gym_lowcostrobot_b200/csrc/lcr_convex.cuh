@@ -132,12 +132,14 @@ __device__ __noinline__ void dual_mesh_support(const Ws<T, NC>& w, const T* __re
   for (int k = 0; k < 3; k++) { outA[k] += w.xpos[A.body][k]; outB[k] += w.xpos[B.body][k]; }
 }
 
-template <typename T, int NC>
+// DUAL: evaluate two hulls with dual_mesh_support (shorter dependent chain: the lockstep / fused kernels, where a few warps
+// scan at a time); the phased job kernel, where every warp of the GPU scans at once, is faster with the plain scans
+template <typename T, int NC, bool DUAL>
 DI void md_support(const Ws<T, NC>& w, const T* __restrict__ verts, const Shape<T>& A, const Shape<T>& B, const T* dir, SPoint<T>& p) {
   // (both directions are private copies: `dir` may point into a caller array that the optimiser also uses as an output)
   const T dx = dir[0], dy = dir[1], dz = dir[2];
   T da[3] = {dx, dy, dz}, db[3] = {-dx, -dy, -dz};
-  if (A.kind == 1 && B.kind == 1) dual_mesh_support(w, verts, A, B, da, db, p.v1, p.v2);
+  if (DUAL && A.kind == 1 && B.kind == 1) dual_mesh_support(w, verts, A, B, da, db, p.v1, p.v2);
   else {
     shape_support(w, verts, A, da, p.v1);
     shape_support(w, verts, B, db, p.v2);
@@ -216,7 +218,7 @@ template <typename T> DI void find_pos(const SPoint<T>* P, T* pos) {
 
 // returns 1 and fills depth / pdir / pos if the shapes penetrate; 0 if a separating direction was found (returned
 // in pdir: max over A-B of x.pdir <= 0); -1 if separated without a usable direction (warp-uniform)
-template <typename T, int NC>
+template <typename T, int NC, bool DUAL>
 __device__ __noinline__ int mpr_penetration(const Ws<T, NC>& w, const T* __restrict__ verts, const Shape<T>& A, const Shape<T>& B, T& depth,
                                              T* pdir, T* pos) {
   const T tol = (T)1e-6;
@@ -228,7 +230,7 @@ __device__ __noinline__ int mpr_penetration(const Ws<T, NC>& w, const T* __restr
 #pragma unroll
   for (int k = 0; k < 3; k++) dir[k] = -P[0].v[k];
   normalize3(dir);
-  md_support(w, verts, A, B, dir, P[1]);
+  md_support<T, NC, DUAL>(w, verts, A, B, dir, P[1]);
   d = dot3(P[1].v, dir);
   if (is_zero(d) || d < 0) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; return 0; }
   cross3(dir, P[0].v, P[1].v);
@@ -242,7 +244,7 @@ __device__ __noinline__ int mpr_penetration(const Ws<T, NC>& w, const T* __restr
     return 1;
   }
   normalize3(dir);
-  md_support(w, verts, A, B, dir, P[2]);
+  md_support<T, NC, DUAL>(w, verts, A, B, dir, P[2]);
   d = dot3(P[2].v, dir);
   if (is_zero(d) || d < 0) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; return 0; }
 #pragma unroll
@@ -256,7 +258,7 @@ __device__ __noinline__ int mpr_penetration(const Ws<T, NC>& w, const T* __restr
 #pragma unroll 1
   for (int guard = 0;; guard++) {
     if (guard > 100) return -1;
-    md_support(w, verts, A, B, dir, P[3]);
+    md_support<T, NC, DUAL>(w, verts, A, B, dir, P[3]);
     d = dot3(P[3].v, dir);
     if (is_zero(d) || d < 0) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; return 0; }
     bool cont = false;
@@ -278,7 +280,7 @@ __device__ __noinline__ int mpr_penetration(const Ws<T, NC>& w, const T* __restr
     portal_dir(P, dir);
     d = dot3(dir, P[1].v);
     if (is_zero(d) || d > 0) break;
-    md_support(w, verts, A, B, dir, v4);
+    md_support<T, NC, DUAL>(w, verts, A, B, dir, v4);
     d = dot3(v4.v, dir);
     if (!(is_zero(d) || d > 0)) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; return 0; }
     if (reach_tolerance(P, v4, dir, tol)) return -1;
@@ -287,7 +289,7 @@ __device__ __noinline__ int mpr_penetration(const Ws<T, NC>& w, const T* __restr
 #pragma unroll 1
   for (int it = 0;; it++) {
     portal_dir(P, dir);
-    md_support(w, verts, A, B, dir, v4);
+    md_support<T, NC, DUAL>(w, verts, A, B, dir, v4);
     if (reach_tolerance(P, v4, dir, tol) || it > 50) {
       T wit[3];
       depth = sqrt(origin_tri_dist2(P[1].v, P[2].v, P[3].v, wit));
@@ -646,7 +648,7 @@ template <typename T, int NC> DI void key_shapes(const Ws<T, NC>& w, const DevMo
 // refreshed; -1: separated without a usable axis.  For codes 0 and 3, SA = res[1] and SB = res[5] are the support
 // values of the two shapes about their bounding-sphere centres along +dir / -dir (meshes only), which the cache keeps
 // for hull_support_bound.  `w` is only read (it may live in HBM, or belong to another warp of the CTA).
-template <typename T, int NC>
+template <typename T, int NC, bool DUAL>
 __device__ __noinline__ void narrowphase_job(const Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, int key, T* res) {
   Shape<T> A, B;
   key_shapes(w, m, key, A, B);
@@ -660,19 +662,19 @@ __device__ __noinline__ void narrowphase_job(const Ws<T, NC>& w, const DevModel<
     const int slot = __ffs(hit) - 1;
     d[0] = w.sa_dir[slot][0]; d[1] = w.sa_dir[slot][1]; d[2] = w.sa_dir[slot][2];
     // (the vertex-free bound along this axis already failed in the broadphase, see cached_axis_separates)
-    md_support(w, verts, A, B, d, p);  // exact test: two hull scans
+    md_support<T, NC, DUAL>(w, verts, A, B, d, p);  // exact test: two hull scans
     if (dot3(p.v, d) < (T)-1e-6) code = 3;
   }
   if (code == -2) {
     T depth = 0, pos[3] = {0, 0, 0};
-    code = mpr_penetration(w, verts, A, B, depth, d, pos);
+    code = mpr_penetration<T, NC, DUAL>(w, verts, A, B, depth, d, pos);
     if (code != 0) {
       res[0] = (T)code; res[1] = depth;
       res[2] = d[0]; res[3] = d[1]; res[4] = d[2];
       res[5] = pos[0]; res[6] = pos[1]; res[7] = pos[2];
       return;
     }
-    md_support(w, verts, A, B, d, p);  // supports along the new axis, kept with it
+    md_support<T, NC, DUAL>(w, verts, A, B, d, p);  // supports along the new axis, kept with it
   }
   // code 0 or 3: MPR stops at the first direction that separates, usually a grazing one.  The parts of this arm are
   // box-like and face each other across millimetre gaps, so the widest gap is (nearly) along a face normal of one of
@@ -707,7 +709,7 @@ __device__ __noinline__ void narrowphase_job(const Ws<T, NC>& w, const DevModel<
       if (est > best) { best = est; dn[0] = ax[0]; dn[1] = ax[1]; dn[2] = ax[2]; }
     }
     SPoint<T> q;
-    md_support(w, verts, A, B, dn, q);
+    md_support<T, NC, DUAL>(w, verts, A, B, dn, q);
     if (-dot3(q.v, dn) > -dot3(p.v, d)) { p = q; d[0] = dn[0]; d[1] = dn[1]; d[2] = dn[2]; }
   }
   res[0] = (T)code;
@@ -725,7 +727,7 @@ __device__ __noinline__ void run_jobs_inline(Ws<T, NC>& w, const DevModel<T>& m,
   T (*res)[8] = cand_res(w);
   for (int k = 0; k < n; k++) {
     T r[8];
-    narrowphase_job(w, m, verts, w.cand_key[k], r);
+    narrowphase_job<T, NC, true>(w, m, verts, w.cand_key[k], r);
     __syncwarp();
     if (LANE < 8) res[k][LANE] = r[LANE];
     __syncwarp();

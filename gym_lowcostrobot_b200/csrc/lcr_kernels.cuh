@@ -1377,7 +1377,7 @@ DI void cta_jobs(Ws<T, NC>* wsa, int W, const DevModel<T>& m, const T* __restric
     }
     Ws<T, NC>& we = wsa[e];
     T r[8];
-    narrowphase_job(we, m, verts, we.cand_key[j], r);
+    narrowphase_job<T, NC, true>(we, m, verts, we.cand_key[j], r);
     __syncwarp();
     if (LANE < 8) cand_res(we)[j][LANE] = r[LANE];
   }
@@ -1577,7 +1577,7 @@ __global__ void __launch_bounds__(32, 16) k_ph_job(const DevModel<T>* __restrict
   T (*res)[8] = cand_res(w);
   for (int k = slot; k < n; k += LCR_NSLOT) {
     T r[8];
-    narrowphase_job(w, *dm, verts, w.cand_key[k], r);
+    narrowphase_job<T, NC, false>(w, *dm, verts, w.cand_key[k], r);
     if (LANE < 8) res[k][LANE] = r[LANE];
   }
 }
