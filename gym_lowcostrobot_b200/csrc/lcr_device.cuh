@@ -81,27 +81,31 @@ struct Ws {  // per-warp shared-memory workspace
   int diag[LCR_NDIAG];
   unsigned long long rng[4];
   // kinematics
-  T xpos[NB][3], xquat[NB][4], xmat[NB][9], xipos[LCR_NABODY][3], axis[LCR_NARM][3];
+  alignas(16) T xpos[NB][3];  // (16-byte aligned starts: the phased kernels stage the workspace by region, see load_ws_range)
+  T xquat[NB][4], xmat[NB][9], xipos[LCR_NABODY][3], axis[LCR_NARM][3];
   T Iw[LCR_NABODY][6];
   T gc[LCR_MAXMESH][3];  // world centres of the mesh bounding spheres / boxes
-  T M[LCR_NARM][LCR_NARM];
+  alignas(16) T M[LCR_NARM][LCR_NARM];
   T bias[NVV], smooth[NVV], qacc_smooth[NVV], qacc[NVV], Ma[NVV], grad[NVV], search[NVV], Mv[NVV];
-  T H[NVV][NVV + 1];
+  alignas(16) T H[NVV][NVV + 1];
   // contacts
-  T c_pos[LCR_MAXCON][3], c_frame[LCR_MAXCON][9], c_dist[LCR_MAXCON], c_mu[LCR_MAXCON], c_c1[LCR_MAXCON], c_c2[LCR_MAXCON];
+  alignas(16) T c_pos[LCR_MAXCON][3];
+  T c_frame[LCR_MAXCON][9], c_dist[LCR_MAXCON], c_mu[LCR_MAXCON], c_c1[LCR_MAXCON], c_c2[LCR_MAXCON];
   short c_par[LCR_MAXCON];  // index into the contiguous CPar tables of DevModel, see DevModel::par()
   short c_efc[LCR_MAXCON];
   signed char c_b1[LCR_MAXCON], c_b2[LCR_MAXCON];
   // constraint rows
-  T e_pos[LCR_MAXEFC], e_D[LCR_MAXEFC], e_aref[LCR_MAXEFC], e_jar[LCR_MAXEFC];
+  alignas(16) T e_pos[LCR_MAXEFC];
+  T e_D[LCR_MAXEFC], e_aref[LCR_MAXEFC], e_jar[LCR_MAXEFC];
   union {  // solver rows / RNE temporaries of inertia_and_bias (dead before the constraint rows are built)
     struct { T e_jv[LCR_MAXEFC], e_force[LCR_MAXEFC]; };
     struct { T rw[LCR_NABODY][3], ral[LCR_NABODY][3], ra[LCR_NABODY][3], F[LCR_NABODY][3], Nn[LCR_NABODY][3]; };
   };
   T e_w[LCR_MAXEFC], e_g[LCR_MAXEFC], e_p[LCR_MAXEFC];  // Hessian pieces, see contact_eval
-  short e_unit[LCR_MAXEFC];  // >= 0: contact index; < 0: limit row of joint -1-e_unit
+  alignas(16) short e_unit[LCR_MAXEFC];  // >= 0: contact index; < 0: limit row of joint -1-e_unit
   signed char e_r[LCR_MAXEFC];  // row index within its contact
-  int ncon, nefc, nlim;
+  alignas(16) int ncon;
+  int nefc, nlim;
   // separating-axis cache of the convex narrowphase (see lcr_convex.cuh): one contiguous 16-byte aligned block
   // that travels with the env record (DevState::sa)
   alignas(16) T sa_dir[LCR_NSA][3];
@@ -112,7 +116,7 @@ struct Ws {  // per-warp shared-memory workspace
   int sa_pad[3];
   static constexpr int SA_WORDS = LCR_NSA * 11;  // dir, S, u
   static constexpr int SA_BYTES = SA_WORDS * (int)sizeof(T) + LCR_NSA * 2 + 16;
-  short cand_key[LCR_MAXCAND];  // convex-pair candidates of this substep (results alias e_w / e_g / e_p)
+  alignas(16) short cand_key[LCR_MAXCAND];  // convex-pair candidates of this substep (results alias e_w / e_g / e_p)
   int ncand;
   int skip;          // phased execution: this env was auto-reset by the current step, substep kernels pass
   int redo_forward;  // phased execution: state was reset after a bad qacc, re-run mj_forward before integrating

@@ -1507,11 +1507,26 @@ DI void load_ws(Ws<T, NC>& w, const Ws<T, NC>* g, int env, bool with_J) {
   constexpr int HEAD = (int)(offsetof(WsT, J) / 16), JROW = WsT::JS * (int)sizeof(T);
   const uint4* src = reinterpret_cast<const uint4*>(g + env);
   uint4* dst = reinterpret_cast<uint4*>(&w);
-  for (int i = LANE; i < HEAD; i += 32) dst[i] = src[i];
+  // the parked workspace comes from L2 / HBM: request it in batches of 8 x 128 bit per lane before the first store, so the
+  // copy costs a few round trips instead of one per 512 bytes
+  constexpr int B = 8;
+  for (int base = LANE; base < HEAD; base += 32 * B) {
+    uint4 t[B];
+#pragma unroll
+    for (int k = 0; k < B; k++) { const int i = base + 32 * k; if (i < HEAD) t[k] = src[i]; }
+#pragma unroll
+    for (int k = 0; k < B; k++) { const int i = base + 32 * k; if (i < HEAD) dst[i] = t[k]; }
+  }
   __syncwarp();
   if (with_J) {
     const int n4 = (w.nefc * JROW + 15) / 16;
-    for (int i = LANE; i < n4; i += 32) dst[HEAD + i] = src[HEAD + i];
+    for (int base = LANE; base < n4; base += 32 * B) {
+      uint4 t[B];
+#pragma unroll
+      for (int k = 0; k < B; k++) { const int i = base + 32 * k; if (i < n4) t[k] = src[HEAD + i]; }
+#pragma unroll
+      for (int k = 0; k < B; k++) { const int i = base + 32 * k; if (i < n4) dst[HEAD + i] = t[k]; }
+    }
     __syncwarp();
   }
 }
@@ -1527,6 +1542,43 @@ DI void store_ws(const Ws<T, NC>& w, Ws<T, NC>* g, int env, bool with_J) {
     const int n4 = (w.nefc * JROW + 15) / 16;
     for (int i = LANE; i < n4; i += 32) dst[HEAD + i] = src[HEAD + i];
   }
+}
+
+// Staging by region.  The members of Ws are declared in the order state | kinematics | dynamics vectors | Hessian |
+// contacts | rows | counts + cache | candidates | J with 16-byte aligned region starts; a phase kernel only moves the
+// regions it reads / the ones it changed (the parked workspaces do not fit L2 for large batches, so every byte is HBM
+// traffic and every dependent 512 bytes a round trip).
+#define LCR_OFF(member) ((int)offsetof(WsT, member))
+template <typename T, int NC>
+DI void load_ws_range(Ws<T, NC>& w, const Ws<T, NC>* g, int env, int off0, int off1) {
+  const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(g + env) + off0);
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(&w) + off0);
+  const int n4 = (off1 - off0) / 16;
+  constexpr int B = 8;
+  for (int base = LANE; base < n4; base += 32 * B) {
+    uint4 t[B];
+#pragma unroll
+    for (int k = 0; k < B; k++) { const int i = base + 32 * k; if (i < n4) t[k] = src[i]; }
+#pragma unroll
+    for (int k = 0; k < B; k++) { const int i = base + 32 * k; if (i < n4) dst[i] = t[k]; }
+  }
+}
+template <typename T, int NC>
+DI void store_ws_range(const Ws<T, NC>& w, Ws<T, NC>* g, int env, int off0, int off1) {
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(g + env) + off0);
+  const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(&w) + off0);
+  const int n4 = (off1 - off0) / 16;
+  for (int i = LANE; i < n4; i += 32) dst[i] = src[i];
+}
+template <typename T, int NC>
+DI void load_ws_J(Ws<T, NC>& w, const Ws<T, NC>* g, int env) {  // the live rows of J (needs w.nefc)
+  typedef Ws<T, NC> WsT;
+  load_ws_range(w, g, env, LCR_OFF(J), LCR_OFF(J) + ((w.nefc * WsT::JS * (int)sizeof(T) + 15) / 16) * 16);
+}
+template <typename T, int NC>
+DI void store_ws_J(const Ws<T, NC>& w, Ws<T, NC>* g, int env) {
+  typedef Ws<T, NC> WsT;
+  store_ws_range(w, g, env, LCR_OFF(J), LCR_OFF(J) + ((w.nefc * WsT::JS * (int)sizeof(T) + 15) / 16) * 16);
 }
 
 template <typename T, int NC>
@@ -1549,13 +1601,19 @@ __global__ void __launch_bounds__(32, 16) k_ph_begin(const DevModel<T>* __restri
 // [integrate the previous substep] -> checks -> kinematics -> inertia / bias -> smooth forces
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int first, int env0) {
+  typedef Ws<T, NC> WsT;
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = env0 + blockIdx.x;
   if (gws[env].skip) return;
-  load_ws(w, gws, env, false);
+  // reads: state, dynamics vectors (M, qacc for the integration of the previous substep), counts + cache, candidate block
+  load_ws_range(w, gws, env, 0, LCR_OFF(xpos));
+  load_ws_range(w, gws, env, LCR_OFF(M), LCR_OFF(H));
+  load_ws_range(w, gws, env, LCR_OFF(ncon), LCR_OFF(J));
+  __syncwarp();
   const DevModel<T>& m = *dm;
+  bool redone = false;
   if (!first) {
-    if (w.redo_forward) { forward(w, m, verts); if (LANE == 0) w.redo_forward = 0; __syncwarp(); }
+    if (w.redo_forward) { forward(w, m, verts); if (LANE == 0) w.redo_forward = 0; __syncwarp(); redone = true; }
     integrate(w, m);
   }
   check_state(w, m);
@@ -1563,7 +1621,10 @@ __global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict
   inertia_and_bias(w, m);
   smooth_forces(w, m);
   collect_candidates(w, m);
-  store_ws(w, gws, env, false);
+  __syncwarp();
+  // writes: state, kinematics, dynamics vectors, candidate block (+ the cache if mj_forward was re-run)
+  store_ws_range(w, gws, env, 0, LCR_OFF(H));
+  store_ws_range(w, gws, env, redone ? LCR_OFF(ncon) : LCR_OFF(cand_key), LCR_OFF(J));
 }
 // narrowphase jobs: one warp per (env, slot); the workspace stays in HBM/L2 and is only read, results go to the
 // candidate result rows.  No shared memory, so the hull vertices stay L1 resident.
@@ -1584,23 +1645,46 @@ __global__ void __launch_bounds__(32, 16) k_ph_job(const DevModel<T>* __restrict
 
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0) {
+  typedef Ws<T, NC> WsT;
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = env0 + blockIdx.x;
   if (gws[env].skip) return;
-  load_ws(w, gws, env, false);
+  // reads: state, kinematics, the job results (they alias e_w / e_g / e_p), counts + cache, candidate block
+  load_ws_range(w, gws, env, 0, LCR_OFF(M));
+  load_ws_range(w, gws, env, LCR_OFF(e_w), LCR_OFF(e_unit));
+  load_ws_range(w, gws, env, LCR_OFF(ncon), LCR_OFF(J));
+  __syncwarp();
   make_constraints(w, *dm, verts, true);
-  store_ws(w, gws, env, true);
+  __syncwarp();
+  // writes: diag (state block), contacts, row parameters, row -> contact maps, counts + cache, J
+  store_ws_range(w, gws, env, 0, LCR_OFF(xpos));
+  store_ws_range(w, gws, env, LCR_OFF(c_pos), LCR_OFF(e_jar));
+  store_ws_range(w, gws, env, LCR_OFF(e_unit), LCR_OFF(cand_key));
+  store_ws_J(w, gws, env);
 }
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_sol(const DevModel<T>* __restrict__ dm, Ws<T, NC>* __restrict__ gws, int env0) {
+  typedef Ws<T, NC> WsT;
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = env0 + blockIdx.x;
   if (gws[env].skip) return;
-  load_ws(w, gws, env, true);
+  // reads: state (warm start), dynamics vectors, contact scalars (not positions / frames), row parameters, counts, flags, J
+  load_ws_range(w, gws, env, 0, LCR_OFF(xpos));
+  load_ws_range(w, gws, env, LCR_OFF(M), LCR_OFF(H));
+  load_ws_range(w, gws, env, LCR_OFF(c_dist), LCR_OFF(e_jar));
+  load_ws_range(w, gws, env, LCR_OFF(ncon), LCR_OFF(sa_dir));
+  load_ws_range(w, gws, env, LCR_OFF(cand_key), LCR_OFF(J));
+  __syncwarp();
+  load_ws_J(w, gws, env);
+  __syncwarp();
   const DevModel<T>& m = *dm;
   solve_constraints<T, NC, false>(w, m, solver_tol<T>(m));
   if (check_acc(w, m)) { if (LANE == 0) w.redo_forward = 1; }
-  store_ws(w, gws, env, false);
+  __syncwarp();
+  // writes: state (warm start, diag; qpos / qvel if the env was reset), dynamics vectors (qacc), flags
+  store_ws_range(w, gws, env, 0, LCR_OFF(xpos));
+  store_ws_range(w, gws, env, LCR_OFF(M), LCR_OFF(H));
+  store_ws_range(w, gws, env, LCR_OFF(cand_key), LCR_OFF(J));
 }
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_end(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
@@ -1609,7 +1693,11 @@ __global__ void __launch_bounds__(32, 16) k_ph_end(const DevModel<T>* __restrict
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = env0 + blockIdx.x;
   if (gws[env].skip) return;
-  load_ws(w, gws, env, false);
+  typedef Ws<T, NC> WsT;
+  load_ws_range(w, gws, env, 0, LCR_OFF(xpos));          // state
+  load_ws_range(w, gws, env, LCR_OFF(M), LCR_OFF(H));    // M, qacc
+  load_ws_range(w, gws, env, LCR_OFF(ncon), LCR_OFF(J)); // counts + cache (stored with the state), flags
+  __syncwarp();
   const DevModel<T>& m = *dm;
   const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
   if (w.redo_forward) forward(w, m, verts);
