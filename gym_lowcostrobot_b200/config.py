@@ -14,9 +14,10 @@ ENV_IDS = {
     "LiftCube-v0": "lift",
     "PickPlaceCube-v0": "pick_place",
     "StackTwoCubes-v0": "stack",
+    "PushCubeLoop-v0": "push_loop",  # push_cube_loop_env.py, registered at gym_lowcostrobot/__init__.py:39-43
 }
 # reference defaults of block_gripper per task
-BLOCK_GRIPPER_DEFAULT = {"reach": True, "push": True, "lift": False, "pick_place": False, "stack": False}
+BLOCK_GRIPPER_DEFAULT = {"reach": True, "push": True, "lift": False, "pick_place": False, "stack": False, "push_loop": True}
 MAX_EPISODE_STEPS = 50
 
 
@@ -56,4 +57,4 @@ def action_dim(cfg):
 
 
 def obs_dim(task):
-    return 15 if task in ("reach", "lift") else 18
+    return 15 if task in ("reach", "lift", "push_loop") else 18

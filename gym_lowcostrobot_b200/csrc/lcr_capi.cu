@@ -91,11 +91,10 @@ void build_model(const LcrModel& m, const LcrEnvCfg& c, DevModel<T>& d) {
     d.body_mass[b] = (T)m.body_mass[b];
     d.body_invweight0[b][0] = (T)m.body_invweight0[b][0]; d.body_invweight0[b][1] = (T)m.body_invweight0[b][1];
   }
-  static const double qpos0[5][2][3] = {{{0, 0.2, 0.01}}, {{0, 0.2, 0.01}}, {{0, 0.2, 0.01}}, {{0, 0.2, 0.01}}, {{0.1, 0.1, 0.01}, {-0.1, -0.1, 0.01}}};
   for (int cb = 0; cb < m.ncube; cb++) {
     d.body_invweight0[LCR_NABODY + cb][0] = (T)m.cube_invweight0[cb][0]; d.body_invweight0[LCR_NABODY + cb][1] = (T)m.cube_invweight0[cb][1];
     d.cube_mass[cb] = (T)m.cube_mass[cb]; d.cube_inertia[cb] = (T)m.cube_inertia[cb][0];
-    for (int k = 0; k < 3; k++) { d.cube_size[cb][k] = (T)m.cube_size[cb][k]; d.cube_qpos0[cb][k] = (T)qpos0[m.task][cb][k]; }
+    for (int k = 0; k < 3; k++) { d.cube_size[cb][k] = (T)m.cube_size[cb][k]; d.cube_qpos0[cb][k] = (T)m.cube_pos0[cb][k]; }
   }
   for (int j = 0; j < LCR_NARM; j++) {
     for (int k = 0; k < 3; k++) d.jnt_axis[j][k] = (T)m.jnt_axis[j][k];
@@ -123,6 +122,24 @@ void build_model(const LcrModel& m, const LcrEnvCfg& c, DevModel<T>& d) {
   if (m.ncube == 2) {
     Mixed x = mix(m, gfloor + 1, gfloor + 2);
     fill_par(d.par_cube_cube, x.dim, x.fr, x.solref, x.solimp, m.timestep);
+  }
+  // static wall boxes (PushCubeLoop): box index ncube + w, geom gfloor + 1 + ncube + w
+  for (int wi = 0; wi < m.nwall; wi++) {
+    const int c = m.ncube + wi, gw = gfloor + 1 + c;
+    for (int k = 0; k < 3; k++) { d.cube_size[c][k] = (T)m.wall_size[wi][k]; d.wall_pos[wi][k] = (T)m.wall_pos[wi][k]; }
+    for (int cb = 0; cb < m.ncube; cb++) {
+      Mixed x = mix(m, gw, gfloor + 1 + cb);
+      fill_par(d.par_wall_cube[wi][cb], x.dim, x.fr, x.solref, x.solimp, m.timestep);
+    }
+    for (int g = 0; g < m.nmesh; g++) {
+      Mixed y = mix(m, gw, g);
+      fill_par(d.par_cube_mesh[c][g], y.dim, y.fr, y.solref, y.solimp, m.timestep);
+    }
+  }
+  for (int k = 0; k < 3; k++) {  // push_cube_loop_env.py:127-135, same float64 operations as numpy
+    d.goal_center[0][k] = m.goal_center[0][k]; d.goal_center[1][k] = m.goal_center[1][k];
+    d.goal_high[k] = m.goal_size[k] / 2;
+    if (k < 2) d.goal_high[k] -= 0.008;
   }
   for (int g = 0; g < m.nmesh; g++) {
     Mixed x = mix(m, gfloor, g);
@@ -162,9 +179,10 @@ struct Impl {
     CUDA_OK(cudaMalloc(&s.st, sizeof(T) * (size_t)s.nfp * n));
     CUDA_OK(cudaMalloc(&s.ib, sizeof(int32_t) * LCR_IB_WORDS * (size_t)n));
     CUDA_OK(cudaMalloc(&s.sa, (size_t)Ws<T, 1>::SA_BYTES * n));
-    if (c.exec_mode == 1) CUDA_OK(cudaMalloc(&gws, lcr::Launch<T>::smem_bytes(m.ncube) * (size_t)n));
-    lcr::Launch<T>::prepare(m.ncube);
-    lcr::Launch<T>::init_state(m.ncube, dm, s, 0);
+    const int nc = scene_class(m.task, m.ncube);
+    if (c.exec_mode == 1) CUDA_OK(cudaMalloc(&gws, lcr::Launch<T>::smem_bytes(nc) * (size_t)n));
+    lcr::Launch<T>::prepare(nc);
+    lcr::Launch<T>::init_state(nc, dm, s, 0);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaDeviceSynchronize());
     return 0;
@@ -199,21 +217,25 @@ struct LcrSim {
 
 extern "C" {
 
-int lcr_obs_dim(int task) { return (task == LCR_TASK_REACH || task == LCR_TASK_LIFT) ? 15 : 18; }
+int lcr_obs_dim(int task) { return (task == LCR_TASK_REACH || task == LCR_TASK_LIFT || task == LCR_TASK_PUSH_LOOP) ? 15 : 18; }
 int lcr_action_dim(const LcrEnvCfg* cfg) { return (cfg->action_mode ? 3 : 5) + (cfg->block_gripper ? 0 : 1); }
 
 int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg* cfg, int n_envs, int device, int precision, LcrSim** out) {
   if (!model || !cfg || !out || (!hull_verts && model->nvert > 0)) return fail("lcr_create: null argument");
   if (n_envs <= 0) return fail("lcr_create: n_envs must be positive");
-  if (model->ncube < 1 || model->ncube > LCR_MAXCUBE || model->nmesh > LCR_MAXMESH || model->npair > LCR_MAXPAIR)
+  if (model->ncube < 1 || model->ncube > LCR_MAXCUBE || model->nmesh > LCR_MAXMESH || model->npair > LCR_MAXPAIR ||
+      model->nwall < 0 || model->nwall > LCR_MAXWALL || model->nmesh + 1 + model->ncube + model->nwall > LCR_MAXGEOM)
     return fail("lcr_create: model exceeds compiled caps");
+  if (model->task < LCR_TASK_REACH || model->task > LCR_TASK_PUSH_LOOP) return fail("lcr_create: unknown task");
+  if ((model->task == LCR_TASK_PUSH_LOOP) != (model->nwall > 0) || (model->task == LCR_TASK_PUSH_LOOP && (model->ncube != 1 || model->nwall != LCR_MAXWALL)))
+    return fail("lcr_create: static wall boxes are the four rails of the PushCubeLoop scene (one cube)");
   if (precision != LCR_F32 && precision != LCR_F64) return fail("lcr_create: precision must be LCR_F32 or LCR_F64");
   int ndev = 0;
   CUDA_OK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail("lcr_create: no such CUDA device");
   CUDA_OK(cudaSetDevice(device));
   LcrSim* s = new LcrSim();
-  s->precision = precision; s->device = device; s->n = n_envs; s->ncube = model->ncube; s->task = model->task; s->launches = 0;
+  s->precision = precision; s->device = device; s->n = n_envs; s->ncube = scene_class(model->task, model->ncube); s->task = model->task; s->launches = 0;
   s->model = *model; s->cfg = *cfg;
   int rc = precision == LCR_F32 ? s->f.create(*model, hull_verts, *cfg, n_envs) : s->d.create(*model, hull_verts, *cfg, n_envs);
   if (rc) { delete s; return rc; }

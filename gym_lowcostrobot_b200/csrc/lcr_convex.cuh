@@ -358,15 +358,16 @@ DI bool obb_apart(const Ws<T, NC>& w, const DevModel<T>& m, int g1, int g2) {
   return false;
 }
 
-// ---------------------------------------------------------------- box-box (cube 0 vs cube 1): SAT + clipping
+// ---------------------------------------------------------------- box-box (boxes cA, cB: cube or static wall): SAT + clipping
 template <typename T, int NC>
-__device__ __noinline__ void collide_cube_cube(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc) {
-  const int bA = LCR_NABODY, bB = LCR_NABODY + 1;
+__device__ __noinline__ void collide_box_box(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, int cA, int cB, const CPar<T>* par) {
+  const int bA = LCR_NABODY + cA, bB = LCR_NABODY + cB;
   const T* pA = w.xpos[bA];
   const T* pB = w.xpos[bB];
   const T* RA = w.xmat[bA];
   const T* RB = w.xmat[bB];
-  T hA[3] = {m.cube_size[0][0], m.cube_size[0][1], m.cube_size[0][2]}, hB[3] = {m.cube_size[1][0], m.cube_size[1][1], m.cube_size[1][2]};
+  T hA[3] = {m.cube_size[cA][0], m.cube_size[cA][1], m.cube_size[cA][2]}, hB[3] = {m.cube_size[cB][0], m.cube_size[cB][1], m.cube_size[cB][2]};
+  const int idA = box_body<NC>(cA), idB = box_body<NC>(cB);  // body ids of the contact records (-1: world)
   T t[3] = {pB[0] - pA[0], pB[1] - pA[1], pB[2] - pA[2]};
   {
     const T r = sqrt(dot3(hA, hA)) + sqrt(dot3(hB, hB));
@@ -404,7 +405,6 @@ __device__ __noinline__ void collide_cube_cube(Ws<T, NC>& w, const DevModel<T>& 
     }
   }
   if (code < 0) return;
-  const CPar<T>* par = &m.par_cube_cube;
   if (code >= 6) {
     const int ia = (code - 6) / 3, ib = (code - 6) % 3;
     T ea[3] = {pA[0], pA[1], pA[2]}, eb[3] = {pB[0], pB[1], pB[2]};
@@ -421,7 +421,7 @@ __device__ __noinline__ void collide_cube_cube(Ws<T, NC>& w, const DevModel<T>& 
     sa = clampT(sa, -hA[ia], hA[ia]); sb = clampT(sb, -hB[ib], hB[ib]);
     T pos[3];
     for (int k = 0; k < 3; k++) pos[k] = (T)0.5 * (ea[k] + sa * ua[k] + eb[k] + sb * ub[k]);
-    add_contact(w, m, ncon, nefc, par, bA, bB, pos, bestn, -(best / (T)1.05));
+    add_contact(w, m, ncon, nefc, par, idA, idB, pos, bestn, -(best / (T)1.05));
     return;
   }
   const bool refA = code < 3;
@@ -491,7 +491,7 @@ __device__ __noinline__ void collide_cube_cube(Ws<T, NC>& w, const DevModel<T>& 
     const T depth = hR[ir] - dot3(rp, nr);
     if (depth <= 0) continue;
     T pos[3] = {poly[v][0] + (T)0.5 * depth * nr[0], poly[v][1] + (T)0.5 * depth * nr[1], poly[v][2] + (T)0.5 * depth * nr[2]};
-    if (add_contact(w, m, ncon, nefc, par, bA, bB, pos, bestn, -depth)) cnt++;
+    if (add_contact(w, m, ncon, nefc, par, idA, idB, pos, bestn, -depth)) cnt++;
   }
 }
 
@@ -512,7 +512,7 @@ template <typename T, int NC> DI void sa_clear(Ws<T, NC>& w) {
 //   1. collect_candidates : sphere + oriented-box broadphase, candidate keys in canonical (contact generation) order
 //   2. narrowphase_job    : cached separating-axis test or full MPR for ONE candidate; reads the workspace only
 //   3. consume_candidates : separating-axis cache updates and add_contact, in candidate order
-// key: mesh-mesh pair p -> p; cube c vs mesh g -> LCR_KEY_CUBE + LCR_MAXMESH * c + g
+// key: mesh-mesh pair p -> p; box c (cube, or static wall behind the cubes) vs mesh g -> LCR_KEY_CUBE + LCR_MAXMESH * c + g
 #define LCR_KEY_CUBE 200
 
 template <typename T, int NC> DI T (*cand_res(Ws<T, NC>& w))[8] { return reinterpret_cast<T(*)[8]>(w.e_w); }
@@ -576,7 +576,7 @@ __device__ __noinline__ void collect_candidates(Ws<T, NC>& w, const DevModel<T>&
   __syncwarp();
   int n = 0;
   if (cmask & LCR_COLLIDE_CUBE_MESH)
-    for (int c = 0; c < NC; c++) {
+    for (int c = 0; c < Scene<NC>::NCUBE; c++) {
       const int bc = LCR_NABODY + c;
       bool cand = false;
       if (lane < m.nmesh) {
@@ -584,6 +584,26 @@ __device__ __noinline__ void collect_candidates(Ws<T, NC>& w, const DevModel<T>&
         const T r = m.mesh_rbound[lane] + sqrt(dot3(hc, hc));
         T d[3] = {w.gc[lane][0] - w.xpos[bc][0], w.gc[lane][1] - w.xpos[bc][1], w.gc[lane][2] - w.xpos[bc][2]};
         cand = !(dot3(d, d) > r * r);
+        if (cand) cand = !cached_axis_separates(w, m, LCR_KEY_CUBE + LCR_MAXMESH * c + lane);
+      }
+      const unsigned mask = __ballot_sync(FULLMASK, cand);
+      if (cand) {
+        const int k = n + __popc(mask & ((1u << lane) - 1));
+        if (k < LCR_MAXCAND) w.cand_key[k] = (short)(LCR_KEY_CUBE + LCR_MAXMESH * c + lane);
+      }
+      n += __popc(mask);
+    }
+  if (Scene<NC>::NWALL > 0 && (cmask & LCR_COLLIDE_WALL_MESH))
+    // static boxes vs the meshes of the moving arm bodies (base_link is welded to the world like the walls): bounding
+    // sphere against the axis-aligned box, then the cached axis
+    for (int c = Scene<NC>::NCUBE; c < Scene<NC>::NBOX; c++) {
+      const int bc = LCR_NABODY + c;
+      bool cand = false;
+      if (lane < m.nmesh && m.mesh_body[lane] != 0) {
+        T d2 = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { const T e = fabs(w.gc[lane][k] - w.xpos[bc][k]) - m.cube_size[c][k]; if (e > 0) d2 += e * e; }
+        cand = !(d2 > m.mesh_rbound[lane] * m.mesh_rbound[lane]);
         if (cand) cand = !cached_axis_separates(w, m, LCR_KEY_CUBE + LCR_MAXMESH * c + lane);
       }
       const unsigned mask = __ballot_sync(FULLMASK, cand);
@@ -761,7 +781,7 @@ DI void apply_result(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, i
   T dir[3] = {r[2], r[3], r[4]}, pos[3] = {r[5], r[6], r[7]};
   if (key >= LCR_KEY_CUBE) {
     const int c = (key - LCR_KEY_CUBE) / LCR_MAXMESH, g = (key - LCR_KEY_CUBE) % LCR_MAXMESH;
-    add_contact(w, m, ncon, nefc, &m.par_cube_mesh[c][g], LCR_NABODY + c, m.mesh_body[g], pos, dir, -r[1]);
+    add_contact(w, m, ncon, nefc, &m.par_cube_mesh[c][g], box_body<NC>(c), m.mesh_body[g], pos, dir, -r[1]);
   } else {
     add_contact(w, m, ncon, nefc, &m.par_mesh_mesh[key], m.mesh_body[m.pair_g1[key]], m.mesh_body[m.pair_g2[key]], pos, dir, -r[1]);
   }

@@ -20,6 +20,18 @@
 #define FULLMASK 0xffffffffu
 #define LCR_MAXCAND (3 * LCR_MAXEFC / 8)  // candidate results (8 words each) live in the e_w / e_g / e_p rows
 
+// Scene class = the template parameter NC of the workspace and of every kernel: 1 / 2 = that many free cubes and no
+// static boxes (Reach / Push / Lift / PickPlace, StackTwoCubes); LCR_NC_LOOP = one cube + the LCR_MAXWALL static wall
+// boxes of PushCubeLoop.  Boxes are indexed cubes first, walls after them; box c has the pose slot LCR_NABODY + c of
+// Ws::xpos / xquat / xmat (the wall slots are constants rewritten by every kinematics pass).
+#define LCR_NC_LOOP 5
+template <int NC> struct Scene {
+  static constexpr int NCUBE = NC == LCR_NC_LOOP ? 1 : NC, NWALL = NC == LCR_NC_LOOP ? LCR_MAXWALL : 0, NBOX = NCUBE + NWALL;
+};
+// body id of box c in contact records: the cube's free body, or the world (-1) for a static wall
+template <int NC> __host__ __device__ constexpr int box_body(int c) { return c < Scene<NC>::NCUBE ? LCR_NABODY + c : -1; }
+inline int scene_class(int task, int ncube) { return task == LCR_TASK_PUSH_LOOP ? LCR_NC_LOOP : ncube; }
+
 // contact parameter classes, precomputed on the host by the MuJoCo mixing rule
 template <typename T>
 struct CPar {
@@ -38,7 +50,9 @@ struct DevModel {
   T jnt_axis[LCR_NARM][3], jnt_range[LCR_NARM][2], jnt_armature[LCR_NARM], jnt_damping[LCR_NARM];
   T jnt_frcrange[LCR_NARM][2], dof_invweight0[LCR_NARM], act_kp[LCR_NARM], act_kv[LCR_NARM], act_ctrlrange[LCR_NARM][2];
   T site_pos[3];
-  T cube_mass[LCR_MAXCUBE], cube_inertia[LCR_MAXCUBE], cube_size[LCR_MAXCUBE][3], cube_qpos0[LCR_MAXCUBE][3];
+  T cube_mass[LCR_MAXCUBE], cube_inertia[LCR_MAXCUBE], cube_qpos0[LCR_MAXCUBE][3];
+  T cube_size[LCR_MAXBOX][3];  // half sizes of the boxes: cubes, then the static walls
+  T wall_pos[LCR_MAXWALL][3];
   int mesh_body[LCR_MAXMESH], mesh_vertadr[LCR_MAXMESH], mesh_vertnum[LCR_MAXMESH];
   T mesh_center[LCR_MAXMESH][3], mesh_half[LCR_MAXMESH][3], mesh_rbound[LCR_MAXMESH], mesh_com[LCR_MAXMESH][3];
   int pair_g1[LCR_MAXPAIR], pair_g2[LCR_MAXPAIR];
@@ -47,12 +61,15 @@ struct DevModel {
   CPar<T> par_floor_cube[LCR_MAXCUBE];
   CPar<T> par_cube_cube;
   CPar<T> par_floor_mesh[LCR_MAXMESH];
-  CPar<T> par_cube_mesh[LCR_MAXCUBE][LCR_MAXMESH];
+  CPar<T> par_cube_mesh[LCR_MAXBOX][LCR_MAXMESH];  // box (cube or wall) vs mesh
+  CPar<T> par_wall_cube[LCR_MAXWALL][LCR_MAXCUBE];
   CPar<T> par_mesh_mesh[LCR_MAXPAIR];
   // env config
   int action_mode, block_gripper, reward_type, n_substeps, max_episode_steps, autoreset, collision_mask;
   T distance_threshold, height_threshold;
   double cube_low[3], cube_high[3], target_low[3], target_high[3];  // reset draws are float64 like numpy
+  // PushCubeLoop: goal region centres and the sampling / overlap half box (push_cube_loop_env.py:127-135), float64 like numpy
+  double goal_center[2][3], goal_high[3];
   __host__ __device__ const CPar<T>* par(int idx) const { return par_limit + idx; }
   __host__ __device__ int par_index(const CPar<T>* p) const { return (int)(p - par_limit); }
 };
@@ -72,7 +89,8 @@ struct DevState {
 
 template <typename T, int NC>
 struct Ws {  // per-warp shared-memory workspace
-  static constexpr int NQ = LCR_NARM + 7 * NC, NVV = LCR_NARM + 6 * NC, NB = LCR_NABODY + NC;
+  static constexpr int NCU = Scene<NC>::NCUBE;
+  static constexpr int NQ = LCR_NARM + 7 * NCU, NVV = LCR_NARM + 6 * NCU, NB = LCR_NABODY + Scene<NC>::NBOX;
   static constexpr int NF = NQ + 2 * NVV + LCR_NARM + LCR_NAUX;
   static constexpr int JS = NVV + 1;  // padded row stride of J (odd -> conflict-free row-parallel access)
   static constexpr int NFP = (NF + 3) & ~3;  // record length in T, multiple of 16 bytes

@@ -250,7 +250,16 @@ __device__ __noinline__ void kinematics(Ws<T, NC>& w, const DevModel<T>& m) {
       T* s = w.site_xpos();
       s[0] = w.xpos[b][0] + t[0]; s[1] = w.xpos[b][1] + t[1]; s[2] = w.xpos[b][2] + t[2];
     }
-  } else if (lane < LCR_NABODY + NC) {
+  } else if (lane < LCR_NABODY + Scene<NC>::NBOX && lane >= LCR_NABODY + Scene<NC>::NCUBE) {
+    // static wall boxes: constant pose in the slots after the cubes
+    const int b = lane, wi = lane - LCR_NABODY - Scene<NC>::NCUBE;
+#pragma unroll
+    for (int k = 0; k < 3; k++) w.xpos[b][k] = m.wall_pos[wi][k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) w.xquat[b][k] = k == 0 ? (T)1 : (T)0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) w.xmat[b][k] = (k & 3) == 0 ? (T)1 : (T)0;
+  } else if (lane < LCR_NABODY + Scene<NC>::NCUBE) {
     const int c = lane - LCR_NABODY, b = lane;
     const T* qp = qpos + LCR_NARM + 7 * c;
     T qq[4] = {qp[3], qp[4], qp[5], qp[6]}, R[9];
@@ -587,11 +596,14 @@ __device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m
     collect_candidates(w, m);
     run_jobs_inline(w, m, verts);
   }
-  // generation order (= drop order at the caps): floor-cube, cube-cube, cube-mesh, floor-mesh, mesh-mesh
+  // generation order (= drop order at the caps): floor-cube, cube-cube, wall-cube, cube-mesh, wall-mesh, floor-mesh, mesh-mesh
   if (cmask & LCR_COLLIDE_FLOOR_CUBE)
-    for (int c = 0; c < NC; c++) collide_floor_cube(w, m, ncon, nefc, c);
-  if (NC == 2 && (cmask & LCR_COLLIDE_CUBE_CUBE)) collide_cube_cube(w, m, ncon, nefc);
-  if (cmask & LCR_COLLIDE_CUBE_MESH) consume_candidates(w, m, ncon, nefc, true);
+    for (int c = 0; c < Scene<NC>::NCUBE; c++) collide_floor_cube(w, m, ncon, nefc, c);
+  if (Scene<NC>::NCUBE == 2 && (cmask & LCR_COLLIDE_CUBE_CUBE)) collide_box_box(w, m, ncon, nefc, 0, 1, &m.par_cube_cube);
+  if (Scene<NC>::NWALL > 0 && (cmask & LCR_COLLIDE_WALL_CUBE))
+    for (int wi = 0; wi < Scene<NC>::NWALL; wi++)
+      for (int c = 0; c < Scene<NC>::NCUBE; c++) collide_box_box(w, m, ncon, nefc, Scene<NC>::NCUBE + wi, c, &m.par_wall_cube[wi][c]);
+  if (cmask & (LCR_COLLIDE_CUBE_MESH | LCR_COLLIDE_WALL_MESH)) consume_candidates(w, m, ncon, nefc, true);
   if (cmask & LCR_COLLIDE_FLOOR_MESH) collide_floor_meshes(w, m, verts, ncon, nefc);
   if (cmask & LCR_COLLIDE_MESH_MESH) consume_candidates(w, m, ncon, nefc, false);
   if (lane == 0) { w.ncon = ncon; w.nefc = nefc; w.nlim = nlim; }
@@ -1009,7 +1021,7 @@ template <typename T, int NC> DI void reset_data(Ws<T, NC>& w, const DevModel<T>
   const int lane = LANE;
   for (int i = lane; i < Ws<T, NC>::NF - LCR_NAUX + 1; i += 32) w.st[i] = 0;  // qpos qvel ctrl warm time
   __syncwarp();
-  if (lane < NC) {
+  if (lane < Scene<NC>::NCUBE) {
     T* qp = w.qpos() + LCR_NARM + 7 * lane;
     qp[0] = m.cube_qpos0[lane][0]; qp[1] = m.cube_qpos0[lane][1]; qp[2] = m.cube_qpos0[lane][2]; qp[3] = 1;
   }
@@ -1060,7 +1072,7 @@ __device__ __noinline__ void integrate(Ws<T, NC>& w, const DevModel<T>& m) {
   if (lane < NVV) qvel[lane] += h * a;
   __syncwarp();
   if (lane < LCR_NARM) qpos[lane] += h * qvel[lane];
-  else if (lane < LCR_NARM + NC) {
+  else if (lane < LCR_NARM + Scene<NC>::NCUBE) {
     const int c = lane - LCR_NARM;
     T* qp = qpos + LCR_NARM + 7 * c;
     const T* qv = qvel + LCR_NARM + 6 * c;
@@ -1097,7 +1109,7 @@ template <typename T, int NC> DI void write_obs(Ws<T, NC>& w, const DevModel<T>&
   const T* qpos = w.qpos();
   const T* qvel = w.qvel();
   const bool has_target = task == LCR_TASK_PUSH || task == LCR_TASK_PICK_PLACE;
-  const int od = (task == LCR_TASK_REACH || task == LCR_TASK_LIFT) ? 15 : 18;
+  const int od = (task == LCR_TASK_REACH || task == LCR_TASK_LIFT || task == LCR_TASK_PUSH_LOOP) ? 15 : 18;
   if (lane < od) {
     T v;
     if (lane < 6) v = qpos[lane];
@@ -1114,7 +1126,18 @@ __device__ __noinline__ void env_reset(Ws<T, NC>& w, const DevModel<T>& m, const
   T* qpos = w.qpos();
   if (lane == 0) {
     for (int j = 0; j < 6; j++) qpos[j] = 0;
-    for (int c = 0; c < NC; c++) {
+    if (task == LCR_TASK_PUSH_LOOP) {
+      // push_cube_loop_env.py:302-320: the cube is drawn inside the region of the CURRENT goal (target[0], persists across resets)
+      const int cg = w.target()[0] != (T)0;
+      T* qp = qpos + 6;
+      for (int k = 0; k < 3; k++) {
+        const double hi = m.goal_high[k], lo = k < 2 ? hi * -1.0 : hi;
+        const double p = lo + (hi - lo) * pcg64_double(w.rng);
+        qp[k] = (T)(k < 2 ? p + m.goal_center[cg][k] : p);
+      }
+      qp[3] = 1; qp[4] = qp[5] = qp[6] = 0;
+    } else
+    for (int c = 0; c < Scene<NC>::NCUBE; c++) {
       T* qp = qpos + 6 + 7 * c;
       for (int k = 0; k < 3; k++) qp[k] = (T)(m.cube_low[k] + (m.cube_high[k] - m.cube_low[k]) * pcg64_double(w.rng));
       qp[3] = 1; qp[4] = qp[5] = qp[6] = 0;
@@ -1218,17 +1241,77 @@ __device__ __noinline__ bool env_step_begin(Ws<T, NC>& w, const DevModel<T>& m, 
   return true;
 }
 
+// get_reward / get_cube_overlap of PushCubeLoop (push_cube_loop_env.py:337-383).  The reference mixes numpy float32
+// (cube_position), numpy float64 (model arrays) and Python scalars; the dtype of every intermediate follows NumPy >= 2
+// promotion (NEP 50: a Python scalar adopts the dtype of the numpy operand), tracked explicitly like in the oracle.
+// Correctly rounded intrinsics: the float32 build compiles with approximate division and with FMA contraction.
+struct PyNum { double v; int k; };  // k: 0 numpy float64, 1 numpy float32, 2 Python scalar (weak)
+DI PyNum pn(double v, int k) { PyNum r; r.v = v; r.k = k; return r; }
+DI PyNum pn_op(PyNum a, PyNum b, int op) {  // 0 +, 1 -, 2 *, 3 /
+  const int k = (a.k == 0 || b.k == 0) ? 0 : ((a.k == 1 || b.k == 1) ? 1 : 2);
+  if (k == 1) {
+    const float x = (float)a.v, y = (float)b.v;
+    const float z = op == 0 ? __fadd_rn(x, y) : op == 1 ? __fsub_rn(x, y) : op == 2 ? __fmul_rn(x, y) : __fdiv_rn(x, y);
+    return pn((double)z, 1);
+  }
+  return pn(op == 0 ? __dadd_rn(a.v, b.v) : op == 1 ? __dsub_rn(a.v, b.v) : op == 2 ? __dmul_rn(a.v, b.v) : __ddiv_rn(a.v, b.v), k);
+}
+DI PyNum pn_min(PyNum a, PyNum b) { return b.v < a.v ? b : a; }  // Python min / max return the first extremal operand
+DI PyNum pn_max(PyNum a, PyNum b) { return b.v > a.v ? b : a; }
+
+// lane 0 only; returns success, flips the current goal (target[0]) on success
+template <typename T, int NC>
+__device__ __noinline__ bool loop_reward(Ws<T, NC>& w, const DevModel<T>& m, float& reward) {
+  const T* qpos = w.qpos();
+  const int cg = w.target()[0] != (T)0;
+  const PyNum half = pn(0.015 / 2, 2);  // self.cube_size (push_cube_loop_env.py:124)
+  PyNum ov[2];
+#pragma unroll 1
+  for (int k = 0; k < 2; k++) {
+    const PyNum c = pn((double)(float)qpos[6 + k], 1);  // data.qpos[6:9].astype(np.float32)
+    const PyNum g = pn(m.goal_center[cg][k], 0), wg = pn(m.goal_high[k], 0);
+    const PyNum up = pn_min(pn_op(c, half, 0), pn_op(g, wg, 0)), dn = pn_max(pn_op(c, half, 1), pn_op(g, wg, 1));
+    ov[k] = pn_max(pn(0, 2), pn_op(up, dn, 1));
+  }
+  const PyNum overlap = pn_op(pn_op(ov[0], ov[1], 2), pn(0.0075 * 0.0075 * 4, 2), 3);
+  if (overlap.v > 0.95) {
+    reward = 5.0f;
+    w.target()[0] = cg ? (T)0 : (T)1;
+    return true;
+  }
+  if (overlap.v > 0.0) { reward = (float)pn_op(overlap, pn(1, 2), 1).v; return false; }
+  const double edge = __dadd_rn(m.goal_high[1] * -1.0, m.goal_center[cg][1]);
+  const double diff = __dsub_rn((double)(float)qpos[7], edge), dist = sqrt(__dmul_rn(diff, diff));
+  double r = __dsub_rn(__ddiv_rn(-dist, 0.16), 1.0);
+  r = r > -2 ? r : -2;
+  r = -1 < r ? -1 : r;
+  reward = (float)r;
+  return false;
+}
+
 template <typename T, int NC>
 __device__ __noinline__ void env_step_end(Ws<T, NC>& w, const DevModel<T>& m, float* obs, float* reward, uint8_t* term, uint8_t* trunc,
                                           uint8_t* succ) {
   const int lane = LANE, task = m.task;
   write_obs(w, m, obs);
+  if (task == LCR_TASK_PUSH_LOOP) {  // push_cube_loop_env.py:322-335: never terminates; TimeLimit truncates
+    if (lane == 0) {
+      float r;
+      const bool su = loop_reward(w, m, r);
+      const int el = ++w.ints[0];
+      const bool tr = m.max_episode_steps > 0 && el >= m.max_episode_steps;
+      w.ints[1] = tr ? 1 : 0;
+      *reward = r; *term = 0; *trunc = tr; *succ = su;
+    }
+    __syncwarp();
+    return;
+  }
   if (lane == 0) {
     T pa[3], pb[3];
     const T* site = w.site_xpos();
     const T* c0 = w.cube_xpos(0);
     if (task == LCR_TASK_REACH || task == LCR_TASK_LIFT) { for (int k = 0; k < 3; k++) { pa[k] = site[k]; pb[k] = c0[k]; } }
-    else if (task == LCR_TASK_STACK) { const T* c1 = w.cube_xpos(NC - 1); for (int k = 0; k < 3; k++) { pa[k] = c1[k]; pb[k] = c0[k]; } pb[2] += (T)0.03; }
+    else if (task == LCR_TASK_STACK) { const T* c1 = w.cube_xpos(Scene<NC>::NCUBE - 1); for (int k = 0; k < 3; k++) { pa[k] = c1[k]; pb[k] = c0[k]; } pb[2] += (T)0.03; }
     else { for (int k = 0; k < 3; k++) { pa[k] = c0[k]; pb[k] = w.target()[k]; } }
     T dx = pa[0] - pb[0], dy = pa[1] - pb[1], dz = pa[2] - pb[2];
     T d = sqrt(dx * dx + dy * dy + dz * dz);
@@ -1833,16 +1916,20 @@ template <typename T, int NC> static void set_smem_attr() {
 
 template <typename T>
 void Launch<T>::prepare(int ncube) {
-  if (ncube == 1) set_smem_attr<T, 1>(); else set_smem_attr<T, 2>();
+  // (`ncube` of the launchers is the scene class: 1 / 2 cubes, or LCR_NC_LOOP = one cube + the static walls)
+  if (ncube == 1) set_smem_attr<T, 1>(); else if (ncube == 2) set_smem_attr<T, 2>(); else set_smem_attr<T, LCR_NC_LOOP>();
 }
 template <typename T>
-size_t Launch<T>::smem_bytes(int ncube) { return (ncube == 1 ? sizeof(Ws<T, 1>) : sizeof(Ws<T, 2>)) * LCR_WPB; }
+size_t Launch<T>::smem_bytes(int ncube) {
+  return (ncube == 1 ? sizeof(Ws<T, 1>) : ncube == 2 ? sizeof(Ws<T, 2>) : sizeof(Ws<T, LCR_NC_LOOP>)) * LCR_WPB;
+}
 
 #define LCR_GRID(s) (((s).n + LCR_WPB - 1) / LCR_WPB)
 #define LCR_LAUNCH(KERNEL, ...)                                                                          \
   do {                                                                                                   \
     if (ncube == 1) KERNEL<T, 1><<<LCR_GRID(s), LCR_WPB * 32, sizeof(Ws<T, 1>) * LCR_WPB, st>>>(__VA_ARGS__); \
-    else KERNEL<T, 2><<<LCR_GRID(s), LCR_WPB * 32, sizeof(Ws<T, 2>) * LCR_WPB, st>>>(__VA_ARGS__);           \
+    else if (ncube == 2) KERNEL<T, 2><<<LCR_GRID(s), LCR_WPB * 32, sizeof(Ws<T, 2>) * LCR_WPB, st>>>(__VA_ARGS__);      \
+    else KERNEL<T, LCR_NC_LOOP><<<LCR_GRID(s), LCR_WPB * 32, sizeof(Ws<T, LCR_NC_LOOP>) * LCR_WPB, st>>>(__VA_ARGS__);  \
   } while (0)
 
 template <typename T>
@@ -1876,7 +1963,8 @@ void Launch<T>::step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, 
                               cudaStream_t st) {
 #define LCR_LS_GO(NCV, PROFV) k_step_ls<T, NCV, PROFV><<<grid, 32 * warps, sizeof(Ws<T, NCV>) * epc, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm, epc, prof)
   if (ncube == 1) { if (prof) LCR_LS_GO(1, true); else LCR_LS_GO(1, false); }
-  else { if (prof) LCR_LS_GO(2, true); else LCR_LS_GO(2, false); }
+  else if (ncube == 2) { if (prof) LCR_LS_GO(2, true); else LCR_LS_GO(2, false); }
+  else { if (prof) LCR_LS_GO(LCR_NC_LOOP, true); else LCR_LS_GO(LCR_NC_LOOP, false); }
 #undef LCR_LS_GO
 }
 // one chain of 2 + 3*n_substeps launches over the env range [env0, env0 + cnt) on stream st
@@ -1899,7 +1987,8 @@ template <typename T>
 int Launch<T>::step_phased(int ncube, int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, const float* actions,
                            float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, cudaStream_t st) {
   if (ncube == 1) phased_chain<T, 1>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, st);
-  else phased_chain<T, 2>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, st);
+  else if (ncube == 2) phased_chain<T, 2>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, st);
+  else phased_chain<T, LCR_NC_LOOP>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, st);
   return 2 + 4 * n_substeps;
 }
 template <typename T>
@@ -1913,12 +2002,14 @@ void Launch<T>::ik(int ncube, const DevModel<T>* dm, const T* verts, DevState<T>
 template <typename T>
 void Launch<T>::get_state(int ncube, DevState<T> s, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,
                           cudaStream_t st) {
-  k_get_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, 6 + 7 * ncube, 6 + 6 * ncube, qpos, qvel, ctrl, warm, aux, ints);
+  const int ncu = ncube == LCR_NC_LOOP ? 1 : ncube;
+  k_get_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, 6 + 7 * ncu, 6 + 6 * ncu, qpos, qvel, ctrl, warm, aux, ints);
 }
 template <typename T>
 void Launch<T>::set_state(int ncube, DevState<T> s, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
                           const double* aux, const int32_t* ints, cudaStream_t st) {
-  k_set_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, 6 + 7 * ncube, 6 + 6 * ncube, qpos, qvel, ctrl, warm, aux, ints);
+  const int ncu = ncube == LCR_NC_LOOP ? 1 : ncube;
+  k_set_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, 6 + 7 * ncu, 6 + 6 * ncu, qpos, qvel, ctrl, warm, aux, ints);
 }
 template <typename T>
 void Launch<T>::init_state(int ncube, const DevModel<T>* dm, DevState<T> s, cudaStream_t st) {

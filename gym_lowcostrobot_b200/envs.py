@@ -2,7 +2,8 @@
 
 Each class mirrors the constructor kwargs, ``reset`` / ``step`` / ``close`` interface, observation
 keys and action shapes of its reference counterpart
-(``gym_lowcostrobot/envs/{reach,push,lift,pick_place}_cube_env.py``, ``stack_two_cubes_env.py``) but
+(``gym_lowcostrobot/envs/{reach,push,lift,pick_place}_cube_env.py``, ``stack_two_cubes_env.py``,
+``push_cube_loop_env.py``) but
 holds ``num_envs`` instances on one GPU and returns batched torch tensors.  Everything behind
 ``step`` runs in liblcrsim.so (hand-written sm_100a CUDA); torch only owns the buffers and streams.
 """
@@ -21,6 +22,7 @@ _OBS_LAYOUT = {
     "push": (("arm_qpos", 6), ("arm_qvel", 6), ("target_pos", 3), ("cube_pos", 3)),
     "pick_place": (("arm_qpos", 6), ("arm_qvel", 6), ("target_pos", 3), ("cube_pos", 3)),
     "stack": (("arm_qpos", 6), ("arm_qvel", 6), ("cube_red_pos", 3), ("cube_blue_pos", 3)),
+    "push_loop": (("arm_qpos", 6), ("arm_qvel", 6), ("cube_pos", 3)),  # push_cube_loop_env.py:286-300
 }
 
 
@@ -259,5 +261,43 @@ class StackTwoCubesEnv(BatchedLowCostRobotEnv):
     task = "stack"
 
 
+class PushCubeLoopEnv(BatchedLowCostRobotEnv):
+    """``PushCubeLoop-v0`` (push_cube_loop_env.py): push the cube back and forth between two goal regions inside four
+    rails.  The reference constructor takes ``observation_mode, action_mode, block_gripper, n_substeps, render_mode``
+    (:77-84); ``step`` never terminates (:331-333, the registered TimeLimit truncates), the reward is the overlap
+    reward of ``get_reward`` (:337-365) and ``info`` carries ``timestamp`` and ``success`` (:329).  The goal an env
+    currently pushes towards (``current_goal``, :136) lives in ``aux[:, 1]`` of ``get_state`` / ``set_state``."""
+
+    task = "push_loop"
+
+    def __init__(self, num_envs=1, device="cuda:0", observation_mode="state", action_mode="joint", block_gripper=True,
+                 n_substeps=20, render_mode=None, **kwargs):
+        for k in ("reward_type", "distance_threshold", "height_threshold", "cube_xy_range", "target_xy_range", "goal_z_range"):
+            if k in kwargs:
+                raise TypeError(f"PushCubeLoopEnv has no argument {k!r}")  # not in the reference signature
+        super().__init__(num_envs=num_envs, device=device, observation_mode=observation_mode, action_mode=action_mode,
+                         block_gripper=block_gripper, n_substeps=n_substeps, render_mode=render_mode, **kwargs)
+
+    def _timestamp(self):
+        aux = torch.zeros(self.num_envs, model.NAUX, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            capi.check(self._L.lcr_get_state(self._h, None, None, None, None, _ptr(aux), None, self._stream()))
+        return aux[:, 0]
+
+    @property
+    def current_goal(self):
+        """0 / 1 per env: the goal region the cube is to be pushed into (push_cube_loop_env.py:136,346)."""
+        return self.get_state()["aux"][:, 1].to(torch.int64)
+
+    def reset(self, seed=None, options=None, mask=None):
+        obs, _ = super().reset(seed=seed, options=options, mask=mask)
+        return obs, {"timestamp": 0.0}  # push_cube_loop_env.py:320
+
+    def step(self, actions):
+        obs, reward, te, tr, su = self.step_flat(actions)
+        info = {"timestamp": self._timestamp(), "success": su.to(torch.int64)}  # push_cube_loop_env.py:329
+        return self._split(obs.clone()), reward.clone(), te.bool(), tr.bool(), info
+
+
 ENV_CLASSES = {"reach": ReachCubeEnv, "push": PushCubeEnv, "lift": LiftCubeEnv, "pick_place": PickPlaceCubeEnv,
-               "stack": StackTwoCubesEnv}
+               "stack": StackTwoCubesEnv, "push_loop": PushCubeLoopEnv}

@@ -22,13 +22,14 @@ import xml.etree.ElementTree as ET
 
 import numpy as np
 
-TASK_IDS = {"reach": 0, "push": 1, "lift": 2, "pick_place": 3, "stack": 4}
+TASK_IDS = {"reach": 0, "push": 1, "lift": 2, "pick_place": 3, "stack": 4, "push_loop": 5}
 TASK_XML = {
     "reach": "reach_cube.xml",
     "push": "push_cube.xml",
     "lift": "lift_cube.xml",
     "pick_place": "pick_place_cube.xml",
     "stack": "stack_two_cubes.xml",
+    "push_loop": "push_cube_loop.xml",
 }
 
 # MuJoCo built-in element defaults (public MJCF reference documentation).
@@ -189,7 +190,8 @@ def compile_model(assets_dir, task):
             mesh_files[m.attrib["name"]] = os.path.join(assets_dir, meshdir, m.attrib["file"])
 
     # ---- walk the body tree ----
-    arm_bodies, cubes, meshes = [], [], []
+    arm_bodies, cubes, meshes, walls = [], [], [], []
+    goals = {}
     floor = None
     site = None
     joint_names = []
@@ -206,8 +208,40 @@ def compile_model(assets_dir, task):
             contype=int(a["contype"]), conaffinity=int(a["conaffinity"]),
         )
 
+    def world_geom(g):
+        """Colliding geom of the world body (or of a jointless static body at the world origin): the z = 0 floor plane or
+        an axis-aligned static box (the rails of push_cube_loop.xml:45-48); non-colliding boxes named goal_region_* are
+        the goal regions push_cube_loop_env.py:127-133 reads from the model."""
+        nonlocal floor
+        ga = defaults.resolve("geom", g, None, _GEOM_BUILTIN)
+        p = geom_params(ga)
+        name = ga.get("name", "")
+        if not (p["contype"] or p["conaffinity"]):
+            if name.startswith("goal_region_") and ga["type"] == "box":
+                goals[name] = (_floats(ga["pos"], 3), _floats(ga["size"], 3))
+            return  # target_region: visual only (push_cube.xml:35)
+        if ga["type"] == "plane":
+            if np.any(_floats(ga["pos"], 3) != 0) or np.any(_quat_normalize(_floats(ga["quat"], 4)) != [1, 0, 0, 0]):
+                raise NotImplementedError("the only plane supported is z = 0")
+            floor = p
+        elif ga["type"] == "box":
+            if np.any(_quat_normalize(_floats(ga["quat"], 4)) != [1, 0, 0, 0]) or "euler" in ga:
+                raise NotImplementedError("static boxes must be axis aligned")
+            p.update(pos=_floats(ga["pos"], 3), size=_floats(ga["size"], 3), name=name)
+            walls.append(p)
+        else:
+            raise NotImplementedError("colliding world geoms: the z = 0 plane and axis-aligned boxes")
+
     def walk(body, parent_idx, childclass, depth):
         nonlocal floor, site
+        if (parent_idx is None and not body.findall("joint") and not body.findall("freejoint") and not body.findall("body")
+                and body.find("inertial") is None and all("mesh" not in g.attrib for g in body.findall("geom"))):
+            # static body welded to the world holding world geometry (<body name="floor">, push_cube_loop.xml:24-26)
+            if np.any(_floats(body.attrib.get("pos", "0 0 0"), 3) != 0) or "quat" in body.attrib or "euler" in body.attrib:
+                raise NotImplementedError("static bodies must sit at the world origin")
+            for g in body.findall("geom"):
+                world_geom(g)
+            return
         childclass = body.attrib.get("childclass", childclass)
         name = body.attrib.get("name", "")
         joints = body.findall("joint")
@@ -279,13 +313,7 @@ def compile_model(assets_dir, task):
 
     for wb in root.findall("worldbody"):
         for g in wb.findall("geom"):
-            ga = defaults.resolve("geom", g, None, _GEOM_BUILTIN)
-            p = geom_params(ga)
-            if not (p["contype"] or p["conaffinity"]):
-                continue  # target_region: visual only (push_cube.xml:35)
-            if ga["type"] != "plane" or np.any(_floats(ga["pos"], 3) != 0):
-                raise NotImplementedError("the only colliding world geom supported is the z=0 plane")
-            floor = p
+            world_geom(g)
         for b in wb.findall("body"):
             walk(b, None, None, 0)
 
@@ -393,8 +421,20 @@ def compile_model(assets_dir, task):
         if np.any(c["ipos"] != 0) or np.any(c["iquat"] != [1, 0, 0, 0]) or len(set(c["inertia"])) != 1:
             raise NotImplementedError("cube inertia must be isotropic and centred")
 
-    # geom parameter table: rows 0..nmesh-1 arm meshes, then floor, cube0, cube1
-    geoms = meshes + [floor] + [c["geom"] for c in cubes]
+    if walls:
+        out["wall_pos"] = np.stack([w["pos"] for w in walls])
+        out["wall_size"] = np.stack([w["size"] for w in walls])
+        out["wall_names"] = np.array([w["name"] for w in walls])
+    if goals:
+        if sorted(goals) != ["goal_region_1", "goal_region_2"]:
+            raise NotImplementedError("expected goal_region_1 and goal_region_2")
+        out["goal_center"] = np.stack([goals["goal_region_1"][0], goals["goal_region_2"][0]])
+        out["goal_size"] = goals["goal_region_1"][1]
+    if task == "push_loop" and (len(walls) == 0 or not goals or ncube != 1):
+        raise NotImplementedError("push_loop needs one cube, the rails and the two goal regions")
+
+    # geom parameter table: rows 0..nmesh-1 arm meshes, then floor, cube0, cube1, walls
+    geoms = meshes + [floor] + [c["geom"] for c in cubes] + walls
     out["geom_condim"] = np.array([g["condim"] for g in geoms], np.int32)
     out["geom_priority"] = np.array([g["priority"] for g in geoms], np.int32)
     out["geom_friction"] = np.stack([g["friction"] for g in geoms])

@@ -5,7 +5,9 @@
  * mujoco.MjModel.from_xml_path(<scene>.xml)  (reference gym_lowcostrobot/envs/reach_cube_env.py:89,
  * push_cube_env.py:92, lift_cube_env.py:90, pick_place_cube_env.py:93, stack_two_cubes_env.py:90)
  * specialised to the one model family in scope: follower.xml (base_link + 6 hinged links,
- * 20 convex mesh geoms, 6 position servos, one ee site) + floor plane + 1 or 2 free cubes.
+ * 20 convex mesh geoms, 6 position servos, one ee site) + floor plane + 1 or 2 free cubes
+ * (+ the four static box rails and the two goal regions of push_cube_loop.xml:40-48, read by
+ * push_cube_loop_env.py:89,127-136).
  * It is a data format, not an algorithm: every field is a number read from the MJCF/STL
  * files or derived from them at qpos0 (invweight0, meaninertia).
  *
@@ -15,7 +17,9 @@
  *   cube c = 0..ncube-1 : free bodies; "body id" LCR_NABODY + c in contact records
  *   qpos = [arm q[6], cube0 pos[3] quat[4] (w,x,y,z), cube1 ...]         nq = 6 + 7*ncube
  *   qvel = [arm qd[6], cube0 lin[3] (world) ang[3] (body-local), ...]    nv = 6 + 6*ncube
- *   geom g              : 0..nmesh-1 arm meshes, nmesh = floor, nmesh+1+c = cube c
+ *   geom g              : 0..nmesh-1 arm meshes, nmesh = floor, nmesh+1+c = cube c,
+ *                         nmesh+1+ncube+w = static wall box w (world body, axis aligned)
+ *   box index           : cube c -> c, wall w -> ncube + w (convex-pair keys, contact parameter tables)
  */
 #ifndef LCR_MODEL_H_
 #define LCR_MODEL_H_
@@ -26,18 +30,22 @@
 #define LCR_NABODY 7
 #define LCR_MAXCUBE 2
 #define LCR_MAXMESH 24
+#define LCR_MAXWALL 4
+#define LCR_MAXBOX (LCR_MAXCUBE + LCR_MAXWALL)
+/* rows of the geom parameter table: meshes, floor, cubes, walls (the one scene with walls has one cube and 20 meshes,
+ * so the table keeps its size: 20 + 1 + 1 + 4 <= 27) */
 #define LCR_MAXGEOM (LCR_MAXMESH + 1 + LCR_MAXCUBE)
 #define LCR_MAXPAIR 160
 #define LCR_MAXNV (LCR_NARM + 6 * LCR_MAXCUBE)
 #define LCR_MAXNQ (LCR_NARM + 7 * LCR_MAXCUBE)
 /* per-env caps of the contact list and of the constraint rows; contacts past a cap are dropped in
- * generation order (limits, floor-cube, cube-cube, cube-mesh, floor-mesh, mesh-mesh) and counted */
+ * generation order (limits, floor-cube, cube-cube, wall-cube, cube-mesh, wall-mesh, floor-mesh, mesh-mesh) and counted */
 #define LCR_MAXCON 32
 #define LCR_MAXEFC 96
 /* entries of the per-env separating-axis cache of the convex narrowphase (performance only) */
 #define LCR_NSA 16
 
-enum { LCR_TASK_REACH = 0, LCR_TASK_PUSH = 1, LCR_TASK_LIFT = 2, LCR_TASK_PICK_PLACE = 3, LCR_TASK_STACK = 4 };
+enum { LCR_TASK_REACH = 0, LCR_TASK_PUSH = 1, LCR_TASK_LIFT = 2, LCR_TASK_PICK_PLACE = 3, LCR_TASK_STACK = 4, LCR_TASK_PUSH_LOOP = 5 };
 
 typedef struct LcrModel {
   int32_t task, ncube, nq, nv;
@@ -70,6 +78,15 @@ typedef struct LcrModel {
   double mesh_com[LCR_MAXMESH][3];
   /* candidate arm self-collision mesh pairs after the body-pair filter */
   int32_t pair_g1[LCR_MAXPAIR], pair_g2[LCR_MAXPAIR];
+  /* static world boxes (push_cube_loop.xml:45-48: the rails that contain the cube): centre and half sizes, world frame,
+   * axis aligned.  They collide with the cube (box-box) and with the meshes of the moving arm bodies (box-mesh). */
+  int32_t nwall, pad2;
+  double wall_pos[LCR_MAXWALL][3], wall_size[LCR_MAXWALL][3];
+  /* goal regions of PushCubeLoop (push_cube_loop.xml:40-43; non-colliding boxes): geom_pos of goal_region_1 / _2 and
+   * geom_size of goal_region_1, as read by push_cube_loop_env.py:127-133 */
+  double goal_center[2][3], goal_size[3];
+  /* body pos of the cubes in the MJCF = their qpos0 (what mj_resetData restores after a bad qacc) */
+  double cube_pos0[LCR_MAXCUBE][3];
 } LcrModel;
 
 /* Per-env-class configuration = the reference Env constructor kwargs
@@ -83,7 +100,7 @@ typedef struct LcrEnvCfg {
   int32_t n_substeps;       /* 20 */
   int32_t max_episode_steps;/* 50; <= 0 disables truncation */
   int32_t autoreset;        /* 0 = never (caller resets), 1 = next-step autoreset of done envs */
-  int32_t collision_mask;   /* bit0 floor-cube, bit1 floor-mesh, bit2 cube-mesh, bit3 cube-cube, bit4 mesh-mesh */
+  int32_t collision_mask;   /* bit0 floor-cube, bit1 floor-mesh, bit2 cube-mesh, bit3 cube-cube, bit4 mesh-mesh, bit5 wall-cube, bit6 wall-mesh */
   int32_t exec_mode;        /* 0 = one fused kernel per step (one warp per CTA), 1 = phased (one small kernel per mj_step phase),
                              * 2 = lockstep (one kernel per step, CTAs of several envs aligned at the phase boundaries) */
   double distance_threshold;/* 0.05 */
@@ -97,6 +114,8 @@ typedef struct LcrEnvCfg {
 #define LCR_COLLIDE_CUBE_MESH 4
 #define LCR_COLLIDE_CUBE_CUBE 8
 #define LCR_COLLIDE_MESH_MESH 16
-#define LCR_COLLIDE_ALL 31
+#define LCR_COLLIDE_WALL_CUBE 32
+#define LCR_COLLIDE_WALL_MESH 64
+#define LCR_COLLIDE_ALL 127
 
 #endif /* LCR_MODEL_H_ */

@@ -32,7 +32,7 @@
 #define MAXIMP 0.9999
 #define MINMU 1e-5
 #define MAXVAL 1e10
-#define NB (LCR_NABODY + LCR_MAXCUBE) /* dynamic bodies: 7 arm + 2 cubes */
+#define NB (LCR_NABODY + LCR_MAXBOX) /* pose slots: 7 arm bodies, then the boxes (cubes, then the static walls) */
 #define NV LCR_MAXNV
 
 typedef struct {
@@ -158,6 +158,13 @@ static void kinematics(OrcSim *s) {
     memcpy(s->xipos[b], s->xpos[b], 3 * sizeof(double));
     memcpy(s->ximat[b], s->xmat[b], 9 * sizeof(double));
     memcpy(s->cube_xpos[c], s->xpos[b], 3 * sizeof(double));
+  }
+  for (int w = 0; w < m->nwall; w++) { /* static boxes of the world body: constant pose in the slots after the cubes */
+    int b = LCR_NABODY + m->ncube + w;
+    static const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, q1[4] = {1, 0, 0, 0};
+    memcpy(s->xpos[b], m->wall_pos[w], 3 * sizeof(double));
+    memcpy(s->xquat[b], q1, sizeof q1);
+    memcpy(s->xmat[b], I3, sizeof I3);
   }
   mat_vec(t, s->xmat[m->site_body], m->site_pos);
   for (int k = 0; k < 3; k++) s->site_xpos[k] = s->xpos[m->site_body][k] + t[k];
@@ -355,10 +362,12 @@ static void mix_params(const LcrModel *m, int g1, int g2, Contact *c) {
   c->g1 = g1; c->g2 = g2;
 }
 
+/* boxes: index c < ncube = free cube c, c >= ncube = static wall c - ncube; pose slot LCR_NABODY + c, geom nmesh + 1 + c */
+static const double *box_half(const LcrModel *m, int c) { return c < m->ncube ? m->cube_size[c] : m->wall_size[c - m->ncube]; }
 static int geom_body(const LcrModel *m, int g) {
   if (g < m->nmesh) return m->mesh_body[g];
   if (g == m->nmesh) return -1;
-  return LCR_NABODY + (g - m->nmesh - 1);
+  return g - m->nmesh - 1 < m->ncube ? LCR_NABODY + (g - m->nmesh - 1) : -1; /* walls belong to the world */
 }
 
 static Contact *add_contact(OrcSim *s, int g1, int g2, const double *pos, const double *normal, double dist) {
@@ -451,11 +460,14 @@ static void collision(OrcSim *s) {
   CandRes res[LCR_MAXCAND];
   const int ncand_all = collect_candidates(s, keys), ncand = ncand_all < LCR_MAXCAND ? ncand_all : LCR_MAXCAND;
   for (int k = 0; k < ncand; k++) cand_job(s, keys[k], &res[k]);
-  /* generation order (= drop order at the caps): floor-cube, cube-cube, cube-mesh, floor-mesh, mesh-mesh */
+  /* generation order (= drop order at the caps): floor-cube, cube-cube, wall-cube, cube-mesh, wall-mesh, floor-mesh, mesh-mesh */
   if (mask & LCR_COLLIDE_FLOOR_CUBE)
     for (int c = 0; c < m->ncube; c++) collide_floor_cube(s, c);
-  if ((mask & LCR_COLLIDE_CUBE_CUBE) && m->ncube == 2) collide_cube_cube(s);
-  if (mask & LCR_COLLIDE_CUBE_MESH)
+  if ((mask & LCR_COLLIDE_CUBE_CUBE) && m->ncube == 2) collide_box_box(s, 0, 1);
+  if (mask & LCR_COLLIDE_WALL_CUBE)
+    for (int w = 0; w < m->nwall; w++)
+      for (int c = 0; c < m->ncube; c++) collide_box_box(s, m->ncube + w, c);
+  if (mask & (LCR_COLLIDE_CUBE_MESH | LCR_COLLIDE_WALL_MESH))
     for (int k = 0; k < ncand; k++) if (keys[k] >= 200) cand_apply(s, &res[k]);
   if (mask & LCR_COLLIDE_FLOOR_MESH)
     for (int g = 0; g < m->nmesh; g++)
@@ -834,9 +846,8 @@ static void reset_data(OrcSim *s) { /* mj_resetData: qpos0, everything else zero
   memset(s->qpos, 0, sizeof s->qpos); memset(s->qvel, 0, sizeof s->qvel);
   memset(s->ctrl, 0, sizeof s->ctrl); memset(s->warm, 0, sizeof s->warm);
   s->time = 0;
-  static const double p0[5][2][3] = {{{0, 0.2, 0.01}}, {{0, 0.2, 0.01}}, {{0, 0.2, 0.01}}, {{0, 0.2, 0.01}}, {{0.1, 0.1, 0.01}, {-0.1, -0.1, 0.01}}};
   for (int c = 0; c < m->ncube; c++) {
-    memcpy(s->qpos + LCR_NARM + 7 * c, p0[m->task][c], 3 * sizeof(double));
+    memcpy(s->qpos + LCR_NARM + 7 * c, m->cube_pos0[c], 3 * sizeof(double));
     s->qpos[LCR_NARM + 7 * c + 3] = 1;
   }
 }
@@ -845,10 +856,11 @@ static void reset_data(OrcSim *s) { /* mj_resetData: qpos0, everything else zero
 static const double TARGET_LOW[6] = {-3.14159, -1.5708, -1.48353, -1.91986, -2.96706, -1.74533};
 static const double TARGET_HIGH[6] = {3.14159, 1.22173, 1.74533, 1.91986, 2.96706, 0.0523599};
 
-int orc_obs_dim(int task) { return (task == LCR_TASK_REACH || task == LCR_TASK_LIFT) ? 15 : 18; }
+int orc_obs_dim(int task) { return (task == LCR_TASK_REACH || task == LCR_TASK_LIFT || task == LCR_TASK_PUSH_LOOP) ? 15 : 18; }
 int orc_action_dim(const LcrEnvCfg *cfg) { return (cfg->action_mode ? 3 : 5) + (cfg->block_gripper ? 0 : 1); }
 
-/* get_observation (reach_cube_env.py:281-295, push_cube_env.py:291-306, stack_two_cubes_env.py:290-305) */
+/* get_observation (reach_cube_env.py:281-295, push_cube_env.py:291-306, stack_two_cubes_env.py:290-305,
+ * push_cube_loop_env.py:286-300: arm_qpos, arm_qvel, cube_pos like Reach) */
 static void write_obs(const OrcSim *s, float *obs) {
   int k = 0, task = s->m.task;
   for (int j = 0; j < 6; j++) obs[k++] = (float)s->qpos[j];
@@ -861,10 +873,28 @@ static void write_obs(const OrcSim *s, float *obs) {
 /* Env.reset (reach_cube_env.py:297-311, push_cube_env.py:308-328, lift_cube_env.py:306-320,
  * pick_place_cube_env.py:316-336, stack_two_cubes_env.py:307-324).  qvel/ctrl/warmstart/time are
  * deliberately NOT reset (the reference never calls mj_resetData). */
+/* sampling box of PushCubeLoop (push_cube_loop_env.py:133-135): high = geom_size / 2, high[:2] -= 0.008, low = high * (-1, -1, 1) */
+static void loop_goal_box(const LcrModel *m, double *lo, double *hi) {
+  for (int k = 0; k < 3; k++) hi[k] = m->goal_size[k] / 2;
+  hi[0] -= 0.008; hi[1] -= 0.008;
+  lo[0] = hi[0] * -1.0; lo[1] = hi[1] * -1.0; lo[2] = hi[2] * 1.0;
+}
+
 static void reset_(OrcSim *s, float *obs) {
   const LcrModel *m = &s->m;
   double p[3];
   for (int j = 0; j < 6; j++) s->qpos[j] = 0;
+  if (m->task == LCR_TASK_PUSH_LOOP) {
+    /* push_cube_loop_env.py:302-320: the cube is drawn inside the region of the CURRENT goal (which persists across
+     * resets; kept in target[0]); nothing else is reset */
+    double lo[3], hi[3];
+    const int cg = s->target[0] != 0;
+    loop_goal_box(m, lo, hi);
+    draw_uniform3(s->rng, lo, hi, p);
+    p[0] += m->goal_center[cg][0]; p[1] += m->goal_center[cg][1]; /* (1 - cg) * c1 + cg * c2 is exact for cg in {0, 1} */
+    double *qp = s->qpos + 6;
+    qp[0] = p[0]; qp[1] = p[1]; qp[2] = p[2]; qp[3] = 1; qp[4] = qp[5] = qp[6] = 0;
+  } else
   for (int c = 0; c < m->ncube; c++) {
     draw_uniform3(s->rng, s->cfg.cube_low, s->cfg.cube_high, p);
     double *qp = s->qpos + 6 + 7 * c;
@@ -965,6 +995,56 @@ static void apply_action(OrcSim *s, const float *action_in) {
 
 /* Env.step (reach_cube_env.py:313-348, push_cube_env.py:330-361, lift_cube_env.py:322-346,
  * pick_place_cube_env.py:338-369, stack_two_cubes_env.py:326-363) + TimeLimit */
+/* get_reward / get_cube_overlap of PushCubeLoop (push_cube_loop_env.py:337-383).  The reference mixes numpy float32
+ * (cube_position), numpy float64 (model arrays) and Python scalars; the dtype of every intermediate follows NumPy >= 2
+ * promotion (NEP 50: a Python scalar adopts the dtype of the numpy operand), tracked explicitly here. */
+typedef struct { double v; int k; } PyNum; /* k: 0 numpy float64, 1 numpy float32, 2 Python scalar (weak) */
+static PyNum pn(double v, int k) { PyNum r = {v, k}; return r; }
+static PyNum pn_op(PyNum a, PyNum b, int op) { /* 0 +, 1 -, 2 *, 3 / */
+  const int k = (a.k == 0 || b.k == 0) ? 0 : ((a.k == 1 || b.k == 1) ? 1 : 2);
+  if (k == 1) {
+    const float x = (float)a.v, y = (float)b.v;
+    const float z = op == 0 ? x + y : op == 1 ? x - y : op == 2 ? x * y : x / y;
+    return pn((double)z, 1);
+  }
+  return pn(op == 0 ? a.v + b.v : op == 1 ? a.v - b.v : op == 2 ? a.v * b.v : a.v / b.v, k);
+}
+static PyNum pn_min(PyNum a, PyNum b) { return b.v < a.v ? b : a; } /* Python min / max return the first extremal operand */
+static PyNum pn_max(PyNum a, PyNum b) { return b.v > a.v ? b : a; }
+
+static void loop_reward(OrcSim *s, float *reward, uint8_t *success) {
+  const LcrModel *m = &s->m;
+  const int cg = s->target[0] != 0;
+  double lo[3], hi[3];
+  loop_goal_box(m, lo, hi);
+  const PyNum w = pn(0.015 / 2, 2); /* self.cube_size (push_cube_loop_env.py:124) */
+  PyNum ov[2];
+  for (int k = 0; k < 2; k++) {
+    const PyNum c = pn((double)(float)s->qpos[6 + k], 1); /* data.qpos[6:9].astype(np.float32) */
+    const PyNum g = pn(m->goal_center[cg][k], 0), wg = pn(hi[k], 0);
+    const PyNum up = pn_min(pn_op(c, w, 0), pn_op(g, wg, 0)), dn = pn_max(pn_op(c, w, 1), pn_op(g, wg, 1));
+    ov[k] = pn_max(pn(0, 2), pn_op(up, dn, 1));
+  }
+  const PyNum area = pn_op(ov[0], ov[1], 2);
+  const PyNum cube_area = pn(0.0075 * 0.0075 * 4, 2); /* w_cube * l_cube * 4, Python floats */
+  const PyNum overlap = pn_op(area, cube_area, 3);
+  *success = 0;
+  if (overlap.v > 0.95) { /* success: +5 and the goal switches */
+    *success = 1;
+    *reward = 5.0f;
+    s->target[0] = cg ? 0.0 : 1.0;
+  } else if (overlap.v > 0.0) {
+    *reward = (float)pn_op(overlap, pn(1, 2), 1).v;
+  } else { /* distance to the near edge of the goal region along y only */
+    const double edge = lo[1] + m->goal_center[cg][1];
+    const double diff = (double)(float)s->qpos[7] - edge, dist = sqrt(diff * diff);
+    double r = (-dist / 0.16) - 1;
+    r = r > -2 ? r : -2; /* max(r, -2) */
+    r = -1 < r ? -1 : r; /* min(., -1) */
+    *reward = (float)r;
+  }
+}
+
 void orc_step(OrcSim *s, const float *action, float *obs, float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *success) {
   const LcrEnvCfg *cfg = &s->cfg;
   int task = s->m.task;
@@ -976,6 +1056,14 @@ void orc_step(OrcSim *s, const float *action, float *obs, float *reward, uint8_t
   s->max_nefc = 0;
   apply_action(s, action);
   write_obs(s, obs);
+  if (task == LCR_TASK_PUSH_LOOP) { /* push_cube_loop_env.py:322-335: never terminates; TimeLimit truncates */
+    loop_reward(s, reward, success);
+    *terminated = 0;
+    s->elapsed++;
+    *truncated = (cfg->max_episode_steps > 0 && s->elapsed >= cfg->max_episode_steps);
+    s->needs_reset = *truncated;
+    return;
+  }
   double d = 0, a[3], b[3];
   if (task == LCR_TASK_REACH || task == LCR_TASK_LIFT) { memcpy(a, s->site_xpos, sizeof a); memcpy(b, s->cube_xpos[0], sizeof b); }
   else if (task == LCR_TASK_STACK) { memcpy(a, s->cube_xpos[1], sizeof a); memcpy(b, s->cube_xpos[0], sizeof b); b[2] += 0.03; }
@@ -1043,9 +1131,10 @@ int orc_get(const OrcSim *s, const char *name, double *out, int cap) {
   const double *src = NULL;
   int n = 0, nv = s->m.nv;
   static double tmp[LCR_MAXEFC * NV > LCR_MAXCON * 32 ? LCR_MAXEFC * NV : LCR_MAXCON * 32];
-  if (!strcmp(name, "xpos")) { src = &s->xpos[0][0]; n = NB * 3; }
-  else if (!strcmp(name, "xmat")) { src = &s->xmat[0][0]; n = NB * 9; }
-  else if (!strcmp(name, "xipos")) { src = &s->xipos[0][0]; n = NB * 3; }
+  const int nbd = LCR_NABODY + LCR_MAXCUBE; /* the dynamic bodies (the wall slots behind them are constants) */
+  if (!strcmp(name, "xpos")) { src = &s->xpos[0][0]; n = nbd * 3; }
+  else if (!strcmp(name, "xmat")) { src = &s->xmat[0][0]; n = nbd * 9; }
+  else if (!strcmp(name, "xipos")) { src = &s->xipos[0][0]; n = nbd * 3; }
   else if (!strcmp(name, "axis")) { src = &s->axis[0][0]; n = 18; }
   else if (!strcmp(name, "site_xpos")) { src = s->site_xpos; n = 3; }
   else if (!strcmp(name, "M")) { for (int i = 0; i < nv; i++) for (int j = 0; j < nv; j++) tmp[i * nv + j] = s->M[i][j]; src = tmp; n = nv * nv; }

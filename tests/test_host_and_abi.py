@@ -48,8 +48,10 @@ def test_create_fails_loudly_without_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(capi.LcrError):
         glr.make("ReachCube-v0", num_envs=2)
+    with pytest.raises(capi.LcrError):
+        glr.make("PushCubeLoop-v0", num_envs=2)
     with pytest.raises(KeyError):
-        glr.make("PushCubeLoop-v0")
+        glr.make("NoSuchTask-v0")
     with pytest.raises(NotImplementedError):
         glr.make("ReachCube-v0", observation_mode="image")
 
