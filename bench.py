@@ -22,9 +22,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 IDS = {"reach": "ReachCube-v0", "push": "PushCube-v0", "lift": "LiftCube-v0", "pick_place": "PickPlaceCube-v0",
-       "stack": "StackTwoCubes-v0"}
+       "stack": "StackTwoCubes-v0", "push_loop": "PushCubeLoop-v0"}
 # algorithmic bytes per env-step: persistent state read + written, action in, obs/reward/flags out
-ALGO_BYTES = {"reach": 446, "lift": 450, "push": 482, "pick_place": 478, "stack": 614}
+ALGO_BYTES = {"reach": 446, "lift": 450, "push": 482, "pick_place": 478, "stack": 614, "push_loop": 454}
 METRIC = "env-steps/sec"
 
 

@@ -1220,7 +1220,8 @@ __device__ __noinline__ bool env_step_begin(Ws<T, NC>& w, const DevModel<T>& m, 
   if (m.action_mode == 1) {
     T* sc = w.search;  // free before the first and after the last mj_forward of the IK loop
     const T* site = w.site_xpos();
-    if (lane < 3) { T t = site[lane] + a * (T)0.05; if (lane == 2 && t < 0) t = 0; sc[lane] = t; }
+    // `ee_action * 0.05` is a float32 product in the reference (float32 array times a Python float), rounded before the sum
+    if (lane < 3) { T t = site[lane] + (T)__fmul_rn((float)a, 0.05f); if (lane == 2 && t < 0) t = 0; sc[lane] = t; }
     __syncwarp();
     T tgt[3] = {sc[0], sc[1], sc[2]};
     __syncwarp();
@@ -1230,7 +1231,7 @@ __device__ __noinline__ bool env_step_begin(Ws<T, NC>& w, const DevModel<T>& m, 
     if (lane == 5 && !gripper_task) tq = 0;
     // gripper (lift_cube_env.py:253-257): q6 + 0.2*a[3] clipped to ctrlrange
     const T ga = na > 3 ? __shfl_sync(FULLMASK, a, 3) : (T)0;
-    if (lane == 5 && gripper_task) tq = clampT(qpos[5] + ga * (T)0.2, m.act_ctrlrange[5][0], m.act_ctrlrange[5][1]);
+    if (lane == 5 && gripper_task) tq = clampT(qpos[5] + (T)__fmul_rn((float)ga, 0.2f), m.act_ctrlrange[5][0], m.act_ctrlrange[5][1]);
   } else {
     const T alast = __shfl_sync(FULLMASK, a, na - 1);
     if (lane < 5) tq = clampT(a + qpos[lane], (T)kTargetLow[lane], (T)kTargetHigh[lane]);

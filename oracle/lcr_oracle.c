@@ -974,7 +974,9 @@ static void apply_action(OrcSim *s, const float *action_in) {
   for (int k = 0; k < na; k++) a[k] = clampd((double)action_in[k], -1.0, 1.0);
   if (cfg->action_mode == 1) {
     double tgt[3];
-    for (int k = 0; k < 3; k++) tgt[k] = s->site_xpos[k] + a[k] * 0.05;
+    /* `ee_action * 0.05` is a float32 array times a Python float: the product is rounded to float32 before it is added to
+     * the float64 site position (reach_cube_env.py:241; NumPy promotion) */
+    for (int k = 0; k < 3; k++) tgt[k] = s->site_xpos[k] + (double)((float)a[k] * 0.05f);
     if (tgt[2] < 0) tgt[2] = 0;
     inverse_kinematics(s, tgt, tq, 1);
     if (!gripper_task) tq[5] = 0;
@@ -982,7 +984,8 @@ static void apply_action(OrcSim *s, const float *action_in) {
       /* action[3] (lift_cube_env.py:242); with block_gripper=True the action has 3 entries and the
        * reference would raise IndexError -- we use 0 for the missing gripper entry */
       double ga = na > 3 ? a[3] : 0.0;
-      tq[5] = clampd(s->qpos[5] + ga * 0.2, m->act_ctrlrange[5][0], m->act_ctrlrange[5][1]);
+      /* `gripper_action * 0.2`: np.float32 scalar times a Python float stays float32 (NumPy >= 2, NEP 50; lift_cube_env.py:253) */
+      tq[5] = clampd(s->qpos[5] + (double)((float)ga * 0.2f), m->act_ctrlrange[5][0], m->act_ctrlrange[5][1]);
     }
   } else {
     for (int j = 0; j < 5; j++) tq[j] = clampd(a[j] + s->qpos[j], TARGET_LOW[j], TARGET_HIGH[j]);

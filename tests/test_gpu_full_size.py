@@ -26,7 +26,7 @@ def _rollout(env_id, n, steps, seed=0, **kw):
     return torch.stack(recs), st, dg
 
 
-@pytest.mark.parametrize("env_id,n", [("ReachCube-v0", 4096), ("PushCube-v0", 16384)])
+@pytest.mark.parametrize("env_id,n", [("ReachCube-v0", 4096), ("PushCube-v0", 16384), ("PushCubeLoop-v0", 8192)])
 def test_full_batch_is_deterministic_and_mode_independent(env_id, n):
     a, sa, _ = _rollout(env_id, n, 6, exec_mode="lockstep")
     b, sb, _ = _rollout(env_id, n, 6, exec_mode="lockstep")
@@ -78,7 +78,7 @@ def test_random_sample_of_a_full_batch_tracks_the_oracle():
     assert ok >= 7, ok
 
 
-@pytest.mark.parametrize("env_id,n", [("ReachCube-v0", 4096), ("StackTwoCubes-v0", 8192), ("PickPlaceCube-v0", 8192)])
+@pytest.mark.parametrize("env_id,n", [("ReachCube-v0", 4096), ("StackTwoCubes-v0", 8192), ("PickPlaceCube-v0", 8192), ("PushCubeLoop-v0", 8192)])
 def test_state_invariants_after_random_rollouts(env_id, n):
     mode = "ee" if env_id.startswith("PickPlace") else "joint"
     recs, st, dg = _rollout(env_id, n, 12, action_mode=mode)
@@ -99,3 +99,10 @@ def test_state_invariants_after_random_rollouts(env_id, n):
     obs_dim = recs.shape[2] - 4
     flags = recs[:, :, obs_dim + 1:]
     assert ((flags == 0) | (flags == 1)).all()
+    if env_id.startswith("PushCubeLoop"):
+        # the rails (12 mm high) keep a pushed cube inside the 0.23 x 0.07 m pen; random flailing can flip it over a rail in a few envs
+        inside = (qpos[:, 6].abs() < 0.105) & (qpos[:, 7] > 0.105) & (qpos[:, 7] < 0.165)
+        assert float(inside.float().mean()) > 0.9
+        reward = recs[:, :, obs_dim]
+        assert ((reward == 5) | ((reward >= -2) & (reward < 0))).all()  # push_cube_loop_env.py:343-364
+        assert not recs[:, :, obs_dim + 1].any()  # never terminates

@@ -14,7 +14,7 @@ from oracle.oracle import Oracle
 pytestmark = pytest.mark.gpu
 
 IDS = {"reach": "ReachCube-v0", "push": "PushCube-v0", "lift": "LiftCube-v0", "pick_place": "PickPlaceCube-v0",
-       "stack": "StackTwoCubes-v0"}
+       "stack": "StackTwoCubes-v0", "push_loop": "PushCubeLoop-v0"}
 
 
 def rollout_pair(task, action_mode, precision, n_env, n_step, seed=0, act_scale=1.0, **kw):
@@ -40,7 +40,7 @@ def rollout_pair(task, action_mode, precision, n_env, n_step, seed=0, act_scale=
     return out, diag, oracles
 
 
-@pytest.mark.parametrize("task", ["reach", "push", "lift", "pick_place", "stack"])
+@pytest.mark.parametrize("task", ["reach", "push", "lift", "pick_place", "stack", "push_loop"])
 def test_f64_joint_rollout_matches_oracle(task):
     out, diag, oracles = rollout_pair(task, "joint", "float64", n_env=16, n_step=6)
     for st, ref_st, r, r_ref, te, te_ref, tr, tr_ref in out:
@@ -52,7 +52,7 @@ def test_f64_joint_rollout_matches_oracle(task):
         np.testing.assert_array_equal(tr, tr_ref)
 
 
-@pytest.mark.parametrize("task", ["reach", "pick_place"])
+@pytest.mark.parametrize("task", ["reach", "pick_place", "push_loop"])
 def test_f64_ee_rollout_matches_oracle(task):
     out, diag, oracles = rollout_pair(task, "ee", "float64", n_env=8, n_step=4)
     for st, ref_st, r, r_ref, te, te_ref, tr, tr_ref in out:
@@ -93,6 +93,17 @@ def random_states(task, n, rng, nq, nv):
     for i in range(0, n, 3):
         xpos, _, _ = mjcf.arm_kinematics(m, qpos[i, :6])
         qpos[i, 6:9] = xpos[rng.integers(1, 7)] + rng.uniform(-0.03, 0.03, 3)
+    if task == "push_loop":
+        # two thirds of the envs: cube touching / inside one of the four rails (wall-cube contacts); one third: the gripper
+        # lowered towards a point of a long rail (wall-mesh contacts)
+        walls = np.array([[-0.125, 0.135, 0.005], [0.125, 0.135, 0.005], [0, 0.09, 0.005], [0, 0.18, 0.005]])
+        half = np.array([[0.01, 0.055, 0.007]] * 2 + [[0.125, 0.01, 0.007]] * 2)
+        for i in range(n):
+            k = rng.integers(0, 4)
+            if i % 3 != 2:
+                qpos[i, 6:9] = walls[k] + rng.uniform(-1, 1, 3) * (half[k] + 0.012) + [0, 0, 0.008]
+            else:
+                qpos[i, :6] = rng.uniform([-0.7, 0.7, 0.6, -1.0, -1.5, -1.0], [0.7, 1.22, 1.7, 1.9, 1.5, 0.0])
     if ncube == 2:  # half of the envs: blue cube on / inside the red one
         k = n // 2
         qpos[:k, 13:16] = qpos[:k, 6:9] + rng.uniform(-0.02, 0.02, size=(k, 3)) + np.array([0, 0, 0.02])
@@ -130,7 +141,8 @@ def _contact_err(g, oc):
 # hundreds of nearly coplanar hull vertices, so a last-bit difference (CUDA sincos vs glibc) can flip a vertex in
 # deeply interpenetrating random poses: those envs are counted, not compared.
 @pytest.mark.parametrize("task,mask,min_exact", [("push", 1, 1.0), ("stack", 8, 1.0), ("push", 4, 0.98), ("push", 2, 0.97),
-                                                 ("push", 16, 0.9), ("stack", 31, 0.85)])
+                                                 ("push", 16, 0.9), ("stack", 31, 0.85), ("push_loop", 32, 1.0), ("push_loop", 64, 0.9),
+                                                 ("push_loop", 127, 0.85)])
 def test_f64_contact_geometry_matches_oracle(task, mask, min_exact):
     con, ncon, ref = _contact_lists(task, "float64", mask)
     n = len(ref)
@@ -140,13 +152,13 @@ def test_f64_contact_geometry_matches_oracle(task, mask, min_exact):
     assert exact >= min_exact * n, f"only {exact} of {n} envs have identical contact lists"
 
 
-@pytest.mark.parametrize("task", ["push", "lift", "stack"])
+@pytest.mark.parametrize("task", ["push", "lift", "stack", "push_loop"])
 def test_f64_one_substep_map_from_random_states(task):
     """Single mj_step from identical contact-rich states (all collision types active), CUDA float64 vs oracle.
     Envs whose contact lists agree must agree in the resulting state to 1e-7 (qpos) / 1e-4 (qvel: accelerations
     reach 1e4 rad/s^2 in these deeply penetrating poses and the Newton solver stops at a 1e-8 relative tolerance)."""
     n = 192
-    con, ncon, ref_con = _contact_lists(task, "float64", 31, n=n)
+    con, ncon, ref_con = _contact_lists(task, "float64", 127, n=n)
     env = glr.make(IDS[task], num_envs=n, precision="float64")
     rng = np.random.default_rng(7)
     qpos, qvel, ctrl = random_states(task, n, rng, env.nq, env.nv)
@@ -202,7 +214,7 @@ def test_f32_one_substep_map_from_rollout_states():
     env.close()
 
 
-@pytest.mark.parametrize("task,mode", [("reach", "joint"), ("stack", "joint"), ("pick_place", "ee")])
+@pytest.mark.parametrize("task,mode", [("reach", "joint"), ("stack", "joint"), ("pick_place", "ee"), ("push_loop", "joint"), ("push_loop", "ee")])
 def test_phased_execution_is_bitwise_identical_to_fused(task, mode):
     """exec_mode="phased" (one kernel per mj_step phase, workspace parked in HBM) runs the same device functions as
     the fused kernel: float32 results must be bit-identical, including autoreset at the TimeLimit."""
@@ -229,7 +241,8 @@ def test_phased_execution_is_bitwise_identical_to_fused(task, mode):
 
 @pytest.mark.parametrize("task,mode,warps,flags,sort", [("reach", "joint", 0, 31, 1), ("stack", "joint", 0, 31, 1), ("pick_place", "ee", 4, 31, 1),
                                                         ("push", "joint", 8, 7, 0), ("lift", "joint", 3, 24, 1), ("stack", "joint", 5, 0, 0),
-                                                        ("reach", "joint", 4, 23, 1), ("stack", "joint", 6, 23, 2)])
+                                                        ("reach", "joint", 4, 23, 1), ("stack", "joint", 6, 23, 2), ("push_loop", "joint", 0, 23, 1),
+                                                        ("push_loop", "ee", 5, 31, 0)])
 def test_lockstep_execution_is_bitwise_identical_to_fused(task, mode, warps, flags, sort, monkeypatch):
     """exec_mode="lockstep" (CTAs of several envs re-aligned by barriers at the phase boundaries / Newton iterations, CTA-wide
     narrowphase job pool, envs processed in a work-aware order) runs the same per-env arithmetic as the fused kernel: float32 results must be bit-identical for every

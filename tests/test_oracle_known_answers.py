@@ -245,3 +245,142 @@ def test_mpr_box_mesh_and_self_collision_contacts_are_sane():
         assert -0.03 < c[12] < 0 and abs(np.linalg.norm(c[3:6]) - 1) < 1e-9
         assert c[4] < -0.5  # normal from the cube (geom1) towards the mesh (geom2): -y here
     assert o.diag()["overflow"] == 0
+
+
+# ------------------------------------------------------------------ PushCubeLoop scene (push_cube_loop.xml, push_cube_loop_env.py)
+def test_push_loop_model_constants():
+    m = model.load_compiled("push_loop")
+    s, _ = model.pack_model(m)
+    assert s.task == 5 and s.ncube == 1 and s.nwall == 4
+    np.testing.assert_allclose(np.ctypeslib.as_array(s.wall_pos), [[-0.125, 0.135, 0.005], [0.125, 0.135, 0.005], [0, 0.09, 0.005], [0, 0.18, 0.005]])
+    np.testing.assert_allclose(np.ctypeslib.as_array(s.wall_size), [[0.01, 0.055, 0.007]] * 2 + [[0.125, 0.01, 0.007]] * 2)
+    np.testing.assert_allclose(np.ctypeslib.as_array(s.goal_center), [[0.06, 0.135, 0.01], [-0.06, 0.135, 0.01]])
+    np.testing.assert_allclose(np.ctypeslib.as_array(s.cube_pos0)[0], [0.06, 0.135, 0.017])
+    assert s.cube_mass[0] == 0.05 and s.impratio == 100.0
+    g = s.nmesh  # floor, cube, walls
+    assert list(np.ctypeslib.as_array(s.geom_solref)[g]) == [0.0, 0.0]  # floor solref="0 0" (push_cube_loop.xml:25)
+    assert s.geom_condim[g + 1] == 4 and s.geom_priority[g + 1] == 1
+    np.testing.assert_allclose(np.ctypeslib.as_array(s.geom_friction)[g + 1], [1.5, 1.5, 1.5])
+    assert list(s.geom_condim[g + 2:g + 6]) == [3, 3, 3, 3]
+
+
+def test_push_loop_reset_samples_inside_the_current_goal_region():
+    """push_cube_loop_env.py:302-320 with numpy's generator: low/high = (+-0.0095, +-0.0145, 0.0035), shifted to the
+    centre of the current goal region; the goal persists across resets."""
+    hi = np.array([0.035, 0.045, 0.007]) / 2
+    hi[:2] -= 0.008
+    lo = hi * np.array([-1.0, -1.0, 1.0])
+    centers = np.array([[0.06, 0.135], [-0.06, 0.135]])
+    for goal in (0, 1):
+        o = Oracle("push_loop")
+        st = o.get_state()
+        st["aux"][1] = goal
+        o.set_state(aux=st["aux"])
+        for seed in (0, 5, 99):
+            obs = o.reset(seed=seed)
+            p = np.random.default_rng(seed).uniform(lo, hi)
+            p[:2] += centers[goal]
+            np.testing.assert_array_equal(obs[12:15], p.astype(np.float32))
+            np.testing.assert_array_equal(obs[:12], 0)
+
+
+def _loop_reward_numpy(cube_xy, goal):
+    """get_reward / get_cube_overlap (push_cube_loop_env.py:337-383) restated with the reference's dtypes."""
+    cube = np.asarray(cube_xy, dtype=np.float64).astype(np.float32)
+    centers = np.array([[0.06, 0.135, 0.01], [-0.06, 0.135, 0.01]])
+    high = np.array([0.035, 0.045, 0.007]) / 2
+    high[:2] -= 0.008
+    low = high * np.array([-1.0, -1.0, 1.0])
+    w = 0.015 / 2
+    gx, gy = centers[goal][:2]
+    wg, lg = high[:2]
+    xo = max(0, min(cube[0] + w, gx + wg) - max(cube[0] - w, gx - wg))
+    yo = max(0, min(cube[1] + w, gy + lg) - max(cube[1] - w, gy - lg))
+    overlap = xo * yo / (w * w * 4)
+    if overlap > 0.95:
+        return 5.0, 1, 1 - goal
+    if overlap > 0.0:
+        return float(overlap - 1), 0, goal
+    edge = low[1] + centers[goal][1]
+    d = np.sqrt((cube[1] - edge) ** 2)
+    return float(min(max((-d / 0.16) - 1, -2), -1)), 0, goal
+
+
+def test_push_loop_reward_overlap_and_goal_switch():
+    rng = np.random.default_rng(11)
+    o = Oracle("push_loop", n_substeps=0, max_episode_steps=0)
+    seen = set()
+    for k in range(400):
+        goal = k % 2
+        xy = np.array([rng.uniform(-0.09, 0.09), rng.uniform(0.1, 0.17)])
+        if k % 5 == 0:
+            xy = np.array([0.06, 0.135]) * [1 - 2 * goal, 1] + rng.uniform(-0.002, 0.002, 2)
+        st = o.get_state()
+        st["aux"][1] = goal
+        qpos = st["qpos"].copy()
+        qpos[6:8] = xy
+        o.set_state(qpos=qpos, aux=st["aux"])
+        obs, r, te, tr, su = o.step(np.zeros(5, np.float32))
+        r_ref, su_ref, goal_ref = _loop_reward_numpy(xy, goal)
+        assert r == np.float32(r_ref) and su == bool(su_ref) and not te and not tr, (k, r, r_ref)
+        assert int(o.get_state()["aux"][1]) == goal_ref
+        seen.add("success" if su else ("partial" if r > -1 else "outside"))
+    assert seen == {"success", "partial", "outside"}
+
+
+def test_push_loop_time_limit_truncates_and_never_terminates():
+    o = Oracle("push_loop")
+    o.reset(seed=0)
+    flags = [o.step(np.zeros(5, np.float32))[2:4] for _ in range(50)]
+    assert not any(f[0] for f in flags) and [f[1] for f in flags] == [False] * 49 + [True]
+
+
+def test_push_loop_rails_contain_the_cube():
+    """A cube sliding at 0.6 m/s into each rail from 4 mm away (floor friction 1.5 would stop it within 12 mm) is stopped
+    by the rail: it never gets further than the rail's inner face (plus a transient soft-contact penetration) and stays
+    on the floor inside the 0.23 x 0.07 m pen."""
+    # (axis, direction) -> coordinate of the cube centre when its face touches the rail's inner face
+    inner = {(0, 1): 0.115 - 0.015, (0, -1): -(0.115 - 0.015), (1, 1): 0.17 - 0.015, (1, -1): 0.10 + 0.015}
+    for (ax, sg), lim in inner.items():
+        o = Oracle("push_loop")
+        xy = np.array([0.0, 0.135])
+        xy[ax] = lim - 0.004 * sg
+        qpos = np.r_[np.zeros(6), xy, 0.0149, 1, 0, 0, 0]
+        qvel = np.zeros(12)
+        qvel[6 + ax] = 0.6 * sg
+        o.set_state(qpos=qpos, qvel=qvel, ctrl=np.zeros(6))
+        far, wall_contacts = -1.0, 0
+        for _ in range(300):
+            o.substep(1)
+            far = max(far, sg * (o.get_state()["qpos"][6 + ax] - lim))
+            con = o.get("contacts").reshape(-1, 27)
+            wall_contacts += int(np.sum((con[:, 14] >= 22) & (con[:, 15] == 21)))  # geom1 = a wall (geoms 22..25), geom2 = the cube
+        assert wall_contacts > 0, (ax, sg)
+        # soft contact (solref time constant 0.02 s): the 0.6 m/s impact penetrates a few mm, then the cube is pushed back out
+        assert -1e-3 < far < 4e-3, (ax, sg, far)
+        st = o.get_state()
+        assert sg * (st["qpos"][6 + ax] - lim) < 2e-4, (ax, sg, st["qpos"][6:8])
+        assert abs(st["qpos"][8] - 0.01489) < 5e-4 and np.abs(st["qvel"][6:9]).max() < 0.05
+
+
+def test_push_loop_arm_collides_with_the_rails():
+    """Gripper driven (by the IK helper) onto the two long rails: wall-mesh contacts appear with the wall as geom1 and a
+    moving arm mesh as geom2, unit normals pointing from the rail into the arm (upwards for a touch from above)."""
+    o = Oracle("push_loop", collision_mask=model.COLLIDE_WALL_MESH)
+    found, up = 0, 0
+    rng = np.random.default_rng(3)
+    for k in range(40):
+        target = np.array([rng.uniform(-0.1, 0.1), (0.09, 0.18)[k % 2], rng.uniform(0.0, 0.015)])
+        q = np.zeros(6)
+        for _ in range(4):  # 4 x 10 damped-least-squares iterations
+            o.set_state(qpos=np.r_[q, 0.06, 0.135, 0.0149, 1, 0, 0, 0], qvel=np.zeros(12), ctrl=q)
+            o.forward()
+            q = o.ik(target).astype(np.float64)
+        o.set_state(qpos=np.r_[q, 0.06, 0.135, 0.0149, 1, 0, 0, 0], qvel=np.zeros(12), ctrl=q)
+        o.forward()
+        for c in o.get("contacts").reshape(-1, 27):
+            assert c[14] >= 22 and c[15] < 20  # wall first, arm mesh second
+            assert c[12] < 0 and abs(np.linalg.norm(c[3:6]) - 1) < 1e-9
+            found += 1
+            up += c[5] > 0.5
+    assert found >= 20 and up >= found // 2, (found, up)

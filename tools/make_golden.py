@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 from oracle.oracle import Oracle  # noqa: E402
 
 CASES = [("reach", "joint"), ("reach", "ee"), ("push", "joint"), ("lift", "joint"), ("lift", "ee"),
-         ("pick_place", "joint"), ("pick_place", "ee"), ("stack", "joint")]
+         ("pick_place", "joint"), ("pick_place", "ee"), ("stack", "joint"), ("push_loop", "joint"), ("push_loop", "ee")]
 N_ENV, N_STEP = 4, 12
 
 out_dir = os.path.join(ROOT, "tests", "golden")
