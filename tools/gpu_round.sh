@@ -12,8 +12,14 @@ $B > gpurun_out/bench_reach4096.json 2> gpurun_out/bench_reach4096.err
 $B --no-cpu-baseline --task push --envs 16384 > gpurun_out/bench_push16384.json 2> gpurun_out/bench_push16384.err
 $B --no-cpu-baseline --task pick_place --action-mode ee --envs 8192 > gpurun_out/bench_pickplace_ee8192.json 2> gpurun_out/bench_pickplace_ee8192.err
 $B --no-cpu-baseline --task stack --envs 8192 > gpurun_out/bench_stack8192.json 2> gpurun_out/bench_stack8192.err
+$B --no-cpu-baseline --task push_loop > gpurun_out/bench_pushloop4096.json 2> gpurun_out/bench_pushloop4096.err
+$B --no-cpu-baseline --task push_loop --envs 16384 > gpurun_out/bench_pushloop16384.json 2> gpurun_out/bench_pushloop16384.err
+$B --no-cpu-baseline --envs 16384 > gpurun_out/bench_reach16384.json 2> gpurun_out/bench_reach16384.err
+$B --no-cpu-baseline --envs 65536 --steps 10 > gpurun_out/bench_reach65536.json 2> gpurun_out/bench_reach65536.err
 timeout 300 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 [ "$1" = quick ] && exit 0
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_phased16k.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --envs 16384 > gpurun_out/ncu_list_phased.log 2>&1
+[ "$1" = lists ] && exit 0
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_lockstep.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_step_ls -s 20 -c 1 -o gpurun_out/prof_lockstep python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 timeout 300 python tools/phase_clocks.py ReachCube-v0 4096 25 > gpurun_out/phase_clocks.txt 2>&1
