@@ -1,5 +1,5 @@
 /* lcrsim.h -- C-ABI of liblcrsim.so: the B200 batched replacement for the per-step hot path of
- * gym_lowcostrobot.envs.{ReachCube,PushCube,LiftCube,PickPlaceCube,StackTwoCubes}Env.
+ * gym_lowcostrobot.envs.{ReachCube,PushCube,LiftCube,PickPlaceCube,StackTwoCubes,PushCubeLoop}Env.
  *
  * Every entry point below replaces a piece of the reference's Python->MuJoCo interface; the
  * reference file:line it stands in for is cited per function.  All `d_*` pointers are BORROWED
@@ -28,7 +28,8 @@ enum { LCR_F32 = 0, LCR_F64 = 1 };
  * stack_two_cubes_env.py:290-305; all `.astype(np.float32)`):
  *   Reach/Lift      : arm_qpos[6] arm_qvel[6] cube_pos[3]                      (15)
  *   Push/PickPlace  : arm_qpos[6] arm_qvel[6] target_pos[3] cube_pos[3]        (18)
- *   Stack           : arm_qpos[6] arm_qvel[6] cube_red_pos[3] cube_blue_pos[3] (18) */
+ *   Stack           : arm_qpos[6] arm_qvel[6] cube_red_pos[3] cube_blue_pos[3] (18)
+ *   PushCubeLoop    : arm_qpos[6] arm_qvel[6] cube_pos[3]                      (15)   (push_cube_loop_env.py:286-300) */
 int lcr_obs_dim(int task);
 /* Action width: {joint:5, ee:3} + (block_gripper ? 0 : 1)   (reach_cube_env.py:95-97). */
 int lcr_action_dim(const LcrEnvCfg* cfg);
@@ -48,18 +49,21 @@ int lcr_destroy(LcrSim* sim);
 int lcr_seed(LcrSim* sim, const uint64_t* h_state, void* stream);
 
 /* Replaces Env.reset (reach_cube_env.py:297-311, push_cube_env.py:308-328, lift_cube_env.py:306-320,
- * pick_place_cube_env.py:316-336, stack_two_cubes_env.py:307-324): for every env with
+ * pick_place_cube_env.py:316-336, stack_two_cubes_env.py:307-324, push_cube_loop_env.py:302-320): for every env with
  * d_mask[i] != 0 (all envs if d_mask is NULL) draw cube (and target / second cube) positions
  * from the env's PCG64 stream, write qpos, run mj_forward, and write the observation row.
- * Like the reference it does NOT reset qvel / ctrl / warmstart / time.  Rows of unmasked envs in
- * d_obs are left untouched. */
+ * Like the reference it does NOT reset qvel / ctrl / warmstart / time (nor PushCubeLoop's current goal, in whose
+ * region the cube is drawn).  Rows of unmasked envs in d_obs are left untouched. */
 int lcr_reset(LcrSim* sim, const uint8_t* d_mask, float* d_obs, void* stream);
 
 /* Replaces Env.step (reach_cube_env.py:313-333 = apply_action :223-279 incl. inverse_kinematics
  * :148-221 and the 20x mj_step loop :276-277, get_observation :281-295, is_success/compute_reward
  * :335-348; and the same methods of the other four envs) plus TimeLimit (gym_lowcostrobot/__init__.py).
  * d_actions: [n_envs][action_dim] float32.  Outputs: d_obs [n_envs][obs_dim] f32, d_reward [n_envs]
- * f32, d_terminated / d_truncated / d_success [n_envs] uint8. */
+ * f32, d_terminated / d_truncated / d_success [n_envs] uint8.
+ * PushCubeLoop (push_cube_loop_env.py:322-383): reward = get_reward's overlap reward (+5 on success, overlap - 1, or the
+ * clipped y distance to the goal edge), d_success = info["success"], the env's current goal switches on success,
+ * d_terminated is always 0. */
 int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated,
              uint8_t* d_truncated, uint8_t* d_success, void* stream);
 
@@ -74,7 +78,8 @@ int lcr_pack_outputs(LcrSim* sim, const float* d_obs, const float* d_reward, con
  * reach_cube_env.py:182,185,252,273,285-294,305-306) and provides checkpoint/resume.  Row-major
  * DEVICE arrays of float64 regardless of precision: qpos [n][nq], qvel [n][nv], ctrl [n][6],
  * warm (qacc_warmstart) [n][nv], aux [n][LCR_NAUX] = time, target[3], site_xpos[3],
- * cube_xpos[3*2]; ints [n][LCR_NINT] = elapsed_steps, needs_reset.  Any pointer may be NULL. */
+ * cube_xpos[3*2]; ints [n][LCR_NINT] = elapsed_steps, needs_reset.  Any pointer may be NULL.
+ * PushCubeLoop keeps `current_goal` (0 / 1, push_cube_loop_env.py:136) in target[0]; aux[0] is info["timestamp"]. */
 #define LCR_NAUX 13
 #define LCR_NINT 2
 int lcr_get_state(LcrSim* sim, double* d_qpos, double* d_qvel, double* d_ctrl, double* d_warm, double* d_aux,

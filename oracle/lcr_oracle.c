@@ -13,8 +13,12 @@
  *       solref/solimp impedance, elliptic-cone primal Newton solver, position actuators with
  *       per-joint force range) specialised to the model family of
  *       assets/low_cost_robot_6dof/follower.xml + one scene file.
- * It is pinned by analytic known-answer tests (tests/test_oracle_*.py) and by an independent numpy
- * restatement of the kinematics/dynamics (oracle/np_check.py), not by MuJoCo outputs.
+ * (1) IS PINNED TO THE REFERENCE: tools/make_reference_glue_golden.py imports the unmodified reference env classes
+ * (with stand-ins for the two absent third-party packages and n_substeps=0) and records reset sampling, action maps,
+ * IK iterations, observations, rewards, success flags and PushCubeLoop's goal switching; tests/test_reference_glue.py
+ * replays those fixtures through this file (to 1e-9) and through the CUDA path.
+ * (2) is pinned by analytic known-answer tests (tests/test_oracle_known_answers.py, incl. an independent numpy
+ * restatement of the kinematics / inertia and Lagrangian finite differences), not by MuJoCo outputs.
  * tools/dump_mujoco_golden.py produces MuJoCo golden vectors wherever MuJoCo exists.
  *
  * Plain C99, one environment per OrcSim, scalar double arithmetic.

@@ -22,9 +22,9 @@ def main(ref_root, out_dir):
     import mujoco
 
     ids = {"reach": "ReachCube-v0", "push": "PushCube-v0", "lift": "LiftCube-v0", "pick_place": "PickPlaceCube-v0",
-           "stack": "StackTwoCubes-v0"}
+           "stack": "StackTwoCubes-v0", "push_loop": "PushCubeLoop-v0"}
     cases = [("reach", "joint"), ("reach", "ee"), ("push", "joint"), ("lift", "joint"), ("lift", "ee"),
-             ("pick_place", "joint"), ("pick_place", "ee"), ("stack", "joint")]
+             ("pick_place", "joint"), ("pick_place", "ee"), ("stack", "joint"), ("push_loop", "joint"), ("push_loop", "ee")]
     n_env, n_step = 4, 12
     os.makedirs(out_dir, exist_ok=True)
     for task, mode in cases:
