@@ -242,7 +242,7 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
   s->launches = 1;
   if (cfg->exec_mode == 1) {
     const char* e = getenv("LCR_GROUPS");
-    int g = e ? atoi(e) : 4;
+    int g = e ? atoi(e) : 2;  // measured on B200 (profiles/r01j_sweep32_groups.jsonl): 2 chains overlap each other's launch tails, more only shrink the launches
     g = std::max(1, std::min(16, std::min(g, n_envs)));
     s->ngroups = g;
     for (int k = 0; k < g; k++) {

@@ -101,11 +101,11 @@ class BatchedLowCostRobotEnv:
         """"auto": the lockstep kernel (one launch per step) for small batches, where the step time is the chain of the
         most expensive env and its CTA-wide job pool shortens that chain; the phased chain (one small kernel per mj_step
         phase over all envs) once several waves of envs queue per SM, where its barrier-free scheduling wins (measured
-        crossover on B200 between 4096 and 8192 envs, profiles/README.md).  All modes give bit-identical results
+        crossover on B200 between 4096 and 5120 envs, profiles/README.md).  All modes give bit-identical results
         (tests/test_gpu_parity.py)."""
         if exec_mode != "auto":
             return exec_mode
-        return "phased" if num_envs >= 6144 else "lockstep"
+        return "phased" if num_envs >= 5120 else "lockstep"
 
     # -- helpers ---------------------------------------------------------------------------
     def _stream(self):
