@@ -1,16 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-: > gpurun_out/sweep33.jsonl
-run() { echo "{\"label\": \"$1\"}" >> gpurun_out/sweep33.jsonl; shift; env "$@" >> gpurun_out/sweep33.jsonl 2>> gpurun_out/sweep33.err; }
-B="timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline"
-run "reach5k auto" $B --envs 5120
-run "reach5k lockstep" $B --envs 5120 --exec-mode lockstep
-run "reach8k auto" $B --envs 8192
-run "reach8k G3" LCR_GROUPS=3 $B --envs 8192
-run "reach16k G3" LCR_GROUPS=3 $B --envs 16384
-run "reach64k auto" $B --envs 65536 --steps 10
-run "push16k auto" $B --task push --envs 16384
-run "pp8k ee auto" $B --task pick_place --action-mode ee --envs 8192
-run "stack8k auto" $B --task stack --envs 8192
-run "loop16k auto" $B --task push_loop --envs 16384
-tail -3 gpurun_out/sweep33.err
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_ph_sol -s 820 -c 1 -o gpurun_out/prof_phsol python bench.py --steps 2 --warmup 20 --no-cpu-baseline --envs 16384 > gpurun_out/ncu_full_phsol.log 2>&1
+tail -2 gpurun_out/ncu_full_phsol.log
+timeout 300 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_reach4096.json 2> gpurun_out/bench_reach4096.err; cut -c1-200 gpurun_out/bench_reach4096.json
