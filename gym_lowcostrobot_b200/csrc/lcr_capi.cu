@@ -252,6 +252,12 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
       }
     }
     cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming);
+    // work-aware seats (LCR_PH_SORT=0: identity): the envs with the most constraint rows in their previous step are launched
+    // first in every phase kernel, so that the long Newton solves / MPR jobs do not end up in the tail of the launch
+    const char* ps = getenv("LCR_PH_SORT");
+    if (!ps || atoi(ps) != 0) {
+      if (cudaMalloc(&s->perm, sizeof(int) * (2 * (size_t)n_envs + 16)) != cudaSuccess) { fail("lcr_create: cudaMalloc(perm) failed"); return 1; }
+    }
   }
   if (cfg->exec_mode == 2) {  // tuning overrides for experiments; the defaults are the measured best
     const char* e = getenv("LCR_LS_WARPS");
@@ -311,17 +317,22 @@ int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward,
   if (sim->cfg.exec_mode == 1) {
     cudaStream_t st = (cudaStream_t)stream;
     const int G = sim->ngroups, per = (sim->n + G - 1) / G;
+    if (sim->perm) {  // seats in work-aware order: group g owns perm[g * per, (g + 1) * per), heaviest envs first, -1 = padding
+      if (sim->precision == LCR_F32) lcr::Launch<float>::sched(sim->f.s, sim->perm, per, 1, st);
+      else lcr::Launch<double>::sched(sim->d.s, sim->perm, per, 1, st);
+      sim->launches++;
+    }
     CUDA_OK(cudaEventRecord(sim->ev_begin, st));
     for (int g = 0; g < G; g++) {
-      const int env0 = g * per, cnt = std::min(per, sim->n - env0);
-      if (cnt <= 0) break;
+      const int env0 = g * per, cnt = sim->perm ? per : std::min(per, sim->n - env0);
+      if (env0 >= sim->n) break;
       CUDA_OK(cudaStreamWaitEvent(sim->gstream[g], sim->ev_begin, 0));
       if (sim->precision == LCR_F32)
         sim->launches += lcr::Launch<float>::step_phased(sim->ncube, sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, d_actions, d_obs,
-                                                         d_reward, d_terminated, d_truncated, d_success, env0, cnt, sim->gstream[g]);
+                                                         d_reward, d_terminated, d_truncated, d_success, env0, cnt, sim->perm, sim->gstream[g]);
       else
         sim->launches += lcr::Launch<double>::step_phased(sim->ncube, sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, d_actions, d_obs,
-                                                          d_reward, d_terminated, d_truncated, d_success, env0, cnt, sim->gstream[g]);
+                                                          d_reward, d_terminated, d_truncated, d_success, env0, cnt, sim->perm, sim->gstream[g]);
       CUDA_OK(cudaEventRecord(sim->ev_done[g], sim->gstream[g]));
       CUDA_OK(cudaStreamWaitEvent(st, sim->ev_done[g], 0));
     }

@@ -167,7 +167,7 @@ struct Launch {
                             uint8_t* term, uint8_t* trunc, uint8_t* succ, int grid, int warps, int epc, int flags, const int* perm, long long* prof,
                             cudaStream_t st);
   static int step_phased(int ncube, int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, const float* actions,
-                         float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, cudaStream_t st);
+                         float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, const int* perm, cudaStream_t st);
   static void substeps(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, int n, cudaStream_t st);
   static void ik(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* target, float* q_out, cudaStream_t st);
   static void get_state(int ncube, DevState<T> s, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,

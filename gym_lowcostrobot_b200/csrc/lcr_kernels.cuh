@@ -1667,13 +1667,18 @@ DI void store_ws_J(const Ws<T, NC>& w, Ws<T, NC>* g, int env) {
   store_ws_range(w, g, env, LCR_OFF(J), LCR_OFF(J) + ((w.nefc * WsT::JS * (int)sizeof(T) + 15) / 16) * 16);
 }
 
+// seat -> env of the phased chain: identity, or the work-aware order written by k_sched (heaviest envs of the previous
+// step first, dealt out to the env groups like cards; -1 = padding seat)
+DI int ph_env(const int* __restrict__ perm, int seat) { return perm ? perm[seat] : seat; }
+
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_begin(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
                                                      Ws<T, NC>* __restrict__ gws, const float* __restrict__ actions, float* __restrict__ obs,
                                                      float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
-                                                     uint8_t* __restrict__ succ, int env0) {
+                                                     uint8_t* __restrict__ succ, int env0, const int* __restrict__ perm) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = env0 + blockIdx.x;
+  const int env = ph_env(perm, env0 + blockIdx.x);
+  if (env < 0) return;
   load_state(w, s, env);
   const DevModel<T>& m = *dm;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
@@ -1686,11 +1691,11 @@ __global__ void __launch_bounds__(32, 16) k_ph_begin(const DevModel<T>* __restri
 
 // [integrate the previous substep] -> checks -> kinematics -> inertia / bias -> smooth forces
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int first, int env0) {
+__global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int first, int env0, const int* __restrict__ perm) {
   typedef Ws<T, NC> WsT;
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = env0 + blockIdx.x;
-  if (gws[env].skip) return;
+  const int env = ph_env(perm, env0 + blockIdx.x);
+  if (env < 0 || gws[env].skip) return;
   // reads: state, dynamics vectors (M, qacc for the integration of the previous substep), counts + cache, candidate block
   load_ws_range(w, gws, env, 0, LCR_OFF(xpos));
   load_ws_range(w, gws, env, LCR_OFF(M), LCR_OFF(H));
@@ -1716,8 +1721,9 @@ __global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict
 // candidate result rows.  No shared memory, so the hull vertices stay L1 resident.
 #define LCR_NSLOT 4
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_ph_job(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0) {
-  const int env = env0 + blockIdx.x / LCR_NSLOT, slot = blockIdx.x % LCR_NSLOT;
+__global__ void __launch_bounds__(32, 16) k_ph_job(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0, const int* __restrict__ perm) {
+  const int env = ph_env(perm, env0 + blockIdx.x / LCR_NSLOT), slot = blockIdx.x % LCR_NSLOT;
+  if (env < 0) return;
   Ws<T, NC>& w = gws[env];
   if (w.skip) return;
   const int n = w.ncand < LCR_MAXCAND ? w.ncand : LCR_MAXCAND;
@@ -1730,11 +1736,11 @@ __global__ void __launch_bounds__(32, 16) k_ph_job(const DevModel<T>* __restrict
 }
 
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0) {
+__global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0, const int* __restrict__ perm) {
   typedef Ws<T, NC> WsT;
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = env0 + blockIdx.x;
-  if (gws[env].skip) return;
+  const int env = ph_env(perm, env0 + blockIdx.x);
+  if (env < 0 || gws[env].skip) return;
   // reads: state, kinematics, the job results (they alias e_w / e_g / e_p), counts + cache, candidate block
   load_ws_range(w, gws, env, 0, LCR_OFF(M));
   load_ws_range(w, gws, env, LCR_OFF(e_w), LCR_OFF(e_unit));
@@ -1749,11 +1755,11 @@ __global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict
   store_ws_J(w, gws, env);
 }
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_ph_sol(const DevModel<T>* __restrict__ dm, Ws<T, NC>* __restrict__ gws, int env0) {
+__global__ void __launch_bounds__(32, 16) k_ph_sol(const DevModel<T>* __restrict__ dm, Ws<T, NC>* __restrict__ gws, int env0, const int* __restrict__ perm) {
   typedef Ws<T, NC> WsT;
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = env0 + blockIdx.x;
-  if (gws[env].skip) return;
+  const int env = ph_env(perm, env0 + blockIdx.x);
+  if (env < 0 || gws[env].skip) return;
   // reads: state (warm start), dynamics vectors, contact scalars (not positions / frames), row parameters, counts, flags, J
   load_ws_range(w, gws, env, 0, LCR_OFF(xpos));
   load_ws_range(w, gws, env, LCR_OFF(M), LCR_OFF(H));
@@ -1775,10 +1781,11 @@ __global__ void __launch_bounds__(32, 16) k_ph_sol(const DevModel<T>* __restrict
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_end(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
                                                    Ws<T, NC>* __restrict__ gws, float* __restrict__ obs, float* __restrict__ reward,
-                                                   uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ, int env0) {
+                                                   uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ, int env0,
+                                                   const int* __restrict__ perm) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = env0 + blockIdx.x;
-  if (gws[env].skip) return;
+  const int env = ph_env(perm, env0 + blockIdx.x);
+  if (env < 0 || gws[env].skip) return;
   typedef Ws<T, NC> WsT;
   load_ws_range(w, gws, env, 0, LCR_OFF(xpos));          // state
   load_ws_range(w, gws, env, LCR_OFF(M), LCR_OFF(H));    // M, qacc
@@ -1973,25 +1980,25 @@ void Launch<T>::step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, 
 // one chain of 2 + 3*n_substeps launches over the env range [env0, env0 + cnt) on stream st
 template <typename T, int NC>
 static void phased_chain(int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws_, const float* actions, float* obs,
-                         float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, cudaStream_t st) {
+                         float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, const int* perm, cudaStream_t st) {
   typedef Ws<T, NC> W;
   W* gws = reinterpret_cast<W*>(gws_);
   const size_t sm = sizeof(W);
-  k_ph_begin<T, NC><<<cnt, 32, sm, st>>>(dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0);
+  k_ph_begin<T, NC><<<cnt, 32, sm, st>>>(dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, perm);
   for (int k = 0; k < n_substeps; k++) {
-    k_ph_dyn<T, NC><<<cnt, 32, sm, st>>>(dm, verts, gws, k == 0, env0);
-    k_ph_job<T, NC><<<cnt * LCR_NSLOT, 32, 0, st>>>(dm, verts, gws, env0);
-    k_ph_col<T, NC><<<cnt, 32, sm, st>>>(dm, verts, gws, env0);
-    k_ph_sol<T, NC><<<cnt, 32, sm, st>>>(dm, gws, env0);
+    k_ph_dyn<T, NC><<<cnt, 32, sm, st>>>(dm, verts, gws, k == 0, env0, perm);
+    k_ph_job<T, NC><<<cnt * LCR_NSLOT, 32, 0, st>>>(dm, verts, gws, env0, perm);
+    k_ph_col<T, NC><<<cnt, 32, sm, st>>>(dm, verts, gws, env0, perm);
+    k_ph_sol<T, NC><<<cnt, 32, sm, st>>>(dm, gws, env0, perm);
   }
-  k_ph_end<T, NC><<<cnt, 32, sm, st>>>(dm, verts, s, gws, obs, reward, term, trunc, succ, env0);
+  k_ph_end<T, NC><<<cnt, 32, sm, st>>>(dm, verts, s, gws, obs, reward, term, trunc, succ, env0, perm);
 }
 template <typename T>
 int Launch<T>::step_phased(int ncube, int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, const float* actions,
-                           float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, cudaStream_t st) {
-  if (ncube == 1) phased_chain<T, 1>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, st);
-  else if (ncube == 2) phased_chain<T, 2>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, st);
-  else phased_chain<T, LCR_NC_LOOP>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, st);
+                           float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, const int* perm, cudaStream_t st) {
+  if (ncube == 1) phased_chain<T, 1>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, perm, st);
+  else if (ncube == 2) phased_chain<T, 2>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, perm, st);
+  else phased_chain<T, LCR_NC_LOOP>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, perm, st);
   return 2 + 4 * n_substeps;
 }
 template <typename T>

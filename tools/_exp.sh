@@ -1,8 +1,15 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_ph_sol -s 820 -c 1 -o gpurun_out/prof_phsol python bench.py --steps 2 --warmup 20 --no-cpu-baseline --envs 16384 > gpurun_out/ncu_full_phsol.log 2>&1
-tail -2 gpurun_out/ncu_full_phsol.log
-timeout 300 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_reach4096.json 2> gpurun_out/bench_reach4096.err; cut -c1-200 gpurun_out/bench_reach4096.json
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py tests/test_golden.py -m gpu -q -k "phased or mode_independent or shards or invariants or packed" 2>&1 | tail -3
+: > gpurun_out/sweep35.jsonl
+run() { echo "{\"label\": \"$1\"}" >> gpurun_out/sweep35.jsonl; shift; env "$@" >> gpurun_out/sweep35.jsonl 2>> gpurun_out/sweep35.err; }
+B="timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline"
+run "reach16k sorted" $B --envs 16384
+run "reach16k unsorted" LCR_PH_SORT=0 $B --envs 16384
+run "stack8k sorted" $B --task stack --envs 8192
+run "stack8k unsorted" LCR_PH_SORT=0 $B --task stack --envs 8192
+run "pp8k ee sorted" $B --task pick_place --action-mode ee --envs 8192
+run "reach5k sorted" $B --envs 5120
+run "reach4k phased sorted" $B --exec-mode phased
+run "reach64k sorted" $B --envs 65536 --steps 10
+tail -3 gpurun_out/sweep35.err
