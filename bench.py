@@ -289,9 +289,9 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = min(n_local, 64 * cores)
-            rate, dt = CpuRollout(args.task, args.action_mode, sample, cores).run(300)
+            rate, dt = CpuRollout(args.task, args.action_mode, sample, cores).run(600)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"{sample} envs x 300 env.steps (episodes of 50, autoreset) on {cores} threads ({dt:.1f} s); float64 oracle port, "
+                                    "sample": f"{sample} envs x 600 env.steps (episodes of 50, autoreset) on {cores} threads ({dt:.1f} s); float64 oracle port, "
                                               "MuJoCo not installable here"}
         print(json.dumps(line), flush=True)
     if world > 1:
