@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
-timeout 300 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; cut -c1-300 gpurun_out/bench_default.json
-timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --task push_loop --envs 16384 > gpurun_out/bench_pushloop16384.json 2>/dev/null; cut -c1-120 gpurun_out/bench_pushloop16384.json
+T="timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5"
+$T > gpurun_out/bench_2gpu_reach4096.json 2> gpurun_out/bench_2gpu.err; tail -1 gpurun_out/bench_2gpu_reach4096.json | cut -c1-200
+$T --task stack --envs 8192 > gpurun_out/bench_2gpu_stack.json 2>> gpurun_out/bench_2gpu.err; tail -1 gpurun_out/bench_2gpu_stack.json | cut -c1-200
+timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_1of2gpu_reach4096.json 2>> gpurun_out/bench_2gpu.err; cut -c1-120 gpurun_out/bench_1of2gpu_reach4096.json
+tail -3 gpurun_out/bench_2gpu.err
