@@ -1,7 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-T="timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5"
-$T > gpurun_out/bench_2gpu_reach4096.json 2> gpurun_out/bench_2gpu.err; tail -1 gpurun_out/bench_2gpu_reach4096.json | cut -c1-200
-$T --task stack --envs 8192 > gpurun_out/bench_2gpu_stack.json 2>> gpurun_out/bench_2gpu.err; tail -1 gpurun_out/bench_2gpu_stack.json | cut -c1-200
-timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_1of2gpu_reach4096.json 2>> gpurun_out/bench_2gpu.err; cut -c1-120 gpurun_out/bench_1of2gpu_reach4096.json
-tail -3 gpurun_out/bench_2gpu.err
+: > gpurun_out/sanitizer.log
+for cfg in "PushCubeLoop-v0 phased" "PushCubeLoop-v0 lockstep" "PushCubeLoop-v0 fused" "StackTwoCubes-v0 phased"; do
+  echo "### memcheck $cfg" >> gpurun_out/sanitizer.log
+  timeout 150 compute-sanitizer --tool memcheck --print-limit 5 python tools/san_small.py $cfg 24 3 2>&1 | grep -v "^$" | tail -6 >> gpurun_out/sanitizer.log
+done
+echo "### racecheck PushCubeLoop-v0 lockstep" >> gpurun_out/sanitizer.log
+timeout 200 compute-sanitizer --tool racecheck --print-limit 5 python tools/san_small.py PushCubeLoop-v0 lockstep 24 2 2>&1 | grep -v "^$" | tail -8 >> gpurun_out/sanitizer.log
+cat gpurun_out/sanitizer.log
