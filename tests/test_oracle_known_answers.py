@@ -384,3 +384,40 @@ def test_push_loop_arm_collides_with_the_rails():
             found += 1
             up += c[5] > 0.5
     assert found >= 20 and up >= found // 2, (found, up)
+
+
+@pytest.mark.parametrize("task", ["push", "stack", "push_loop"])
+def test_separating_axis_cache_never_changes_the_physics(task):
+    """The cache of the convex narrowphase only decides HOW a separation is proven (cached axis with vertex-free bounds,
+    exact support test, or MPR), never the contacts: a rollout whose cache is emptied before every substep (set_state does
+    that) must be bit-identical to the free-running one."""
+    import ctypes
+
+    from oracle.oracle import lib
+
+    stats = (ctypes.c_long * 8)()
+    lib().orc_stats(stats, 1)
+    rng = np.random.default_rng(5)
+    for seed in range(3):
+        a, b = Oracle(task), Oracle(task)
+        a.reset(seed=seed)
+        b.reset(seed=seed)
+        lo = np.array([-3.14159, -1.5708, -1.48353, -1.91986, -2.96706])
+        hi = np.array([3.14159, 1.22173, 1.74533, 1.91986, 2.96706])
+        ncon = 0
+        for step in range(4):
+            ctrl = np.r_[np.clip(a.get_state()["qpos"][:5] + rng.uniform(-1, 1, 5), lo, hi), 0.0]
+            for o in (a, b):
+                o.set_state(ctrl=ctrl)
+            for k in range(20):
+                a.substep(1)
+                st = b.get_state()
+                b.set_state(qpos=st["qpos"], qvel=st["qvel"], ctrl=st["ctrl"], warm=st["warm"])  # empties b's cache
+                b.substep(1)
+                ncon += a.diag()["ncon"]
+            sa, sb = a.get_state(), b.get_state()
+            np.testing.assert_array_equal(sa["qpos"], sb["qpos"])
+            np.testing.assert_array_equal(sa["qvel"], sb["qvel"])
+        assert ncon > 0
+    lib().orc_stats(stats, 0)
+    assert stats[0] > 0 and stats[6] > 0, list(stats)  # MPR ran, and cached axes answered broadphase survivors
