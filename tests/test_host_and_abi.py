@@ -72,10 +72,11 @@ def test_compiled_models_are_consistent():
 
 @pytest.mark.skipif(not os.path.isdir(REF_ASSETS), reason="reference assets not mounted")
 def test_compiled_assets_match_a_fresh_parse_of_the_reference_mjcf():
-    for task in ("reach", "stack"):
+    for task in ("reach", "stack", "push_loop"):
         fresh = mjcf.compile_model(REF_ASSETS, task)
         stored = model.load_compiled(task)
-        for k in ("body_pos", "body_quat", "body_mass", "jnt_axis", "jnt_range", "verts", "mesh_vertadr", "pair_g1",
+        extra = ("wall_pos", "wall_size", "goal_center", "goal_size", "cube_pos0", "geom_solref") if task == "push_loop" else ()
+        for k in extra + ("body_pos", "body_quat", "body_mass", "jnt_axis", "jnt_range", "verts", "mesh_vertadr", "pair_g1",
                   "geom_friction", "geom_solimp", "dof_invweight0", "body_invweight0", "meaninertia", "mesh_com"):
             np.testing.assert_allclose(np.asarray(fresh[k], float), np.asarray(stored[k], float), atol=1e-12, err_msg=k)
 
