@@ -421,3 +421,77 @@ def test_separating_axis_cache_never_changes_the_physics(task):
         assert ncon > 0
     lib().orc_stats(stats, 0)
     assert stats[0] > 0 and stats[6] > 0, list(stats)  # MPR ran, and cached axes answered broadphase survivors
+
+
+def _constraint_cost(a, M, a0, J, aref, D, nlim, contacts):
+    """MuJoCo's primal objective, restated in numpy from the published formulation (Gauss term + limit rows + elliptic
+    cones in their three zones): 1/2 (a - a0)^T M (a - a0) + sum_units s(J a - aref)."""
+    jar = J @ a - aref
+    da = a - a0
+    cost = 0.5 * da @ M @ da
+    for i in range(nlim):
+        if jar[i] < 0:
+            cost += 0.5 * D[i] * jar[i] ** 2
+    i = nlim
+    for dim, mu, fr in contacts:
+        x = jar[i:i + dim]
+        if dim == 1:
+            cost += 0.5 * D[i] * x[0] ** 2 if x[0] < 0 else 0.0
+        else:
+            scale = np.r_[mu, fr[:dim - 1]]
+            u = x * scale
+            N, T = u[0], np.linalg.norm(u[1:])
+            if N >= mu * T or (T <= 0 and N >= 0):
+                pass
+            elif mu * N + T <= 0 or (T <= 0 and N < 0):
+                cost += 0.5 * np.sum(D[i:i + dim] * x * x)
+            else:
+                cost += 0.5 * D[i] / (mu * mu * (1 + mu * mu)) * (N - mu * T) ** 2
+        i += dim
+    return cost
+
+
+@pytest.mark.parametrize("task", ["push", "stack", "push_loop"])
+def test_newton_solution_minimises_the_published_objective(task):
+    """The oracle's qacc must be a minimiser of MuJoCo's convex primal objective evaluated by an independent numpy
+    restatement: a general-purpose optimiser (scipy BFGS, restarted from the oracle's point and from qacc_smooth) finds
+    no point that is better by more than the solver tolerance."""
+    from scipy.optimize import minimize
+
+    rng = np.random.default_rng(21)
+    m = model.load_compiled(task)
+    lo = np.array([-3.14159, -1.5708, -1.48353, -1.91986, -2.96706, -1.74533])
+    hi = np.array([3.14159, 1.22173, 1.74533, 1.91986, 2.96706, 0.0523599])
+    checked, zones = 0, 0
+    for trial in range(40):
+        o = Oracle(task)
+        nq, nv = o.nq, o.nv
+        qpos = np.zeros(nq)
+        qpos[:6] = rng.uniform(lo, hi)
+        xpos, _, _ = mjcf.arm_kinematics(m, qpos[:6])
+        for c in range((nq - 6) // 7):
+            p = qpos[6 + 7 * c: 13 + 7 * c]
+            p[:3] = xpos[rng.integers(1, 7)] + rng.uniform(-0.03, 0.03, 3) if trial % 2 else [rng.uniform(-0.1, 0.1), rng.uniform(0.1, 0.2), rng.uniform(0.0, 0.02)]
+            q = rng.normal(size=4)
+            p[3:] = q / np.linalg.norm(q)
+        o.set_state(qpos=qpos, qvel=rng.normal(scale=0.5, size=nv), ctrl=rng.uniform(lo, hi), warm=np.zeros(nv))
+        o.forward()
+        d = o.diag()
+        if d["nefc"] == 0 or d["overflow"]:
+            continue
+        nefc = d["nefc"]
+        M = o.get("M").reshape(nv, nv)
+        J = o.get("efc_J").reshape(nefc, nv)
+        D, aref, a0, a = o.get("efc_D"), o.get("efc_aref"), o.get("qacc_smooth"), o.get("qacc")
+        con = o.get("contacts").reshape(-1, 27)
+        contacts = [(int(c[13]), c[16], c[17:22]) for c in con]
+        nlim = nefc - sum(c[0] for c in contacts)
+        f = lambda x: _constraint_cost(x, M, a0, J, aref, D, nlim, contacts)
+        c_oracle = f(a)
+        best = min(minimize(f, x0, method="BFGS", options={"gtol": 1e-10, "maxiter": 2000}).fun for x0 in (a, a0))
+        scale = abs(c_oracle) + 1e-3
+        assert c_oracle <= best + 1e-6 * scale, (task, trial, c_oracle, best, d)
+        assert c_oracle <= f(a0) + 1e-12  # never worse than the unconstrained acceleration
+        checked += 1
+        zones += c_oracle > 1e-9
+    assert checked >= 15 and zones >= 8, (checked, zones)
