@@ -1,10 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-: > gpurun_out/sanitizer.log
-for cfg in "PushCubeLoop-v0 phased" "PushCubeLoop-v0 lockstep" "PushCubeLoop-v0 fused" "StackTwoCubes-v0 phased"; do
-  echo "### memcheck $cfg" >> gpurun_out/sanitizer.log
-  timeout 150 compute-sanitizer --tool memcheck --print-limit 5 python tools/san_small.py $cfg 24 3 2>&1 | grep -v "^$" | tail -6 >> gpurun_out/sanitizer.log
-done
-echo "### racecheck PushCubeLoop-v0 lockstep" >> gpurun_out/sanitizer.log
-timeout 200 compute-sanitizer --tool racecheck --print-limit 5 python tools/san_small.py PushCubeLoop-v0 lockstep 24 2 2>&1 | grep -v "^$" | tail -8 >> gpurun_out/sanitizer.log
-cat gpurun_out/sanitizer.log
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_lockstep.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
+tail -2 gpurun_out/ncu_list.log | cut -c1-150
+B="timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline"
+$B --task lift > gpurun_out/bench_lift4096.json 2>/dev/null; cut -c1-100 gpurun_out/bench_lift4096.json
+$B --task push_loop --action-mode ee --envs 8192 > gpurun_out/bench_pushloop_ee8192.json 2>/dev/null; cut -c1-100 gpurun_out/bench_pushloop_ee8192.json
