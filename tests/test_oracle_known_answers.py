@@ -495,3 +495,82 @@ def test_newton_solution_minimises_the_published_objective(task):
         checked += 1
         zones += c_oracle > 1e-9
     assert checked >= 15 and zones >= 8, (checked, zones)
+
+
+@pytest.mark.parametrize("task", ["push", "stack", "push_loop"])
+def test_contact_jacobian_matches_finite_differences_of_the_kinematics(task):
+    """Row r of efc_J times a generalized velocity v is the relative velocity of the two bodies' material points at the
+    contact (translational rows) / their relative angular velocity (torsional and rolling rows) along the contact frame
+    axes, body 2 minus body 1.  Checked against central differences of the forward kinematics alone (cube angular
+    velocity is body-local, as in MuJoCo's free joint)."""
+    rng = np.random.default_rng(8)
+    m = model.load_compiled(task)
+    nmesh = len(m["mesh_body"])
+    lo = np.array([-3.14159, -1.5708, -1.48353, -1.91986, -2.96706, -1.74533])
+    hi = np.array([3.14159, 1.22173, 1.74533, 1.91986, 2.96706, 0.0523599])
+
+    def body_of(g, ncube):
+        if g < nmesh:
+            return int(m["mesh_body"][g])
+        c = g - nmesh - 1
+        return 7 + c if 0 <= c < ncube else -1  # floor / static walls: the world
+
+    def integrate(qpos, v, eps, ncube):
+        q = qpos.copy()
+        q[:6] += eps * v[:6]
+        for c in range(ncube):
+            q[6 + 7 * c: 9 + 7 * c] += eps * v[6 + 6 * c: 9 + 6 * c]
+            w = eps * v[9 + 6 * c: 12 + 6 * c]  # body-local rotation vector
+            ang = np.linalg.norm(w)
+            dq = np.r_[np.cos(ang / 2), (np.sin(ang / 2) / ang) * w] if ang > 0 else np.array([1.0, 0, 0, 0])
+            q[9 + 7 * c: 13 + 7 * c] = mjcf.quat_mul(q[9 + 7 * c: 13 + 7 * c], dq)
+        return q
+
+    def poses(o, qpos, nv):
+        o.set_state(qpos=qpos, qvel=np.zeros(nv))
+        o.forward()
+        return o.get("xpos").reshape(9, 3).copy(), o.get("xmat").reshape(9, 3, 3).copy()
+
+    rows_checked = 0
+    for trial in range(12):
+        o = Oracle(task)
+        nq, nv = o.nq, o.nv
+        ncube = (nq - 6) // 7
+        qpos = np.zeros(nq)
+        qpos[:6] = rng.uniform(lo, hi)
+        xp, _, _ = mjcf.arm_kinematics(m, qpos[:6])
+        for c in range(ncube):
+            p = qpos[6 + 7 * c: 13 + 7 * c]
+            p[:3] = xp[rng.integers(1, 7)] + rng.uniform(-0.03, 0.03, 3) if trial % 2 else [rng.uniform(-0.1, 0.1), rng.uniform(0.1, 0.2), 0.01]
+            q = rng.normal(size=4)
+            p[3:] = q / np.linalg.norm(q)
+        x0, R0 = poses(o, qpos, nv)
+        d = o.diag()
+        if d["nefc"] == 0 or d["overflow"]:
+            continue
+        J = o.get("efc_J").reshape(d["nefc"], nv)
+        con = o.get("contacts").reshape(-1, 27)
+        nlim = d["nefc"] - int(con[:, 13].sum())
+        v = rng.normal(size=nv)
+        eps = 1e-6
+        (xa, Ra), (xb, Rb) = poses(o, integrate(qpos, v, eps, ncube), nv), poses(o, integrate(qpos, v, -eps, ncube), nv)
+        row = nlim
+        for c in con:
+            dim, frame, pos = int(c[13]), c[3:12].reshape(3, 3), c[0:3]
+            rel_v, rel_w = np.zeros(3), np.zeros(3)
+            for b, sg in ((body_of(int(c[14]), ncube), -1.0), (body_of(int(c[15]), ncube), 1.0)):
+                if b < 0:
+                    continue
+                local = R0[b].T @ (pos - x0[b])
+                rel_v += sg * ((xa[b] + Ra[b] @ local) - (xb[b] + Rb[b] @ local)) / (2 * eps)
+                W = (Ra[b] @ Rb[b].T - Rb[b] @ Ra[b].T) / (4 * eps)  # skew part of dR R^T / (2 eps)
+                rel_w += sg * np.array([W[2, 1], W[0, 2], W[1, 0]])
+            expect = np.r_[frame @ rel_v, frame @ rel_w][:dim if dim <= 3 else None]
+            if dim == 1:
+                expect = expect[:1]
+            elif dim == 4:
+                expect = np.r_[frame @ rel_v, (frame @ rel_w)[:1]]
+            np.testing.assert_allclose(J[row:row + dim] @ v, expect[:dim], rtol=0, atol=2e-7)
+            row += dim
+            rows_checked += dim
+    assert rows_checked >= 60, rows_checked
