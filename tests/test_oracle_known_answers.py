@@ -574,3 +574,37 @@ def test_contact_jacobian_matches_finite_differences_of_the_kinematics(task):
             row += dim
             rows_checked += dim
     assert rows_checked >= 60, rows_checked
+
+
+@pytest.mark.parametrize("task,mu,mass", [("push", 0.5, 0.1), ("pick_place", 0.5, 10.0), ("push_loop", 1.5, 0.05)])
+def test_sliding_contacts_sit_on_the_coulomb_cone(task, mu, mass):
+    """A cube sliding flat on the floor: every active contact carries a friction force of exactly mu times its normal
+    force, opposed to the sliding direction (elliptic cone boundary; mu = the cube geom's sliding friction, which has
+    priority over the floor's: push_cube.xml:28, push_cube_loop.xml:31), the four normal forces carry the weight and the
+    normal acceleration the solver asks for, and the cube's deceleration is the friction sum over its mass."""
+    o = Oracle(task)
+    assert np.isclose(model.load_compiled(task)["cube_mass"][0], mass)
+    qpos = np.r_[np.zeros(6), 0.0, 0.135, 0.014892, 1, 0, 0, 0]
+    qvel = np.zeros(12)
+    qvel[6] = 0.4
+    o.set_state(qpos=qpos, qvel=qvel, ctrl=np.zeros(6))
+    o.substep(1)
+    con = o.get("contacts").reshape(-1, 27)
+    f = o.get("efc_force")
+    assert len(con) == 4 and all(int(c[13]) == 4 for c in con)
+    fx, active = 0.0, 0
+    for k, c in enumerate(con):
+        fn, ft = f[4 * k], f[4 * k + 1: 4 * k + 3]
+        frame = c[3:12].reshape(3, 3)
+        if fn == 0:  # mu > 1: the friction torque unloads the trailing edge (the cube starts to tip)
+            assert mu > 1 and np.all(ft == 0)
+            continue
+        active += 1
+        np.testing.assert_allclose(np.linalg.norm(ft), mu * fn, rtol=1e-6)
+        world = fn * frame[0] + ft[0] * frame[1] + ft[1] * frame[2]  # force on the cube (geom 2 of the floor-cube pair)
+        assert world[0] < 0 and abs(world[1]) < 1e-9 * fn + 1e-12
+        fx += world[0]
+        assert abs(f[4 * k + 3]) < 1e-9  # no torsion
+    assert active == (4 if mu < 1 else 2)
+    decel = (0.4 - o.get_state()["qvel"][6]) / 0.002
+    np.testing.assert_allclose(decel, -fx / mass, rtol=1e-9)
