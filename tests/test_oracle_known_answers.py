@@ -608,3 +608,15 @@ def test_sliding_contacts_sit_on_the_coulomb_cone(task, mu, mass):
     assert active == (4 if mu < 1 else 2)
     decel = (0.4 - o.get_state()["qvel"][6]) / 0.002
     np.testing.assert_allclose(decel, -fx / mass, rtol=1e-9)
+
+
+@pytest.mark.parametrize("task,mass", [("push", 0.1), ("pick_place", 10.0), ("push_loop", 0.05)])
+def test_resting_cube_is_carried_by_its_weight(task, mass):
+    """Equilibrium on the floor: the four corner contacts share the weight equally and carry no friction."""
+    o = Oracle(task)
+    o.set_state(qpos=np.r_[np.zeros(6), 0.0, 0.135, 0.0149, 1, 0, 0, 0], qvel=np.zeros(12), ctrl=np.zeros(6))
+    o.substep(600)
+    f = o.get("efc_force").reshape(4, 4)
+    np.testing.assert_allclose(f[:, 0], mass * 9.81 / 4, rtol=1e-6)
+    assert np.abs(f[:, 1:]).max() < 1e-9 * mass * 9.81 + 1e-12
+    assert np.abs(o.get_state()["qvel"][6:]).max() < 1e-9
