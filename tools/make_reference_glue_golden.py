@@ -210,10 +210,24 @@ def sample_state(env, rng, i):
 
 out_dir = os.path.join(ROOT, "tests", "golden", "ref_glue")
 os.makedirs(out_dir, exist_ok=True)
-for task, cls in CASES:
-    for mode in ("joint", "ee"):
+import json  # noqa: E402
+
+# default constructor arguments for every env x action mode, plus variants with non-default kwargs (the quirks they pin:
+# LiftCube with block_gripper=True uses action[-1] = the 5th arm action for the gripper too, lift_cube_env.py:264;
+# block_gripper=False adds an ignored action entry in Reach / PushCubeLoop; sampling ranges and thresholds)
+RUNS = [(task, cls, mode, "", {}) for task, cls in CASES for mode in ("joint", "ee")] + [
+    ("lift", "LiftCubeEnv", "joint", "blocked", dict(block_gripper=True)),
+    ("reach", "ReachCubeEnv", "joint", "gripper", dict(block_gripper=False, distance_threshold=0.03, cube_xy_range=0.2)),
+    ("push", "PushCubeEnv", "ee", "ranges", dict(cube_xy_range=0.2, target_xy_range=0.25, distance_threshold=0.08)),
+    ("pick_place", "PickPlaceCubeEnv", "joint", "ranges", dict(goal_z_range=0.2, target_xy_range=0.1, block_gripper=True)),
+    ("stack", "StackTwoCubesEnv", "ee", "ranges", dict(cube_xy_range=0.15, distance_threshold=0.02)),
+    ("push_loop", "PushCubeLoopEnv", "joint", "gripper", dict(block_gripper=False)),
+    ("push_loop", "PushCubeLoopEnv", "ee", "gripper", dict(block_gripper=False)),
+]
+for task, cls, mode, variant, extra in RUNS:
+    if True:
         rng = np.random.default_rng(77)
-        kw = dict(observation_mode="state", action_mode=mode, n_substeps=0)
+        kw = dict(observation_mode="state", action_mode=mode, n_substeps=0, **extra)
         envs = {}
         has_reward_type = task not in ("lift", "push_loop")
         for rt in (("sparse", "dense") if has_reward_type else (None,)):
@@ -246,6 +260,6 @@ for task, cls in CASES:
             rec["qpos_after"].append(env.data.qpos.copy())
             rec["goal_after"].append(env.current_goal if task == "push_loop" else 0)
             rec["dense"].append(rt == "dense")
-        path = os.path.join(out_dir, f"{task}_{mode}.npz")
-        np.savez_compressed(path, obs_keys=np.array(list(obs)), **{k: np.asarray(v) for k, v in rec.items()})
+        path = os.path.join(out_dir, f"{task}_{mode}" + (f"__{variant}" if variant else "") + ".npz")
+        np.savez_compressed(path, obs_keys=np.array(list(obs)), kwargs=np.array(json.dumps(extra)), **{k: np.asarray(v) for k, v in rec.items()})
         print(path, os.path.getsize(path), "success:", int(np.sum(rec["success"])), "of", K)
