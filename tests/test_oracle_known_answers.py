@@ -620,3 +620,35 @@ def test_resting_cube_is_carried_by_its_weight(task, mass):
     np.testing.assert_allclose(f[:, 0], mass * 9.81 / 4, rtol=1e-6)
     assert np.abs(f[:, 1:]).max() < 1e-9 * mass * 9.81 + 1e-12
     assert np.abs(o.get_state()["qvel"][6:]).max() < 1e-9
+
+
+def test_joint_limit_row_matches_the_published_impedance_formulas():
+    """Joint 3 held 5 mm-equivalent (0.005 rad) beyond its upper limit at rest: one limit row with
+    pos = -r, impedance d = dmax = 0.95 (|pos| >= width 0.001), aref = -B vel - K d pos with K = 1 / (dmax^2 tc^2 zeta^2),
+    B = 2 / (dmax tc) for solref (0.02, 1), R = (1 - d) / d * dof_invweight0, D = 1 / R, Jacobian -e_3."""
+    o = Oracle("reach", collision_mask=0)
+    m = model.load_compiled("reach")
+    r, j = 0.005, 2
+    q = np.zeros(6)
+    q[j] = m["jnt_range"][j][1] + r
+    for vel in (0.0, 0.3):
+        qvel = np.zeros(12)
+        qvel[j] = vel
+        o.set_state(qpos=np.r_[q, 0.0, 0.3, 0.0149, 1, 0, 0, 0], qvel=qvel, ctrl=q)
+        o.forward()
+        assert o.diag()["nefc"] == 1
+        J = o.get("efc_J").reshape(1, 12)
+        expect_J = np.zeros(12)
+        expect_J[j] = -1.0
+        np.testing.assert_array_equal(J[0], expect_J)
+        np.testing.assert_allclose(o.get("efc_pos")[0], -r, atol=1e-15)
+        K, B, d = 1 / (0.95**2 * 0.02**2), 2 / (0.95 * 0.02), 0.95
+        np.testing.assert_allclose(o.get("efc_aref")[0], -B * (-vel) - K * d * (-r), rtol=1e-12)
+        R = (1 - d) / d * m["dof_invweight0"][j]
+        np.testing.assert_allclose(o.get("efc_R")[0], R, rtol=1e-12)
+        np.testing.assert_allclose(o.get("efc_D")[0], 1 / R, rtol=1e-12)
+        f = o.get("efc_force")[0]
+        assert f >= 0  # unilateral: can only push the joint back inside (0 when the servo, whose target is clamped to the range, already does)
+        np.testing.assert_allclose(o.get("qfrc_constraint")[j], -f, rtol=1e-12, atol=1e-15)
+        jar = J[0] @ o.get("qacc") - o.get("efc_aref")[0]
+        np.testing.assert_allclose(f, max(0.0, -jar / R), rtol=1e-9, atol=1e-12)  # f = -D min(0, J a - aref)
