@@ -652,3 +652,36 @@ def test_joint_limit_row_matches_the_published_impedance_formulas():
         np.testing.assert_allclose(o.get("qfrc_constraint")[j], -f, rtol=1e-12, atol=1e-15)
         jar = J[0] @ o.get("qacc") - o.get("efc_aref")[0]
         np.testing.assert_allclose(f, max(0.0, -jar / R), rtol=1e-9, atol=1e-12)  # f = -D min(0, J a - aref)
+
+
+@pytest.mark.parametrize("task,mass,fr", [("push", 0.1, (0.5, 0.005)), ("push_loop", 0.05, (1.5, 1.5))])
+def test_contact_rows_match_the_published_regularisation(task, mass, fr):
+    """Floor-cube corner contact (condim 4, cube priority 1) of a cube at rest, penetration r at the corners:
+    normal row R0 = (1 - d) / d * (1 / m) with d = d(r) from solimp (0.9, 0.95, 0.001, 0.5, 2), aref0 = -B v - K d (-r);
+    elliptic cone: R1 = R2 = R0 / impratio, R3 = R1 mu1^2 / mu_torsion^2, friction rows have no position term, and the
+    regularised cone's mu = mu1 sqrt(R1 / R0) = mu1 / sqrt(impratio) (impratio = 100 from follower.xml:3)."""
+    o = Oracle(task)
+    z = 0.0148
+    o.set_state(qpos=np.r_[np.zeros(6), 0.0, 0.135, z, 1, 0, 0, 0], qvel=np.zeros(12), ctrl=np.zeros(6))
+    o.forward()
+    con = o.get("contacts").reshape(-1, 27)
+    assert len(con) == 4 and o.diag()["nefc"] == 16
+    r = 0.015 - z
+    x = r / 0.001
+    assert x < 1
+    y = x**2 / 0.5 if x <= 0.5 else 1 - (1 - x) ** 2 / 0.5  # power 2, midpoint 0.5
+    d = 0.9 + y * 0.05
+    K, B = 1 / (0.95**2 * 0.02**2), 2 / (0.95 * 0.02)
+    R, aref, pos = o.get("efc_R"), o.get("efc_aref"), o.get("efc_pos")
+    for k, c in enumerate(con):
+        assert int(c[13]) == 4
+        np.testing.assert_allclose(c[12], -r, atol=1e-12)
+        np.testing.assert_allclose(c[16], fr[0] / 10.0, rtol=1e-12)  # contact.mu
+        np.testing.assert_allclose(c[17:20], [fr[0], fr[0], fr[1]], rtol=1e-12)
+        R0 = (1 - d) / d / mass
+        np.testing.assert_allclose(R[4 * k], R0, rtol=1e-9)
+        np.testing.assert_allclose(R[4 * k + 1: 4 * k + 3], R0 / 100, rtol=1e-9)
+        np.testing.assert_allclose(R[4 * k + 3], R0 / 100 * fr[0] ** 2 / fr[1] ** 2, rtol=1e-9)
+        np.testing.assert_allclose(aref[4 * k], K * d * r, rtol=1e-9)
+        np.testing.assert_allclose(aref[4 * k + 1: 4 * k + 4], 0, atol=1e-12)
+        np.testing.assert_allclose(pos[4 * k], -r, atol=1e-12)
