@@ -685,3 +685,27 @@ def test_contact_rows_match_the_published_regularisation(task, mass, fr):
         np.testing.assert_allclose(aref[4 * k], K * d * r, rtol=1e-9)
         np.testing.assert_allclose(aref[4 * k + 1: 4 * k + 4], 0, atol=1e-12)
         np.testing.assert_allclose(pos[4 * k], -r, atol=1e-12)
+
+
+def test_wall_cube_contacts_have_the_expected_geometry():
+    """Cube face 1 mm inside the inner face of each rail: face contacts with the normal pointing from the rail (geom 1)
+    into the pen towards the cube (geom 2), depth 1 mm, contact points on the overlap rectangle of the two faces
+    (z between the floor-level bottom of the cube and the 12 mm top of the rail)."""
+    cases = {22: ((-0.115 + 0.015 - 0.001, 0.135), (1, 0, 0)), 23: ((0.115 - 0.015 + 0.001, 0.135), (-1, 0, 0)),
+             24: ((0.0, 0.10 + 0.015 - 0.001), (0, 1, 0)), 25: ((0.0, 0.17 - 0.015 + 0.001), (0, -1, 0))}
+    for wall, (xy, normal) in cases.items():
+        o = Oracle("push_loop", collision_mask=model.COLLIDE_WALL_CUBE)
+        o.set_state(qpos=np.r_[np.zeros(6), xy, 0.015, 1, 0, 0, 0], qvel=np.zeros(12), ctrl=np.zeros(6))
+        o.forward()
+        con = o.get("contacts").reshape(-1, 27)
+        assert len(con) == 4, (wall, len(con))
+        for c in con:
+            assert (int(c[14]), int(c[15]), int(c[13])) == (wall, 21, 4)
+            np.testing.assert_allclose(c[3:6], normal, atol=1e-12)
+            np.testing.assert_allclose(c[12], -0.001, atol=1e-12)
+            assert -1e-12 <= c[2] <= 0.012 + 1e-12
+            np.testing.assert_allclose(c[17:20], [1.5, 1.5, 1.5])  # the cube's friction (priority 1)
+        # mid-surface points: half a depth inside the rail's face
+        axis = int(np.argmax(np.abs(normal)))
+        face = {22: -0.115, 23: 0.115, 24: 0.10, 25: 0.17}[wall]
+        np.testing.assert_allclose(con[:, axis], face - 0.0005 * normal[axis], atol=1e-12)  # between the two overlapping faces
