@@ -709,3 +709,61 @@ def test_wall_cube_contacts_have_the_expected_geometry():
         axis = int(np.argmax(np.abs(normal)))
         face = {22: -0.115, 23: 0.115, 24: 0.10, 25: 0.17}[wall]
         np.testing.assert_allclose(con[:, axis], face - 0.0005 * normal[axis], atol=1e-12)  # between the two overlapping faces
+
+
+@pytest.mark.parametrize("task", ["push", "push_loop"])
+def test_mpr_depth_is_bracketed_by_exact_hull_geometry(task):
+    """Convex narrowphase (MPR) against plain numpy / Qhull on the hull vertices.  MPR reports the distance from the origin
+    to the final portal triangle (a triangle inscribed in the boundary of the Minkowski difference A - B whose plane is
+    within the tolerance of a supporting plane) and the direction to its closest point, so for every box-mesh / mesh-mesh
+    contact: exact minimum penetration depth (nearest facet of the Minkowski difference) <= reported depth <= overlap of
+    the two hulls along the reported normal, max_A a.n - min_B b.n; the normal is a unit vector from geom 1 to geom 2 and
+    the contact point lies inside the overlap slab."""
+    from scipy.spatial import ConvexHull
+
+    rng = np.random.default_rng(31)
+    m = model.load_compiled(task)
+    nmesh = len(m["mesh_body"])
+    lo = np.array([-3.14159, -1.5708, -1.48353, -1.91986, -2.96706, -1.74533])
+    hi = np.array([3.14159, 1.22173, 1.74533, 1.91986, 2.96706, 0.0523599])
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float)
+
+    def world_verts(o, g, qpos):
+        xpos, xmat = o.get("xpos").reshape(9, 3), o.get("xmat").reshape(9, 3, 3)
+        if g < nmesh:
+            b = int(m["mesh_body"][g])
+            v = m["verts"][m["mesh_vertadr"][g]: m["mesh_vertadr"][g] + m["mesh_vertnum"][g]]
+            return xpos[b] + v @ xmat[b].T
+        c = g - nmesh - 1
+        if c < int(m["ncube"]):
+            return xpos[7 + c] + (corners * m["cube_size"][c]) @ xmat[7 + c].T
+        w = c - int(m["ncube"])
+        return m["wall_pos"][w] + corners * m["wall_size"][w]
+
+    checked, exact_checked, tight = 0, 0, 0
+    for trial in range(60):
+        o = Oracle(task, collision_mask=model.COLLIDE_CUBE_MESH | model.COLLIDE_MESH_MESH | model.COLLIDE_WALL_MESH)
+        qpos = np.zeros(13)
+        qpos[:6] = rng.uniform(lo, hi)
+        xp, _, _ = mjcf.arm_kinematics(m, qpos[:6])
+        qpos[6:9] = xp[rng.integers(1, 7)] + rng.uniform(-0.03, 0.03, 3)
+        q = rng.normal(size=4)
+        qpos[9:13] = q / np.linalg.norm(q)
+        o.set_state(qpos=qpos, qvel=np.zeros(12), ctrl=qpos[:6])
+        o.forward()
+        for c in o.get("contacts").reshape(-1, 27):
+            g1, g2, n, depth = int(c[14]), int(c[15]), c[3:6], -c[12]
+            A, B = world_verts(o, g1, qpos), world_verts(o, g2, qpos)
+            assert abs(np.linalg.norm(n) - 1) < 1e-9 and depth > 0
+            overlap = (A @ n).max() - (B @ n).min()
+            assert depth <= overlap + 1e-6, (g1, g2, overlap, depth)
+            tight += abs(overlap - depth) < 1e-5
+            assert (B @ n).min() - 1e-6 <= c[0:3] @ n <= (A @ n).max() + 1e-6
+            assert (A.mean(0) - B.mean(0)) @ n < overlap  # n points from geom 1 towards geom 2
+            checked += 1
+            if exact_checked < 12 and len(A) * len(B) < 60000:
+                hull = ConvexHull((A[:, None, :] - B[None, :, :]).reshape(-1, 3))
+                assert np.all(hull.equations[:, 3] < 1e-9)  # the origin is inside: the hulls do intersect
+                assert -hull.equations[:, 3].max() <= depth + 1e-5, (g1, g2, -hull.equations[:, 3].max(), depth)
+                exact_checked += 1
+    assert checked >= 40 and exact_checked >= 8 and tight >= checked // 4, (checked, exact_checked, tight)
