@@ -767,3 +767,21 @@ def test_mpr_depth_is_bracketed_by_exact_hull_geometry(task):
                 assert -hull.equations[:, 3].max() <= depth + 1e-5, (g1, g2, -hull.equations[:, 3].max(), depth)
                 exact_checked += 1
     assert checked >= 40 and exact_checked >= 8 and tight >= checked // 4, (checked, exact_checked, tight)
+
+
+def test_free_cube_rotation_is_the_exact_quaternion_exponential():
+    """Torque-free cube with isotropic inertia: the body-local angular velocity stays constant and the orientation after
+    n substeps is exp(n h w / 2) exactly (each step multiplies by the exponential of h w, as mju_quatIntegrate does)."""
+    o = Oracle("reach", collision_mask=0)
+    w = np.array([1.0, -2.0, 3.0])
+    qvel = np.zeros(12)
+    qvel[9:12] = w
+    o.set_state(qpos=np.r_[np.zeros(6), 0.0, 0.3, 0.5, 1, 0, 0, 0], qvel=qvel, ctrl=np.zeros(6))
+    n = 100
+    o.substep(n)
+    st = o.get_state()
+    ang = np.linalg.norm(w) * n * 0.002
+    expect = np.r_[np.cos(ang / 2), np.sin(ang / 2) * w / np.linalg.norm(w)]
+    np.testing.assert_allclose(st["qpos"][9:13], expect, atol=1e-13)
+    np.testing.assert_allclose(st["qvel"][9:12], w, atol=1e-13)
+    np.testing.assert_allclose(st["qvel"][6:9], [0, 0, -9.81 * n * 0.002], atol=1e-12)
