@@ -1,8 +1,7 @@
 """lcr_ik (the batched IK helper of the C-ABI, reference inverse_kinematics reach_cube_env.py:148-221 called on its own)
-against the oracle.  Written after the GPU budget of round 1 was spent: NOT YET RUN ON HARDWARE, hence the non-strict
-xfail marker (a pass shows up as XPASS, a failure cannot mask the validated tests); remove the marker after the first
-green GPU run.  The in-step IK that shares the device function is covered by tests/test_gpu_parity.py (ee rollouts) and
-tests/test_reference_glue.py (reference fixtures)."""
+against the oracle; the helper must not modify the simulation.  The in-step IK that shares the device function is covered
+by tests/test_gpu_parity.py (ee rollouts) and tests/test_reference_glue.py (reference fixtures).  Green on B200:
+profiles/r01l_ik_helper_gpu.log."""
 import numpy as np
 import pytest
 import torch
@@ -10,7 +9,7 @@ import torch
 import gym_lowcostrobot_b200 as glr
 from oracle.oracle import Oracle
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet run on hardware (round-1 GPU budget spent)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("precision,tol", [("float64", 2e-6), ("float32", 2e-3)])
