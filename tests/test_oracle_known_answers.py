@@ -824,3 +824,49 @@ def test_box_box_depth_is_the_exact_minimum_translation():
         assert deepest <= overlap + 1e-9 and deepest >= 0.3 * overlap  # clipped points never deeper than the overlap
         checked += 1
     assert checked >= 40
+
+
+def test_floor_contacts_are_hull_vertices_below_the_plane():
+    """Plane-box and plane-hull contacts against plain numpy on the vertices: every floor contact sits at a vertex of the
+    other geom that is below z = 0 (dist = its z, position = the vertex lifted by half the depth, normal +z), a geom has
+    at most 4 of them, and its first one is the deepest vertex of a mesh / the contacts of a cube are all its corners
+    below the plane."""
+    rng = np.random.default_rng(19)
+    m = model.load_compiled("push")
+    nmesh = len(m["mesh_body"])
+    lo = np.array([-3.14159, -1.5708, -1.48353, -1.91986, -2.96706, -1.74533])
+    hi = np.array([3.14159, 1.22173, 1.74533, 1.91986, 2.96706, 0.0523599])
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float) * 0.015
+    n_mesh_contacts = n_cube_contacts = 0
+    for trial in range(40):
+        o = Oracle("push", collision_mask=model.COLLIDE_FLOOR_CUBE | model.COLLIDE_FLOOR_MESH)
+        qpos = np.zeros(13)
+        qpos[:6] = rng.uniform(lo, hi)
+        qpos[6:9] = [rng.uniform(-0.1, 0.1), rng.uniform(0.1, 0.25), rng.uniform(0.0, 0.02)]
+        q = rng.normal(size=4)
+        qpos[9:13] = q / np.linalg.norm(q)
+        o.set_state(qpos=qpos, qvel=np.zeros(12), ctrl=qpos[:6])
+        o.forward()
+        if o.diag()["overflow"]:
+            continue
+        con = o.get("contacts").reshape(-1, 27)
+        xpos, xmat = o.get("xpos").reshape(9, 3), o.get("xmat").reshape(9, 3, 3)
+        for g in sorted(set(con[:, 15].astype(int))):
+            cs = con[con[:, 15] == g]
+            assert np.all(cs[:, 14] == nmesh) and len(cs) <= 4
+            if g < nmesh:
+                b = int(m["mesh_body"][g])
+                V = xpos[b] + m["verts"][m["mesh_vertadr"][g]: m["mesh_vertadr"][g] + m["mesh_vertnum"][g]] @ xmat[b].T
+                np.testing.assert_allclose(cs[0, 12], V[:, 2].min(), atol=1e-12)  # deepest vertex first
+                n_mesh_contacts += len(cs)
+            else:
+                V = xpos[7] + corners @ xmat[7].T
+                assert len(cs) == min(4, int((V[:, 2] < 0).sum()))
+                n_cube_contacts += len(cs)
+            for c in cs:
+                np.testing.assert_allclose(c[3:6], [0, 0, 1], atol=1e-15)
+                k = int(np.argmin(np.abs(V[:, 2] - c[12]) + np.linalg.norm(V[:, :2] - c[0:2], axis=1)))
+                np.testing.assert_allclose(c[12], V[k, 2], atol=1e-12)
+                np.testing.assert_allclose(c[0:3], V[k] - [0, 0, 0.5 * V[k, 2]], atol=1e-12)
+                assert V[k, 2] < 0
+    assert n_mesh_contacts >= 30 and n_cube_contacts >= 30, (n_mesh_contacts, n_cube_contacts)
