@@ -16,9 +16,10 @@ F32, F64 = 0, 1
 
 # every symbol declared in include/lcrsim.h
 SYMBOLS = (
-    "lcr_obs_dim", "lcr_action_dim", "lcr_create", "lcr_destroy", "lcr_seed", "lcr_reset", "lcr_step", "lcr_pack_outputs",
-    "lcr_get_state", "lcr_set_state", "lcr_substeps", "lcr_ik", "lcr_get_diag", "lcr_debug_contacts", "lcr_debug_phase_clocks", "lcr_n_envs",
-    "lcr_kernel_launches", "lcr_last_error", "lcr_version", "lcr_sizeof_model", "lcr_sizeof_cfg",
+    "lcr_obs_dim", "lcr_action_dim", "lcr_create", "lcr_destroy", "lcr_seed", "lcr_reset", "lcr_step", "lcr_step_rec", "lcr_pack_outputs",
+    "lcr_get_state", "lcr_set_state", "lcr_substeps", "lcr_ik", "lcr_get_diag", "lcr_debug_contacts", "lcr_debug_phase_clocks",
+    "lcr_debug_flow_stats", "lcr_flow_status", "lcr_n_envs", "lcr_kernel_launches", "lcr_last_error", "lcr_version", "lcr_sizeof_model",
+    "lcr_sizeof_cfg",
 )
 
 _LIB = None
@@ -38,17 +39,20 @@ def lib():
         vp, i = C.c_void_p, C.c_int
         L.lcr_create.argtypes = [vp, vp, vp, i, i, i, C.POINTER(vp)]
         L.lcr_destroy.argtypes = [vp]
-        L.lcr_seed.argtypes = [vp, vp, vp]
+        L.lcr_seed.argtypes = [vp, vp, vp, vp]
         L.lcr_reset.argtypes = [vp, vp, vp, vp]
         L.lcr_step.argtypes = [vp] * 8
+        L.lcr_step_rec.argtypes = [vp] * 9
         L.lcr_pack_outputs.argtypes = [vp] * 8
-        L.lcr_get_state.argtypes = [vp] * 8
-        L.lcr_set_state.argtypes = [vp] * 8
+        L.lcr_get_state.argtypes = [vp] * 9
+        L.lcr_set_state.argtypes = [vp] * 9
         L.lcr_substeps.argtypes = [vp, i, vp]
         L.lcr_ik.argtypes = [vp, vp, vp, vp]
         L.lcr_get_diag.argtypes = [vp, vp, vp]
         L.lcr_debug_contacts.argtypes = [vp, vp, vp, vp]
         L.lcr_debug_phase_clocks.argtypes = [vp, vp]
+        L.lcr_debug_flow_stats.argtypes = [vp, vp]
+        L.lcr_flow_status.argtypes = [vp, vp]
         L.lcr_n_envs.argtypes = [vp]
         L.lcr_kernel_launches.argtypes = [vp]
         L.lcr_action_dim.argtypes = [vp]

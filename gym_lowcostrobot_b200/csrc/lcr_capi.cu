@@ -156,13 +156,32 @@ void build_model(const LcrModel& m, const LcrEnvCfg& c, DevModel<T>& d) {
   for (int k = 0; k < 3; k++) { d.cube_low[k] = c.cube_low[k]; d.cube_high[k] = c.cube_high[k]; d.target_low[k] = c.target_low[k]; d.target_high[k] = c.target_high[k]; }
 }
 
+// dispatch on the scene class (S = 1, 2 cubes or LCR_NC_LOOP)
+#define LCR_DISPATCH(T, nc, CALL)                          \
+  do {                                                     \
+    if ((nc) == 1) lcr::LaunchNC<T, 1>::CALL;              \
+    else if ((nc) == 2) lcr::LaunchNC<T, 2>::CALL;         \
+    else lcr::LaunchNC<T, LCR_NC_LOOP>::CALL;              \
+  } while (0)
+#define LCR_DISPATCH_RET(T, nc, out, CALL)                 \
+  do {                                                     \
+    if ((nc) == 1) out = lcr::LaunchNC<T, 1>::CALL;        \
+    else if ((nc) == 2) out = lcr::LaunchNC<T, 2>::CALL;   \
+    else out = lcr::LaunchNC<T, LCR_NC_LOOP>::CALL;        \
+  } while (0)
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 template <typename T>
 struct Impl {
   DevModel<T>* dm = nullptr;
   T* verts = nullptr;
   DevState<T> s{};
-  void* gws = nullptr;  // per-env workspaces for the phased execution mode
-  int nf = 0;
+  void* gws = nullptr;  // per-env parked workspaces of the phased and flow execution modes
+  int nf = 0, nc = 0;
 
   int create(const LcrModel& m, const double* hv, const LcrEnvCfg& c, int n) {
     DevModel<T> h;
@@ -179,10 +198,14 @@ struct Impl {
     CUDA_OK(cudaMalloc(&s.st, sizeof(T) * (size_t)s.nfp * n));
     CUDA_OK(cudaMalloc(&s.ib, sizeof(int32_t) * LCR_IB_WORDS * (size_t)n));
     CUDA_OK(cudaMalloc(&s.sa, (size_t)Ws<T, 1>::SA_BYTES * n));
-    const int nc = scene_class(m.task, m.ncube);
-    if (c.exec_mode == 1) CUDA_OK(cudaMalloc(&gws, lcr::Launch<T>::smem_bytes(nc) * (size_t)n));
-    lcr::Launch<T>::prepare(nc);
-    lcr::Launch<T>::init_state(nc, dm, s, 0);
+    nc = scene_class(m.task, m.ncube);
+    if (c.exec_mode == 1 || c.exec_mode == 3) {
+      size_t wsb = 0;
+      LCR_DISPATCH_RET(T, nc, wsb, ws_bytes());
+      CUDA_OK(cudaMalloc(&gws, wsb * (size_t)n));
+    }
+    LCR_DISPATCH(T, nc, prepare());
+    lcr::Launch<T>::init_state(dm, s, 0);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaDeviceSynchronize());
     return 0;
@@ -195,16 +218,25 @@ struct Impl {
 }  // namespace
 
 struct LcrSim {
-  int precision, device, n, ncube, task, launches;
+  int precision = 0, device = 0, n = 0, ncube = 0, task = 0, launches = 0;
   // phased mode: the env range is cut into groups, each with its own stream, so that the tail of one group's
   // variable-cost kernels (collision, solver) overlaps the other groups' work
   int ngroups = 0;
   long long* prof = nullptr;  // debug: per-env phase clocks of the last lockstep step, see lcr_debug_phase_clocks
-  int* perm = nullptr;  // lockstep mode: work-aware env order of the current step (device, int[n])
+  int* perm = nullptr;  // lockstep / phased mode: work-aware env order of the current step (device)
   int ls_striped = 1;  // seat order of the lockstep scheduler, see k_sched
   int ls_warps = 0, ls_flags = 0;  // lockstep mode: envs per CTA (0 = as many as fit one SM) and LCR_LS_* barrier flags
-  cudaStream_t gstream[16];
-  cudaEvent_t ev_begin, ev_done[16];
+  cudaStream_t gstream[16] = {};
+  cudaEvent_t ev_begin = nullptr, ev_done[16] = {};
+  // envs that outgrew the fast workspace in the current call: device counter + list, redone over the big workspace
+  int* redo = nullptr;
+  // flow mode: queue control block + rings, grid, tunables
+  FlowQ fq{};
+  unsigned* fq_mem = nullptr;
+  unsigned long long* fq_rings = nullptr;
+  int flow_grid = 0, flow_bigcta = 0, flow_flags = 0, flow_thi = 0, flow_tbig = 0;
+  unsigned long long* flow_stats = nullptr;  // debug: busy clocks per phase of the flow kernel, see lcr_debug_flow_stats
+  unsigned long long* seed_buf = nullptr;    // device staging of lcr_seed
   LcrModel model;
   LcrEnvCfg cfg;
   Impl<float> f;
@@ -214,6 +246,58 @@ struct LcrSim {
 #define WITH_DEVICE(sim)                                  \
   if (!(sim)) return fail("null handle");                 \
   CUDA_OK(cudaSetDevice((sim)->device));
+
+// run CALL (a LaunchNC member call) in the sim's precision and scene class
+#define LCR_RUN(sim, CALL_F, CALL_D)                                          \
+  do {                                                                        \
+    if ((sim)->precision == LCR_F32) LCR_DISPATCH(float, (sim)->ncube, CALL_F); \
+    else LCR_DISPATCH(double, (sim)->ncube, CALL_D);                          \
+  } while (0)
+
+namespace {
+Redo redo_of(const LcrSim* s) { return Redo{s->redo, s->redo + 1}; }
+
+unsigned next_pow2(size_t x) { unsigned p = 1; while (p < x) p <<= 1; return p; }
+
+int create_flow(LcrSim* s) {
+  if (s->n >= LCR_FQ_MAXENV) return fail("lcr_create: flow mode holds at most 2^20 - 1 envs per device");
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, s->device));
+  s->flow_grid = std::max(2, env_int("LCR_FLOW_GRID", prop.multiProcessorCount));
+  // BIG CTAs: the envs that need the big workspace are ~1e-3 of the batch but each keeps a warp busy for the whole step
+  // (measured on B200, PushCube 16 384 mid-episode: 4 BIG CTAs 41.9 ms / step, 8: 38.4, 16: 36.8 -- the envs on the BIG path are the
+  //  tail of the step, each keeps one warp busy for 10 - 20 ms)
+  s->flow_bigcta = std::max(0, std::min(s->flow_grid - 1, env_int("LCR_FLOW_BIGCTA", s->n >= 12288 ? 12 : (s->n >= 2048 ? 6 : 2))));  // (0: debug only)
+  s->flow_flags = env_int("LCR_FLOW_FLAGS", 1);
+  if (env_int("LCR_STACK", 0) > 0) CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)env_int("LCR_STACK", 0)));  // debug
+  s->flow_thi = env_int("LCR_FLOW_THI", 40);
+  // envs start on the BIG path only if their previous step ended far beyond the fast caps (measured: predicting at 88 rows sent
+  // envs there that would not have overflowed again: 41.9 ms / step against 39.2 with migration alone)
+  s->flow_tbig = env_int("LCR_FLOW_TBIG", 112);
+  // rings: one per phase and priority, n entries each; the JOB rings hold one item per convex candidate
+  // (64-bit slots seq << 32 | item; slot i starts free for ticket i; twice the items that can be outstanding, so that a
+  // producer practically never waits for the consumer of the previous lap)
+  size_t slots = 0, off[LCR_FQ_NQ];
+  for (int q = 0; q < LCR_FQ_NQ; q++) {
+    const size_t cap = next_pow2(2 * ((q / 2 == FQ_JOB) ? (size_t)s->n * (3 * LCR_MAXEFC / 8) : (size_t)s->n));
+    s->fq.mask[q] = (unsigned)(cap - 1);
+    off[q] = slots;
+    slots += cap;
+  }
+  CUDA_OK(cudaMalloc(&s->fq_mem, LCR_FQ_CTL_WORDS * sizeof(unsigned)));
+  CUDA_OK(cudaMemset(s->fq_mem, 0, LCR_FQ_CTL_WORDS * sizeof(unsigned)));
+  CUDA_OK(cudaMalloc(&s->fq_rings, slots * sizeof(unsigned long long)));
+  {
+    std::vector<unsigned long long> init(slots);
+    for (int q = 0; q < LCR_FQ_NQ; q++)
+      for (size_t i = 0; i <= s->fq.mask[q]; i++) init[off[q] + i] = (unsigned long long)i << 32;
+    CUDA_OK(cudaMemcpy(s->fq_rings, init.data(), slots * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  }
+  s->fq.ctl = s->fq_mem;
+  for (int q = 0; q < LCR_FQ_NQ; q++) s->fq.ring[q] = reinterpret_cast<unsigned*>(s->fq_rings + off[q]);
+  return 0;
+}
+}  // namespace
 
 extern "C" {
 
@@ -230,47 +314,46 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
   if ((model->task == LCR_TASK_PUSH_LOOP) != (model->nwall > 0) || (model->task == LCR_TASK_PUSH_LOOP && (model->ncube != 1 || model->nwall != LCR_MAXWALL)))
     return fail("lcr_create: static wall boxes are the four rails of the PushCubeLoop scene (one cube)");
   if (precision != LCR_F32 && precision != LCR_F64) return fail("lcr_create: precision must be LCR_F32 or LCR_F64");
+  if (cfg->exec_mode < 0 || cfg->exec_mode > 3) return fail("lcr_create: exec_mode must be 0 (fused), 1 (phased), 2 (lockstep) or 3 (flow)");
   int ndev = 0;
   CUDA_OK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail("lcr_create: no such CUDA device");
   CUDA_OK(cudaSetDevice(device));
   LcrSim* s = new LcrSim();
-  s->precision = precision; s->device = device; s->n = n_envs; s->ncube = scene_class(model->task, model->ncube); s->task = model->task; s->launches = 0;
+  s->precision = precision; s->device = device; s->n = n_envs; s->ncube = scene_class(model->task, model->ncube); s->task = model->task;
   s->model = *model; s->cfg = *cfg;
-  int rc = precision == LCR_F32 ? s->f.create(*model, hull_verts, *cfg, n_envs) : s->d.create(*model, hull_verts, *cfg, n_envs);
-  if (rc) { delete s; return rc; }
+  // (every failure below goes through lcr_destroy: nothing allocated so far is leaked)
+#define LCR_CREATE_OK(call) do { if ((call) != cudaSuccess) { fail(std::string("lcr_create: ") + #call + " failed: " + cudaGetErrorString(cudaGetLastError())); lcr_destroy(s); return 1; } } while (0)
+  if (precision == LCR_F32 ? s->f.create(*model, hull_verts, *cfg, n_envs) : s->d.create(*model, hull_verts, *cfg, n_envs)) { lcr_destroy(s); return 1; }
   s->launches = 1;
+  LCR_CREATE_OK(cudaMalloc(&s->redo, sizeof(int) * ((size_t)n_envs + 1)));
+  LCR_CREATE_OK(cudaMemset(s->redo, 0, sizeof(int)));
+  LCR_CREATE_OK(cudaMalloc(&s->seed_buf, 32 * (size_t)n_envs));
   if (cfg->exec_mode == 1) {
-    const char* e = getenv("LCR_GROUPS");
-    int g = e ? atoi(e) : 2;  // measured on B200 (profiles/r01j_sweep32_groups.jsonl): 2 chains overlap each other's launch tails, more only shrink the launches
+    int g = env_int("LCR_GROUPS", 2);  // measured on B200 (profiles/r01j_sweep32_groups.jsonl): 2 chains overlap each other's launch tails, more only shrink the launches
     g = std::max(1, std::min(16, std::min(g, n_envs)));
-    s->ngroups = g;
     for (int k = 0; k < g; k++) {
-      if (cudaStreamCreateWithFlags(&s->gstream[k], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_done[k], cudaEventDisableTiming) != cudaSuccess) {
-        fail("lcr_create: stream/event creation failed");
-        return 1;
-      }
+      LCR_CREATE_OK(cudaStreamCreateWithFlags(&s->gstream[k], cudaStreamNonBlocking));
+      LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_done[k], cudaEventDisableTiming));
+      s->ngroups = k + 1;
     }
-    cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming);
+    LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming));
     // work-aware seats (LCR_PH_SORT=0: identity): the envs with the most constraint rows in their previous step are launched
     // first in every phase kernel, so that the long Newton solves / MPR jobs do not end up in the tail of the launch
-    const char* ps = getenv("LCR_PH_SORT");
-    if (!ps || atoi(ps) != 0) {
-      if (cudaMalloc(&s->perm, sizeof(int) * (2 * (size_t)n_envs + 16)) != cudaSuccess) { fail("lcr_create: cudaMalloc(perm) failed"); return 1; }
-    }
+    if (env_int("LCR_PH_SORT", 1) != 0) LCR_CREATE_OK(cudaMalloc(&s->perm, sizeof(int) * (2 * (size_t)n_envs + 16)));
   }
   if (cfg->exec_mode == 2) {  // tuning overrides for experiments; the defaults are the measured best
-    const char* e = getenv("LCR_LS_WARPS");
-    s->ls_warps = e ? atoi(e) : 0;
-    e = getenv("LCR_LS_FLAGS");
-    s->ls_flags = e ? atoi(e) : 23;
-    e = getenv("LCR_LS_SORT");
-    if (!e || atoi(e) != 0) {
-      if (cudaMalloc(&s->perm, sizeof(int) * ((size_t)n_envs + 16)) != cudaSuccess) { fail("lcr_create: cudaMalloc(perm) failed"); return 1; }
+    s->ls_warps = env_int("LCR_LS_WARPS", 0);
+    s->ls_flags = env_int("LCR_LS_FLAGS", 23);
+    const int srt = env_int("LCR_LS_SORT", -1);
+    if (srt != 0) {
+      LCR_CREATE_OK(cudaMalloc(&s->perm, sizeof(int) * ((size_t)n_envs + 16)));
       // striped seats while the step time is set by the most expensive env, sorted seats once there are many waves
-      s->ls_striped = atoi(e ? e : "0") == 2 ? 0 : (atoi(e ? e : "0") == 1 ? 1 : (n_envs < 12288 ? 1 : 0));
+      s->ls_striped = srt == 2 ? 0 : (srt == 1 ? 1 : (n_envs < 12288 ? 1 : 0));
     }
   }
+  if (cfg->exec_mode == 3 && create_flow(s)) { lcr_destroy(s); return 1; }
+#undef LCR_CREATE_OK
   *out = s;
   return 0;
 }
@@ -279,46 +362,59 @@ int lcr_destroy(LcrSim* sim) {
   if (!sim) return 0;
   cudaSetDevice(sim->device);
   if (sim->precision == LCR_F32) sim->f.destroy(); else sim->d.destroy();
-  for (int k = 0; k < sim->ngroups; k++) { cudaStreamDestroy(sim->gstream[k]); cudaEventDestroy(sim->ev_done[k]); }
-  if (sim->ngroups) cudaEventDestroy(sim->ev_begin);
-  cudaFree(sim->perm);
+  for (int k = 0; k < 16; k++) {
+    if (sim->gstream[k]) cudaStreamDestroy(sim->gstream[k]);
+    if (sim->ev_done[k]) cudaEventDestroy(sim->ev_done[k]);
+  }
+  if (sim->ev_begin) cudaEventDestroy(sim->ev_begin);
+  cudaFree(sim->perm); cudaFree(sim->redo); cudaFree(sim->fq_mem); cudaFree(sim->fq_rings); cudaFree(sim->seed_buf);
   delete sim;
   return 0;
 }
 
-int lcr_seed(LcrSim* sim, const uint64_t* h_state, void* stream) {
+int lcr_seed(LcrSim* sim, const uint64_t* h_state, const uint8_t* d_mask, void* stream) {
   WITH_DEVICE(sim);
   if (!h_state) return fail("lcr_seed: null state");
-  const size_t n = sim->n;
-  unsigned long long* tmp = nullptr;
-  CUDA_OK(cudaMalloc(&tmp, 32 * n));
-  CUDA_OK(cudaMemcpyAsync(tmp, h_state, 32 * n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  if (sim->precision == LCR_F32) lcr::Launch<float>::seed(sim->f.s, tmp, (cudaStream_t)stream);
-  else lcr::Launch<double>::seed(sim->d.s, tmp, (cudaStream_t)stream);
-  sim->launches++;
-  CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-  CUDA_OK(cudaFree(tmp));
-  return 0;
-}
-
-int lcr_reset(LcrSim* sim, const uint8_t* d_mask, float* d_obs, void* stream) {
-  WITH_DEVICE(sim);
-  if (sim->precision == LCR_F32) lcr::Launch<float>::reset(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_mask, d_obs, (cudaStream_t)stream);
-  else lcr::Launch<double>::reset(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_mask, d_obs, (cudaStream_t)stream);
+  // (pageable host memory: the copy is staged by the runtime before the call returns, the caller's buffer is free afterwards)
+  CUDA_OK(cudaMemcpyAsync(sim->seed_buf, h_state, 32 * (size_t)sim->n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  if (sim->precision == LCR_F32) lcr::Launch<float>::seed(sim->f.s, sim->seed_buf, d_mask, (cudaStream_t)stream);
+  else lcr::Launch<double>::seed(sim->d.s, sim->seed_buf, d_mask, (cudaStream_t)stream);
   sim->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated,
-             uint8_t* d_success, void* stream) {
+int lcr_reset(LcrSim* sim, const uint8_t* d_mask, float* d_obs, void* stream) {
+  WITH_DEVICE(sim);
+  LCR_RUN(sim, reset(sim->f.dm, sim->f.verts, sim->f.s, d_mask, d_obs, (cudaStream_t)stream), reset(sim->d.dm, sim->d.verts, sim->d.s, d_mask, d_obs, (cudaStream_t)stream));
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_step_rec(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated,
+                 uint8_t* d_success, float* d_record, void* stream) {
   WITH_DEVICE(sim);
   if (!d_actions || !d_obs || !d_reward || !d_terminated || !d_truncated || !d_success) return fail("lcr_step: null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const StepIO io{d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, d_record};
+  const Redo redo = redo_of(sim);
+  const bool f32 = sim->precision == LCR_F32;
+  if (sim->cfg.exec_mode == 3) {
+    // one scheduler launch + one persistent kernel; the envs that need the big workspace are handled inside
+    LCR_RUN(sim, step_flow(sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, io, &sim->fq, sim->flow_grid, sim->flow_bigcta, sim->flow_flags, sim->flow_thi,
+                           sim->flow_tbig, sim->flow_stats, st),
+            step_flow(sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, io, &sim->fq, sim->flow_grid, sim->flow_bigcta, sim->flow_flags, sim->flow_thi,
+                      sim->flow_tbig, sim->flow_stats, st));
+    sim->launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  CUDA_OK(cudaMemsetAsync(sim->redo, 0, sizeof(int), st));
   if (sim->cfg.exec_mode == 1) {
-    cudaStream_t st = (cudaStream_t)stream;
     const int G = sim->ngroups, per = (sim->n + G - 1) / G;
     if (sim->perm) {  // seats in work-aware order: group g owns perm[g * per, (g + 1) * per), heaviest envs first, -1 = padding
-      if (sim->precision == LCR_F32) lcr::Launch<float>::sched(sim->f.s, sim->perm, per, 1, st);
+      if (f32) lcr::Launch<float>::sched(sim->f.s, sim->perm, per, 1, st);
       else lcr::Launch<double>::sched(sim->d.s, sim->perm, per, 1, st);
       sim->launches++;
     }
@@ -327,59 +423,58 @@ int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward,
       const int env0 = g * per, cnt = sim->perm ? per : std::min(per, sim->n - env0);
       if (env0 >= sim->n) break;
       CUDA_OK(cudaStreamWaitEvent(sim->gstream[g], sim->ev_begin, 0));
-      if (sim->precision == LCR_F32)
-        sim->launches += lcr::Launch<float>::step_phased(sim->ncube, sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, d_actions, d_obs,
-                                                         d_reward, d_terminated, d_truncated, d_success, env0, cnt, sim->perm, sim->gstream[g]);
-      else
-        sim->launches += lcr::Launch<double>::step_phased(sim->ncube, sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, d_actions, d_obs,
-                                                          d_reward, d_terminated, d_truncated, d_success, env0, cnt, sim->perm, sim->gstream[g]);
+      int nl = 0;
+      if (f32) LCR_DISPATCH_RET(float, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g]));
+      else LCR_DISPATCH_RET(double, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g]));
+      sim->launches += nl;
       CUDA_OK(cudaEventRecord(sim->ev_done[g], sim->gstream[g]));
       CUDA_OK(cudaStreamWaitEvent(st, sim->ev_done[g], 0));
     }
   } else if (sim->cfg.exec_mode == 2) {
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool f32 = sim->precision == LCR_F32;
-    const int W = f32 ? lcr::Launch<float>::lockstep_warps(sim->ncube, sim->ls_warps) : lcr::Launch<double>::lockstep_warps(sim->ncube, sim->ls_warps);
+    int W = 0;
+    if (f32) LCR_DISPATCH_RET(float, sim->ncube, W, lockstep_warps(sim->ls_warps));
+    else LCR_DISPATCH_RET(double, sim->ncube, W, lockstep_warps(sim->ls_warps));
     const int grid = (sim->n + W - 1) / W;
-#define LCR_LS_LAUNCH(GRID, WARPS, EPC, PERM, ST)                                                                                                  \
-  do {                                                                                                                                         \
-    if (f32) lcr::Launch<float>::step_lockstep(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, \
-                                               d_success, GRID, WARPS, EPC, sim->ls_flags, PERM, sim->prof, ST);                                 \
-    else lcr::Launch<double>::step_lockstep(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_actions, d_obs, d_reward, d_terminated, d_truncated,   \
-                                            d_success, GRID, WARPS, EPC, sim->ls_flags, PERM, sim->prof, ST);                                    \
-    sim->launches++;                                                                                                                           \
-  } while (0)
     if (sim->perm) {
       if (f32) lcr::Launch<float>::sched(sim->f.s, sim->perm, W, sim->ls_striped, st);
       else lcr::Launch<double>::sched(sim->d.s, sim->perm, W, sim->ls_striped, st);
       sim->launches++;
     }
-    LCR_LS_LAUNCH(grid, W, W, sim->perm, st);
-#undef LCR_LS_LAUNCH
+    LCR_RUN(sim, step_lockstep(sim->f.dm, sim->f.verts, sim->f.s, io, redo, grid, W, W, sim->ls_flags, sim->perm, sim->prof, st),
+            step_lockstep(sim->d.dm, sim->d.verts, sim->d.s, io, redo, grid, W, W, sim->ls_flags, sim->perm, sim->prof, st));
+    sim->launches++;
   } else {
-    if (sim->precision == LCR_F32)
-      lcr::Launch<float>::step(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
-    else
-      lcr::Launch<double>::step(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, (cudaStream_t)stream);
+    LCR_RUN(sim, step(sim->f.dm, sim->f.verts, sim->f.s, io, redo, st), step(sim->d.dm, sim->d.verts, sim->d.s, io, redo, st));
     sim->launches++;
   }
-  CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-int lcr_get_state(LcrSim* sim, double* q, double* v, double* c, double* w, double* a, int32_t* i, void* stream) {
-  WITH_DEVICE(sim);
-  if (sim->precision == LCR_F32) lcr::Launch<float>::get_state(sim->ncube, sim->f.s, q, v, c, w, a, i, (cudaStream_t)stream);
-  else lcr::Launch<double>::get_state(sim->ncube, sim->d.s, q, v, c, w, a, i, (cudaStream_t)stream);
+  // the envs that outgrew the fast workspace: the same step from the same start state over the big workspace
+  LCR_RUN(sim, step_big(sim->f.dm, sim->f.verts, sim->f.s, io, redo, st), step_big(sim->d.dm, sim->d.verts, sim->d.s, io, redo, st));
   sim->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int lcr_set_state(LcrSim* sim, const double* q, const double* v, const double* c, const double* w, const double* a, const int32_t* i, void* stream) {
+int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated,
+             uint8_t* d_success, void* stream) {
+  return lcr_step_rec(sim, d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, nullptr, stream);
+}
+
+int lcr_get_state(LcrSim* sim, double* q, double* v, double* c, double* w, double* a, int32_t* i, uint64_t* rng, void* stream) {
   WITH_DEVICE(sim);
-  if (sim->precision == LCR_F32) lcr::Launch<float>::set_state(sim->ncube, sim->f.s, q, v, c, w, a, i, (cudaStream_t)stream);
-  else lcr::Launch<double>::set_state(sim->ncube, sim->d.s, q, v, c, w, a, i, (cudaStream_t)stream);
+  const int ncu = sim->model.ncube;
+  if (sim->precision == LCR_F32) lcr::Launch<float>::get_state(ncu, sim->f.s, q, v, c, w, a, i, (unsigned long long*)rng, (cudaStream_t)stream);
+  else lcr::Launch<double>::get_state(ncu, sim->d.s, q, v, c, w, a, i, (unsigned long long*)rng, (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_set_state(LcrSim* sim, const double* q, const double* v, const double* c, const double* w, const double* a, const int32_t* i,
+                  const uint64_t* rng, void* stream) {
+  WITH_DEVICE(sim);
+  const int ncu = sim->model.ncube;
+  if (sim->precision == LCR_F32) lcr::Launch<float>::set_state(ncu, sim->f.s, q, v, c, w, a, i, (const unsigned long long*)rng, (cudaStream_t)stream);
+  else lcr::Launch<double>::set_state(ncu, sim->d.s, q, v, c, w, a, i, (const unsigned long long*)rng, (cudaStream_t)stream);
   sim->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -388,9 +483,12 @@ int lcr_set_state(LcrSim* sim, const double* q, const double* v, const double* c
 int lcr_substeps(LcrSim* sim, int n, void* stream) {
   WITH_DEVICE(sim);
   if (n < 0) return fail("lcr_substeps: n < 0");
-  if (sim->precision == LCR_F32) lcr::Launch<float>::substeps(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, n, (cudaStream_t)stream);
-  else lcr::Launch<double>::substeps(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, n, (cudaStream_t)stream);
-  sim->launches++;
+  cudaStream_t st = (cudaStream_t)stream;
+  const Redo redo = redo_of(sim);
+  CUDA_OK(cudaMemsetAsync(sim->redo, 0, sizeof(int), st));
+  LCR_RUN(sim, substeps(sim->f.dm, sim->f.verts, sim->f.s, n, redo, st), substeps(sim->d.dm, sim->d.verts, sim->d.s, n, redo, st));
+  LCR_RUN(sim, substeps_big(sim->f.dm, sim->f.verts, sim->f.s, n, redo, st), substeps_big(sim->d.dm, sim->d.verts, sim->d.s, n, redo, st));
+  sim->launches += 2;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -398,8 +496,7 @@ int lcr_substeps(LcrSim* sim, int n, void* stream) {
 int lcr_ik(LcrSim* sim, const float* d_ee_target, float* d_q_out, void* stream) {
   WITH_DEVICE(sim);
   if (!d_ee_target || !d_q_out) return fail("lcr_ik: null buffer");
-  if (sim->precision == LCR_F32) lcr::Launch<float>::ik(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_ee_target, d_q_out, (cudaStream_t)stream);
-  else lcr::Launch<double>::ik(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_ee_target, d_q_out, (cudaStream_t)stream);
+  LCR_RUN(sim, ik(sim->f.dm, sim->f.verts, sim->f.s, d_ee_target, d_q_out, (cudaStream_t)stream), ik(sim->d.dm, sim->d.verts, sim->d.s, d_ee_target, d_q_out, (cudaStream_t)stream));
   sim->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -418,8 +515,8 @@ int lcr_get_diag(LcrSim* sim, int32_t* d_diag, void* stream) {
 int lcr_debug_contacts(LcrSim* sim, double* d_contacts, int32_t* d_ncon, void* stream) {
   WITH_DEVICE(sim);
   if (!d_contacts || !d_ncon) return fail("lcr_debug_contacts: null buffer");
-  if (sim->precision == LCR_F32) lcr::Launch<float>::debug_contacts(sim->ncube, sim->f.dm, sim->f.verts, sim->f.s, d_contacts, d_ncon, (cudaStream_t)stream);
-  else lcr::Launch<double>::debug_contacts(sim->ncube, sim->d.dm, sim->d.verts, sim->d.s, d_contacts, d_ncon, (cudaStream_t)stream);
+  LCR_RUN(sim, debug_contacts(sim->f.dm, sim->f.verts, sim->f.s, d_contacts, d_ncon, (cudaStream_t)stream),
+          debug_contacts(sim->d.dm, sim->d.verts, sim->d.s, d_contacts, d_ncon, (cudaStream_t)stream));
   sim->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -442,10 +539,29 @@ int lcr_debug_phase_clocks(LcrSim* sim, long long* d_clocks) {
   return 0;
 }
 
+int lcr_debug_flow_stats(LcrSim* sim, unsigned long long* d_stats) {
+  if (!sim) return fail("null handle");
+  if (sim->cfg.exec_mode != 3) return fail("lcr_debug_flow_stats: flow mode only");
+  sim->flow_stats = d_stats;
+  return 0;
+}
+
+int lcr_flow_status(LcrSim* sim, int32_t* h_status) {
+  WITH_DEVICE(sim);
+  if (!h_status) return fail("lcr_flow_status: null buffer");
+  for (int k = 0; k < 8; k++) h_status[k] = 0;
+  if (sim->cfg.exec_mode != 3) return 0;
+  unsigned v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CUDA_OK(cudaMemcpy(&v[0], sim->fq.ctl + 64 * LCR_FQ_NQ, sizeof(unsigned), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(&v[1], sim->fq.ctl + 64 * LCR_FQ_NQ + 32, 7 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 8; k++) h_status[k] = (int32_t)v[k];
+  return 0;
+}
+
 int lcr_n_envs(const LcrSim* sim) { return sim ? sim->n : 0; }
 int lcr_kernel_launches(const LcrSim* sim) { return sim ? sim->launches : 0; }
 const char* lcr_last_error(void) { return g_err.c_str(); }
-const char* lcr_version(void) { return "lcrsim 0.1 (sm_100a)"; }
+const char* lcr_version(void) { return "lcrsim 0.2 (sm_100a)"; }
 int lcr_sizeof_model(void) { return (int)sizeof(LcrModel); }
 int lcr_sizeof_cfg(void) { return (int)sizeof(LcrEnvCfg); }
 

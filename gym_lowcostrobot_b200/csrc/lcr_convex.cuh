@@ -589,7 +589,7 @@ __device__ __noinline__ void collect_candidates(Ws<T, NC>& w, const DevModel<T>&
       const unsigned mask = __ballot_sync(FULLMASK, cand);
       if (cand) {
         const int k = n + __popc(mask & ((1u << lane) - 1));
-        if (k < LCR_MAXCAND) w.cand_key[k] = (short)(LCR_KEY_CUBE + LCR_MAXMESH * c + lane);
+        if (k < Ws<T, NC>::MAXCAND) w.cand_key[k] = (short)(LCR_KEY_CUBE + LCR_MAXMESH * c + lane);
       }
       n += __popc(mask);
     }
@@ -609,7 +609,7 @@ __device__ __noinline__ void collect_candidates(Ws<T, NC>& w, const DevModel<T>&
       const unsigned mask = __ballot_sync(FULLMASK, cand);
       if (cand) {
         const int k = n + __popc(mask & ((1u << lane) - 1));
-        if (k < LCR_MAXCAND) w.cand_key[k] = (short)(LCR_KEY_CUBE + LCR_MAXMESH * c + lane);
+        if (k < Ws<T, NC>::MAXCAND) w.cand_key[k] = (short)(LCR_KEY_CUBE + LCR_MAXMESH * c + lane);
       }
       n += __popc(mask);
     }
@@ -643,12 +643,12 @@ __device__ __noinline__ void collect_candidates(Ws<T, NC>& w, const DevModel<T>&
       const unsigned mask = __ballot_sync(FULLMASK, cand);
       if (cand) {
         const int k = n + __popc(mask & ((1u << lane) - 1));
-        if (k < LCR_MAXCAND) w.cand_key[k] = (short)p;
+        if (k < Ws<T, NC>::MAXCAND) w.cand_key[k] = (short)p;
       }
       n += __popc(mask);
     }
   }
-  if (lane == 0) w.ncand = n;  // n > LCR_MAXCAND: the tail is recomputed inline by consume_candidates (rare)
+  if (lane == 0) w.ncand = n;  // n > Ws<T, NC>::MAXCAND: the tail is recomputed inline by consume_candidates (rare)
   __syncwarp();
 }
 
@@ -743,7 +743,7 @@ __device__ __noinline__ void narrowphase_job(const Ws<T, NC>& w, const DevModel<
 
 template <typename T, int NC>
 __device__ __noinline__ void run_jobs_inline(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts) {
-  const int n = w.ncand < LCR_MAXCAND ? w.ncand : LCR_MAXCAND;
+  const int n = w.ncand < Ws<T, NC>::MAXCAND ? w.ncand : Ws<T, NC>::MAXCAND;
   T (*res)[8] = cand_res(w);
   for (int k = 0; k < n; k++) {
     T r[8];
@@ -787,11 +787,11 @@ DI void apply_result(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, i
   }
 }
 
-// contacts of the candidates [k0, k1) whose keys satisfy cube == (key >= LCR_KEY_CUBE); candidates past LCR_MAXCAND
+// contacts of the candidates [k0, k1) whose keys satisfy cube == (key >= LCR_KEY_CUBE); candidates past Ws<T, NC>::MAXCAND
 // have no stored key / result and are not processed (counted as overflow)
 template <typename T, int NC>
 __device__ __noinline__ void consume_candidates(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, bool cube) {
-  const int n = w.ncand < LCR_MAXCAND ? w.ncand : LCR_MAXCAND;
+  const int n = w.ncand < Ws<T, NC>::MAXCAND ? w.ncand : Ws<T, NC>::MAXCAND;
   T (*res)[8] = cand_res(w);
   for (int k = 0; k < n; k++) {
     const int key = w.cand_key[k];
@@ -801,7 +801,7 @@ __device__ __noinline__ void consume_candidates(Ws<T, NC>& w, const DevModel<T>&
     for (int j = 0; j < 8; j++) r[j] = res[k][j];
     apply_result(w, m, ncon, nefc, key, r);
   }
-  if (!cube && w.ncand > LCR_MAXCAND && LANE == 0) w.diag[4] += w.ncand - LCR_MAXCAND;
+  if (!cube && w.ncand > Ws<T, NC>::MAXCAND && LANE == 0) { w.diag[4] += w.ncand - Ws<T, NC>::MAXCAND; w.ovf = 1; }
 }
 
 }  // namespace lcr

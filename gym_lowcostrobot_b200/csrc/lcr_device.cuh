@@ -18,15 +18,22 @@
 
 #define LCR_WPB 1          // warps (= envs) per CTA: every env is an independent 32-thread CTA
 #define FULLMASK 0xffffffffu
-#define LCR_MAXCAND (3 * LCR_MAXEFC / 8)  // candidate results (8 words each) live in the e_w / e_g / e_p rows
 
 // Scene class = the template parameter NC of the workspace and of every kernel: 1 / 2 = that many free cubes and no
 // static boxes (Reach / Push / Lift / PickPlace, StackTwoCubes); LCR_NC_LOOP = one cube + the LCR_MAXWALL static wall
 // boxes of PushCubeLoop.  Boxes are indexed cubes first, walls after them; box c has the pose slot LCR_NABODY + c of
 // Ws::xpos / xquat / xmat (the wall slots are constants rewritten by every kinematics pass).
+// Bit 4 of NC (LCR_NC_BIG) selects the BIG workspace caps (LCR_MAXCON_BIG / LCR_MAXEFC_BIG, include/lcr_model.h): the
+// same device functions instantiated over a larger workspace, used by the slow path that takes over the envs whose
+// contact list or constraint rows outgrow the fast caps.
 #define LCR_NC_LOOP 5
+#define LCR_NC_BIG 16
 template <int NC> struct Scene {
-  static constexpr int NCUBE = NC == LCR_NC_LOOP ? 1 : NC, NWALL = NC == LCR_NC_LOOP ? LCR_MAXWALL : 0, NBOX = NCUBE + NWALL;
+  static constexpr int S = NC & 15;
+  static constexpr bool BIG = (NC & LCR_NC_BIG) != 0;
+  static constexpr int NCUBE = S == LCR_NC_LOOP ? 1 : S, NWALL = S == LCR_NC_LOOP ? LCR_MAXWALL : 0, NBOX = NCUBE + NWALL;
+  static constexpr int MAXCON = BIG ? LCR_MAXCON_BIG : LCR_MAXCON, MAXEFC = BIG ? LCR_MAXEFC_BIG : LCR_MAXEFC;
+  static constexpr int MAXCAND = 3 * MAXEFC / 8;  // candidate results (8 words each) live in the e_w / e_g / e_p rows
 };
 // body id of box c in contact records: the cube's free body, or the world (-1) for a static wall
 template <int NC> __host__ __device__ constexpr int box_body(int c) { return c < Scene<NC>::NCUBE ? LCR_NABODY + c : -1; }
@@ -90,6 +97,7 @@ struct DevState {
 template <typename T, int NC>
 struct Ws {  // per-warp shared-memory workspace
   static constexpr int NCU = Scene<NC>::NCUBE;
+  static constexpr int MAXCON = Scene<NC>::MAXCON, MAXEFC = Scene<NC>::MAXEFC, MAXCAND = Scene<NC>::MAXCAND;
   static constexpr int NQ = LCR_NARM + 7 * NCU, NVV = LCR_NARM + 6 * NCU, NB = LCR_NABODY + Scene<NC>::NBOX;
   static constexpr int NF = NQ + 2 * NVV + LCR_NARM + LCR_NAUX;
   static constexpr int JS = NVV + 1;  // padded row stride of J (odd -> conflict-free row-parallel access)
@@ -107,21 +115,21 @@ struct Ws {  // per-warp shared-memory workspace
   T bias[NVV], smooth[NVV], qacc_smooth[NVV], qacc[NVV], Ma[NVV], grad[NVV], search[NVV], Mv[NVV];
   alignas(16) T H[NVV][NVV + 1];
   // contacts
-  alignas(16) T c_pos[LCR_MAXCON][3];
-  T c_frame[LCR_MAXCON][9], c_dist[LCR_MAXCON], c_mu[LCR_MAXCON], c_c1[LCR_MAXCON], c_c2[LCR_MAXCON];
-  short c_par[LCR_MAXCON];  // index into the contiguous CPar tables of DevModel, see DevModel::par()
-  short c_efc[LCR_MAXCON];
-  signed char c_b1[LCR_MAXCON], c_b2[LCR_MAXCON];
+  alignas(16) T c_pos[MAXCON][3];
+  T c_frame[MAXCON][9], c_dist[MAXCON], c_mu[MAXCON], c_c1[MAXCON], c_c2[MAXCON];
+  short c_par[MAXCON];  // index into the contiguous CPar tables of DevModel, see DevModel::par()
+  short c_efc[MAXCON];
+  signed char c_b1[MAXCON], c_b2[MAXCON];
   // constraint rows
-  alignas(16) T e_pos[LCR_MAXEFC];
-  T e_D[LCR_MAXEFC], e_aref[LCR_MAXEFC], e_jar[LCR_MAXEFC];
+  alignas(16) T e_pos[MAXEFC];
+  T e_D[MAXEFC], e_aref[MAXEFC], e_jar[MAXEFC];
   union {  // solver rows / RNE temporaries of inertia_and_bias (dead before the constraint rows are built)
-    struct { T e_jv[LCR_MAXEFC], e_force[LCR_MAXEFC]; };
+    struct { T e_jv[MAXEFC], e_force[MAXEFC]; };
     struct { T rw[LCR_NABODY][3], ral[LCR_NABODY][3], ra[LCR_NABODY][3], F[LCR_NABODY][3], Nn[LCR_NABODY][3]; };
   };
-  T e_w[LCR_MAXEFC], e_g[LCR_MAXEFC], e_p[LCR_MAXEFC];  // Hessian pieces, see contact_eval
-  alignas(16) short e_unit[LCR_MAXEFC];  // >= 0: contact index; < 0: limit row of joint -1-e_unit
-  signed char e_r[LCR_MAXEFC];  // row index within its contact
+  T e_w[MAXEFC], e_g[MAXEFC], e_p[MAXEFC];  // Hessian pieces, see contact_eval
+  alignas(16) short e_unit[MAXEFC];  // >= 0: contact index; < 0: limit row of joint -1-e_unit
+  signed char e_r[MAXEFC];  // row index within its contact
   alignas(16) int ncon;
   int nefc, nlim;
   // separating-axis cache of the convex narrowphase (see lcr_convex.cuh): one contiguous 16-byte aligned block
@@ -134,11 +142,14 @@ struct Ws {  // per-warp shared-memory workspace
   int sa_pad[3];
   static constexpr int SA_WORDS = LCR_NSA * 11;  // dir, S, u
   static constexpr int SA_BYTES = SA_WORDS * (int)sizeof(T) + LCR_NSA * 2 + 16;
-  alignas(16) short cand_key[LCR_MAXCAND];  // convex-pair candidates of this substep (results alias e_w / e_g / e_p)
+  alignas(16) short cand_key[MAXCAND];  // convex-pair candidates of this substep (results alias e_w / e_g / e_p)
   int ncand;
   int skip;          // phased execution: this env was auto-reset by the current step, substep kernels pass
   int redo_forward;  // phased execution: state was reset after a bad qacc, re-run mj_forward before integrating
-  alignas(16) T J[LCR_MAXEFC][JS];  // last member: only the first nefc rows are live (and staged)
+  int ovf;           // a cap of THIS workspace was hit since the record was loaded (fast path: the env moves to the BIG path)
+  int substep;       // flow execution: mj_step calls of the current env.step completed so far
+  int jobs_left;     // flow execution: narrowphase jobs of the current substep still running (global atomic counter)
+  alignas(16) T J[MAXEFC][JS];  // last member: only the first nefc rows are live (and staged)
 
   __device__ T* qpos() { return st; }
   __device__ T* qvel() { return st + NQ; }
@@ -150,33 +161,72 @@ struct Ws {  // per-warp shared-memory workspace
   __device__ T* cube_xpos(int c) { return aux() + 7 + 3 * c; }
 };
 
-// host-side launchers, instantiated in lcr_kernels_f32.cu / lcr_kernels_f64.cu
+// Device buffers of one lcr_step call (borrowed from the caller, row-major over the envs).  `rec` (optional) is the packed
+// float32 record [n][obs_dim + 4] = obs | reward | terminated | truncated | success: the unit of the one all-gather per step
+// and of the device -> host copy, written by the step kernels themselves (no separate pack launch).
+struct StepIO {
+  const float* actions;
+  float* obs;
+  float* reward;
+  uint8_t* term;
+  uint8_t* trunc;
+  uint8_t* succ;
+  float* rec;
+};
+// Envs that hit a cap of the FAST workspace during a step are not written back; they are appended here and the same
+// step is redone from the same start state over the BIG workspace (k_step / k_substeps with NC | LCR_NC_BIG).
+struct Redo {
+  int* count;  // null: no redirection (BIG kernels: whatever exceeds the BIG caps is dropped and counted in diag)
+  int* list;
+};
+// Work queues of the flow kernel (lcr_flow.cuh): one ring per phase and priority.
+enum { FQ_BEGIN = 0, FQ_DYN = 1, FQ_JOB = 2, FQ_COL = 3, FQ_SOL = 4, FQ_END = 5, FQ_BIG = 6, FQ_NPH = 7 };
+#define LCR_FQ_NQ (2 * FQ_NPH)  // two priorities per phase: queue 2 p = express (envs that were expensive in their previous step)
+#define LCR_FQ_EMPTY 0xffffffffu
+#define LCR_FQ_CTL_WORDS (64 * LCR_FQ_NQ + 64 + 64)
+#define LCR_FQ_MAXENV (1 << 20)  // item = env (20 bits) | aux (10 bits) << 20 | express << 30
+struct FlowQ {
+  unsigned* ctl;  // [LCR_FQ_NQ][64]: head at +0, tail at +32 (own 128-byte lines) | remaining | error -- zeroed by k_sched_flow
+  unsigned* ring[LCR_FQ_NQ];  // entries are LCR_FQ_EMPTY except between a push and its pop
+  unsigned mask[LCR_FQ_NQ];
+};
+
+// host-side launchers.  LaunchNC<T, S> (everything that depends on the scene class S = 1, 2, LCR_NC_LOOP) is instantiated
+// in one translation unit per (T, S) (lcr_nc.cu); Launch<T> (scene-independent kernels) in lcr_common.cu.
 namespace lcr {
+template <typename T, int S>
+struct LaunchNC {
+  static void prepare();
+  static size_t ws_bytes();
+  static void reset(const DevModel<T>* dm, const T* verts, DevState<T> s, const uint8_t* mask, float* obs, cudaStream_t st);
+  static void step(const DevModel<T>* dm, const T* verts, DevState<T> s, StepIO io, Redo redo, cudaStream_t st);
+  static void step_big(const DevModel<T>* dm, const T* verts, DevState<T> s, StepIO io, Redo list, cudaStream_t st);
+  static int lockstep_warps(int warps);
+  static void step_lockstep(const DevModel<T>* dm, const T* verts, DevState<T> s, StepIO io, Redo redo, int grid, int warps, int epc, int flags,
+                            const int* perm, long long* prof, cudaStream_t st);
+  static int step_phased(int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, StepIO io, Redo redo, int env0, int cnt,
+                         const int* perm, cudaStream_t st);
+  static int flow_warps();
+  static int flow_bigslots();
+  static int flow_smem();
+  static void step_flow(const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, StepIO io, const void* fq, int grid, int nbigcta, int flags,
+                        int t_hi, int t_big, unsigned long long* stats, cudaStream_t st);
+  static void substeps(const DevModel<T>* dm, const T* verts, DevState<T> s, int n, Redo redo, cudaStream_t st);
+  static void substeps_big(const DevModel<T>* dm, const T* verts, DevState<T> s, int n, Redo list, cudaStream_t st);
+  static void ik(const DevModel<T>* dm, const T* verts, DevState<T> s, const float* target, float* q_out, cudaStream_t st);
+  static void debug_contacts(const DevModel<T>* dm, const T* verts, DevState<T> s, double* out, int32_t* ncon, cudaStream_t st);
+};
 template <typename T>
 struct Launch {
-  static void prepare(int ncube);
-  static size_t smem_bytes(int ncube);
-  static void reset(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const uint8_t* mask, float* obs, cudaStream_t st);
-  static void step(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
-                   uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st);
-  static int lockstep_warps(int ncube, int warps);
   static void sched(DevState<T> s, int* perm, int W, int striped, cudaStream_t st);
   static void pack(const float* obs, const float* reward, const uint8_t* term, const uint8_t* trunc, const uint8_t* succ, float* rec, int n, int od,
                    cudaStream_t st);
-  static void step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
-                            uint8_t* term, uint8_t* trunc, uint8_t* succ, int grid, int warps, int epc, int flags, const int* perm, long long* prof,
-                            cudaStream_t st);
-  static int step_phased(int ncube, int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, const float* actions,
-                         float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, const int* perm, cudaStream_t st);
-  static void substeps(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, int n, cudaStream_t st);
-  static void ik(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* target, float* q_out, cudaStream_t st);
   static void get_state(int ncube, DevState<T> s, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,
-                        cudaStream_t st);
+                        unsigned long long* rng, cudaStream_t st);
   static void set_state(int ncube, DevState<T> s, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
-                        const double* aux, const int32_t* ints, cudaStream_t st);
-  static void init_state(int ncube, const DevModel<T>* dm, DevState<T> s, cudaStream_t st);
+                        const double* aux, const int32_t* ints, const unsigned long long* rng, cudaStream_t st);
+  static void init_state(const DevModel<T>* dm, DevState<T> s, cudaStream_t st);
   static void get_diag(DevState<T> s, int32_t* out, cudaStream_t st);
-  static void debug_contacts(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, double* out, int32_t* ncon, cudaStream_t st);
-  static void seed(DevState<T> s, const unsigned long long* d_state, cudaStream_t st);
+  static void seed(DevState<T> s, const unsigned long long* d_state, const uint8_t* d_mask, cudaStream_t st);
 };
 }  // namespace lcr

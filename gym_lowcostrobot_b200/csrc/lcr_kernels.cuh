@@ -385,8 +385,8 @@ template <typename T> DI void make_frame(T* f) {
 template <typename T, int NC>
 DI bool add_contact(Ws<T, NC>& w, const DevModel<T>& m, int& ncon, int& nefc, const CPar<T>* par, int b1, int b2, const T* pos, const T* normal, T dist) {
   const int dim = par->dim;
-  if (ncon >= LCR_MAXCON || nefc + dim > LCR_MAXEFC) {
-    if (LANE == 0) w.diag[4]++;
+  if (ncon >= Ws<T, NC>::MAXCON || nefc + dim > Ws<T, NC>::MAXEFC) {
+    if (LANE == 0) { w.diag[4]++; w.ovf = 1; }
     return false;
   }
   const int ci = ncon;
@@ -606,6 +606,15 @@ __device__ __noinline__ void make_constraints(Ws<T, NC>& w, const DevModel<T>& m
   if (cmask & (LCR_COLLIDE_CUBE_MESH | LCR_COLLIDE_WALL_MESH)) consume_candidates(w, m, ncon, nefc, true);
   if (cmask & LCR_COLLIDE_FLOOR_MESH) collide_floor_meshes(w, m, verts, ncon, nefc);
   if (cmask & LCR_COLLIDE_MESH_MESH) consume_candidates(w, m, ncon, nefc, false);
+#ifdef LCR_FLOW_DEBUG
+  {  // debug: the counts are warp-uniform registers -- every lane must hold the same values
+    const int n0 = __shfl_sync(FULLMASK, ncon, 0), e0 = __shfl_sync(FULLMASK, nefc, 0);
+    if (__any_sync(FULLMASK, ncon != n0 || nefc != e0 || ncon > Ws<T, NC>::MAXCON || nefc > Ws<T, NC>::MAXEFC)) {
+      if (lane == 24) printf("make_constraints: lane counts differ blk %d warp %d lane0 ncon %d nefc %d lane24 ncon %d nefc %d ncand %d nlim %d pre %d\n", blockIdx.x, threadIdx.x >> 5, n0, e0, ncon, nefc, w.ncand, nlim, (int)precomputed);
+      __trap();
+    }
+  }
+#endif
   if (lane == 0) { w.ncon = ncon; w.nefc = nefc; w.nlim = nlim; }
   __syncwarp();
   // contact rows: lane <-> row
@@ -1010,6 +1019,9 @@ template <> DI float solver_tol<float>(const DevModel<float>& m) { return fmaxf(
 
 template <typename T, int NC>
 __device__ __noinline__ void forward(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts) {
+#ifdef LCR_FLOW_DEBUG
+  if (!Scene<NC>::BIG && LANE == 0 && gridDim.x == 148 && blockDim.x == 512) printf("forward() blk %d warp %d substep %d redo %d ints %d %d\n", blockIdx.x, threadIdx.x >> 5, w.substep, w.redo_forward, w.ints[0], w.ints[1]);
+#endif
   kinematics(w, m);
   inertia_and_bias(w, m);
   make_constraints(w, m, verts, false);
@@ -1106,7 +1118,7 @@ __device__ __noinline__ void substep(Ws<T, NC>& w, const DevModel<T>& m, const T
 // ---------------------------------------------------------------- env glue
 // width of an observation row (get_observation of the six envs; lcr_obs_dim of the C-ABI)
 DI int obs_dim(int task) { return (task == LCR_TASK_REACH || task == LCR_TASK_LIFT || task == LCR_TASK_PUSH_LOOP) ? 15 : 18; }
-template <typename T, int NC> DI void write_obs(Ws<T, NC>& w, const DevModel<T>& m, float* obs) {
+template <typename T, int NC> DI void write_obs(Ws<T, NC>& w, const DevModel<T>& m, float* obs, float* rec = nullptr) {
   const int lane = LANE, task = m.task;
   const T* qpos = w.qpos();
   const T* qvel = w.qvel();
@@ -1118,7 +1130,18 @@ template <typename T, int NC> DI void write_obs(Ws<T, NC>& w, const DevModel<T>&
     else if (lane < 12) v = qvel[lane - 6];
     else if (lane < 15) v = has_target ? w.target()[lane - 12] : qpos[6 + lane - 12];
     else v = has_target ? qpos[6 + lane - 15] : qpos[13 + lane - 15];
-    obs[lane] = (float)v;
+    if (obs) obs[lane] = (float)v;
+    if (rec) rec[lane] = (float)v;
+  }
+}
+// observation row + the scalars of one env (lane 0 holds reward / flags)
+template <typename T, int NC> DI void write_outputs(Ws<T, NC>& w, const DevModel<T>& m, const StepIO& io, int env, float r, bool te, bool tr, bool su) {
+  const int od = obs_dim(m.task);
+  float* rec = io.rec ? io.rec + (size_t)env * (od + 4) : nullptr;
+  write_obs(w, m, io.obs + (size_t)env * od, rec);
+  if (LANE == 0) {
+    io.reward[env] = r; io.term[env] = te; io.trunc[env] = tr; io.succ[env] = su;
+    if (rec) { rec[od] = r; rec[od + 1] = te ? 1.0f : 0.0f; rec[od + 2] = tr ? 1.0f : 0.0f; rec[od + 3] = su ? 1.0f : 0.0f; }
   }
 }
 
@@ -1202,19 +1225,18 @@ __device__ const double kTargetLow[6] = {-3.14159, -1.5708, -1.48353, -1.91986, 
 __device__ const double kTargetHigh[6] = {3.14159, 1.22173, 1.74533, 1.91986, 2.96706, 0.0523599};
 
 template <typename T, int NC>
-__device__ __noinline__ bool env_step_begin(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const float* action, float* obs,
-                                            float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ) {
+__device__ __noinline__ bool env_step_begin(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const StepIO& io, int env) {
   // returns false if the env was auto-reset instead of stepped (outputs already written)
   const int lane = LANE, task = m.task;
   if (m.autoreset && w.ints[1]) {
     env_reset(w, m, verts);
-    write_obs(w, m, obs);
-    if (lane == 0) { *reward = 0; *term = 0; *trunc = 0; *succ = 0; }
+    if (Scene<NC>::BIG || !w.ovf) write_outputs(w, m, io, env, 0.0f, false, false, false);
     __syncwarp();
     return false;
   }
   if (lane == 0) w.diag[3] = 0;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
+  const float* action = io.actions + (size_t)env * na;
   const bool gripper_task = task == LCR_TASK_LIFT || task == LCR_TASK_PICK_PLACE || task == LCR_TASK_STACK;
   T* qpos = w.qpos();
   T a = lane < na ? clampT((T)action[lane], (T)-1, (T)1) : (T)0;
@@ -1293,54 +1315,50 @@ __device__ __noinline__ bool loop_reward(Ws<T, NC>& w, const DevModel<T>& m, flo
 }
 
 template <typename T, int NC>
-__device__ __noinline__ void env_step_end(Ws<T, NC>& w, const DevModel<T>& m, float* obs, float* reward, uint8_t* term, uint8_t* trunc,
-                                          uint8_t* succ) {
-  const int lane = LANE, task = m.task;
-  write_obs(w, m, obs);
-  if (task == LCR_TASK_PUSH_LOOP) {  // push_cube_loop_env.py:322-335: never terminates; TimeLimit truncates
-    if (lane == 0) {
-      float r;
-      const bool su = loop_reward(w, m, r);
-      const int el = ++w.ints[0];
-      const bool tr = m.max_episode_steps > 0 && el >= m.max_episode_steps;
-      w.ints[1] = tr ? 1 : 0;
-      *reward = r; *term = 0; *trunc = tr; *succ = su;
-    }
-    __syncwarp();
-    return;
-  }
-  if (lane == 0) {
-    T pa[3], pb[3];
-    const T* site = w.site_xpos();
-    const T* c0 = w.cube_xpos(0);
-    if (task == LCR_TASK_REACH || task == LCR_TASK_LIFT) { for (int k = 0; k < 3; k++) { pa[k] = site[k]; pb[k] = c0[k]; } }
-    else if (task == LCR_TASK_STACK) { const T* c1 = w.cube_xpos(Scene<NC>::NCUBE - 1); for (int k = 0; k < 3; k++) { pa[k] = c1[k]; pb[k] = c0[k]; } pb[2] += (T)0.03; }
-    else { for (int k = 0; k < 3; k++) { pa[k] = c0[k]; pb[k] = w.target()[k]; } }
-    T dx = pa[0] - pb[0], dy = pa[1] - pb[1], dz = pa[2] - pb[2];
-    T d = sqrt(dx * dx + dy * dy + dz * dz);
-    bool te = false, su = false;
-    float r;
-    if (task == LCR_TASK_LIFT) r = (float)((c0[2] - m.height_threshold) + d);
-    else {
-      su = d < m.distance_threshold;
-      te = su;
-      r = m.reward_type == 0 ? -(float)(d > m.distance_threshold) : (float)(-d);
+__device__ __noinline__ void env_step_end(Ws<T, NC>& w, const DevModel<T>& m, const StepIO& io, int env) {
+  const int task = m.task;
+  float r = 0;
+  bool te = false, tr = false, su = false;
+  if (LANE == 0) {
+    if (task == LCR_TASK_PUSH_LOOP) {  // push_cube_loop_env.py:322-335: never terminates; TimeLimit truncates
+      su = loop_reward(w, m, r);
+    } else {
+      T pa[3], pb[3];
+      const T* site = w.site_xpos();
+      const T* c0 = w.cube_xpos(0);
+      if (task == LCR_TASK_REACH || task == LCR_TASK_LIFT) { for (int k = 0; k < 3; k++) { pa[k] = site[k]; pb[k] = c0[k]; } }
+      else if (task == LCR_TASK_STACK) { const T* c1 = w.cube_xpos(Scene<NC>::NCUBE - 1); for (int k = 0; k < 3; k++) { pa[k] = c1[k]; pb[k] = c0[k]; } pb[2] += (T)0.03; }
+      else { for (int k = 0; k < 3; k++) { pa[k] = c0[k]; pb[k] = w.target()[k]; } }
+      T dx = pa[0] - pb[0], dy = pa[1] - pb[1], dz = pa[2] - pb[2];
+      T d = sqrt(dx * dx + dy * dy + dz * dz);
+      if (task == LCR_TASK_LIFT) r = (float)((c0[2] - m.height_threshold) + d);
+      else {
+        su = d < m.distance_threshold;
+        te = su;
+        r = m.reward_type == 0 ? -(float)(d > m.distance_threshold) : (float)(-d);
+      }
     }
     const int el = ++w.ints[0];
-    const bool tr = m.max_episode_steps > 0 && el >= m.max_episode_steps;
+    tr = m.max_episode_steps > 0 && el >= m.max_episode_steps;
     w.ints[1] = (te || tr) ? 1 : 0;
-    *reward = r; *term = te; *trunc = tr; *succ = su;
   }
+  write_outputs(w, m, io, env, r, te, tr, su);
   __syncwarp();
 }
 
+DI void redo_push(const Redo& rd, int env) {
+  if (LANE == 0) rd.list[atomicAdd(rd.count, 1)] = env;
+}
+// true if this env must leave the fast path (never on the BIG path: what exceeds the big caps is dropped and counted)
+template <typename T, int NC> DI bool moved(const Ws<T, NC>& w) { return !Scene<NC>::BIG && w.ovf != 0; }
+
 template <typename T, int NC>
-DI void env_step(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const float* action, float* obs, float* reward,
-                 uint8_t* term, uint8_t* trunc, uint8_t* succ) {
-  if (!env_step_begin(w, m, verts, action, obs, reward, term, trunc, succ)) return;
+DI void env_step(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const StepIO& io, int env) {
+  if (!env_step_begin(w, m, verts, io, env)) return;
 #pragma unroll 1
   for (int k = 0; k < m.n_substeps; k++) substep(w, m, verts);
-  env_step_end(w, m, obs, reward, term, trunc, succ);
+  // (an env that outgrew the fast workspace is redone over the big one: no outputs from this pass)
+  if (!moved(w)) env_step_end(w, m, io, env);
 }
 
 // ---------------------------------------------------------------- state staging HBM <-> shared
@@ -1357,6 +1375,7 @@ DI void load_state(Ws<T, NC>& w, const DevState<T>& s, int env) {
   const uint4* sas = reinterpret_cast<const uint4*>(s.sa + (size_t)env * Ws<T, NC>::SA_BYTES);
   uint4* sad = reinterpret_cast<uint4*>(w.sa_dir);
   for (int i = LANE; i < NSA4; i += 32) sad[i] = sas[i];
+  if (LANE == 0) { w.ovf = 0; w.substep = 0; w.jobs_left = 0; }
   __syncwarp();
 }
 template <typename T, int NC>
@@ -1374,21 +1393,28 @@ DI void store_state(Ws<T, NC>& w, const DevState<T>& s, int env) {
   for (int i = LANE; i < NSA4; i += 32) sad[i] = sas[i];
 }
 
-// ---------------------------------------------------------------- kernels (grid = n_envs CTAs of one warp)
+// ---------------------------------------------------------------- kernels (one warp per env)
 extern __shared__ __align__(16) unsigned char lcr_smem[];
 
+// env handled by CTA `i` of a fused kernel: identity, or entry i of a device-side list (the BIG redo pass)
+DI int list_env(const int* __restrict__ list, int i) { return list ? list[i] : i; }
+
+// One CTA = one warp = one env, the whole step in one launch.  With `list` the grid strides over a device-side env list
+// (BIG pass over the envs that outgrew the fast workspace).  A fast env that hits a cap is not written back: redo list.
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_step(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
-                                             const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
-                                             uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ) {
+__global__ void __launch_bounds__(32, Scene<NC>::BIG ? 2 : 16) k_step(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                                                      StepIO io, Redo redo, const int* __restrict__ list, const int* __restrict__ count) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = blockIdx.x;
-  load_state(w, s, env);
   const DevModel<T>& m = *dm;
-  const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
-  const int od = obs_dim(m.task);
-  env_step(w, m, verts, actions + (size_t)env * na, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
-  store_state(w, s, env);
+  const int n = list ? *count : s.n;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int env = list_env(list, i);
+    load_state(w, s, env);
+    env_step(w, m, verts, io, env);
+    if (moved(w)) redo_push(redo, env);
+    else store_state(w, s, env);
+    __syncwarp();
+  }
 }
 
 template <typename T, int NC>
@@ -1406,14 +1432,20 @@ __global__ void __launch_bounds__(32, 16) k_reset(const DevModel<T>* __restrict_
 }
 
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_substeps(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s, int nsub) {
+__global__ void __launch_bounds__(32, Scene<NC>::BIG ? 2 : 16) k_substeps(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s, int nsub,
+                                                                          Redo redo, const int* __restrict__ list, const int* __restrict__ count) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
-  const int env = blockIdx.x;
-  load_state(w, s, env);
-  if (LANE == 0) w.diag[3] = 0;
-  if (nsub == 0) forward(w, *dm, verts);
-  for (int k = 0; k < nsub; k++) substep(w, *dm, verts);
-  store_state(w, s, env);
+  const int n = list ? *count : s.n;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int env = list_env(list, i);
+    load_state(w, s, env);
+    if (LANE == 0) w.diag[3] = 0;
+    if (nsub == 0) forward(w, *dm, verts);
+    for (int k = 0; k < nsub; k++) substep(w, *dm, verts);
+    if (moved(w)) redo_push(redo, env);
+    else store_state(w, s, env);
+    __syncwarp();
+  }
 }
 
 template <typename T, int NC>
@@ -1447,8 +1479,9 @@ __global__ void __launch_bounds__(32) k_ik(const DevModel<T>* __restrict__ dm, c
 
 template <typename T, int NC>
 DI void cta_jobs(Ws<T, NC>* wsa, int W, const DevModel<T>& m, const T* __restrict__ verts, int* next) {
+  constexpr int MC = Ws<T, NC>::MAXCAND;
   int tot = 0;
-  for (int e = 0; e < W; e++) { const int c = wsa[e].ncand; tot += c < LCR_MAXCAND ? c : LCR_MAXCAND; }
+  for (int e = 0; e < W; e++) { const int c = wsa[e].ncand; tot += c < MC ? c : MC; }
   for (;;) {
     int j = 0;
     if (LANE == 0) j = atomicAdd(next, 1);
@@ -1457,7 +1490,7 @@ DI void cta_jobs(Ws<T, NC>* wsa, int W, const DevModel<T>& m, const T* __restric
     int e = 0;
     for (;; e++) {
       int c = wsa[e].ncand;
-      c = c < LCR_MAXCAND ? c : LCR_MAXCAND;
+      c = c < MC ? c : MC;
       if (j < c) break;
       j -= c;
     }
@@ -1510,10 +1543,8 @@ __global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__
 }
 
 template <typename T, int NC, bool PROF>
-__global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
-                                                    const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
-                                                    uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ, int flags,
-                                                    const int* __restrict__ perm, int epc, long long* __restrict__ prof) {
+__global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s, StepIO io, Redo redo,
+                                                    int flags, const int* __restrict__ perm, int epc, long long* __restrict__ prof) {
   // blockDim.x / 32 warps, the first `epc` of them own an env (seat blockIdx.x * epc + warp), the others only help
   // with narrowphase jobs; shared memory holds epc workspaces
   Ws<T, NC>* wsa = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
@@ -1525,8 +1556,6 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
   if (!__syncthreads_or(valid)) return;
   Ws<T, NC>& w = wsa[owner ? warp : 0];
   const DevModel<T>& m = *dm;
-  const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
-  const int od = obs_dim(m.task);
   // optional per-env phase timing (debug hook, prof == nullptr in production): clock64 deltas summed over the substeps
   long long tp[PROF ? 10 : 1] = {0}, t0 = 0;
 #define LCR_TICK(k) do { if (PROF) { (void)*(volatile int*)&job_next; /* BAR.SYNC defers blocking to the next memory access */ \
@@ -1535,7 +1564,7 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
   bool go = false;
   if (valid) {
     load_state(w, s, env);
-    go = env_step_begin(w, m, verts, actions + (size_t)env * na, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
+    go = env_step_begin(w, m, verts, io, env);
   }
   if (!go && owner) { if (LANE == 0) w.ncand = 0; __syncwarp(); }
   const T tol = solver_tol<T>(m);
@@ -1573,8 +1602,13 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
     }
     LCR_TICK(9);  // integrate
   }
-  if (go) env_step_end(w, m, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
-  if (valid) store_state(w, s, env);
+  if (valid) {
+    if (moved(w)) redo_push(redo, env);  // outgrew the fast workspace: redone over the big one, nothing written here
+    else {
+      if (go) env_step_end(w, m, io, env);
+      store_state(w, s, env);
+    }
+  }
   if (PROF && valid && LANE == 0) {
     LCR_TICK(0);
     for (int k = 0; k < 10; k++) prof[(size_t)env * 10 + k] = tp[k];
@@ -1587,35 +1621,8 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
 // parked in HBM/L2 between launches.  Every launch has a small, homogeneous instruction footprint (the fused
 // kernel is instruction-fetch bound: ~200 KB of code per substep against a 32 KB L1.5 I-cache) and variable-cost
 // phases (collision, Newton solve) no longer hold the uniform ones back.  Staging is coalesced 128-bit copies.
-template <typename T, int NC>
-DI void load_ws(Ws<T, NC>& w, const Ws<T, NC>* g, int env, bool with_J) {
-  typedef Ws<T, NC> WsT;
-  constexpr int HEAD = (int)(offsetof(WsT, J) / 16), JROW = WsT::JS * (int)sizeof(T);
-  const uint4* src = reinterpret_cast<const uint4*>(g + env);
-  uint4* dst = reinterpret_cast<uint4*>(&w);
-  // the parked workspace comes from L2 / HBM: request it in batches of 8 x 128 bit per lane before the first store, so the
-  // copy costs a few round trips instead of one per 512 bytes
-  constexpr int B = 8;
-  for (int base = LANE; base < HEAD; base += 32 * B) {
-    uint4 t[B];
-#pragma unroll
-    for (int k = 0; k < B; k++) { const int i = base + 32 * k; if (i < HEAD) t[k] = src[i]; }
-#pragma unroll
-    for (int k = 0; k < B; k++) { const int i = base + 32 * k; if (i < HEAD) dst[i] = t[k]; }
-  }
-  __syncwarp();
-  if (with_J) {
-    const int n4 = (w.nefc * JROW + 15) / 16;
-    for (int base = LANE; base < n4; base += 32 * B) {
-      uint4 t[B];
-#pragma unroll
-      for (int k = 0; k < B; k++) { const int i = base + 32 * k; if (i < n4) t[k] = src[HEAD + i]; }
-#pragma unroll
-      for (int k = 0; k < B; k++) { const int i = base + 32 * k; if (i < n4) dst[HEAD + i] = t[k]; }
-    }
-    __syncwarp();
-  }
-}
+// (Superseded by the flow kernel of lcr_flow.cuh, which runs the same phases from device-side queues inside one
+// persistent launch; kept as the launch-per-phase reference the flow kernel is tested against bit by bit.)
 template <typename T, int NC>
 DI void store_ws(const Ws<T, NC>& w, Ws<T, NC>* g, int env, bool with_J) {
   typedef Ws<T, NC> WsT;
@@ -1673,19 +1680,18 @@ DI int ph_env(const int* __restrict__ perm, int seat) { return perm ? perm[seat]
 
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_begin(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
-                                                     Ws<T, NC>* __restrict__ gws, const float* __restrict__ actions, float* __restrict__ obs,
-                                                     float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
-                                                     uint8_t* __restrict__ succ, int env0, const int* __restrict__ perm) {
+                                                     Ws<T, NC>* __restrict__ gws, StepIO io, Redo redo, int env0, const int* __restrict__ perm) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = ph_env(perm, env0 + blockIdx.x);
   if (env < 0) return;
   load_state(w, s, env);
   const DevModel<T>& m = *dm;
-  const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
-  const int od = obs_dim(m.task);
-  const bool go = env_step_begin(w, m, verts, actions + (size_t)env * na, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
+  const bool go = env_step_begin(w, m, verts, io, env);
   if (LANE == 0) { w.skip = go ? 0 : 1; w.redo_forward = 0; w.nefc = 0; w.ncon = 0; w.nlim = 0; }
-  if (!go) store_state(w, s, env);
+  if (moved(w)) {  // the IK / reset forward passes outgrew the fast workspace: the whole step is redone over the big one
+    if (LANE == 0) w.skip = 1;
+    redo_push(redo, env);
+  } else if (!go) store_state(w, s, env);
   store_ws(w, gws, env, false);
 }
 
@@ -1704,7 +1710,7 @@ __global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict
   const DevModel<T>& m = *dm;
   bool redone = false;
   if (!first) {
-    if (w.redo_forward) { forward(w, m, verts); if (LANE == 0) w.redo_forward = 0; __syncwarp(); redone = true; }
+    if (w.redo_forward) { const int ov = w.ovf; forward(w, m, verts); if (LANE == 0) { w.redo_forward = 0; w.ovf = ov; } __syncwarp(); redone = true; }
     integrate(w, m);
   }
   check_state(w, m);
@@ -1726,7 +1732,7 @@ __global__ void __launch_bounds__(32, 16) k_ph_job(const DevModel<T>* __restrict
   if (env < 0) return;
   Ws<T, NC>& w = gws[env];
   if (w.skip) return;
-  const int n = w.ncand < LCR_MAXCAND ? w.ncand : LCR_MAXCAND;
+  const int n = w.ncand < Ws<T, NC>::MAXCAND ? w.ncand : Ws<T, NC>::MAXCAND;
   T (*res)[8] = cand_res(w);
   for (int k = slot; k < n; k += LCR_NSLOT) {
     T r[8];
@@ -1753,6 +1759,7 @@ __global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict
   store_ws_range(w, gws, env, LCR_OFF(c_pos), LCR_OFF(e_jar));
   store_ws_range(w, gws, env, LCR_OFF(e_unit), LCR_OFF(cand_key));
   store_ws_J(w, gws, env);
+  if (w.ovf && LANE == 0) gws[env].ovf = 1;  // (the flags block is not written back by this phase)
 }
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_sol(const DevModel<T>* __restrict__ dm, Ws<T, NC>* __restrict__ gws, int env0, const int* __restrict__ perm) {
@@ -1780,9 +1787,7 @@ __global__ void __launch_bounds__(32, 16) k_ph_sol(const DevModel<T>* __restrict
 }
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_end(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
-                                                   Ws<T, NC>* __restrict__ gws, float* __restrict__ obs, float* __restrict__ reward,
-                                                   uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ succ, int env0,
-                                                   const int* __restrict__ perm) {
+                                                   Ws<T, NC>* __restrict__ gws, StepIO io, Redo redo, int env0, const int* __restrict__ perm) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = ph_env(perm, env0 + blockIdx.x);
   if (env < 0 || gws[env].skip) return;
@@ -1791,18 +1796,19 @@ __global__ void __launch_bounds__(32, 16) k_ph_end(const DevModel<T>* __restrict
   load_ws_range(w, gws, env, LCR_OFF(M), LCR_OFF(H));    // M, qacc
   load_ws_range(w, gws, env, LCR_OFF(ncon), LCR_OFF(J)); // counts + cache (stored with the state), flags
   __syncwarp();
+  if (moved(w)) { redo_push(redo, env); return; }  // a substep outgrew the fast workspace: redone over the big one
   const DevModel<T>& m = *dm;
-  const int od = obs_dim(m.task);
   if (w.redo_forward) forward(w, m, verts);
   integrate(w, m);
-  env_step_end(w, m, obs + (size_t)env * od, reward + env, term + env, trunc + env, succ + env);
+  env_step_end(w, m, io, env);
   store_state(w, s, env);
 }
 
-// debug / test hook: mj_forward on the current state (not written back) and dump of the contact list
+// debug / test hook: mj_forward on the current state (not written back) and dump of the contact list; always over the
+// BIG workspace, so that the list is never cut by the fast caps
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_debug_contacts(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
-                                                           double* __restrict__ out, int32_t* __restrict__ ncon_out) {
+__global__ void __launch_bounds__(32, 2) k_debug_contacts(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
+                                                          double* __restrict__ out, int32_t* __restrict__ ncon_out) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = blockIdx.x;
   load_state(w, s, env);
@@ -1810,7 +1816,7 @@ __global__ void __launch_bounds__(32, 16) k_debug_contacts(const DevModel<T>* __
   const int ncon = w.ncon;
   if (LANE == 0) ncon_out[env] = ncon;
   for (int ci = LANE; ci < ncon; ci += 32) {
-    double* o = out + ((size_t)env * LCR_MAXCON + ci) * 12;
+    double* o = out + ((size_t)env * LCR_MAXCON_BIG + ci) * 12;
     for (int k = 0; k < 3; k++) { o[k] = (double)w.c_pos[ci][k]; o[3 + k] = (double)w.c_frame[ci][k]; }
     o[6] = (double)w.c_dist[ci]; o[7] = w.c_b1[ci]; o[8] = w.c_b2[ci]; o[9] = dm->par(w.c_par[ci])->dim; o[10] = (double)w.c_mu[ci]; o[11] = w.c_efc[ci];
   }
@@ -1824,9 +1830,10 @@ template <typename T> DI void sa_empty(DevState<T> s, int e) {
   int* next = reinterpret_cast<int*>(blk + Ws<T, 1>::SA_WORDS * sizeof(T) + LCR_NSA * 2);
   for (int k = 0; k < 4; k++) next[k] = 0;
 }
-// row-major float64 <-> per-env records of T
+// row-major float64 <-> per-env records of T; rng = the PCG64 state of the env's reset stream (4 x u64)
 template <typename T>
-__global__ void k_get_state(DevState<T> s, int nq, int nv, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints) {
+__global__ void k_get_state(DevState<T> s, int nq, int nv, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,
+                            unsigned long long* rng) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= s.n) return;
   const T* r = s.st + (size_t)e * s.nfp;
@@ -1837,10 +1844,14 @@ __global__ void k_get_state(DevState<T> s, int nq, int nv, double* qpos, double*
   for (int k = 0; k < nv; k++, f++) if (warm) warm[(size_t)e * nv + k] = (double)r[f];
   for (int k = 0; k < LCR_NAUX; k++, f++) if (aux) aux[(size_t)e * LCR_NAUX + k] = (double)r[f];
   if (ints) for (int k = 0; k < LCR_NINT; k++) ints[(size_t)e * LCR_NINT + k] = s.ib[(size_t)e * LCR_IB_WORDS + k];
+  if (rng) {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(s.ib + (size_t)e * LCR_IB_WORDS + 8);
+    for (int k = 0; k < 4; k++) rng[4 * (size_t)e + k] = src[k];
+  }
 }
 template <typename T>
 __global__ void k_set_state(DevState<T> s, int nq, int nv, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
-                            const double* aux, const int32_t* ints) {
+                            const double* aux, const int32_t* ints, const unsigned long long* rng) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= s.n) return;
   T* r = s.st + (size_t)e * s.nfp;
@@ -1851,7 +1862,11 @@ __global__ void k_set_state(DevState<T> s, int nq, int nv, const double* qpos, c
   for (int k = 0; k < nv; k++, f++) if (warm) r[f] = (T)warm[(size_t)e * nv + k];
   for (int k = 0; k < LCR_NAUX; k++, f++) if (aux) r[f] = (T)aux[(size_t)e * LCR_NAUX + k];
   if (ints) for (int k = 0; k < LCR_NINT; k++) s.ib[(size_t)e * LCR_IB_WORDS + k] = ints[(size_t)e * LCR_NINT + k];
-  sa_empty<T>(s, e);  // the separating-axis cache is not part of the checkpointed state
+  if (rng) {
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(s.ib + (size_t)e * LCR_IB_WORDS + 8);
+    for (int k = 0; k < 4; k++) dst[k] = rng[4 * (size_t)e + k];
+  }
+  sa_empty<T>(s, e);  // the separating-axis cache is not part of the checkpointed state (it never changes a result)
 }
 template <typename T>
 __global__ void k_init_state(const DevModel<T>* dm, DevState<T> s) {
@@ -1875,16 +1890,17 @@ __global__ void k_get_diag(DevState<T> s, int32_t* out) {
   if (e >= s.n) return;
   for (int k = 0; k < LCR_NDIAG; k++) out[(size_t)e * LCR_NDIAG + k] = s.ib[(size_t)e * LCR_IB_WORDS + LCR_NINT + k];
 }
+// per-env PCG64 states; with a mask only the selected envs are reseeded (the streams of the others go on)
 template <typename T>
-__global__ void k_seed(DevState<T> s, const unsigned long long* st) {
+__global__ void k_seed(DevState<T> s, const unsigned long long* st, const uint8_t* __restrict__ mask) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= s.n) return;
+  if (e >= s.n || (mask && !mask[e])) return;
   unsigned long long* rng = reinterpret_cast<unsigned long long*>(s.ib + (size_t)e * LCR_IB_WORDS + 8);
   for (int k = 0; k < 4; k++) rng[k] = st[4 * (size_t)e + k];
 }
 
-// obs | reward | terminated | truncated | success as one float32 record per env (the send buffer of the one all-gather
-// per step, and the single device->host copy of the host-facing path)
+// obs | reward | terminated | truncated | success as one float32 record per env, from separate arrays (the step kernels
+// write the record themselves when lcr_step_rec is given one; this is the stand-alone version of the C-ABI)
 static __global__ void k_pack(const float* __restrict__ obs, const float* __restrict__ reward, const uint8_t* __restrict__ term,
                        const uint8_t* __restrict__ trunc, const uint8_t* __restrict__ succ, float* __restrict__ rec, int n, int od) {
   const int w = od + 4, total = n * w;
@@ -1900,64 +1916,119 @@ static __global__ void k_pack(const float* __restrict__ obs, const float* __rest
   }
 }
 
+}  // namespace lcr
+#include "lcr_flow.cuh"
+namespace lcr {
+
 // ---------------------------------------------------------------- launchers
-template <typename T, int NC> static void set_smem_attr() {
-  static bool done = false;  // per process; attributes are per device but identical
-  const int bytes = (int)(sizeof(Ws<T, NC>) * LCR_WPB);
-  (void)done;
-  cudaFuncSetAttribute(k_step<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_reset<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_substeps<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_ik<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_debug_contacts<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_ph_begin<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_ph_dyn<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_ph_col<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_ph_sol<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_ph_end<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_step_ls<T, NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
-  cudaFuncSetAttribute(k_step_ls<T, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
+#define LCR_SMEM_MAX (227 * 1024)
+template <typename T, int S>
+void LaunchNC<T, S>::prepare() {
+  constexpr int B = S | LCR_NC_BIG;
+  const int fast = (int)sizeof(Ws<T, S>), big = (int)sizeof(Ws<T, B>);
+  cudaFuncSetAttribute(k_step<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
+  cudaFuncSetAttribute(k_step<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(k_reset<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
+  cudaFuncSetAttribute(k_substeps<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
+  cudaFuncSetAttribute(k_substeps<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(k_ik<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
+  cudaFuncSetAttribute(k_debug_contacts<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(k_ph_begin<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
+  cudaFuncSetAttribute(k_ph_dyn<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
+  cudaFuncSetAttribute(k_ph_col<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
+  cudaFuncSetAttribute(k_ph_sol<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
+  cudaFuncSetAttribute(k_ph_end<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
+  cudaFuncSetAttribute(k_step_ls<T, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
+  cudaFuncSetAttribute(k_step_ls<T, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
+  cudaFuncSetAttribute(k_flow<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, flow_smem());
   // all of the SM's L1/shared array as shared memory: several CTAs of a few workspaces each must fit one SM
-  const char* cv = getenv("LCR_LS_CARVEOUT");  // experiment: percent of the L1/shared array used as shared memory
-  cudaFuncSetAttribute(k_step_ls<T, NC, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(k_step_ls<T, NC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(k_step<T, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_step_ls<T, S, false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_step_ls<T, S, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_flow<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_step<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
+template <typename T, int S> size_t LaunchNC<T, S>::ws_bytes() { return sizeof(Ws<T, S>); }
 
-template <typename T>
-void Launch<T>::prepare(int ncube) {
-  // (`ncube` of the launchers is the scene class: 1 / 2 cubes, or LCR_NC_LOOP = one cube + the static walls)
-  if (ncube == 1) set_smem_attr<T, 1>(); else if (ncube == 2) set_smem_attr<T, 2>(); else set_smem_attr<T, LCR_NC_LOOP>();
+template <typename T, int S>
+void LaunchNC<T, S>::reset(const DevModel<T>* dm, const T* verts, DevState<T> s, const uint8_t* mask, float* obs, cudaStream_t st) {
+  k_reset<T, S><<<s.n, 32, sizeof(Ws<T, S>), st>>>(dm, verts, s, mask, obs);
 }
-template <typename T>
-size_t Launch<T>::smem_bytes(int ncube) {
-  return (ncube == 1 ? sizeof(Ws<T, 1>) : ncube == 2 ? sizeof(Ws<T, 2>) : sizeof(Ws<T, LCR_NC_LOOP>)) * LCR_WPB;
+template <typename T, int S>
+void LaunchNC<T, S>::step(const DevModel<T>* dm, const T* verts, DevState<T> s, StepIO io, Redo redo, cudaStream_t st) {
+  k_step<T, S><<<s.n, 32, sizeof(Ws<T, S>), st>>>(dm, verts, s, io, redo, nullptr, nullptr);
 }
-
-#define LCR_GRID(s) (((s).n + LCR_WPB - 1) / LCR_WPB)
-#define LCR_LAUNCH(KERNEL, ...)                                                                          \
-  do {                                                                                                   \
-    if (ncube == 1) KERNEL<T, 1><<<LCR_GRID(s), LCR_WPB * 32, sizeof(Ws<T, 1>) * LCR_WPB, st>>>(__VA_ARGS__); \
-    else if (ncube == 2) KERNEL<T, 2><<<LCR_GRID(s), LCR_WPB * 32, sizeof(Ws<T, 2>) * LCR_WPB, st>>>(__VA_ARGS__);      \
-    else KERNEL<T, LCR_NC_LOOP><<<LCR_GRID(s), LCR_WPB * 32, sizeof(Ws<T, LCR_NC_LOOP>) * LCR_WPB, st>>>(__VA_ARGS__);  \
-  } while (0)
-
-template <typename T>
-void Launch<T>::reset(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const uint8_t* mask, float* obs, cudaStream_t st) {
-  LCR_LAUNCH(k_reset, dm, verts, s, mask, obs);
-}
-template <typename T>
-void Launch<T>::step(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
-                     uint8_t* term, uint8_t* trunc, uint8_t* succ, cudaStream_t st) {
-  LCR_LAUNCH(k_step, dm, verts, s, actions, obs, reward, term, trunc, succ);
+// the envs of the redo list, from their unchanged start state, over the big workspace
+template <typename T, int S>
+void LaunchNC<T, S>::step_big(const DevModel<T>* dm, const T* verts, DevState<T> s, StepIO io, Redo list, cudaStream_t st) {
+  constexpr int B = S | LCR_NC_BIG;
+  k_step<T, B><<<std::min(s.n, 296), 32, sizeof(Ws<T, B>), st>>>(dm, verts, s, io, Redo{nullptr, nullptr}, list.list, list.count);
 }
 // lockstep kernel: CTAs of `warps` envs; warps <= 0 picks the largest CTA that fits one SM
-template <typename T>
-int Launch<T>::lockstep_warps(int ncube, int warps) {
-  const int fit = (int)(LCR_LS_MAXSMEM / smem_bytes(ncube));
+template <typename T, int S>
+int LaunchNC<T, S>::lockstep_warps(int warps) {
+  const int fit = (int)(LCR_LS_MAXSMEM / sizeof(Ws<T, S>));
   if (warps <= 0) warps = fit;
   return std::max(1, std::min(std::min(warps, fit), 16));
 }
+// `grid` CTAs of `warps` warps, the first `epc` of which own an env (seats from perm, or env = seat if perm is null)
+template <typename T, int S>
+void LaunchNC<T, S>::step_lockstep(const DevModel<T>* dm, const T* verts, DevState<T> s, StepIO io, Redo redo, int grid, int warps, int epc, int flags,
+                                   const int* perm, long long* prof, cudaStream_t st) {
+  if (prof) k_step_ls<T, S, true><<<grid, 32 * warps, sizeof(Ws<T, S>) * epc, st>>>(dm, verts, s, io, redo, flags, perm, epc, prof);
+  else k_step_ls<T, S, false><<<grid, 32 * warps, sizeof(Ws<T, S>) * epc, st>>>(dm, verts, s, io, redo, flags, perm, epc, prof);
+}
+// one chain of 2 + 4 * n_substeps launches over the env range [env0, env0 + cnt) on stream st
+template <typename T, int S>
+int LaunchNC<T, S>::step_phased(int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws_, StepIO io, Redo redo, int env0, int cnt,
+                                const int* perm, cudaStream_t st) {
+  typedef Ws<T, S> W;
+  W* gws = reinterpret_cast<W*>(gws_);
+  const size_t sm = sizeof(W);
+  k_ph_begin<T, S><<<cnt, 32, sm, st>>>(dm, verts, s, gws, io, redo, env0, perm);
+  for (int k = 0; k < n_substeps; k++) {
+    k_ph_dyn<T, S><<<cnt, 32, sm, st>>>(dm, verts, gws, k == 0, env0, perm);
+    k_ph_job<T, S><<<cnt * LCR_NSLOT, 32, 0, st>>>(dm, verts, gws, env0, perm);
+    k_ph_col<T, S><<<cnt, 32, sm, st>>>(dm, verts, gws, env0, perm);
+    k_ph_sol<T, S><<<cnt, 32, sm, st>>>(dm, gws, env0, perm);
+  }
+  k_ph_end<T, S><<<cnt, 32, sm, st>>>(dm, verts, s, gws, io, redo, env0, perm);
+  return 2 + 4 * n_substeps;
+}
+// flow kernel: `warps` fast workspace slots per CTA (<= 16); BIG CTAs hold as many big workspaces as fit
+template <typename T, int S> int LaunchNC<T, S>::flow_warps() { return std::max(1, std::min(16, (int)((LCR_SMEM_MAX - 256) / sizeof(Ws<T, S>)))); }
+template <typename T, int S> int LaunchNC<T, S>::flow_bigslots() { return std::max(1, std::min(16, (int)((LCR_SMEM_MAX - 256) / sizeof(Ws<T, S | LCR_NC_BIG>)))); }
+template <typename T, int S> int LaunchNC<T, S>::flow_smem() {
+  return (int)std::max(sizeof(Ws<T, S>) * flow_warps(), sizeof(Ws<T, S | LCR_NC_BIG>) * flow_bigslots());
+}
+template <typename T, int S>
+void LaunchNC<T, S>::step_flow(const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, StepIO io, const void* fq_, int grid, int nbigcta, int flags,
+                               int t_hi, int t_big, unsigned long long* stats, cudaStream_t st) {
+  const FlowQ& fq = *reinterpret_cast<const FlowQ*>(fq_);
+  k_sched_flow<T><<<1, 1024, 0, st>>>(s, fq, t_hi, t_big);
+  static const int dbg_warps = getenv("LCR_FLOW_WARPS") ? atoi(getenv("LCR_FLOW_WARPS")) : 0;  // debug: fewer warps per CTA
+  const int warps = dbg_warps > 0 ? std::min(dbg_warps, flow_warps()) : flow_warps();
+  k_flow<T, S><<<grid, 32 * warps, flow_smem(), st>>>(dm, verts, s, reinterpret_cast<Ws<T, S>*>(gws), io, fq, nbigcta, std::min(flow_bigslots(), warps), flags, stats);
+}
+template <typename T, int S>
+void LaunchNC<T, S>::substeps(const DevModel<T>* dm, const T* verts, DevState<T> s, int n, Redo redo, cudaStream_t st) {
+  k_substeps<T, S><<<s.n, 32, sizeof(Ws<T, S>), st>>>(dm, verts, s, n, redo, nullptr, nullptr);
+}
+template <typename T, int S>
+void LaunchNC<T, S>::substeps_big(const DevModel<T>* dm, const T* verts, DevState<T> s, int n, Redo list, cudaStream_t st) {
+  constexpr int B = S | LCR_NC_BIG;
+  k_substeps<T, B><<<std::min(s.n, 296), 32, sizeof(Ws<T, B>), st>>>(dm, verts, s, n, Redo{nullptr, nullptr}, list.list, list.count);
+}
+template <typename T, int S>
+void LaunchNC<T, S>::ik(const DevModel<T>* dm, const T* verts, DevState<T> s, const float* target, float* q_out, cudaStream_t st) {
+  k_ik<T, S><<<s.n, 32, sizeof(Ws<T, S>), st>>>(dm, verts, s, target, q_out);
+}
+template <typename T, int S>
+void LaunchNC<T, S>::debug_contacts(const DevModel<T>* dm, const T* verts, DevState<T> s, double* out, int32_t* ncon, cudaStream_t st) {
+  constexpr int B = S | LCR_NC_BIG;
+  k_debug_contacts<T, B><<<s.n, 32, sizeof(Ws<T, B>), st>>>(dm, verts, s, out, ncon);
+}
+
+// ---- kernels that do not depend on the scene class
 template <typename T>
 void Launch<T>::pack(const float* obs, const float* reward, const uint8_t* term, const uint8_t* trunc, const uint8_t* succ, float* rec, int n, int od,
                      cudaStream_t st) {
@@ -1966,73 +2037,23 @@ void Launch<T>::pack(const float* obs, const float* reward, const uint8_t* term,
 }
 template <typename T>
 void Launch<T>::sched(DevState<T> s, int* perm, int W, int striped, cudaStream_t st) { k_sched<T><<<1, 1024, 0, st>>>(s, perm, W, striped); }
-// `grid` CTAs of `warps` warps, the first `epc` of which own an env (seats from perm, or env = seat if perm is null)
-template <typename T>
-void Launch<T>::step_lockstep(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* actions, float* obs, float* reward,
-                              uint8_t* term, uint8_t* trunc, uint8_t* succ, int grid, int warps, int epc, int flags, const int* perm, long long* prof,
-                              cudaStream_t st) {
-#define LCR_LS_GO(NCV, PROFV) k_step_ls<T, NCV, PROFV><<<grid, 32 * warps, sizeof(Ws<T, NCV>) * epc, st>>>(dm, verts, s, actions, obs, reward, term, trunc, succ, flags, perm, epc, prof)
-  if (ncube == 1) { if (prof) LCR_LS_GO(1, true); else LCR_LS_GO(1, false); }
-  else if (ncube == 2) { if (prof) LCR_LS_GO(2, true); else LCR_LS_GO(2, false); }
-  else { if (prof) LCR_LS_GO(LCR_NC_LOOP, true); else LCR_LS_GO(LCR_NC_LOOP, false); }
-#undef LCR_LS_GO
-}
-// one chain of 2 + 3*n_substeps launches over the env range [env0, env0 + cnt) on stream st
-template <typename T, int NC>
-static void phased_chain(int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws_, const float* actions, float* obs,
-                         float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, const int* perm, cudaStream_t st) {
-  typedef Ws<T, NC> W;
-  W* gws = reinterpret_cast<W*>(gws_);
-  const size_t sm = sizeof(W);
-  k_ph_begin<T, NC><<<cnt, 32, sm, st>>>(dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, perm);
-  for (int k = 0; k < n_substeps; k++) {
-    k_ph_dyn<T, NC><<<cnt, 32, sm, st>>>(dm, verts, gws, k == 0, env0, perm);
-    k_ph_job<T, NC><<<cnt * LCR_NSLOT, 32, 0, st>>>(dm, verts, gws, env0, perm);
-    k_ph_col<T, NC><<<cnt, 32, sm, st>>>(dm, verts, gws, env0, perm);
-    k_ph_sol<T, NC><<<cnt, 32, sm, st>>>(dm, gws, env0, perm);
-  }
-  k_ph_end<T, NC><<<cnt, 32, sm, st>>>(dm, verts, s, gws, obs, reward, term, trunc, succ, env0, perm);
-}
-template <typename T>
-int Launch<T>::step_phased(int ncube, int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, const float* actions,
-                           float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* succ, int env0, int cnt, const int* perm, cudaStream_t st) {
-  if (ncube == 1) phased_chain<T, 1>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, perm, st);
-  else if (ncube == 2) phased_chain<T, 2>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, perm, st);
-  else phased_chain<T, LCR_NC_LOOP>(n_substeps, dm, verts, s, gws, actions, obs, reward, term, trunc, succ, env0, cnt, perm, st);
-  return 2 + 4 * n_substeps;
-}
-template <typename T>
-void Launch<T>::substeps(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, int n, cudaStream_t st) {
-  LCR_LAUNCH(k_substeps, dm, verts, s, n);
-}
-template <typename T>
-void Launch<T>::ik(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, const float* target, float* q_out, cudaStream_t st) {
-  LCR_LAUNCH(k_ik, dm, verts, s, target, q_out);
-}
 template <typename T>
 void Launch<T>::get_state(int ncube, DevState<T> s, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,
-                          cudaStream_t st) {
-  const int ncu = ncube == LCR_NC_LOOP ? 1 : ncube;
-  k_get_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, 6 + 7 * ncu, 6 + 6 * ncu, qpos, qvel, ctrl, warm, aux, ints);
+                          unsigned long long* rng, cudaStream_t st) {
+  k_get_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, 6 + 7 * ncube, 6 + 6 * ncube, qpos, qvel, ctrl, warm, aux, ints, rng);
 }
 template <typename T>
 void Launch<T>::set_state(int ncube, DevState<T> s, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
-                          const double* aux, const int32_t* ints, cudaStream_t st) {
-  const int ncu = ncube == LCR_NC_LOOP ? 1 : ncube;
-  k_set_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, 6 + 7 * ncu, 6 + 6 * ncu, qpos, qvel, ctrl, warm, aux, ints);
+                          const double* aux, const int32_t* ints, const unsigned long long* rng, cudaStream_t st) {
+  k_set_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, 6 + 7 * ncube, 6 + 6 * ncube, qpos, qvel, ctrl, warm, aux, ints, rng);
 }
 template <typename T>
-void Launch<T>::init_state(int ncube, const DevModel<T>* dm, DevState<T> s, cudaStream_t st) {
-  k_init_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(dm, s);
-}
-
-template <typename T>
-void Launch<T>::debug_contacts(int ncube, const DevModel<T>* dm, const T* verts, DevState<T> s, double* out, int32_t* ncon, cudaStream_t st) {
-  LCR_LAUNCH(k_debug_contacts, dm, verts, s, out, ncon);
-}
+void Launch<T>::init_state(const DevModel<T>* dm, DevState<T> s, cudaStream_t st) { k_init_state<T><<<(s.n + 127) / 128, 128, 0, st>>>(dm, s); }
 template <typename T>
 void Launch<T>::get_diag(DevState<T> s, int32_t* out, cudaStream_t st) { k_get_diag<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, out); }
 template <typename T>
-void Launch<T>::seed(DevState<T> s, const unsigned long long* d_state, cudaStream_t st) { k_seed<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, d_state); }
+void Launch<T>::seed(DevState<T> s, const unsigned long long* d_state, const uint8_t* d_mask, cudaStream_t st) {
+  k_seed<T><<<(s.n + 127) / 128, 128, 0, st>>>(s, d_state, d_mask);
+}
 
 }  // namespace lcr

@@ -26,6 +26,9 @@ _OBS_LAYOUT = {
 }
 
 
+_EXEC_MODES = {"fused": 0, "phased": 1, "lockstep": 2, "flow": 3}
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -54,7 +57,7 @@ class BatchedLowCostRobotEnv:
                  block_gripper=None, distance_threshold=0.05, height_threshold=0.1, cube_xy_range=0.3,
                  target_xy_range=0.3, goal_z_range=0.1, n_substeps=20, render_mode=None, max_episode_steps=50,
                  autoreset=False, precision="float32", assets_path=None, collision_mask=model.COLLIDE_ALL,
-                 env_offset=0, exec_mode="auto"):
+                 env_offset=0, exec_mode="auto", seed=None):
         if observation_mode != "state":
             raise NotImplementedError("only observation_mode='state' is implemented (image rendering is out of scope)")
         if render_mode is not None:
@@ -68,8 +71,8 @@ class BatchedLowCostRobotEnv:
                                    distance_threshold=distance_threshold, height_threshold=height_threshold,
                                    cube_xy_range=cube_xy_range, target_xy_range=target_xy_range, goal_z_range=goal_z_range,
                                    n_substeps=n_substeps, max_episode_steps=max_episode_steps, autoreset=autoreset,
-                                   collision_mask=collision_mask, exec_mode={"fused": 0, "phased": 1, "lockstep": 2}[self._pick_exec_mode(exec_mode, int(num_envs))])
-        self.exec_mode = {0: "fused", 1: "phased", 2: "lockstep"}[self.cfg.exec_mode]
+                                   collision_mask=collision_mask, exec_mode=_EXEC_MODES[self._pick_exec_mode(exec_mode, int(num_envs))])
+        self.exec_mode = {v: k for k, v in _EXEC_MODES.items()}[self.cfg.exec_mode]
         self.block_gripper = bool(self.cfg.block_gripper)
         self.compiled = model.load_compiled(self.task, assets_path)
         self.cmodel, self.verts = model.pack_model(self.compiled)
@@ -79,8 +82,10 @@ class BatchedLowCostRobotEnv:
         self.env_offset = int(env_offset)  # global index of local env 0 (multi-GPU sharding)
         self._L = capi.lib()
         h = C.c_void_p()
+        if self.device.index is None:  # "cuda" = the current device, which need not be 0
+            self.device = torch.device("cuda", torch.cuda.current_device())
         capi.check(self._L.lcr_create(C.byref(self.cmodel), self.verts.ctypes.data_as(C.c_void_p), C.byref(self.cfg),
-                                      self.num_envs, self.device.index or 0, self.precision, C.byref(h)))
+                                      self.num_envs, self.device.index, self.precision, C.byref(h)))
         self._h = h
         n, dev = self.num_envs, self.device
         self._obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, device=dev)
@@ -94,18 +99,18 @@ class BatchedLowCostRobotEnv:
         self.single_observation_space = spaces.Dict(sub)
         self.action_space = spaces.batch_space(self.single_action_space, n)
         self.observation_space = spaces.batch_space(self.single_observation_space, n)
-        self.seed(0)
+        # like gymnasium, an env that is never given a seed draws one from the OS (reference: Env.reset(seed=None))
+        self.seed(int(np.random.SeedSequence().entropy % (1 << 62)) if seed is None else seed)
 
     @classmethod
     def _pick_exec_mode(cls, exec_mode, num_envs):
-        """"auto": the lockstep kernel (one launch per step) for small batches, where the step time is the chain of the
-        most expensive env and its CTA-wide job pool shortens that chain; the phased chain (one small kernel per mj_step
-        phase over all envs) once several waves of envs queue per SM, where its barrier-free scheduling wins (measured
-        crossover on B200 between 4096 and 5120 envs, profiles/README.md).  All modes give bit-identical results
-        (tests/test_gpu_parity.py)."""
+        """"auto": the flow kernel (one persistent launch per step; the phases of every env run from device-side queues,
+        csrc/lcr_flow.cuh) from a few hundred envs on; the lockstep kernel for tiny batches, where a handful of CTAs
+        cannot fill the GPU either way and one launch without queue traffic is the shortest path.  All modes give
+        bit-identical results (tests/test_gpu_parity.py)."""
         if exec_mode != "auto":
             return exec_mode
-        return "phased" if num_envs >= 5120 else "lockstep"
+        return "flow" if num_envs >= 256 else "lockstep"
 
     # -- helpers ---------------------------------------------------------------------------
     def _stream(self):
@@ -118,28 +123,31 @@ class BatchedLowCostRobotEnv:
             k += width
         return out
 
-    def seed(self, seed):
-        """Env ``i`` gets the stream of ``np.random.default_rng(seed + env_offset + i)``."""
+    def seed(self, seed, mask=None):
+        """Env ``i`` gets the stream of ``np.random.default_rng(seed + env_offset + i)``; with ``mask`` (uint8 device
+        tensor) only the selected envs are reseeded, the streams of the others go on."""
         base = int(seed) + self.env_offset
         st = pcg64_states(range(base, base + self.num_envs))
-        capi.check(self._L.lcr_seed(self._h, st.ctypes.data_as(C.c_void_p), self._stream()))
+        with torch.cuda.device(self.device):
+            capi.check(self._L.lcr_seed(self._h, st.ctypes.data_as(C.c_void_p), _ptr(mask), self._stream()))
 
     # -- gymnasium-style API -----------------------------------------------------------------
     def reset(self, seed=None, options=None, mask=None):
         """Reference ``reset`` (reach_cube_env.py:297-311).  ``mask`` (bool[num_envs]) resets a subset."""
-        if seed is not None:
-            self.seed(seed)
         m = None
         if mask is not None:
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
             if m.shape != (self.num_envs,):
                 raise ValueError("mask must have shape (num_envs,)")
+        if seed is not None:
+            self.seed(seed, m)
         with torch.cuda.device(self.device):
             capi.check(self._L.lcr_reset(self._h, _ptr(m), _ptr(self._obs), self._stream()))
         return self._split(self._obs.clone()), {}
 
-    def step_flat(self, actions):
-        """One control step; returns views of the internal output buffers (no copies)."""
+    def step_flat(self, actions, record=None):
+        """One control step; returns views of the internal output buffers (no copies).  ``record`` (optional,
+        float32 ``[num_envs, obs_dim + 4]``) also receives the packed record, written by the step kernels themselves."""
         if not isinstance(actions, torch.Tensor):
             actions = torch.as_tensor(np.asarray(actions), device=self.device)
         if tuple(actions.shape) != (self.num_envs, self.action_dim):
@@ -147,26 +155,49 @@ class BatchedLowCostRobotEnv:
         a = actions.to(device=self.device, dtype=torch.float32).contiguous()
         f = self._flags
         with torch.cuda.device(self.device):
-            capi.check(self._L.lcr_step(self._h, _ptr(a), _ptr(self._obs), _ptr(self._reward), _ptr(f[0]), _ptr(f[1]),
-                                        _ptr(f[2]), self._stream()))
+            capi.check(self._L.lcr_step_rec(self._h, _ptr(a), _ptr(self._obs), _ptr(self._reward), _ptr(f[0]), _ptr(f[1]),
+                                            _ptr(f[2]), _ptr(record), self._stream()))
         return self._obs, self._reward, f[0], f[1], f[2]
 
     def step_packed(self, actions, out=None):
         """One control step, outputs as one float32 record per env ``[num_envs, obs_dim + 4]`` = obs | reward |
-        terminated | truncated | success (one fused pack kernel): the all-gather / device->host unit of ``dist.ShardedEnv``."""
-        obs, reward, te, tr, su = self.step_flat(actions)
+        terminated | truncated | success, written by the step kernels (no pack launch): the all-gather / device->host
+        unit of ``dist.ShardedEnv``."""
         if out is None:
             if self._record is None:
                 self._record = torch.empty(self.num_envs, self.obs_dim + 4, dtype=torch.float32, device=self.device)
             out = self._record
-        with torch.cuda.device(self.device):
-            capi.check(self._L.lcr_pack_outputs(self._h, _ptr(obs), _ptr(reward), _ptr(te), _ptr(tr), _ptr(su), _ptr(out), self._stream()))
+        if out.dtype != torch.float32 or tuple(out.shape) != (self.num_envs, self.obs_dim + 4) or not out.is_contiguous():
+            raise ValueError("record buffer must be a contiguous float32 [num_envs, obs_dim + 4] tensor")
+        self.step_flat(actions, record=out)
         return out
 
     def step(self, actions):
         obs, reward, te, tr, su = self.step_flat(actions)
         info = {} if self.task == "lift" else {"is_success": su.bool()}  # lift_cube_env.py:337
+        if self.report_failures:
+            info.update(self.failure_info())
         return self._split(obs.clone()), reward.clone(), te.bool(), tr.bool(), info
+
+    report_failures = False  # True: every step() adds failure_info() to info (one more tiny launch per step)
+
+    def failure_info(self):
+        """Per-env failure flags of the last step (device tensors, no host sync): ``nan_reset`` = the env blew up
+        (NaN / huge state or acceleration) and was restored by mj_resetData like MuJoCo does, ``nan_resets`` the running
+        count, ``contact_overflow`` = contacts dropped past the big workspace caps (0 on every tested workload)."""
+        d = self.diagnostics()
+        prev = getattr(self, "_nan_seen", None)
+        now = d["nan_resets"]
+        flag = now > prev if prev is not None else now > 0
+        self._nan_seen = now.clone()
+        return {"nan_reset": flag, "nan_resets": now, "contact_overflow": d["overflow"]}
+
+    def flow_status(self):
+        """(unfinished envs, watchdog code) of the last flow-mode step; (0, 0) when healthy.  Synchronises the device."""
+        s = (C.c_int32 * 8)()
+        capi.check(self._L.lcr_flow_status(self._h, s))
+        self.flow_debug = [int(x) for x in s[2:]]
+        return int(s[0]), int(s[1])
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -187,13 +218,13 @@ class BatchedLowCostRobotEnv:
         n, dev = self.num_envs, self.device
         z = lambda w, dt=torch.float64: torch.zeros(n, w, dtype=dt, device=dev)
         st = dict(qpos=z(self.nq), qvel=z(self.nv), ctrl=z(6), warm=z(self.nv), aux=z(model.NAUX),
-                  ints=z(model.NINT, torch.int32))
+                  ints=z(model.NINT, torch.int32), rng=z(4, torch.int64))  # rng: the 4 x uint64 PCG64 state, bit pattern in int64
         with torch.cuda.device(self.device):
-            capi.check(self._L.lcr_get_state(self._h, *[_ptr(st[k]) for k in ("qpos", "qvel", "ctrl", "warm", "aux", "ints")],
+            capi.check(self._L.lcr_get_state(self._h, *[_ptr(st[k]) for k in ("qpos", "qvel", "ctrl", "warm", "aux", "ints", "rng")],
                                              self._stream()))
         return st
 
-    def set_state(self, qpos=None, qvel=None, ctrl=None, warm=None, aux=None, ints=None):
+    def set_state(self, qpos=None, qvel=None, ctrl=None, warm=None, aux=None, ints=None, rng=None):
         def prep(x, w, dt=torch.float64):
             if x is None:
                 return None
@@ -202,7 +233,7 @@ class BatchedLowCostRobotEnv:
                 raise ValueError(f"expected shape {(self.num_envs, w)}, got {tuple(t.shape)}")
             return t
         args = [prep(qpos, self.nq), prep(qvel, self.nv), prep(ctrl, 6), prep(warm, self.nv), prep(aux, model.NAUX),
-                prep(ints, model.NINT, torch.int32)]
+                prep(ints, model.NINT, torch.int32), prep(rng, 4, torch.int64)]
         with torch.cuda.device(self.device):
             capi.check(self._L.lcr_set_state(self._h, *[_ptr(a) for a in args], self._stream()))
             torch.cuda.current_stream(self.device).synchronize()  # args are temporaries
@@ -281,7 +312,7 @@ class PushCubeLoopEnv(BatchedLowCostRobotEnv):
     def _timestamp(self):
         aux = torch.zeros(self.num_envs, model.NAUX, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            capi.check(self._L.lcr_get_state(self._h, None, None, None, None, _ptr(aux), None, self._stream()))
+            capi.check(self._L.lcr_get_state(self._h, None, None, None, None, _ptr(aux), None, None, self._stream()))
         return aux[:, 0]
 
     @property

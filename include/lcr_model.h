@@ -38,10 +38,17 @@
 #define LCR_MAXPAIR 160
 #define LCR_MAXNV (LCR_NARM + 6 * LCR_MAXCUBE)
 #define LCR_MAXNQ (LCR_NARM + 7 * LCR_MAXCUBE)
-/* per-env caps of the contact list and of the constraint rows; contacts past a cap are dropped in
- * generation order (limits, floor-cube, cube-cube, wall-cube, cube-mesh, wall-mesh, floor-mesh, mesh-mesh) and counted */
+/* Per-env caps of the contact list and of the constraint rows.  MuJoCo has no such caps (its arena is dynamic), so
+ * the library keeps two workspace sizes: the FAST path (LCR_MAXCON / LCR_MAXEFC: what fits 16 envs into the shared
+ * memory of one SM) and the BIG path (LCR_MAXCON_BIG / LCR_MAXEFC_BIG).  An env whose step would exceed a fast cap is
+ * not written back by the fast kernels; it is queued and the same step is redone from the same start state by the
+ * big-workspace kernel, so the caps never change a result.  Only what exceeds the BIG caps is dropped (in generation
+ * order: limits, floor-cube, cube-cube, wall-cube, cube-mesh, wall-mesh, floor-mesh, mesh-mesh) and counted in
+ * diag.overflow -- the tests assert that this never happens on the BASELINE workloads.  The oracle uses the BIG caps. */
 #define LCR_MAXCON 32
 #define LCR_MAXEFC 96
+#define LCR_MAXCON_BIG 128
+#define LCR_MAXEFC_BIG 384
 /* entries of the per-env separating-axis cache of the convex narrowphase (performance only) */
 #define LCR_NSA 16
 
@@ -102,7 +109,8 @@ typedef struct LcrEnvCfg {
   int32_t autoreset;        /* 0 = never (caller resets), 1 = next-step autoreset of done envs */
   int32_t collision_mask;   /* bit0 floor-cube, bit1 floor-mesh, bit2 cube-mesh, bit3 cube-cube, bit4 mesh-mesh, bit5 wall-cube, bit6 wall-mesh */
   int32_t exec_mode;        /* 0 = one fused kernel per step (one warp per CTA), 1 = phased (one small kernel per mj_step phase),
-                             * 2 = lockstep (one kernel per step, CTAs of several envs aligned at the phase boundaries) */
+                             * 2 = lockstep (one kernel per step, CTAs of several envs aligned at the phase boundaries),
+                             * 3 = flow (one persistent kernel per step, the phases of every env run from device-side queues) */
   double distance_threshold;/* 0.05 */
   double height_threshold;  /* 0.1 (Lift) */
   double cube_low[3], cube_high[3];     /* reset sampling box of the cube(s) */

@@ -45,8 +45,10 @@ int lcr_destroy(LcrSim* sim);
 
 /* Replaces Env.reset(seed=...)'s seeding (gymnasium: np_random = Generator(PCG64(SeedSequence(seed)))).
  * `h_state` is a HOST array [n_envs][4] of uint64 = (state_hi, state_lo, inc_hi, inc_lo) of each
- * env's numpy PCG64 bit generator; the device continues that exact stream for every later draw. */
-int lcr_seed(LcrSim* sim, const uint64_t* h_state, void* stream);
+ * env's numpy PCG64 bit generator; the device continues that exact stream for every later draw.
+ * `d_mask` (DEVICE, [n_envs] uint8, may be NULL = all): only the selected envs are reseeded -- a masked reset with a
+ * seed must not rewind the streams of the envs it does not reset.  `h_state` may be reused as soon as the call returns. */
+int lcr_seed(LcrSim* sim, const uint64_t* h_state, const uint8_t* d_mask, void* stream);
 
 /* Replaces Env.reset (reach_cube_env.py:297-311, push_cube_env.py:308-328, lift_cube_env.py:306-320,
  * pick_place_cube_env.py:316-336, stack_two_cubes_env.py:307-324, push_cube_loop_env.py:302-320): for every env with
@@ -66,6 +68,11 @@ int lcr_reset(LcrSim* sim, const uint8_t* d_mask, float* d_obs, void* stream);
  * d_terminated is always 0. */
 int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated,
              uint8_t* d_truncated, uint8_t* d_success, void* stream);
+/* lcr_step that also writes the packed record of lcr_pack_outputs (d_record [n_envs][obs_dim + 4] float32, may be NULL)
+ * from inside the step kernels: the 5-tuple of step() (reach_cube_env.py:333) as ONE buffer = the send buffer of the
+ * one all-gather per step of the sharded path and the single device->host copy of a host-facing caller. */
+int lcr_step_rec(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated,
+                 uint8_t* d_truncated, uint8_t* d_success, float* d_record, void* stream);
 
 /* Packs the outputs of lcr_step into one float32 record per env, d_record [n_envs][obs_dim + 4] =
  * obs | reward | terminated | truncated | success (what the reference's step() returns as a 5-tuple,
@@ -78,14 +85,16 @@ int lcr_pack_outputs(LcrSim* sim, const float* d_obs, const float* d_reward, con
  * reach_cube_env.py:182,185,252,273,285-294,305-306) and provides checkpoint/resume.  Row-major
  * DEVICE arrays of float64 regardless of precision: qpos [n][nq], qvel [n][nv], ctrl [n][6],
  * warm (qacc_warmstart) [n][nv], aux [n][LCR_NAUX] = time, target[3], site_xpos[3],
- * cube_xpos[3*2]; ints [n][LCR_NINT] = elapsed_steps, needs_reset.  Any pointer may be NULL.
+ * cube_xpos[3*2]; ints [n][LCR_NINT] = elapsed_steps, needs_reset; rng [n][4] uint64 = the PCG64 state of the env's reset
+ * stream (np_random of the reference env, state_hi, state_lo, inc_hi, inc_lo) -- without it a restored rollout would draw
+ * other cube / target positions at its next reset than the uninterrupted one.  Any pointer may be NULL.
  * PushCubeLoop keeps `current_goal` (0 / 1, push_cube_loop_env.py:136) in target[0]; aux[0] is info["timestamp"]. */
 #define LCR_NAUX 13
 #define LCR_NINT 2
 int lcr_get_state(LcrSim* sim, double* d_qpos, double* d_qvel, double* d_ctrl, double* d_warm, double* d_aux,
-                  int32_t* d_ints, void* stream);
+                  int32_t* d_ints, uint64_t* d_rng, void* stream);
 int lcr_set_state(LcrSim* sim, const double* d_qpos, const double* d_qvel, const double* d_ctrl,
-                  const double* d_warm, const double* d_aux, const int32_t* d_ints, void* stream);
+                  const double* d_warm, const double* d_aux, const int32_t* d_ints, const uint64_t* d_rng, void* stream);
 
 /* Advance `n` raw substeps (mujoco.mj_step, reach_cube_env.py:277) with the current ctrl, or with
  * n == 0 run mj_forward only (reach_cube_env.py:186,309).  Used by parity tests of the one-substep map. */
@@ -98,12 +107,14 @@ int lcr_substeps(LcrSim* sim, int n, void* stream);
 int lcr_ik(LcrSim* sim, const float* d_ee_target, float* d_q_out, void* stream);
 
 /* Diagnostics of the last lcr_step/lcr_substeps: DEVICE array [n][LCR_NDIAG] int32 =
- * ncon, nefc, solver iterations (last substep), max nefc over the step, overflow count, nan resets. */
+ * ncon, nefc, solver iterations (last substep), max nefc over the step, contacts dropped past the BIG caps of
+ * lcr_model.h in the last substep (0 on every tested workload: the fast caps only route an env to the big workspace,
+ * they never change a result), nan resets (mj_checkPos / mj_checkAcc -> mj_resetData). */
 #define LCR_NDIAG 6
 int lcr_get_diag(LcrSim* sim, int32_t* d_diag, void* stream);
 
 /* Test hook: run mj_forward on the current state WITHOUT writing it back and dump the contact list:
- * d_contacts [n][LCR_MAXCON][12] float64 = pos[3], normal[3], dist, body1, body2, dim, mu, first row;
+ * d_contacts [n][LCR_MAXCON_BIG][12] float64 = pos[3], normal[3], dist, body1, body2, dim, mu, first row;
  * d_ncon [n] int32.  Lets the parity tests compare collision geometry with the oracle directly. */
 int lcr_debug_contacts(LcrSim* sim, double* d_contacts, int32_t* d_ncon, void* stream);
 
@@ -111,6 +122,13 @@ int lcr_debug_contacts(LcrSim* sim, double* d_contacts, int32_t* d_ncon, void* s
  * of the step to d_clocks [n][10] int64 = begin/end, wait top, dynamics+broadphase, wait, narrowphase jobs, wait,
  * constraint rows, wait, Newton solve, integrate (sums over the substeps).  NULL switches it off again. */
 int lcr_debug_phase_clocks(LcrSim* sim, long long* d_clocks);
+/* Debug hook (flow mode): from the next lcr_step on, the warps of the flow kernel add the SM clock cycles they spent per
+ * phase to d_stats [8] uint64 = BEGIN, DYN, JOB, COL, SOL, END, BIG, idle (never reset by the library).  NULL = off. */
+int lcr_debug_flow_stats(LcrSim* sim, unsigned long long* d_stats);
+/* Flow mode health check (synchronises the device): h_status[8]; [0] = envs that did not finish the last step (0 when the
+ * step completed), [1] = watchdog code (0 = none; non-zero: a warp gave up waiting, the state is undefined), [2..7] =
+ * debug words of the first failure (phase, env, ...). */
+int lcr_flow_status(LcrSim* sim, int32_t* h_status);
 
 int lcr_n_envs(const LcrSim* sim);
 int lcr_kernel_launches(const LcrSim* sim); /* kernels launched by this handle so far */

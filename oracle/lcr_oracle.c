@@ -58,14 +58,17 @@ typedef struct OrcSim {
   double xpos[NB][3], xquat[NB][4], xmat[NB][9], xipos[NB][3], ximat[NB][9], axis[LCR_NARM][3];
   double M[NV][NV], Lm[NV][NV];
   double bias[NV], passive[NV], actuator[NV], smooth[NV], qacc_smooth[NV], qacc[NV], qfrc_constraint[NV];
-  Contact con[LCR_MAXCON];
+  Contact con[LCR_MAXCON_BIG];
   int ncon, nefc, niter, overflow, nan_resets, max_nefc;
+  int peak_ncon, peak_nefc, peak_ncand, total_overflow; /* over the lifetime of the sim (test statistics) */
+  int hist_nefc[32], hist_ncon[32]; /* env.steps by their max nefc / 16 and max ncon / 8 */
+  int step_max_ncon;
   int sa_key[LCR_NSA], sa_next; /* separating-axis cache, see lcr_oracle_convex.inc */
   double sa_dir[LCR_NSA][3], sa_S[LCR_NSA][2], sa_u[LCR_NSA][2][3];
-  int efc_type[LCR_MAXEFC]; /* 0 limit, 1 first row of a contact, 2 following row of a contact */
-  int efc_con[LCR_MAXEFC];
-  double J[LCR_MAXEFC][NV], efc_pos[LCR_MAXEFC], efc_vel[LCR_MAXEFC], efc_diag[LCR_MAXEFC];
-  double efc_R[LCR_MAXEFC], efc_D[LCR_MAXEFC], efc_aref[LCR_MAXEFC], efc_force[LCR_MAXEFC], efc_jar[LCR_MAXEFC];
+  int efc_type[LCR_MAXEFC_BIG]; /* 0 limit, 1 first row of a contact, 2 following row of a contact */
+  int efc_con[LCR_MAXEFC_BIG];
+  double J[LCR_MAXEFC_BIG][NV], efc_pos[LCR_MAXEFC_BIG], efc_vel[LCR_MAXEFC_BIG], efc_diag[LCR_MAXEFC_BIG];
+  double efc_R[LCR_MAXEFC_BIG], efc_D[LCR_MAXEFC_BIG], efc_aref[LCR_MAXEFC_BIG], efc_force[LCR_MAXEFC_BIG], efc_jar[LCR_MAXEFC_BIG];
 } OrcSim;
 
 /* ------------------------------------------------------------------ small math */
@@ -375,10 +378,10 @@ static int geom_body(const LcrModel *m, int g) {
 }
 
 static Contact *add_contact(OrcSim *s, int g1, int g2, const double *pos, const double *normal, double dist) {
-  if (s->ncon >= LCR_MAXCON) { s->overflow++; return NULL; }
+  if (s->ncon >= LCR_MAXCON_BIG) { s->overflow++; return NULL; }
   Contact *c = &s->con[s->ncon];
   mix_params(&s->m, g1, g2, c);
-  if (s->nefc + c->dim > LCR_MAXEFC) { s->overflow++; return NULL; }
+  if (s->nefc + c->dim > LCR_MAXEFC_BIG) { s->overflow++; return NULL; }
   memcpy(c->pos, pos, 3 * sizeof(double));
   memcpy(c->frame, normal, 3 * sizeof(double));
   make_frame(c->frame);
@@ -463,6 +466,7 @@ static void collision(OrcSim *s) {
   int keys[LCR_MAXCAND];
   CandRes res[LCR_MAXCAND];
   const int ncand_all = collect_candidates(s, keys), ncand = ncand_all < LCR_MAXCAND ? ncand_all : LCR_MAXCAND;
+  if (ncand_all > s->peak_ncand) s->peak_ncand = ncand_all;
   for (int k = 0; k < ncand; k++) cand_job(s, keys[k], &res[k]);
   /* generation order (= drop order at the caps): floor-cube, cube-cube, wall-cube, cube-mesh, wall-mesh, floor-mesh, mesh-mesh */
   if (mask & LCR_COLLIDE_FLOOR_CUBE)
@@ -580,6 +584,10 @@ static void make_constraints(OrcSim *s) {
   }
   for (int i = 0; i < s->nefc; i++) s->efc_D[i] = 1 / s->efc_R[i];
   if (s->nefc > s->max_nefc) s->max_nefc = s->nefc;
+  if (s->nefc > s->peak_nefc) s->peak_nefc = s->nefc;
+  if (s->ncon > s->peak_ncon) s->peak_ncon = s->ncon;
+  if (s->ncon > s->step_max_ncon) s->step_max_ncon = s->ncon;
+  s->total_overflow += s->overflow;
 }
 
 /* ------------------------------------------------------------------ primal Newton solver (mj_solNewton) */
@@ -603,7 +611,7 @@ static int unit_eval(const OrcSim *s, int i, const double *jar, const double *jv
   }
   const Contact *c = &s->con[s->efc_con[i]];
   int dim = c->dim;
-  double x[6], u[6], fri[6], mu = c->mu;
+  double x[6], u[6] = {0, 0, 0, 0, 0, 0}, fri[6], mu = c->mu;
   for (int j = 0; j < dim; j++) x[j] = jar[i + j] + (jv ? alpha * jv[i + j] : 0);
   if (dim == 1) {
     if (x[0] < 0) {
@@ -703,7 +711,7 @@ static void solve_constraints(OrcSim *s) {
     memset(s->qfrc_constraint, 0, sizeof s->qfrc_constraint);
     return;
   }
-  double jar[LCR_MAXEFC], Ma[NV], grad[NV], search[NV], Mv[NV], jv[LCR_MAXEFC];
+  double jar[LCR_MAXEFC_BIG], Ma[NV], grad[NV], search[NV], Mv[NV], jv[LCR_MAXEFC_BIG];
   double H[NV][NV], L[NV][NV];
   double *force = s->efc_force, *qacc = s->qacc;
   /* if no constraint row touches an arm dof (no limit rows, no contact on links 1..6) the arm block is decoupled:
@@ -1060,8 +1068,9 @@ void orc_step(OrcSim *s, const float *action, float *obs, float *reward, uint8_t
     *reward = 0; *terminated = 0; *truncated = 0; *success = 0;
     return;
   }
-  s->max_nefc = 0;
+  s->max_nefc = 0; s->step_max_ncon = 0;
   apply_action(s, action);
+  { int b = s->max_nefc / 16; s->hist_nefc[b < 31 ? b : 31]++; b = s->step_max_ncon / 8; s->hist_ncon[b < 31 ? b : 31]++; }
   write_obs(s, obs);
   if (task == LCR_TASK_PUSH_LOOP) { /* push_cube_loop_env.py:322-335: never terminates; TimeLimit truncates */
     loop_reward(s, reward, success);
@@ -1129,6 +1138,9 @@ void orc_set_state(OrcSim *s, const double *qpos, const double *qvel, const doub
   if (ints) { s->elapsed = ints[0]; s->needs_reset = ints[1]; }
   sa_clear(s); /* the separating-axis cache is not part of the checkpointed state */
 }
+/* lifetime peaks: contacts, constraint rows, convex candidates of one substep; total dropped contacts */
+void orc_get_peaks(const OrcSim *s, int32_t *d) { d[0] = s->peak_ncon; d[1] = s->peak_nefc; d[2] = s->peak_ncand; d[3] = s->total_overflow; }
+void orc_get_hist(const OrcSim *s, int32_t *nefc16, int32_t *ncon8) { memcpy(nefc16, s->hist_nefc, sizeof s->hist_nefc); memcpy(ncon8, s->hist_ncon, sizeof s->hist_ncon); }
 void orc_get_diag(const OrcSim *s, int32_t *d) {
   d[0] = s->ncon; d[1] = s->nefc; d[2] = s->niter; d[3] = s->max_nefc; d[4] = s->overflow; d[5] = s->nan_resets;
 }
@@ -1137,7 +1149,7 @@ void orc_get_diag(const OrcSim *s, int32_t *d) {
 int orc_get(const OrcSim *s, const char *name, double *out, int cap) {
   const double *src = NULL;
   int n = 0, nv = s->m.nv;
-  static double tmp[LCR_MAXEFC * NV > LCR_MAXCON * 32 ? LCR_MAXEFC * NV : LCR_MAXCON * 32];
+  static double tmp[LCR_MAXEFC_BIG * NV > LCR_MAXCON_BIG * 32 ? LCR_MAXEFC_BIG * NV : LCR_MAXCON_BIG * 32];
   const int nbd = LCR_NABODY + LCR_MAXCUBE; /* the dynamic bodies (the wall slots behind them are constants) */
   if (!strcmp(name, "xpos")) { src = &s->xpos[0][0]; n = nbd * 3; }
   else if (!strcmp(name, "xmat")) { src = &s->xmat[0][0]; n = nbd * 9; }

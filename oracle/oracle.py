@@ -109,13 +109,23 @@ class Oracle:
         qpos, qvel = np.zeros(self.nq), np.zeros(self.nv)
         ctrl, warm, aux = np.zeros(6), np.zeros(self.nv), np.zeros(_model.NAUX)
         ints = np.zeros(_model.NINT, np.int32)
+        rng = np.zeros(4, np.uint64)
         self.L.orc_get_state(self.h, _p(qpos), _p(qvel), _p(ctrl), _p(warm), _p(aux), _p(ints))
-        return dict(qpos=qpos, qvel=qvel, ctrl=ctrl, warm=warm, aux=aux, ints=ints)
+        self.L.orc_get_rng(self.h, _p(rng))
+        return dict(qpos=qpos, qvel=qvel, ctrl=ctrl, warm=warm, aux=aux, ints=ints, rng=rng)
 
-    def set_state(self, qpos=None, qvel=None, ctrl=None, warm=None, aux=None, ints=None):
+    def set_state(self, qpos=None, qvel=None, ctrl=None, warm=None, aux=None, ints=None, rng=None):
         f = lambda a, t=np.float64: None if a is None else np.ascontiguousarray(a, t)
         args = [f(qpos), f(qvel), f(ctrl), f(warm), f(aux), f(ints, np.int32)]
         self.L.orc_set_state(self.h, *[_p(a) for a in args])
+        if rng is not None:
+            self.L.orc_seed(self.h, _p(np.ascontiguousarray(rng, np.uint64)))
+
+    def peaks(self):
+        """lifetime maxima (ncon, nefc, convex candidates of one substep) and the total of dropped contacts"""
+        d = np.zeros(4, np.int32)
+        self.L.orc_get_peaks(self.h, _p(d))
+        return dict(zip(("ncon", "nefc", "ncand", "overflow"), d.tolist()))
 
     def get(self, name):
         buf = np.zeros(_model.MAXEFC * _model.MAXNV)
