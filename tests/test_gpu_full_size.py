@@ -28,12 +28,13 @@ def _rollout(env_id, n, steps, seed=0, **kw):
 
 @pytest.mark.parametrize("env_id,n", [("ReachCube-v0", 4096), ("PushCube-v0", 16384), ("PushCubeLoop-v0", 8192)])
 def test_full_batch_is_deterministic_and_mode_independent(env_id, n):
-    a, sa, _ = _rollout(env_id, n, 6, exec_mode="lockstep")
-    b, sb, _ = _rollout(env_id, n, 6, exec_mode="lockstep")
+    a, sa, _ = _rollout(env_id, n, 6, exec_mode="flow")
+    b, sb, _ = _rollout(env_id, n, 6, exec_mode="flow")
     c, sc, _ = _rollout(env_id, n, 6, exec_mode="phased")
-    assert torch.equal(a, b) and torch.equal(a, c)
+    d, sd, _ = _rollout(env_id, n, 6, exec_mode="lockstep")
+    assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, d)
     for k in sa:
-        assert torch.equal(sa[k], sb[k]) and torch.equal(sa[k], sc[k]), k
+        assert torch.equal(sa[k], sb[k]) and torch.equal(sa[k], sc[k]) and torch.equal(sa[k], sd[k]), k
 
 
 def test_two_shards_reproduce_the_single_device_batch():
@@ -54,28 +55,45 @@ def test_two_shards_reproduce_the_single_device_batch():
         e.close()
 
 
-def test_random_sample_of_a_full_batch_tracks_the_oracle():
-    """8 envs picked from a 4096-env float32 batch vs the float64 oracle after 3 steps (60 substeps): arm joints within 2e-3 rad,
-    cube within 1e-3 m for at least 7 of them (contacts make single envs chaotic; tolerance as in tests/test_golden.py)."""
-    n, steps = 4096, 3
-    env = glr.make("ReachCube-v0", num_envs=n)
+IDS = {"ReachCube-v0": "reach", "PushCube-v0": "push", "PickPlaceCube-v0": "pick_place", "StackTwoCubes-v0": "stack"}
+
+
+@pytest.mark.parametrize("env_id,n,mode", [("ReachCube-v0", 4096, "joint"), ("PushCube-v0", 16384, "joint"), ("PickPlaceCube-v0", 8192, "ee"),
+                                           ("StackTwoCubes-v0", 8192, "joint")])
+def test_random_sample_of_a_full_batch_tracks_the_oracle(env_id, n, mode):
+    """The BASELINE.json configurations at their full per-GPU batch, float32 product path: 32 envs picked at random vs the float64
+    oracle driven with the same seeds and actions for 10 env.steps (200 substeps).  Tolerance: arm joints within 5e-3 rad and
+    cube position(s) within 2e-3 m for at least 28 of the 32 (contact-rich rollouts are chaotic: a float32 rounding difference
+    that flips one contact sends a single env elsewhere; the same bound as tests/test_golden.py, at 10 instead of 12 steps);
+    the median joint error must stay below 2e-4 rad.  No env of the batch may drop a contact (caps) or blow up."""
+    steps, k = 10, 32
+    env = glr.make(env_id, num_envs=n, action_mode=mode)
     env.reset(seed=11)
     rng = np.random.default_rng(3)
-    acts = rng.uniform(-1, 1, size=(steps, n, env.action_dim)).astype(np.float32)
+    picks = rng.choice(n, size=k, replace=False)
+    gen = torch.Generator(device="cuda").manual_seed(17)
+    acts = torch.rand(steps, n, env.action_dim, generator=gen, device="cuda") * 2 - 1
     for t in range(steps):
-        env.step(torch.from_numpy(acts[t]).cuda())
+        env.step_flat(acts[t])
+        dg = env.diagnostics()
+        assert int(dg["overflow"].sum()) == 0 and int(dg["nan_resets"].sum()) == 0
     q = env.get_state()["qpos"].cpu().numpy()
     env.close()
-    picks = rng.choice(n, size=8, replace=False)
-    ok = 0
-    for i in picks:
-        o = Oracle("reach", action_mode="joint")
+    a_host = acts[:, torch.from_numpy(picks).cuda()].cpu().numpy()
+    ok, errs = 0, []
+    for j, i in enumerate(picks):
+        o = Oracle(IDS[env_id], action_mode=mode)
         o.reset(seed=11 + int(i))
         for t in range(steps):
-            o.step(acts[t, i])
+            o.step(a_host[t, j])
         ref = o.get_state()["qpos"]
-        ok += bool(np.abs(ref[:6] - q[i, :6]).max() < 2e-3 and np.abs(ref[6:9] - q[i, 6:9]).max() < 1e-3)
-    assert ok >= 7, ok
+        ea = np.abs(ref[:6] - q[i, :6]).max()
+        ec = max(np.abs(ref[6 + 7 * c:9 + 7 * c] - q[i, 6 + 7 * c:9 + 7 * c]).max() for c in range((len(ref) - 6) // 7))
+        errs.append(ea)
+        ok += bool(ea < 5e-3 and ec < 2e-3)
+    print(env_id, "sample within tolerance:", ok, "of", k, "median joint err", np.median(errs))
+    assert ok >= 28, (ok, np.sort(errs)[-6:])
+    assert np.median(errs) < 2e-4
 
 
 @pytest.mark.parametrize("env_id,n", [("ReachCube-v0", 4096), ("StackTwoCubes-v0", 8192), ("PickPlaceCube-v0", 8192), ("PushCubeLoop-v0", 8192)])
@@ -95,7 +113,7 @@ def test_state_invariants_after_random_rollouts(env_id, n):
         assert (cq[:, 2] > -0.02).all(), "a cube fell through the floor"
         assert ((cq[:, 3:7].norm(dim=1) - 1).abs() < 1e-4).all(), "cube quaternion not normalised"
     assert int(dg["nan_resets"].sum()) == 0
-    assert float((dg["overflow"] > 0).float().mean()) < 0.01  # contact / row caps are hit by < 1 % of the envs
+    assert int(dg["overflow"].sum()) == 0  # nothing is dropped: envs beyond the fast caps run over the big workspace
     obs_dim = recs.shape[2] - 4
     flags = recs[:, :, obs_dim + 1:]
     assert ((flags == 0) | (flags == 1)).all()

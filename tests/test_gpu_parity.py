@@ -208,21 +208,22 @@ def test_f64_one_substep_map_from_random_states(task):
     env.close()
 
 
-def test_f32_one_substep_map_from_rollout_states():
+@pytest.mark.parametrize("task,mode", [("lift", "joint"), ("push", "joint"), ("pick_place", "ee"), ("stack", "joint"), ("push_loop", "joint")])
+def test_f32_one_substep_map_from_rollout_states(task, mode):
     """float32 product path: one mj_step from states harvested out of random-action oracle rollouts (the regime the
     simulator runs in: shallow penetrations).  Contact counts equal for >= 95% of envs; for those the new qvel is
     within 2e-3 * (1 + max|qvel|) of the float64 oracle for >= 95%."""
-    task, n = "lift", 96
+    n = 96
     rng = np.random.default_rng(5)
     oracles = []
     for i in range(n):
-        o = Oracle(task)
+        o = Oracle(task, action_mode=mode)
         o.reset(seed=1000 + i)
         for _ in range(int(rng.integers(2, 9))):
             o.step(rng.uniform(-1, 1, o.na).astype(np.float32))
         oracles.append(o)
     st0 = [o.get_state() for o in oracles]
-    env = glr.make(IDS[task], num_envs=n, precision="float32")
+    env = glr.make(IDS[task], num_envs=n, precision="float32", action_mode=mode)
     env.set_state(**{k: np.stack([s[k] for s in st0]) for k in ("qpos", "qvel", "ctrl", "warm", "aux")})
     env.substeps(1)
     st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
@@ -299,8 +300,155 @@ def test_lockstep_execution_is_bitwise_identical_to_fused(task, mode, warps, fla
         e.close()
 
 
+def _bitwise_pair(task, mode, n, steps, em_a, em_b, seed=3, max_episode_steps=5, precision="float32"):
+    envs = [glr.make(IDS[task], num_envs=n, action_mode=mode, autoreset=True, max_episode_steps=max_episode_steps, exec_mode=em, precision=precision)
+            for em in (em_a, em_b)]
+    for e in envs:
+        e.reset(seed=seed)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(steps):
+        a = torch.rand(n, envs[0].action_dim, generator=gen, device="cuda") * 2 - 1
+        ra, rb = envs[0].step_packed(a), envs[1].step_packed(a)
+        assert torch.equal(ra, rb), (t, (ra != rb).any(1).nonzero().flatten()[:8].tolist())
+    for e in envs:
+        if e.exec_mode == "flow":
+            assert e.flow_status() == (0, 0)
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    da, db = envs[0].diagnostics(), envs[1].diagnostics()
+    for k in ("max_nefc", "overflow", "nan_resets"):
+        assert torch.equal(da[k], db[k]), k
+    assert int(da["overflow"].sum()) == 0
+    for e in envs:
+        e.close()
+
+
+@pytest.mark.parametrize("task,mode,n,flags", [("reach", "joint", 67, 1), ("reach", "joint", 700, 0), ("stack", "joint", 300, 1), ("pick_place", "ee", 300, 3),
+                                               ("push", "joint", 900, 5), ("lift", "joint", 150, 7), ("push_loop", "joint", 400, 1), ("push_loop", "ee", 150, 2)])
+def test_flow_execution_is_bitwise_identical_to_fused(task, mode, n, flags, monkeypatch):
+    """exec_mode="flow" (one persistent kernel per step; the phases of every env run from device-side queues, workspaces
+    staged by the TMA unit, csrc/lcr_flow.cuh) runs the same per-env arithmetic as the fused kernel: float32 outputs, state
+    and diagnostics must be bit-identical for every combination of the phase-fusion flags, autoreset included."""
+    monkeypatch.setenv("LCR_FLOW_FLAGS", str(flags))
+    _bitwise_pair(task, mode, n, 10, "fused", "flow")
+
+
+@pytest.mark.parametrize("em", ["fused", "lockstep", "phased", "flow"])
+def test_envs_beyond_the_fast_caps_take_the_big_path_in_every_mode(em):
+    """Contact-rich states (arm folded into floor and cube: up to ~180 constraint rows) exceed the fast workspace caps (32
+    contacts / 96 rows).  Every execution mode must hand those envs to the BIG workspace -- flow: migration inside the
+    kernel; the others: redo over the big workspace -- and give the result of the float64 oracle's uncapped arithmetic
+    path: here float32 bitwise equality with the fused mode, no dropped contact, and envs above 96 rows present."""
+    n = 256
+    rng = np.random.default_rng(11)
+    envs = [glr.make("PushCube-v0", num_envs=n, exec_mode=m) for m in ("fused", em)]
+    qpos, qvel, ctrl = random_states("push", n, rng, envs[0].nq, envs[0].nv)
+    qpos[:, 1] = rng.uniform(0.9, 1.22, n)   # shoulder forward, elbow down: the arm lies in the floor
+    qpos[:, 2] = rng.uniform(1.2, 1.74, n)
+    for e in envs:
+        e.reset(seed=1)
+        e.set_state(qpos=qpos, qvel=0.2 * qvel, ctrl=qpos[:, :6], warm=np.zeros((n, e.nv)))
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    peak = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for t in range(3):
+        a = 0.2 * (torch.rand(n, envs[0].action_dim, generator=gen, device="cuda") * 2 - 1)
+        ra, rb = envs[0].step_packed(a), envs[1].step_packed(a)
+        assert torch.equal(ra, rb), (em, t)
+        peak = torch.maximum(peak, envs[1].diagnostics()["max_nefc"])
+    assert int((peak > 96).sum()) >= 4, "the states should push some envs beyond the fast caps"
+    assert int(envs[1].diagnostics()["overflow"].sum()) == 0
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    for e in envs:
+        e.close()
+
+
+def test_f64_big_path_matches_the_oracle():
+    """float64 kernels against the oracle on the same beyond-the-caps states, ONE mj_step (the comparison that is well posed in
+    deeply interpenetrating poses, see test_f64_one_substep_map_from_random_states): envs with more than 96 constraint rows
+    -- which only the big workspace can hold -- must be present, and at least 85 % of them (and of all envs) must agree with
+    the oracle to 1e-7 (qpos) / 1e-4 (qvel); nothing may be dropped on either side."""
+    n = 96
+    rng = np.random.default_rng(11)
+    env = glr.make("PushCube-v0", num_envs=n, precision="float64")
+    qpos, qvel, ctrl = random_states("push", n, rng, env.nq, env.nv)
+    qpos[:, 1] = rng.uniform(0.9, 1.22, n)
+    qpos[:, 2] = rng.uniform(1.2, 1.74, n)
+    env.set_state(qpos=qpos, qvel=0.2 * qvel, ctrl=qpos[:, :6], warm=np.zeros((n, env.nv)))
+    env.substeps(1)
+    st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
+    dg = {k: v.cpu().numpy() for k, v in env.diagnostics().items()}
+    env.close()
+    close = big = big_close = 0
+    for i in range(n):
+        o = Oracle("push")
+        o.set_state(qpos=qpos[i], qvel=0.2 * qvel[i], ctrl=qpos[i, :6], warm=np.zeros(env.nv))
+        o.substep(1)
+        ref, d = o.get_state(), o.diag()
+        ok = np.abs(st["qpos"][i] - ref["qpos"]).max() < 1e-7 and np.abs(st["qvel"][i] - ref["qvel"]).max() < 1e-4
+        close += ok
+        if d["nefc"] > 96:
+            big += 1
+            big_close += ok and dg["nefc"][i] == d["nefc"]
+        assert d["overflow"] == 0 and dg["overflow"][i] == 0
+    assert big >= 4, "the states should push some envs beyond the fast caps"
+    assert big_close >= 0.85 * big and close >= 0.85 * n, (big_close, big, close, n)
+
+
+def test_checkpoint_restore_replays_bitwise_across_an_episode_boundary():
+    """get_state / set_state carry the PCG64 state of every env's reset stream: a rollout restored from a checkpoint and
+    replayed through autoresets draws the same cube / target positions and ends in the same state, bit for bit."""
+    n = 64
+    env = glr.make("PushCube-v0", num_envs=n, autoreset=True, max_episode_steps=4)
+    env.reset(seed=21)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    acts = torch.rand(10, n, env.action_dim, generator=gen, device="cuda") * 2 - 1
+    for t in range(3):
+        env.step_flat(acts[t])
+    ck = {k: v.clone() for k, v in env.get_state().items()}
+    first = [env.step_packed(acts[t]).clone() for t in range(3, 10)]
+    end = {k: v.clone() for k, v in env.get_state().items()}
+    other = glr.make("PushCube-v0", num_envs=n, autoreset=True, max_episode_steps=4)  # a fresh simulator, other seeds
+    other.reset(seed=999)
+    other.set_state(**ck)
+    again = [other.step_packed(acts[t]).clone() for t in range(3, 10)]
+    for x, y in zip(first, again):
+        assert torch.equal(x, y)
+    st = other.get_state()
+    for k in end:
+        assert torch.equal(end[k], st[k]), k
+    env.close()
+    other.close()
+
+
+def test_masked_reset_with_a_seed_leaves_the_other_streams_alone():
+    """reset(seed=s, mask=m) reseeds only the masked envs: the others continue their own PCG64 streams."""
+    n = 32
+    a_env, b_env = (glr.make("PushCube-v0", num_envs=n) for _ in range(2))
+    a_env.reset(seed=5)
+    b_env.reset(seed=5)
+    mask = torch.zeros(n, dtype=torch.bool, device="cuda")
+    mask[::3] = True
+    a_env.reset(seed=77, mask=mask)       # reseeds every third env
+    oa, _ = a_env.reset()                 # next draw of every env
+    b_env.reset(mask=mask)                # masked envs draw once more from their old stream ...
+    ob, _ = b_env.reset()                 # ... so only the UNMASKED envs must agree
+    fa = torch.cat([oa[k] for k in oa], 1)
+    fb = torch.cat([ob[k] for k in ob], 1)
+    assert torch.equal(fa[~mask], fb[~mask])
+    assert not torch.equal(fa[mask], fb[mask])
+    ref = glr.make("PushCube-v0", num_envs=n)
+    ref.reset(seed=77)
+    orf, _ = ref.reset()
+    assert torch.equal(fa[mask], torch.cat([orf[k] for k in orf], 1)[mask])
+    for e in (a_env, b_env, ref):
+        e.close()
+
+
 def test_step_packed_matches_the_separate_outputs():
-    """lcr_pack_outputs (the all-gather / device->host record) holds exactly obs | reward | terminated | truncated | success."""
+    """The record the step kernels write (the all-gather / device->host unit) holds exactly obs | reward | terminated | truncated | success."""
     from gym_lowcostrobot_b200.dist import pack_record
     n = 33
     a_env, b_env = (glr.make("PushCube-v0", num_envs=n, autoreset=True, max_episode_steps=4) for _ in range(2))
