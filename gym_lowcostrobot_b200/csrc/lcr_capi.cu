@@ -230,6 +230,11 @@ struct LcrSim {
   cudaEvent_t ev_begin = nullptr, ev_done[16] = {};
   // envs that outgrew the fast workspace in the current call: device counter + list, redone over the big workspace
   int* redo = nullptr;
+  // envs that start over the big workspace (predicted by the scheduler from their previous step): count + list, own stream
+  int* big = nullptr;
+  int tbig = 0;
+  cudaStream_t bstream = nullptr;
+  cudaEvent_t ev_sched = nullptr, ev_big = nullptr;
   // flow mode: queue control block + rings, grid, tunables
   FlowQ fq{};
   unsigned* fq_mem = nullptr;
@@ -329,6 +334,15 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
   LCR_CREATE_OK(cudaMalloc(&s->redo, sizeof(int) * ((size_t)n_envs + 1)));
   LCR_CREATE_OK(cudaMemset(s->redo, 0, sizeof(int)));
   LCR_CREATE_OK(cudaMalloc(&s->seed_buf, 32 * (size_t)n_envs));
+  LCR_CREATE_OK(cudaMalloc(&s->big, sizeof(int) * ((size_t)n_envs + 1)));
+  LCR_CREATE_OK(cudaMemset(s->big, 0, sizeof(int)));
+  LCR_CREATE_OK(cudaStreamCreateWithFlags(&s->bstream, cudaStreamNonBlocking));
+  LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_sched, cudaEventDisableTiming));
+  LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_big, cudaEventDisableTiming));
+  // rows of the previous step from which an env starts on the big workspace, beside the main kernels, instead of being found out and
+  // redone after them.  Phased chain: from the fast cap on (small CTAs, the BIG CTAs run among them: PushCube 16 384, 21.5 -> 20.9 ms per
+  // step); lockstep: never (its CTAs take a whole SM each, the BIG CTAs would only wait for one)
+  s->tbig = env_int("LCR_TBIG", cfg->exec_mode == 1 ? 97 : 100000);
   if (cfg->exec_mode == 1) {
     int g = env_int("LCR_GROUPS", 2);  // measured on B200 (profiles/r01j_sweep32_groups.jsonl): 2 chains overlap each other's launch tails, more only shrink the launches
     g = std::max(1, std::min(16, std::min(g, n_envs)));
@@ -367,6 +381,10 @@ int lcr_destroy(LcrSim* sim) {
     if (sim->ev_done[k]) cudaEventDestroy(sim->ev_done[k]);
   }
   if (sim->ev_begin) cudaEventDestroy(sim->ev_begin);
+  if (sim->bstream) cudaStreamDestroy(sim->bstream);
+  if (sim->ev_sched) cudaEventDestroy(sim->ev_sched);
+  if (sim->ev_big) cudaEventDestroy(sim->ev_big);
+  cudaFree(sim->big);
   cudaFree(sim->perm); cudaFree(sim->redo); cudaFree(sim->fq_mem); cudaFree(sim->fq_rings); cudaFree(sim->seed_buf);
   delete sim;
   return 0;
@@ -411,13 +429,26 @@ int lcr_step_rec(LcrSim* sim, const float* d_actions, float* d_obs, float* d_rew
     return 0;
   }
   CUDA_OK(cudaMemsetAsync(sim->redo, 0, sizeof(int), st));
+  bool predicted = false, big_started = false;
+  // the envs the scheduler sent to the big workspace start now, on their own stream, beside the main kernels
+  auto start_big = [&]() {
+    cudaEventRecord(sim->ev_sched, st);
+    cudaStreamWaitEvent(sim->bstream, sim->ev_sched, 0);
+    const Redo lst{sim->big, sim->big + 1};
+    LCR_RUN(sim, step_big(sim->f.dm, sim->f.verts, sim->f.s, io, lst, sim->bstream), step_big(sim->d.dm, sim->d.verts, sim->d.s, io, lst, sim->bstream));
+    cudaEventRecord(sim->ev_big, sim->bstream);
+    sim->launches++;
+    big_started = true;
+  };
   if (sim->cfg.exec_mode == 1) {
     const int G = sim->ngroups, per = (sim->n + G - 1) / G;
     if (sim->perm) {  // seats in work-aware order: group g owns perm[g * per, (g + 1) * per), heaviest envs first, -1 = padding
-      if (f32) lcr::Launch<float>::sched(sim->f.s, sim->perm, per, 1, st);
-      else lcr::Launch<double>::sched(sim->d.s, sim->perm, per, 1, st);
+      if (f32) lcr::Launch<float>::sched(sim->f.s, sim->perm, per, 1, sim->big, sim->tbig, st);
+      else lcr::Launch<double>::sched(sim->d.s, sim->perm, per, 1, sim->big, sim->tbig, st);
       sim->launches++;
+      predicted = true;
     }
+    if (predicted) start_big();
     CUDA_OK(cudaEventRecord(sim->ev_begin, st));
     for (int g = 0; g < G; g++) {
       const int env0 = g * per, cnt = sim->perm ? per : std::min(per, sim->n - env0);
@@ -436,9 +467,11 @@ int lcr_step_rec(LcrSim* sim, const float* d_actions, float* d_obs, float* d_rew
     else LCR_DISPATCH_RET(double, sim->ncube, W, lockstep_warps(sim->ls_warps));
     const int grid = (sim->n + W - 1) / W;
     if (sim->perm) {
-      if (f32) lcr::Launch<float>::sched(sim->f.s, sim->perm, W, sim->ls_striped, st);
-      else lcr::Launch<double>::sched(sim->d.s, sim->perm, W, sim->ls_striped, st);
+      if (f32) lcr::Launch<float>::sched(sim->f.s, sim->perm, W, sim->ls_striped, sim->big, sim->tbig, st);
+      else lcr::Launch<double>::sched(sim->d.s, sim->perm, W, sim->ls_striped, sim->big, sim->tbig, st);
       sim->launches++;
+      predicted = true;
+      start_big();
     }
     LCR_RUN(sim, step_lockstep(sim->f.dm, sim->f.verts, sim->f.s, io, redo, grid, W, W, sim->ls_flags, sim->perm, sim->prof, st),
             step_lockstep(sim->d.dm, sim->d.verts, sim->d.s, io, redo, grid, W, W, sim->ls_flags, sim->perm, sim->prof, st));
@@ -447,7 +480,10 @@ int lcr_step_rec(LcrSim* sim, const float* d_actions, float* d_obs, float* d_rew
     LCR_RUN(sim, step(sim->f.dm, sim->f.verts, sim->f.s, io, redo, st), step(sim->d.dm, sim->d.verts, sim->d.s, io, redo, st));
     sim->launches++;
   }
-  // the envs that outgrew the fast workspace: the same step from the same start state over the big workspace
+  if (big_started) CUDA_OK(cudaStreamWaitEvent(st, sim->ev_big, 0));
+  (void)predicted;
+  // the envs that outgrew the fast workspace unexpectedly: the same step from the same start state over the big workspace
+  if (env_int("LCR_NO_REDO", 0) == 0)  // (debug knob: timing of the main kernels alone; results are then wrong for those envs)
   LCR_RUN(sim, step_big(sim->f.dm, sim->f.verts, sim->f.s, io, redo, st), step_big(sim->d.dm, sim->d.verts, sim->d.s, io, redo, st));
   sim->launches++;
   CUDA_OK(cudaGetLastError());

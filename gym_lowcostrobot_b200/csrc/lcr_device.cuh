@@ -218,7 +218,7 @@ struct LaunchNC {
 };
 template <typename T>
 struct Launch {
-  static void sched(DevState<T> s, int* perm, int W, int striped, cudaStream_t st);
+  static void sched(DevState<T> s, int* perm, int W, int striped, int* big, int tbig, cudaStream_t st);
   static void pack(const float* obs, const float* reward, const uint8_t* term, const uint8_t* trunc, const uint8_t* succ, float* rec, int n, int od,
                    cudaStream_t st);
   static void get_state(int ncube, DevState<T> s, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,

@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(512, 1) k_flow(const DevModel<T>* __restrict__
         int q = 0;
         if (lane == 0) {
           for (;;) {
-            __nanosleep(200);
+            __nanosleep(100);
             q = LCR_VOL(quit);
             if (LCR_VOL(lq_head) != LCR_VOL(lq_tail) || q || LCR_VOL(scout_lock) == 0) break;
           }
@@ -689,8 +689,13 @@ __global__ void __launch_bounds__(512, 1) k_flow(const DevModel<T>* __restrict__
           // batch: one item per idle warp, or the CTA's fair share of the queue if that is more; bounded by the free ring slots
           const int fill = __shfl_sync(FULLMASK, LCR_VOL(lq_tail) - LCR_VOL(lq_head), 0);
           int room = LCR_LQ - fill;
-          int share = depth / nnormal;
-          share = share > want ? share : want;
+          // (deep queue: a few more than the idle warps need, so that warps finishing soon find work in the ring without
+          //  waiting for a scout round; shallow queue -- the tail of the step --: no hoarding)
+          int share = want;
+          if (depth >= 4 * nnormal) {
+            share = want + nwarps / 2;
+            if (depth / nnormal > share) share = depth / nnormal;
+          }
           share = share < room ? share : room;
           int got = 0;
           for (int prio = 0; prio < 2 && share > 0; prio++) {

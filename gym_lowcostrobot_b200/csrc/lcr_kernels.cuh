@@ -1403,11 +1403,11 @@ DI int list_env(const int* __restrict__ list, int i) { return list ? list[i] : i
 // (BIG pass over the envs that outgrew the fast workspace).  A fast env that hits a cap is not written back: redo list.
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, Scene<NC>::BIG ? 2 : 16) k_step(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s,
-                                                                      StepIO io, Redo redo, const int* __restrict__ list, const int* __restrict__ count) {
+                                                                      StepIO io, Redo redo, const int* __restrict__ list, const int* __restrict__ count, int first) {
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const DevModel<T>& m = *dm;
   const int n = list ? *count : s.n;
-  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+  for (int i = first + blockIdx.x; i < n; i += gridDim.x) {
     const int env = list_env(list, i);
     load_state(w, s, env);
     env_step(w, m, verts, io, env);
@@ -1513,45 +1513,57 @@ DI void cta_jobs(Ws<T, NC>* wsa, int W, const DevModel<T>& m, const T* __restric
 //    first and overlap the cheap ones.
 // One CTA, two passes over the 64-byte int records; the order inside a bucket is arbitrary and does not affect any
 // result.  Empty seats (n not a multiple of W) hold -1.
+// Envs whose previous step needed the BIG workspace (diag[3] >= tbig rows) are not seated at all: they go to the list
+// `big` (big[0] = count, then env ids) and start over the big workspace right away, on a stream of their own, instead of
+// being found out and redone after the main kernels (contacts persist: an env beyond the fast caps usually stays there).
 #define LCR_NBUCKET 16
 template <typename T>
-__global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__ perm, int W, int striped) {
+__global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__ perm, int W, int striped, int* __restrict__ big, int tbig) {
   __shared__ int hist[LCR_NBUCKET], start[LCR_NBUCKET];
   const int ncta = (s.n + W - 1) / W;
   if (threadIdx.x < LCR_NBUCKET) hist[threadIdx.x] = 0;
-  for (int k = s.n + threadIdx.x; k < ncta * W; k += blockDim.x) perm[striped ? ((k % ncta) * W) + k / ncta : k] = -1;
+  for (int k = threadIdx.x; k < ncta * W; k += blockDim.x) perm[k] = -1;
   __syncthreads();
   for (int e = threadIdx.x; e < s.n; e += blockDim.x) {
     const int32_t* ib = s.ib + (size_t)e * LCR_IB_WORDS;
     int key = ib[1] ? 0 : 1 + ib[LCR_NINT + 3] / 8;
-    key = key < LCR_NBUCKET ? key : LCR_NBUCKET - 1;
+    key = key < LCR_NBUCKET - 1 ? key : LCR_NBUCKET - 2;
+    if (big && !ib[1] && ib[LCR_NINT + 3] >= tbig) key = LCR_NBUCKET - 1;
     atomicAdd(&hist[key], 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int k = LCR_NBUCKET - 1; k >= 0; k--) { start[k] = acc; acc += hist[k]; }
+    if (big) big[0] = hist[LCR_NBUCKET - 1];
   }
   __syncthreads();
+  const int nbig = big ? hist[LCR_NBUCKET - 1] : 0;
   for (int e = threadIdx.x; e < s.n; e += blockDim.x) {
     const int32_t* ib = s.ib + (size_t)e * LCR_IB_WORDS;
     int key = ib[1] ? 0 : 1 + ib[LCR_NINT + 3] / 8;
-    key = key < LCR_NBUCKET ? key : LCR_NBUCKET - 1;
-    const int r = atomicAdd(&start[key], 1);
+    key = key < LCR_NBUCKET - 1 ? key : LCR_NBUCKET - 2;
+    const bool isbig = big && !ib[1] && ib[LCR_NINT + 3] >= tbig;
+    if (isbig) key = LCR_NBUCKET - 1;
+    int r = atomicAdd(&start[key], 1);
+    if (isbig) { big[1 + r] = e; continue; }
+    r -= nbig;
     perm[striped ? (r % ncta) * W + r / ncta : r] = e;
   }
 }
 
 template <typename T, int NC, bool PROF>
 __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s, StepIO io, Redo redo,
-                                                    int flags, const int* __restrict__ perm, int epc, long long* __restrict__ prof) {
+                                                    int flags, const int* __restrict__ perm, int epc, long long* __restrict__ prof,
+                                                    const int* __restrict__ count) {
   // blockDim.x / 32 warps, the first `epc` of them own an env (seat blockIdx.x * epc + warp), the others only help
   // with narrowphase jobs; shared memory holds epc workspaces
   Ws<T, NC>* wsa = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   __shared__ int job_next;
   const int W = epc, warp = threadIdx.x >> 5, slot = blockIdx.x * epc + warp;
   const bool owner = warp < epc;
-  const int env = owner ? (perm != nullptr ? perm[slot] : slot) : -1;  // -1 = empty seat
+  // (count, optional: the seats are a device-side list of that many envs -- the BIG pass; seats beyond it are empty)
+  const int env = owner && !(count != nullptr && slot >= *count) ? (perm != nullptr ? perm[slot] : slot) : -1;  // -1 = empty seat
   const bool valid = env >= 0 && env < s.n;
   if (!__syncthreads_or(valid)) return;
   Ws<T, NC>& w = wsa[owner ? warp : 0];
@@ -1940,6 +1952,7 @@ void LaunchNC<T, S>::prepare() {
   cudaFuncSetAttribute(k_ph_end<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
   cudaFuncSetAttribute(k_step_ls<T, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
   cudaFuncSetAttribute(k_step_ls<T, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCR_LS_MAXSMEM);
+  cudaFuncSetAttribute(k_step_ls<T, B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(k_flow<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, flow_smem());
   // all of the SM's L1/shared array as shared memory: several CTAs of a few workspaces each must fit one SM
   cudaFuncSetAttribute(k_step_ls<T, S, false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
@@ -1955,13 +1968,23 @@ void LaunchNC<T, S>::reset(const DevModel<T>* dm, const T* verts, DevState<T> s,
 }
 template <typename T, int S>
 void LaunchNC<T, S>::step(const DevModel<T>* dm, const T* verts, DevState<T> s, StepIO io, Redo redo, cudaStream_t st) {
-  k_step<T, S><<<s.n, 32, sizeof(Ws<T, S>), st>>>(dm, verts, s, io, redo, nullptr, nullptr);
+  k_step<T, S><<<s.n, 32, sizeof(Ws<T, S>), st>>>(dm, verts, s, io, redo, nullptr, nullptr, 0);
 }
-// the envs of the redo list, from their unchanged start state, over the big workspace
+// The envs of the list, from their unchanged start state, over the big workspace.  These are the most expensive envs of
+// the batch (100 - 180 constraint rows, dozens of penetrating hull pairs) and the step waits for them, so each gets a CTA
+// of its own with LCR_BIG_WARPS warps: the lockstep kernel with ONE env per CTA, whose other warps drain the env's
+// narrowphase job pool.  The grid is fixed (the list length lives on the device; CTAs without a seat return at once); a
+// list longer than the grid -- never seen -- is finished by the one-warp kernel from entry LCR_BIG_GRID on.
+#define LCR_BIG_WARPS 8
+#define LCR_BIG_GRID 2048
 template <typename T, int S>
 void LaunchNC<T, S>::step_big(const DevModel<T>* dm, const T* verts, DevState<T> s, StepIO io, Redo list, cudaStream_t st) {
   constexpr int B = S | LCR_NC_BIG;
-  k_step<T, B><<<std::min(s.n, 296), 32, sizeof(Ws<T, B>), st>>>(dm, verts, s, io, Redo{nullptr, nullptr}, list.list, list.count);
+  const int grid = std::min(s.n, LCR_BIG_GRID);
+  k_step_ls<T, B, false><<<grid, 32 * LCR_BIG_WARPS, sizeof(Ws<T, B>), st>>>(dm, verts, s, io, Redo{nullptr, nullptr}, LCR_LS_BAR_TOP | LCR_LS_BAR_CON | LCR_LS_JOB_POOL,
+                                                                          list.list, 1, nullptr, list.count);
+  if (s.n > LCR_BIG_GRID)
+    k_step<T, B><<<296, 32, sizeof(Ws<T, B>), st>>>(dm, verts, s, io, Redo{nullptr, nullptr}, list.list, list.count, LCR_BIG_GRID);
 }
 // lockstep kernel: CTAs of `warps` envs; warps <= 0 picks the largest CTA that fits one SM
 template <typename T, int S>
@@ -1974,8 +1997,8 @@ int LaunchNC<T, S>::lockstep_warps(int warps) {
 template <typename T, int S>
 void LaunchNC<T, S>::step_lockstep(const DevModel<T>* dm, const T* verts, DevState<T> s, StepIO io, Redo redo, int grid, int warps, int epc, int flags,
                                    const int* perm, long long* prof, cudaStream_t st) {
-  if (prof) k_step_ls<T, S, true><<<grid, 32 * warps, sizeof(Ws<T, S>) * epc, st>>>(dm, verts, s, io, redo, flags, perm, epc, prof);
-  else k_step_ls<T, S, false><<<grid, 32 * warps, sizeof(Ws<T, S>) * epc, st>>>(dm, verts, s, io, redo, flags, perm, epc, prof);
+  if (prof) k_step_ls<T, S, true><<<grid, 32 * warps, sizeof(Ws<T, S>) * epc, st>>>(dm, verts, s, io, redo, flags, perm, epc, prof, nullptr);
+  else k_step_ls<T, S, false><<<grid, 32 * warps, sizeof(Ws<T, S>) * epc, st>>>(dm, verts, s, io, redo, flags, perm, epc, prof, nullptr);
 }
 // one chain of 2 + 4 * n_substeps launches over the env range [env0, env0 + cnt) on stream st
 template <typename T, int S>
@@ -2036,7 +2059,9 @@ void Launch<T>::pack(const float* obs, const float* reward, const uint8_t* term,
   k_pack<<<blocks, 256, 0, st>>>(obs, reward, term, trunc, succ, rec, n, od);
 }
 template <typename T>
-void Launch<T>::sched(DevState<T> s, int* perm, int W, int striped, cudaStream_t st) { k_sched<T><<<1, 1024, 0, st>>>(s, perm, W, striped); }
+void Launch<T>::sched(DevState<T> s, int* perm, int W, int striped, int* big, int tbig, cudaStream_t st) {
+  k_sched<T><<<1, 1024, 0, st>>>(s, perm, W, striped, big, tbig);
+}
 template <typename T>
 void Launch<T>::get_state(int ncube, DevState<T> s, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,
                           unsigned long long* rng, cudaStream_t st) {

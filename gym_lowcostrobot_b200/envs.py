@@ -104,13 +104,15 @@ class BatchedLowCostRobotEnv:
 
     @classmethod
     def _pick_exec_mode(cls, exec_mode, num_envs):
-        """"auto": the flow kernel (one persistent launch per step; the phases of every env run from device-side queues,
-        csrc/lcr_flow.cuh) from a few hundred envs on; the lockstep kernel for tiny batches, where a handful of CTAs
-        cannot fill the GPU either way and one launch without queue traffic is the shortest path.  All modes give
-        bit-identical results (tests/test_gpu_parity.py)."""
+        """"auto" = the fastest mode measured on B200 for the batch size (profiles/README.md, stationary window): the lockstep
+        kernel (one launch per step, CTAs of 16 envs aligned at the phase boundaries, CTA-wide narrowphase job pool) for small
+        batches, where the step time is the chain of the most expensive env; the phased chain (one small kernel per mj_step
+        phase over all envs) once several waves of envs queue per SM.  "flow" (one persistent kernel per step, phases run from
+        device-side queues, csrc/lcr_flow.cuh) reaches 0.65 - 1.0 of them and is selectable.  All modes give bit-identical
+        results (tests/test_gpu_parity.py)."""
         if exec_mode != "auto":
             return exec_mode
-        return "flow" if num_envs >= 256 else "lockstep"
+        return "phased" if num_envs >= 5120 else "lockstep"
 
     # -- helpers ---------------------------------------------------------------------------
     def _stream(self):
