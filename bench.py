@@ -255,6 +255,7 @@ class GpuRun:
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         l0 = env.kernel_launches
         torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()  # (ncu --profile-from-start off: only the timed steps are captured)
         for t in range(K):
             flush.zero_()  # L2 flush between timed iterations (outside the event pairs)
             ev[t][0].record()
@@ -265,6 +266,7 @@ class GpuRun:
                 dist.all_gather_into_tensor(self.full, self.rec)
             ev[t][1].record()
         torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
         if self.world > 1:
             dist.barrier()
         launches = env.kernel_launches - l0

@@ -242,6 +242,14 @@ struct LcrSim {
   int flow_grid = 0, flow_bigcta = 0, flow_flags = 0, flow_thi = 0, flow_tbig = 0;
   unsigned long long* flow_stats = nullptr;  // debug: busy clocks per phase of the flow kernel, see lcr_debug_flow_stats
   unsigned long long* seed_buf = nullptr;    // device staging of lcr_seed
+  // phased mode: the whole step (scheduler, BIG branch, the chains of all env groups, redo pass) is captured once into a CUDA
+  // graph and replayed with one launch per step; the actions are staged into act_buf so that the captured kernel arguments
+  // do not depend on the caller's action pointer; the graph is re-captured if the caller's output pointers change
+  int use_graph = 0, ph_striped = 1, graph_nodes = 0;
+  cudaStream_t cstream = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  const void* gkey[6] = {};
+  float* act_buf = nullptr;
   LcrModel model;
   LcrEnvCfg cfg;
   Impl<float> f;
@@ -304,130 +312,12 @@ int create_flow(LcrSim* s) {
 }
 }  // namespace
 
-extern "C" {
-
-int lcr_obs_dim(int task) { return (task == LCR_TASK_REACH || task == LCR_TASK_LIFT || task == LCR_TASK_PUSH_LOOP) ? 15 : 18; }
-int lcr_action_dim(const LcrEnvCfg* cfg) { return (cfg->action_mode ? 3 : 5) + (cfg->block_gripper ? 0 : 1); }
-
-int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg* cfg, int n_envs, int device, int precision, LcrSim** out) {
-  if (!model || !cfg || !out || (!hull_verts && model->nvert > 0)) return fail("lcr_create: null argument");
-  if (n_envs <= 0) return fail("lcr_create: n_envs must be positive");
-  if (model->ncube < 1 || model->ncube > LCR_MAXCUBE || model->nmesh > LCR_MAXMESH || model->npair > LCR_MAXPAIR ||
-      model->nwall < 0 || model->nwall > LCR_MAXWALL || model->nmesh + 1 + model->ncube + model->nwall > LCR_MAXGEOM)
-    return fail("lcr_create: model exceeds compiled caps");
-  if (model->task < LCR_TASK_REACH || model->task > LCR_TASK_PUSH_LOOP) return fail("lcr_create: unknown task");
-  if ((model->task == LCR_TASK_PUSH_LOOP) != (model->nwall > 0) || (model->task == LCR_TASK_PUSH_LOOP && (model->ncube != 1 || model->nwall != LCR_MAXWALL)))
-    return fail("lcr_create: static wall boxes are the four rails of the PushCubeLoop scene (one cube)");
-  if (precision != LCR_F32 && precision != LCR_F64) return fail("lcr_create: precision must be LCR_F32 or LCR_F64");
-  if (cfg->exec_mode < 0 || cfg->exec_mode > 3) return fail("lcr_create: exec_mode must be 0 (fused), 1 (phased), 2 (lockstep) or 3 (flow)");
-  int ndev = 0;
-  CUDA_OK(cudaGetDeviceCount(&ndev));
-  if (device < 0 || device >= ndev) return fail("lcr_create: no such CUDA device");
-  CUDA_OK(cudaSetDevice(device));
-  LcrSim* s = new LcrSim();
-  s->precision = precision; s->device = device; s->n = n_envs; s->ncube = scene_class(model->task, model->ncube); s->task = model->task;
-  s->model = *model; s->cfg = *cfg;
-  // (every failure below goes through lcr_destroy: nothing allocated so far is leaked)
-#define LCR_CREATE_OK(call) do { if ((call) != cudaSuccess) { fail(std::string("lcr_create: ") + #call + " failed: " + cudaGetErrorString(cudaGetLastError())); lcr_destroy(s); return 1; } } while (0)
-  if (precision == LCR_F32 ? s->f.create(*model, hull_verts, *cfg, n_envs) : s->d.create(*model, hull_verts, *cfg, n_envs)) { lcr_destroy(s); return 1; }
-  s->launches = 1;
-  LCR_CREATE_OK(cudaMalloc(&s->redo, sizeof(int) * ((size_t)n_envs + 1)));
-  LCR_CREATE_OK(cudaMemset(s->redo, 0, sizeof(int)));
-  LCR_CREATE_OK(cudaMalloc(&s->seed_buf, 32 * (size_t)n_envs));
-  LCR_CREATE_OK(cudaMalloc(&s->big, sizeof(int) * ((size_t)n_envs + 1)));
-  LCR_CREATE_OK(cudaMemset(s->big, 0, sizeof(int)));
-  LCR_CREATE_OK(cudaStreamCreateWithFlags(&s->bstream, cudaStreamNonBlocking));
-  LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_sched, cudaEventDisableTiming));
-  LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_big, cudaEventDisableTiming));
-  // rows of the previous step from which an env starts on the big workspace, beside the main kernels, instead of being found out and
-  // redone after them.  Phased chain: from the fast cap on (small CTAs, the BIG CTAs run among them: PushCube 16 384, 21.5 -> 20.9 ms per
-  // step); lockstep: never (its CTAs take a whole SM each, the BIG CTAs would only wait for one)
-  s->tbig = env_int("LCR_TBIG", cfg->exec_mode == 1 ? 97 : 100000);
-  if (cfg->exec_mode == 1) {
-    int g = env_int("LCR_GROUPS", 2);  // measured on B200 (profiles/r01j_sweep32_groups.jsonl): 2 chains overlap each other's launch tails, more only shrink the launches
-    g = std::max(1, std::min(16, std::min(g, n_envs)));
-    for (int k = 0; k < g; k++) {
-      LCR_CREATE_OK(cudaStreamCreateWithFlags(&s->gstream[k], cudaStreamNonBlocking));
-      LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_done[k], cudaEventDisableTiming));
-      s->ngroups = k + 1;
-    }
-    LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming));
-    // work-aware seats (LCR_PH_SORT=0: identity): the envs with the most constraint rows in their previous step are launched
-    // first in every phase kernel, so that the long Newton solves / MPR jobs do not end up in the tail of the launch
-    if (env_int("LCR_PH_SORT", 1) != 0) LCR_CREATE_OK(cudaMalloc(&s->perm, sizeof(int) * (2 * (size_t)n_envs + 16)));
-  }
-  if (cfg->exec_mode == 2) {  // tuning overrides for experiments; the defaults are the measured best
-    s->ls_warps = env_int("LCR_LS_WARPS", 0);
-    s->ls_flags = env_int("LCR_LS_FLAGS", 23);
-    const int srt = env_int("LCR_LS_SORT", -1);
-    if (srt != 0) {
-      LCR_CREATE_OK(cudaMalloc(&s->perm, sizeof(int) * ((size_t)n_envs + 16)));
-      // striped seats while the step time is set by the most expensive env, sorted seats once there are many waves
-      s->ls_striped = srt == 2 ? 0 : (srt == 1 ? 1 : (n_envs < 12288 ? 1 : 0));
-    }
-  }
-  if (cfg->exec_mode == 3 && create_flow(s)) { lcr_destroy(s); return 1; }
-#undef LCR_CREATE_OK
-  *out = s;
-  return 0;
-}
-
-int lcr_destroy(LcrSim* sim) {
-  if (!sim) return 0;
-  cudaSetDevice(sim->device);
-  if (sim->precision == LCR_F32) sim->f.destroy(); else sim->d.destroy();
-  for (int k = 0; k < 16; k++) {
-    if (sim->gstream[k]) cudaStreamDestroy(sim->gstream[k]);
-    if (sim->ev_done[k]) cudaEventDestroy(sim->ev_done[k]);
-  }
-  if (sim->ev_begin) cudaEventDestroy(sim->ev_begin);
-  if (sim->bstream) cudaStreamDestroy(sim->bstream);
-  if (sim->ev_sched) cudaEventDestroy(sim->ev_sched);
-  if (sim->ev_big) cudaEventDestroy(sim->ev_big);
-  cudaFree(sim->big);
-  cudaFree(sim->perm); cudaFree(sim->redo); cudaFree(sim->fq_mem); cudaFree(sim->fq_rings); cudaFree(sim->seed_buf);
-  delete sim;
-  return 0;
-}
-
-int lcr_seed(LcrSim* sim, const uint64_t* h_state, const uint8_t* d_mask, void* stream) {
-  WITH_DEVICE(sim);
-  if (!h_state) return fail("lcr_seed: null state");
-  // (pageable host memory: the copy is staged by the runtime before the call returns, the caller's buffer is free afterwards)
-  CUDA_OK(cudaMemcpyAsync(sim->seed_buf, h_state, 32 * (size_t)sim->n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  if (sim->precision == LCR_F32) lcr::Launch<float>::seed(sim->f.s, sim->seed_buf, d_mask, (cudaStream_t)stream);
-  else lcr::Launch<double>::seed(sim->d.s, sim->seed_buf, d_mask, (cudaStream_t)stream);
-  sim->launches++;
-  CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-int lcr_reset(LcrSim* sim, const uint8_t* d_mask, float* d_obs, void* stream) {
-  WITH_DEVICE(sim);
-  LCR_RUN(sim, reset(sim->f.dm, sim->f.verts, sim->f.s, d_mask, d_obs, (cudaStream_t)stream), reset(sim->d.dm, sim->d.verts, sim->d.s, d_mask, d_obs, (cudaStream_t)stream));
-  sim->launches++;
-  CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-int lcr_step_rec(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated,
-                 uint8_t* d_success, float* d_record, void* stream) {
-  WITH_DEVICE(sim);
-  if (!d_actions || !d_obs || !d_reward || !d_terminated || !d_truncated || !d_success) return fail("lcr_step: null buffer");
-  cudaStream_t st = (cudaStream_t)stream;
-  const StepIO io{d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, d_record};
+namespace {
+// the kernels of one control step in the fused / phased / lockstep modes, enqueued on `st` (and on the sim's side streams, which
+// fork from and join `st` through events -- so the same code is what a stream capture records)
+int enqueue_step(LcrSim* sim, const StepIO& io, cudaStream_t st) {
   const Redo redo = redo_of(sim);
   const bool f32 = sim->precision == LCR_F32;
-  if (sim->cfg.exec_mode == 3) {
-    // one scheduler launch + one persistent kernel; the envs that need the big workspace are handled inside
-    LCR_RUN(sim, step_flow(sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, io, &sim->fq, sim->flow_grid, sim->flow_bigcta, sim->flow_flags, sim->flow_thi,
-                           sim->flow_tbig, sim->flow_stats, st),
-            step_flow(sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, io, &sim->fq, sim->flow_grid, sim->flow_bigcta, sim->flow_flags, sim->flow_thi,
-                      sim->flow_tbig, sim->flow_stats, st));
-    sim->launches += 2;
-    CUDA_OK(cudaGetLastError());
-    return 0;
-  }
   CUDA_OK(cudaMemsetAsync(sim->redo, 0, sizeof(int), st));
   bool predicted = false, big_started = false;
   // the envs the scheduler sent to the big workspace start now, on their own stream, beside the main kernels
@@ -443,8 +333,8 @@ int lcr_step_rec(LcrSim* sim, const float* d_actions, float* d_obs, float* d_rew
   if (sim->cfg.exec_mode == 1) {
     const int G = sim->ngroups, per = (sim->n + G - 1) / G;
     if (sim->perm) {  // seats in work-aware order: group g owns perm[g * per, (g + 1) * per), heaviest envs first, -1 = padding
-      if (f32) lcr::Launch<float>::sched(sim->f.s, sim->perm, per, 1, sim->big, sim->tbig, st);
-      else lcr::Launch<double>::sched(sim->d.s, sim->perm, per, 1, sim->big, sim->tbig, st);
+      if (f32) lcr::Launch<float>::sched(sim->f.s, sim->perm, per, sim->ph_striped, sim->big, sim->tbig, st);
+      else lcr::Launch<double>::sched(sim->d.s, sim->perm, per, sim->ph_striped, sim->big, sim->tbig, st);
       sim->launches++;
       predicted = true;
     }
@@ -488,6 +378,171 @@ int lcr_step_rec(LcrSim* sim, const float* d_actions, float* d_obs, float* d_rew
   sim->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int lcr_obs_dim(int task) { return (task == LCR_TASK_REACH || task == LCR_TASK_LIFT || task == LCR_TASK_PUSH_LOOP) ? 15 : 18; }
+int lcr_action_dim(const LcrEnvCfg* cfg) { return (cfg->action_mode ? 3 : 5) + (cfg->block_gripper ? 0 : 1); }
+
+int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg* cfg, int n_envs, int device, int precision, LcrSim** out) {
+  if (!model || !cfg || !out || (!hull_verts && model->nvert > 0)) return fail("lcr_create: null argument");
+  if (n_envs <= 0) return fail("lcr_create: n_envs must be positive");
+  if (model->ncube < 1 || model->ncube > LCR_MAXCUBE || model->nmesh > LCR_MAXMESH || model->npair > LCR_MAXPAIR ||
+      model->nwall < 0 || model->nwall > LCR_MAXWALL || model->nmesh + 1 + model->ncube + model->nwall > LCR_MAXGEOM)
+    return fail("lcr_create: model exceeds compiled caps");
+  if (model->task < LCR_TASK_REACH || model->task > LCR_TASK_PUSH_LOOP) return fail("lcr_create: unknown task");
+  if ((model->task == LCR_TASK_PUSH_LOOP) != (model->nwall > 0) || (model->task == LCR_TASK_PUSH_LOOP && (model->ncube != 1 || model->nwall != LCR_MAXWALL)))
+    return fail("lcr_create: static wall boxes are the four rails of the PushCubeLoop scene (one cube)");
+  if (precision != LCR_F32 && precision != LCR_F64) return fail("lcr_create: precision must be LCR_F32 or LCR_F64");
+  if (cfg->exec_mode < 0 || cfg->exec_mode > 3) return fail("lcr_create: exec_mode must be 0 (fused), 1 (phased), 2 (lockstep) or 3 (flow)");
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("lcr_create: no such CUDA device");
+  CUDA_OK(cudaSetDevice(device));
+  LcrSim* s = new LcrSim();
+  s->precision = precision; s->device = device; s->n = n_envs; s->ncube = scene_class(model->task, model->ncube); s->task = model->task;
+  s->model = *model; s->cfg = *cfg;
+  // (every failure below goes through lcr_destroy: nothing allocated so far is leaked)
+#define LCR_CREATE_OK(call) do { if ((call) != cudaSuccess) { fail(std::string("lcr_create: ") + #call + " failed: " + cudaGetErrorString(cudaGetLastError())); lcr_destroy(s); return 1; } } while (0)
+  if (precision == LCR_F32 ? s->f.create(*model, hull_verts, *cfg, n_envs) : s->d.create(*model, hull_verts, *cfg, n_envs)) { lcr_destroy(s); return 1; }
+  s->launches = 1;
+  LCR_CREATE_OK(cudaMalloc(&s->redo, sizeof(int) * ((size_t)n_envs + 1)));
+  LCR_CREATE_OK(cudaMemset(s->redo, 0, sizeof(int)));
+  LCR_CREATE_OK(cudaMalloc(&s->seed_buf, 32 * (size_t)n_envs));
+  LCR_CREATE_OK(cudaMalloc(&s->big, sizeof(int) * ((size_t)n_envs + 1)));
+  LCR_CREATE_OK(cudaMemset(s->big, 0, sizeof(int)));
+  LCR_CREATE_OK(cudaStreamCreateWithFlags(&s->bstream, cudaStreamNonBlocking));
+  LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_sched, cudaEventDisableTiming));
+  LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_big, cudaEventDisableTiming));
+  // rows of the previous step from which an env starts on the big workspace, beside the main kernels, instead of being found out and
+  // redone after them.  Phased chain: from the fast cap on (small CTAs, the BIG CTAs run among them: PushCube 16 384, 21.5 -> 20.9 ms per
+  // step); lockstep: never (its CTAs take a whole SM each, the BIG CTAs would only wait for one)
+  s->tbig = env_int("LCR_TBIG", cfg->exec_mode == 1 ? 97 : 100000);
+  if (cfg->exec_mode == 1) {
+    // measured on B200 in the stationary window (profiles/r02b_sweep_groups.txt): the chains of the groups overlap each other's launch
+    // tails; up to 8 192 envs 4 groups are best (PickPlace-ee 8 192: 16.6 / 16.0 / 15.7 ms per step with 1 / 2 / 4 groups, Stack 8 192:
+    // 20.4 / 19.6 / 18.8), at 16 384 envs 2 (PushCube: 21.6 / 20.5 / 21.0 / 21.8 with 1 / 2 / 4 / 8): more groups only shrink the launches
+    int g = env_int("LCR_GROUPS", n_envs <= 8192 ? 4 : 2);
+    g = std::max(1, std::min(16, std::min(g, n_envs)));
+    for (int k = 0; k < g; k++) {
+      LCR_CREATE_OK(cudaStreamCreateWithFlags(&s->gstream[k], cudaStreamNonBlocking));
+      LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_done[k], cudaEventDisableTiming));
+      s->ngroups = k + 1;
+    }
+    LCR_CREATE_OK(cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming));
+    // work-aware seats (LCR_PH_SORT=0: identity): the envs with the most constraint rows in their previous step are launched
+    // first in every phase kernel, so that the long Newton solves / MPR jobs do not end up in the tail of the launch
+    if (env_int("LCR_PH_SORT", 1) != 0) LCR_CREATE_OK(cudaMalloc(&s->perm, sizeof(int) * (2 * (size_t)n_envs + 16)));
+    s->ph_striped = env_int("LCR_PH_STRIPED", 1);  // 1: ranks dealt out to the groups like cards; 0: group 0 holds the heaviest envs
+    s->use_graph = env_int("LCR_GRAPH", 1);
+    if (s->use_graph) {
+      LCR_CREATE_OK(cudaStreamCreateWithFlags(&s->cstream, cudaStreamNonBlocking));
+      LCR_CREATE_OK(cudaMalloc(&s->act_buf, sizeof(float) * (size_t)n_envs * lcr_action_dim(cfg)));
+    }
+  }
+  if (cfg->exec_mode == 2) {  // tuning overrides for experiments; the defaults are the measured best
+    s->ls_warps = env_int("LCR_LS_WARPS", 0);
+    s->ls_flags = env_int("LCR_LS_FLAGS", 23);
+    const int srt = env_int("LCR_LS_SORT", -1);
+    if (srt != 0) {
+      LCR_CREATE_OK(cudaMalloc(&s->perm, sizeof(int) * ((size_t)n_envs + 16)));
+      // striped seats while the step time is set by the most expensive env, sorted seats once there are many waves
+      s->ls_striped = srt == 2 ? 0 : (srt == 1 ? 1 : (n_envs < 12288 ? 1 : 0));
+    }
+  }
+  if (cfg->exec_mode == 3 && create_flow(s)) { lcr_destroy(s); return 1; }
+#undef LCR_CREATE_OK
+  *out = s;
+  return 0;
+}
+
+int lcr_destroy(LcrSim* sim) {
+  if (!sim) return 0;
+  cudaSetDevice(sim->device);
+  if (sim->precision == LCR_F32) sim->f.destroy(); else sim->d.destroy();
+  for (int k = 0; k < 16; k++) {
+    if (sim->gstream[k]) cudaStreamDestroy(sim->gstream[k]);
+    if (sim->ev_done[k]) cudaEventDestroy(sim->ev_done[k]);
+  }
+  if (sim->ev_begin) cudaEventDestroy(sim->ev_begin);
+  if (sim->gexec) cudaGraphExecDestroy(sim->gexec);
+  if (sim->cstream) cudaStreamDestroy(sim->cstream);
+  cudaFree(sim->act_buf);
+  if (sim->bstream) cudaStreamDestroy(sim->bstream);
+  if (sim->ev_sched) cudaEventDestroy(sim->ev_sched);
+  if (sim->ev_big) cudaEventDestroy(sim->ev_big);
+  cudaFree(sim->big);
+  cudaFree(sim->perm); cudaFree(sim->redo); cudaFree(sim->fq_mem); cudaFree(sim->fq_rings); cudaFree(sim->seed_buf);
+  delete sim;
+  return 0;
+}
+
+int lcr_seed(LcrSim* sim, const uint64_t* h_state, const uint8_t* d_mask, void* stream) {
+  WITH_DEVICE(sim);
+  if (!h_state) return fail("lcr_seed: null state");
+  // (pageable host memory: the copy is staged by the runtime before the call returns, the caller's buffer is free afterwards)
+  CUDA_OK(cudaMemcpyAsync(sim->seed_buf, h_state, 32 * (size_t)sim->n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  if (sim->precision == LCR_F32) lcr::Launch<float>::seed(sim->f.s, sim->seed_buf, d_mask, (cudaStream_t)stream);
+  else lcr::Launch<double>::seed(sim->d.s, sim->seed_buf, d_mask, (cudaStream_t)stream);
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_reset(LcrSim* sim, const uint8_t* d_mask, float* d_obs, void* stream) {
+  WITH_DEVICE(sim);
+  LCR_RUN(sim, reset(sim->f.dm, sim->f.verts, sim->f.s, d_mask, d_obs, (cudaStream_t)stream), reset(sim->d.dm, sim->d.verts, sim->d.s, d_mask, d_obs, (cudaStream_t)stream));
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lcr_step_rec(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated,
+                 uint8_t* d_success, float* d_record, void* stream) {
+  WITH_DEVICE(sim);
+  if (!d_actions || !d_obs || !d_reward || !d_terminated || !d_truncated || !d_success) return fail("lcr_step: null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const StepIO io{d_actions, d_obs, d_reward, d_terminated, d_truncated, d_success, d_record};
+  if (sim->cfg.exec_mode == 3) {
+    // one scheduler launch + one persistent kernel; the envs that need the big workspace are handled inside
+    LCR_RUN(sim, step_flow(sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, io, &sim->fq, sim->flow_grid, sim->flow_bigcta, sim->flow_flags, sim->flow_thi,
+                           sim->flow_tbig, sim->flow_stats, st),
+            step_flow(sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, io, &sim->fq, sim->flow_grid, sim->flow_bigcta, sim->flow_flags, sim->flow_thi,
+                      sim->flow_tbig, sim->flow_stats, st));
+    sim->launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  if (sim->cfg.exec_mode == 1 && sim->use_graph) {
+    // phased chain as one CUDA graph launch: captured on an internal stream (the caller's may be the legacy default stream,
+    // which cannot be captured), replayed on the caller's stream
+    CUDA_OK(cudaMemcpyAsync(sim->act_buf, d_actions, sizeof(float) * (size_t)sim->n * lcr_action_dim(&sim->cfg), cudaMemcpyDeviceToDevice, st));
+    StepIO gio = io;
+    gio.actions = sim->act_buf;
+    const void* key[6] = {d_obs, d_reward, d_terminated, d_truncated, d_success, d_record};
+    if (!sim->gexec || std::memcmp(key, sim->gkey, sizeof key) != 0) {
+      if (sim->gexec) { cudaGraphExecDestroy(sim->gexec); sim->gexec = nullptr; }
+      const int l0 = sim->launches;
+      CUDA_OK(cudaStreamBeginCapture(sim->cstream, cudaStreamCaptureModeThreadLocal));
+      const int rc = enqueue_step(sim, gio, sim->cstream);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ec = cudaStreamEndCapture(sim->cstream, &graph);
+      sim->graph_nodes = sim->launches - l0;
+      sim->launches = l0;
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ec != cudaSuccess) return fail(std::string("lcr_step: graph capture failed: ") + cudaGetErrorString(ec));
+      const cudaError_t ei = cudaGraphInstantiate(&sim->gexec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ei != cudaSuccess) { sim->gexec = nullptr; return fail(std::string("lcr_step: cudaGraphInstantiate: ") + cudaGetErrorString(ei)); }
+      std::memcpy(sim->gkey, key, sizeof key);
+    }
+    CUDA_OK(cudaGraphLaunch(sim->gexec, st));
+    sim->launches += sim->graph_nodes;  // kernels launched by the replay
+    return 0;
+  }
+  return enqueue_step(sim, io, st);
 }
 
 int lcr_step(LcrSim* sim, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated,

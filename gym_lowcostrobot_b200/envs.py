@@ -106,13 +106,13 @@ class BatchedLowCostRobotEnv:
     def _pick_exec_mode(cls, exec_mode, num_envs):
         """"auto" = the fastest mode measured on B200 for the batch size (profiles/README.md, stationary window): the lockstep
         kernel (one launch per step, CTAs of 16 envs aligned at the phase boundaries, CTA-wide narrowphase job pool) for small
-        batches, where the step time is the chain of the most expensive env; the phased chain (one small kernel per mj_step
-        phase over all envs) once several waves of envs queue per SM.  "flow" (one persistent kernel per step, phases run from
+        batches; the phased chain (one small kernel per mj_step phase over all envs, the whole step replayed as ONE CUDA graph)
+        from 4 096 envs (ReachCube 4 096, mid-episode: 11.2 ms per step against 13.0 for the lockstep kernel).  "flow" (one persistent kernel per step, phases run from
         device-side queues, csrc/lcr_flow.cuh) reaches 0.65 - 1.0 of them and is selectable.  All modes give bit-identical
         results (tests/test_gpu_parity.py)."""
         if exec_mode != "auto":
             return exec_mode
-        return "phased" if num_envs >= 5120 else "lockstep"
+        return "phased" if num_envs >= 4096 else "lockstep"
 
     # -- helpers ---------------------------------------------------------------------------
     def _stream(self):

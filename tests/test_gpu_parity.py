@@ -368,10 +368,13 @@ def test_envs_beyond_the_fast_caps_take_the_big_path_in_every_mode(em):
 def test_f64_big_path_matches_the_oracle():
     """float64 kernels against the oracle on the same beyond-the-caps states, ONE mj_step (the comparison that is well posed in
     deeply interpenetrating poses, see test_f64_one_substep_map_from_random_states).  Envs with more than 96 constraint rows
-    -- which only the big workspace can hold -- must be present; of the envs whose contact and row counts agree with the
-    oracle's (a last-bit support-vertex flip among near-coplanar hull vertices changes the contact list of some of these
-    poses: those are counted, not compared) at least 95 % must agree to 1e-7 (qpos) / 1e-4 (qvel), separately for the
-    big ones, and at least half of the big ones must be comparable; nothing may be dropped on either side."""
+    -- which only the big workspace can hold -- must be present.  As in the one-substep test, an env is compared when its
+    contact LIST (positions, normals, depths to 1e-9, not just the counts) agrees with the oracle's: these arms lie in the
+    floor with 40 - 55 contacts, most of them hull-vs-plane support vertices picked among near-coplanar hull vertices, where a
+    last-bit difference (CUDA sincos vs glibc) flips a vertex in some envs -- those are counted, not compared.  Every
+    compared env must agree to 1e-7 (qpos) / 1e-4 (qvel) unless the oracle's own map is ill-posed there (answers a 1e-13
+    perturbation with more than the tolerance); at least a third of the big envs must be comparable; nothing may be dropped
+    on either side."""
     n = 96
     rng = np.random.default_rng(11)
     env = glr.make("PushCube-v0", num_envs=n, precision="float64")
@@ -379,30 +382,44 @@ def test_f64_big_path_matches_the_oracle():
     qpos[:, 1] = rng.uniform(0.9, 1.22, n)
     qpos[:, 2] = rng.uniform(1.2, 1.74, n)
     env.set_state(qpos=qpos, qvel=0.2 * qvel, ctrl=qpos[:, :6], warm=np.zeros((n, env.nv)))
+    con, ncon = env.debug_contacts()
+    con, ncon = con.cpu().numpy(), ncon.cpu().numpy()
     env.substeps(1)
     st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
     dg = {k: v.cpu().numpy() for k, v in env.diagnostics().items()}
     env.close()
-    cmp_all = ok_all = big = cmp_big = ok_big = 0
-    for i in range(n):
+
+    def oracle_substep(i, dv=0.0):
         o = Oracle("push")
-        o.set_state(qpos=qpos[i], qvel=0.2 * qvel[i], ctrl=qpos[i, :6], warm=np.zeros(env.nv))
+        o.set_state(qpos=qpos[i], qvel=0.2 * qvel[i] + dv, ctrl=qpos[i, :6], warm=np.zeros(env.nv))
+        o.forward()
+        oc = o.get("contacts").reshape(-1, 27).copy()
         o.substep(1)
-        ref, d = o.get_state(), o.diag()
+        return o.get_state(), o.diag(), oc
+
+    cmp_all = big = cmp_big = bad = branch = 0
+    for i in range(n):
+        ref, d, oc = oracle_substep(i)
         assert d["overflow"] == 0 and dg["overflow"][i] == 0
         is_big = d["nefc"] > 96
         big += is_big
-        if dg["nefc"][i] != d["nefc"] or dg["ncon"][i] != d["ncon"]:
+        if len(oc) != ncon[i] or dg["nefc"][i] != d["nefc"] or _contact_err(con[i, :ncon[i]], oc) > 1e-9:
             continue
-        ok = np.abs(st["qpos"][i] - ref["qpos"]).max() < 1e-7 and np.abs(st["qvel"][i] - ref["qvel"]).max() < 1e-4
         cmp_all += 1
-        ok_all += ok
         cmp_big += is_big
-        ok_big += ok and is_big
-    print("big path vs oracle: big", big, "comparable", cmp_big, "close", ok_big, "| all comparable", cmp_all, "close", ok_all)
+        if np.abs(st["qpos"][i] - ref["qpos"]).max() > 1e-7 or np.abs(st["qvel"][i] - ref["qvel"]).max() > 1e-4:
+            pert = np.random.default_rng(i)
+            moved = max(np.abs(oracle_substep(i, pert.normal(scale=1e-13, size=env.nv))[0]["qvel"] - ref["qvel"]).max() for _ in range(6))
+            if moved > 1e-4:
+                branch += 1
+            else:
+                bad += 1
+                print("env", i, "nefc", d["nefc"], "dqpos", np.abs(st["qpos"][i] - ref["qpos"]).max(), "dqvel", np.abs(st["qvel"][i] - ref["qvel"]).max(),
+                      "niter", dg["niter"][i], d["niter"])
+    print("big path vs oracle: big", big, "comparable", cmp_big, "| all comparable", cmp_all, "bad", bad, "branch", branch)
     assert big >= 4, "the states should push some envs beyond the fast caps"
-    assert cmp_big >= 0.5 * big and ok_big >= 0.95 * cmp_big, (big, cmp_big, ok_big)
-    assert cmp_all >= 0.7 * n and ok_all >= 0.95 * cmp_all, (cmp_all, ok_all)
+    assert cmp_big >= big / 3 and cmp_all >= 0.6 * n, (big, cmp_big, cmp_all)
+    assert bad == 0 and branch <= 2, (bad, branch)
 
 
 def test_checkpoint_restore_replays_bitwise_across_an_episode_boundary():
