@@ -623,6 +623,19 @@ int lcr_pack_outputs(LcrSim* sim, const float* d_obs, const float* d_reward, con
   return 0;
 }
 
+int lcr_record_append(const float* d_obs, int obs_dim, const float* d_actions, int action_dim, const uint8_t* d_terminated, const uint8_t* d_truncated,
+                      int n_envs, int horizon, float* d_traj, int32_t* d_len, float* d_pool, int32_t* d_pool_meta, int32_t* d_count, int pool_cap,
+                      void* stream) {
+  if (!d_obs || !d_actions || !d_terminated || !d_truncated || !d_traj || !d_len || !d_pool || !d_pool_meta || !d_count)
+    return fail("lcr_record_append: null buffer");
+  if (obs_dim < 12 || action_dim < 1 || 12 + action_dim > 32 || n_envs <= 0 || horizon <= 0 || pool_cap <= 0)
+    return fail("lcr_record_append: obs_dim >= 12, 1 <= action_dim <= 20, positive n_envs / horizon / pool_cap required");
+  lcr::Launch<float>::rec_append(d_obs, obs_dim, d_actions, action_dim, d_terminated, d_truncated, n_envs, horizon, d_traj, d_len, d_pool, d_pool_meta,
+                                 d_count, pool_cap, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int lcr_debug_phase_clocks(LcrSim* sim, long long* d_clocks) {
   if (!sim) return fail("null handle");
   if (sim->cfg.exec_mode != 2) return fail("lcr_debug_phase_clocks: lockstep mode only");

@@ -221,6 +221,8 @@ struct Launch {
   static void sched(DevState<T> s, int* perm, int W, int striped, int* big, int tbig, cudaStream_t st);
   static void pack(const float* obs, const float* reward, const uint8_t* term, const uint8_t* trunc, const uint8_t* succ, float* rec, int n, int od,
                    cudaStream_t st);
+  static void rec_append(const float* obs, int od, const float* act, int A, const uint8_t* term, const uint8_t* trunc, int n, int h, float* traj,
+                         int32_t* len, float* pool, int32_t* meta, int32_t* count, int cap, cudaStream_t st);
   static void get_state(int ncube, DevState<T> s, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,
                         unsigned long long* rng, cudaStream_t st);
   static void set_state(int ncube, DevState<T> s, const double* qpos, const double* qvel, const double* ctrl, const double* warm,

@@ -1928,6 +1928,42 @@ static __global__ void k_pack(const float* __restrict__ obs, const float* __rest
   }
 }
 
+
+// Batched trajectory recorder (the device side of vec.TrajectoryRecorder; replaces HDF5_Recorder.capture_frame and the episode
+// cut of RecordHDF5Wrapper.step, envs/wrappers/record_hdf5.py:40-45,116-137).  One warp per env: appends the row
+// arm_qpos[6] | arm_qvel[6] | action[A] of this step to the env's open trajectory traj[env][t]; when the episode ended in this
+// step the trajectory moves to the next free slot of the finished-episode pool (slot = atomic counter, meta = env, length)
+// and the env starts a new one.  No host involvement: the host drains the pool whenever it likes (count[0] = episodes in the
+// pool, count[1] = episodes dropped because the pool was full).
+static __global__ void k_rec_append(const float* __restrict__ obs, int od, const float* __restrict__ act, int A, const uint8_t* __restrict__ term,
+                             const uint8_t* __restrict__ trunc, int n, int h, float* __restrict__ traj, int32_t* __restrict__ len,
+                             float* __restrict__ pool, int32_t* __restrict__ meta, int32_t* __restrict__ count, int cap) {
+  const int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31, W = 12 + A;
+  if (env >= n) return;
+  int t = len[env];
+  float* tr = traj + (size_t)env * h * W;
+  const int row = t < h ? t : h - 1;  // (an episode longer than the horizon keeps overwriting its last row)
+  if (lane < W) tr[(size_t)row * W + lane] = lane < 12 ? obs[(size_t)env * od + lane] : act[(size_t)env * A + lane - 12];
+  t++;
+  __syncwarp();
+  if (!(term[env] | trunc[env])) {
+    if (lane == 0) len[env] = t;
+    return;
+  }
+  int slot = 0;
+  if (lane == 0) slot = atomicAdd(&count[0], 1);
+  slot = __shfl_sync(FULLMASK, slot, 0);
+  const int L = t < h ? t : h;
+  if (slot < cap) {
+    float* dst = pool + (size_t)slot * h * W;
+    for (int i = lane; i < L * W; i += 32) dst[i] = tr[i];
+    if (lane == 0) { meta[2 * slot] = env; meta[2 * slot + 1] = L; }
+  } else if (lane == 0) {
+    atomicAdd(&count[1], 1);
+  }
+  if (lane == 0) len[env] = 0;
+}
+
 }  // namespace lcr
 #include "lcr_flow.cuh"
 namespace lcr {
@@ -2057,6 +2093,11 @@ void Launch<T>::pack(const float* obs, const float* reward, const uint8_t* term,
                      cudaStream_t st) {
   const int total = n * (od + 4), blocks = std::min((total + 255) / 256, 148 * 8);
   k_pack<<<blocks, 256, 0, st>>>(obs, reward, term, trunc, succ, rec, n, od);
+}
+template <typename T>
+void Launch<T>::rec_append(const float* obs, int od, const float* act, int A, const uint8_t* term, const uint8_t* trunc, int n, int h, float* traj,
+                           int32_t* len, float* pool, int32_t* meta, int32_t* count, int cap, cudaStream_t st) {
+  k_rec_append<<<(n + 3) / 4, 128, 0, st>>>(obs, od, act, A, term, trunc, n, h, traj, len, pool, meta, count, cap);
 }
 template <typename T>
 void Launch<T>::sched(DevState<T> s, int* perm, int W, int striped, int* big, int tbig, cudaStream_t st) {

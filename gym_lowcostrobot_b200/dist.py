@@ -63,5 +63,10 @@ class ShardedEnv:
             return unpack_record(self._local)
         if self._full is None:
             self._full = torch.empty(self.n_total, self._local.shape[1], dtype=torch.float32, device=self._local.device)
+        nvtx = getattr(self.env, "nvtx", False)
+        if nvtx:
+            torch.cuda.nvtx.range_push(f"lcr_all_gather[{self.n_total} x {self._local.shape[1]} f32]")
         dist.all_gather_into_tensor(self._full, self._local, group=self.group)
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
         return unpack_record(self._full)

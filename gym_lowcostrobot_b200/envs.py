@@ -107,12 +107,18 @@ class BatchedLowCostRobotEnv:
         """"auto" = the fastest mode measured on B200 for the batch size (profiles/README.md, stationary window): the lockstep
         kernel (one launch per step, CTAs of 16 envs aligned at the phase boundaries, CTA-wide narrowphase job pool) for small
         batches; the phased chain (one small kernel per mj_step phase over all envs, the whole step replayed as ONE CUDA graph)
-        from 4 096 envs (ReachCube 4 096, mid-episode: 11.2 ms per step against 13.0 for the lockstep kernel).  "flow" (one persistent kernel per step, phases run from
+        from 2 048 envs (ReachCube mid-episode, ms per step phased / lockstep: 10.2 / 11.1 at 2 048 envs, 11.2 / 13.0 at 4 096;
+        profiles/r02b_sweep_groups.txt).  "flow" (one persistent kernel per step, phases run from
         device-side queues, csrc/lcr_flow.cuh) reaches 0.65 - 1.0 of them and is selectable.  All modes give bit-identical
         results (tests/test_gpu_parity.py)."""
         if exec_mode != "auto":
             return exec_mode
-        return "phased" if num_envs >= 4096 else "lockstep"
+        return "phased" if num_envs >= 2048 else "lockstep"
+
+    @property
+    def obs_layout(self):
+        """((key, width), ...) of the flat observation ``[num_envs, obs_dim]``, in the reference's key order"""
+        return _OBS_LAYOUT[self.task]
 
     # -- helpers ---------------------------------------------------------------------------
     def _stream(self):
@@ -156,9 +162,13 @@ class BatchedLowCostRobotEnv:
             raise ValueError("Action dimension mismatch")  # reach_cube_env.py:231-232
         a = actions.to(device=self.device, dtype=torch.float32).contiguous()
         f = self._flags
+        if self.nvtx:
+            torch.cuda.nvtx.range_push(f"lcr_step[{self.task} x{self.num_envs} {self.exec_mode}]")
         with torch.cuda.device(self.device):
             capi.check(self._L.lcr_step_rec(self._h, _ptr(a), _ptr(self._obs), _ptr(self._reward), _ptr(f[0]), _ptr(f[1]),
                                             _ptr(f[2]), _ptr(record), self._stream()))
+        if self.nvtx:
+            torch.cuda.nvtx.range_pop()
         return self._obs, self._reward, f[0], f[1], f[2]
 
     def step_packed(self, actions, out=None):
@@ -182,6 +192,7 @@ class BatchedLowCostRobotEnv:
         return self._split(obs.clone()), reward.clone(), te.bool(), tr.bool(), info
 
     report_failures = False  # True: every step() adds failure_info() to info (one more tiny launch per step)
+    nvtx = False             # True: NVTX range around every step's enqueue (and around the all-gather in dist.ShardedEnv)
 
     def failure_info(self):
         """Per-env failure flags of the last step (device tensors, no host sync): ``nan_reset`` = the env blew up

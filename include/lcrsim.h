@@ -118,6 +118,20 @@ int lcr_get_diag(LcrSim* sim, int32_t* d_diag, void* stream);
  * d_ncon [n] int32.  Lets the parity tests compare collision geometry with the oracle directly. */
 int lcr_debug_contacts(LcrSim* sim, double* d_contacts, int32_t* d_ncon, void* stream);
 
+/* Batched trajectory recorder: replaces HDF5_Recorder.capture_frame and the episode cut of RecordHDF5Wrapper.step
+ * (gym_lowcostrobot/envs/wrappers/record_hdf5.py:40-45,116-137) for a whole batch, on the device.  Call once per step with the
+ * step's d_obs [n][obs_dim] (columns 0:6 = arm_qpos, 6:12 = arm_qvel in every task), the d_actions [n][action_dim] that
+ * produced it and the two done flags.  Appends the row qpos | qvel | action to the env's open trajectory
+ * d_traj [n][horizon][12 + action_dim] (d_len [n] = rows so far, zero-initialised by the caller); an env whose episode ended
+ * moves its trajectory to slot atomicAdd(d_count[0]) of the finished-episode pool d_pool [pool_cap][horizon][12 + action_dim],
+ * d_pool_meta [pool_cap][2] = env, length (episodes beyond pool_cap are counted in d_count[1] and dropped) and starts a new
+ * one.  The host drains the pool whenever it likes (read d_count, copy the slots, zero d_count[0]) -- no per-step sync.
+ * The datasets the wrapper writes (observations/qpos, observations/qvel, action: record_hdf5.py:52-61) are column slices of
+ * a pool slot.  Stateless: needs no simulator handle. */
+int lcr_record_append(const float* d_obs, int obs_dim, const float* d_actions, int action_dim, const uint8_t* d_terminated,
+                      const uint8_t* d_truncated, int n_envs, int horizon, float* d_traj, int32_t* d_len, float* d_pool,
+                      int32_t* d_pool_meta, int32_t* d_count, int pool_cap, void* stream);
+
 /* Debug hook (lockstep mode): from the next lcr_step on, every env writes the SM clock cycles it spent in each phase
  * of the step to d_clocks [n][10] int64 = begin/end, wait top, dynamics+broadphase, wait, narrowphase jobs, wait,
  * constraint rows, wait, Newton solve, integrate (sums over the substeps).  NULL switches it off again. */
