@@ -1,0 +1,79 @@
+"""Fixture for tests/test_independent_pipeline.py: the scene of push_cube.xml read by a SEPARATE minimal reader.
+
+Deliberately shares nothing with gym_lowcostrobot_b200/mjcf.py (the model compiler that the oracle and the CUDA path both
+use): plain ElementTree walk of follower.xml + push_cube.xml, raw binary STL triangles, scipy's Qhull for the hull vertex
+sets, vertices kept in the RAW mesh frame (MuJoCo recentres meshes on their centre of mass and compensates in the geom
+pose; an independent reader has no reason to).  Usage (in the build container, where /root/reference exists):
+
+    python tools/make_independent_scene.py [/root/reference/gym_lowcostrobot/assets/low_cost_robot_6dof]
+
+writes tests/golden/independent_scene_push.npz.
+"""
+import os
+import struct
+import sys
+import xml.etree.ElementTree as ET
+
+import numpy as np
+from scipy.spatial import ConvexHull
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def read_stl(path):
+    raw = open(path, "rb").read()
+    (ntri,) = struct.unpack_from("<I", raw, 80)
+    assert len(raw) == 84 + 50 * ntri, "binary STL expected"
+    tri = np.frombuffer(raw, dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]), count=ntri, offset=84)
+    return tri["v"].reshape(-1, 3).astype(np.float64)
+
+
+def vec(s, n):
+    v = [float(x) for x in s.split()]
+    assert len(v) == n
+    return np.array(v)
+
+
+def main(assets):
+    arm = ET.parse(os.path.join(assets, "follower.xml")).getroot()
+    scene = ET.parse(os.path.join(assets, "push_cube.xml")).getroot()
+    meshdir = os.path.join(assets, arm.find("compiler").get("meshdir"))
+    files = {m.get("name"): m.get("file") for m in arm.find("asset").findall("mesh")}
+    on_disk = {f.lower(): f for f in os.listdir(meshdir)}
+
+    bodies, geoms = [], []  # bodies: name, parent index, pos, quat, joint axis (or zeros); geoms: body index, mesh name
+
+    def walk(elem, parent):
+        idx = len(bodies)
+        j = elem.find("joint")
+        bodies.append(dict(name=elem.get("name"), parent=parent, pos=vec(elem.get("pos", "0 0 0"), 3), quat=vec(elem.get("quat", "1 0 0 0"), 4),
+                           axis=vec(j.get("axis"), 3) if j is not None else np.zeros(3)))
+        for g in elem.findall("geom"):
+            assert g.get("pos") is None and g.get("quat") is None  # the arm's mesh geoms sit in the body frame
+            geoms.append((idx, g.get("mesh")))
+        for child in elem.findall("body"):
+            walk(child, idx)
+
+    walk(arm.find("worldbody").find("body"), -1)
+    hull_pts, hull_adr = [], [0]
+    for _, mesh in geoms:
+        v = read_stl(os.path.join(meshdir, on_disk[files[mesh].lower()]))
+        v = np.unique(v, axis=0)
+        hv = v[ConvexHull(v).vertices]
+        hull_pts.append(hv)
+        hull_adr.append(hull_adr[-1] + len(hv))
+    excl = [(e.get("body1"), e.get("body2")) for e in arm.find("contact").findall("exclude")]
+    names = [b["name"] for b in bodies]
+    cube = next(b for b in scene.find("worldbody").findall("body") if b.get("name") == "cube")
+    out = os.path.join(ROOT, "tests", "golden", "independent_scene_push.npz")
+    np.savez_compressed(
+        out, body_parent=np.array([b["parent"] for b in bodies]), body_pos=np.stack([b["pos"] for b in bodies]),
+        body_quat=np.stack([b["quat"] for b in bodies]), body_axis=np.stack([b["axis"] for b in bodies]),
+        geom_body=np.array([g[0] for g in geoms]), geom_mesh=np.array([g[1] for g in geoms]), hull_adr=np.array(hull_adr),
+        hull_pts=np.concatenate(hull_pts), exclude=np.array([(names.index(a), names.index(b)) for a, b in excl]),
+        cube_half=vec(cube.find("geom").get("size"), 3), body_names=np.array(names))
+    print("wrote", out, "bodies", len(bodies), "mesh geoms", len(geoms), "hull vertices", hull_adr[-1])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "/root/reference/gym_lowcostrobot/assets/low_cost_robot_6dof")
