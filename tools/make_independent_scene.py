@@ -43,14 +43,59 @@ def main(assets):
 
     bodies, geoms = [], []  # bodies: name, parent index, pos, quat, joint axis (or zeros); geoms: body index, mesh name
 
+    # default classes (only what the contact / joint / actuator parameters need): class -> parent class, per-element attributes
+    classes = {}
+
+    def read_defaults(elem, parent):
+        name = elem.get("class", "main")
+        classes[name] = (parent, {child.tag: dict(child.attrib) for child in elem if child.tag != "default"})
+        for child in elem.findall("default"):
+            read_defaults(child, name)
+
+    read_defaults(arm.find("default"), None)
+
+    def resolved(tag, cls, own):
+        chain = []
+        while cls is not None:
+            chain.append(classes[cls][1].get(tag, {}))
+            cls = classes[cls][0]
+        out = {}
+        for attrs in reversed(chain):
+            out.update(attrs)
+        out.update(own)
+        return out
+
+    def contact_params(attrs):
+        """friction[3], condim, priority, solref[2], solimp[5], solmix with MuJoCo's documented defaults; a shorter attribute
+        sets the leading components only"""
+        def lead(default, text):
+            v = list(default)
+            if text is not None:
+                given = [float(x) for x in text.split()]
+                v[:len(given)] = given
+            return v
+        return (lead([1, 0.005, 0.0001], attrs.get("friction")) + [float(attrs.get("condim", 3)), float(attrs.get("priority", 0))] +
+                lead([0.02, 1], attrs.get("solref")) + lead([0.9, 0.95, 0.001, 0.5, 2], attrs.get("solimp")) + [float(attrs.get("solmix", 1))])
+
+    geom_par, inertial, joints = [], [], []
+
     def walk(elem, parent):
         idx = len(bodies)
         j = elem.find("joint")
         bodies.append(dict(name=elem.get("name"), parent=parent, pos=vec(elem.get("pos", "0 0 0"), 3), quat=vec(elem.get("quat", "1 0 0 0"), 4),
                            axis=vec(j.get("axis"), 3) if j is not None else np.zeros(3)))
+        childclass = elem.get("childclass") or getattr(walk, "childclass", None)
+        walk.childclass = childclass
+        ine = elem.find("inertial")
+        inertial.append(np.r_[vec(ine.get("pos"), 3), vec(ine.get("quat"), 4), float(ine.get("mass")), vec(ine.get("diaginertia"), 3)]
+                        if ine is not None else np.zeros(11))
+        if j is not None:
+            ja = resolved("joint", j.get("class", childclass), dict(j.attrib))
+            joints.append(np.r_[float(ja["armature"]), float(ja["damping"]), vec(ja["actuatorfrcrange"], 2), vec(ja["range"], 2)])
         for g in elem.findall("geom"):
             assert g.get("pos") is None and g.get("quat") is None  # the arm's mesh geoms sit in the body frame
             geoms.append((idx, g.get("mesh")))
+            geom_par.append(contact_params(resolved("geom", g.get("class", childclass), dict(g.attrib))))
         for child in elem.findall("body"):
             walk(child, idx)
 
@@ -65,13 +110,26 @@ def main(assets):
     excl = [(e.get("body1"), e.get("body2")) for e in arm.find("contact").findall("exclude")]
     names = [b["name"] for b in bodies]
     cube = next(b for b in scene.find("worldbody").findall("body") if b.get("name") == "cube")
+    floor = next(g for g in scene.find("worldbody").findall("geom") if g.get("name") == "floor")
+    geom_par.append(contact_params(dict(floor.attrib)))              # geom 20: the floor plane
+    geom_par.append(contact_params(dict(cube.find("geom").attrib)))  # geom 21: the cube
+    cine = cube.find("inertial")
+    act = resolved("position", "follower", {})
+    # <option>: the include is expanded in place, so follower.xml's <option> comes after push_cube.xml's and wins where both set
+    # an attribute (impratio 100 over 10); attributes only one of them sets are kept
+    opt = dict(scene.find("option").attrib)
+    opt.update(arm.find("option").attrib)
+    assert opt["cone"] == "elliptic" and opt["integrator"] == "implicitfast"
     out = os.path.join(ROOT, "tests", "golden", "independent_scene_push.npz")
     np.savez_compressed(
         out, body_parent=np.array([b["parent"] for b in bodies]), body_pos=np.stack([b["pos"] for b in bodies]),
         body_quat=np.stack([b["quat"] for b in bodies]), body_axis=np.stack([b["axis"] for b in bodies]),
         geom_body=np.array([g[0] for g in geoms]), geom_mesh=np.array([g[1] for g in geoms]), hull_adr=np.array(hull_adr),
         hull_pts=np.concatenate(hull_pts), exclude=np.array([(names.index(a), names.index(b)) for a, b in excl]),
-        cube_half=vec(cube.find("geom").get("size"), 3), body_names=np.array(names))
+        cube_half=vec(cube.find("geom").get("size"), 3), body_names=np.array(names),
+        inertial=np.stack(inertial), joints=np.stack(joints), geom_par=np.array(geom_par), cube_mass=float(cine.get("mass")),
+        cube_diaginertia=vec(cine.get("diaginertia"), 3), cube_pos0=vec(cube.get("pos"), 3), act_kp=float(act["kp"]), act_kv=float(act["kv"]),
+        timestep=float(opt["timestep"]), impratio=float(opt["impratio"]), site_pos=vec(arm.find("worldbody").find(".//site").get("pos"), 3))
     print("wrote", out, "bodies", len(bodies), "mesh geoms", len(geoms), "hull vertices", hull_adr[-1])
 
 
