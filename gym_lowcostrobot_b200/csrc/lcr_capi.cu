@@ -246,6 +246,10 @@ struct LcrSim {
   // graph and replayed with one launch per step; the actions are staged into act_buf so that the captured kernel arguments
   // do not depend on the caller's action pointer; the graph is re-captured if the caller's output pointers change
   int use_graph = 0, ph_striped = 1, graph_nodes = 0;
+  // phased mode: migration lists [group][substep][1 + LCR_MIGCAP] and the side stream / fork / join events of every (group, substep)
+  int* mig = nullptr;
+  std::vector<cudaStream_t> mstream;
+  std::vector<cudaEvent_t> mev_fork, mev_join;
   cudaStream_t cstream = nullptr;
   cudaGraphExec_t gexec = nullptr;
   const void* gkey[6] = {};
@@ -339,17 +343,24 @@ int enqueue_step(LcrSim* sim, const StepIO& io, cudaStream_t st) {
       predicted = true;
     }
     if (predicted) start_big();
+    const int nsub = std::max(1, sim->cfg.n_substeps);
+    if (sim->mig) CUDA_OK(cudaMemsetAsync(sim->mig, 0, sizeof(int) * (size_t)G * nsub * (1 + LCR_MIGCAP), st));
     CUDA_OK(cudaEventRecord(sim->ev_begin, st));
     for (int g = 0; g < G; g++) {
       const int env0 = g * per, cnt = sim->perm ? per : std::min(per, sim->n - env0);
       if (env0 >= sim->n) break;
       CUDA_OK(cudaStreamWaitEvent(sim->gstream[g], sim->ev_begin, 0));
       int nl = 0;
-      if (f32) LCR_DISPATCH_RET(float, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g]));
-      else LCR_DISPATCH_RET(double, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g]));
+      int* mg = sim->mig ? sim->mig + (size_t)g * nsub * (1 + LCR_MIGCAP) : nullptr;
+      cudaStream_t* ms = sim->mig ? &sim->mstream[(size_t)g * nsub] : nullptr;
+      cudaEvent_t *mf = sim->mig ? &sim->mev_fork[(size_t)g * nsub] : nullptr, *mj = sim->mig ? &sim->mev_join[(size_t)g * nsub] : nullptr;
+      if (f32) LCR_DISPATCH_RET(float, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g], mg, ms, mf, mj));
+      else LCR_DISPATCH_RET(double, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g], mg, ms, mf, mj));
       sim->launches += nl;
       CUDA_OK(cudaEventRecord(sim->ev_done[g], sim->gstream[g]));
       CUDA_OK(cudaStreamWaitEvent(st, sim->ev_done[g], 0));
+      if (sim->mig)  // the BIG passes over the envs that migrated out of this chain
+        for (int k = 0; k < sim->cfg.n_substeps; k++) CUDA_OK(cudaStreamWaitEvent(st, mj[k], 0));
     }
   } else if (sim->cfg.exec_mode == 2) {
     int W = 0;
@@ -435,6 +446,16 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
     // work-aware seats (LCR_PH_SORT=0: identity): the envs with the most constraint rows in their previous step are launched
     // first in every phase kernel, so that the long Newton solves / MPR jobs do not end up in the tail of the launch
     if (env_int("LCR_PH_SORT", 1) != 0) LCR_CREATE_OK(cudaMalloc(&s->perm, sizeof(int) * (2 * (size_t)n_envs + 16)));
+    if (env_int("LCR_PH_MIGRATE", 1) != 0) {
+      const int nb = s->ngroups * std::max(1, cfg->n_substeps);
+      LCR_CREATE_OK(cudaMalloc(&s->mig, sizeof(int) * (size_t)nb * (1 + LCR_MIGCAP)));
+      s->mstream.assign(nb, nullptr); s->mev_fork.assign(nb, nullptr); s->mev_join.assign(nb, nullptr);
+      for (int k = 0; k < nb; k++) {
+        LCR_CREATE_OK(cudaStreamCreateWithFlags(&s->mstream[k], cudaStreamNonBlocking));
+        LCR_CREATE_OK(cudaEventCreateWithFlags(&s->mev_fork[k], cudaEventDisableTiming));
+        LCR_CREATE_OK(cudaEventCreateWithFlags(&s->mev_join[k], cudaEventDisableTiming));
+      }
+    }
     s->ph_striped = env_int("LCR_PH_STRIPED", 1);  // 1: ranks dealt out to the groups like cards; 0: group 0 holds the heaviest envs
     s->use_graph = env_int("LCR_GRAPH", 1);
     if (s->use_graph) {
@@ -467,6 +488,10 @@ int lcr_destroy(LcrSim* sim) {
     if (sim->ev_done[k]) cudaEventDestroy(sim->ev_done[k]);
   }
   if (sim->ev_begin) cudaEventDestroy(sim->ev_begin);
+  for (cudaStream_t x : sim->mstream) if (x) cudaStreamDestroy(x);
+  for (cudaEvent_t x : sim->mev_fork) if (x) cudaEventDestroy(x);
+  for (cudaEvent_t x : sim->mev_join) if (x) cudaEventDestroy(x);
+  cudaFree(sim->mig);
   if (sim->gexec) cudaGraphExecDestroy(sim->gexec);
   if (sim->cstream) cudaStreamDestroy(sim->cstream);
   cudaFree(sim->act_buf);

@@ -26,6 +26,9 @@
 // Bit 4 of NC (LCR_NC_BIG) selects the BIG workspace caps (LCR_MAXCON_BIG / LCR_MAXEFC_BIG, include/lcr_model.h): the
 // same device functions instantiated over a larger workspace, used by the slow path that takes over the envs whose
 // contact list or constraint rows outgrow the fast caps.
+// phased chain: envs whose constraint rows outgrow the fast workspace in substep k of chain g are appended to the migration list (g, k)
+// (1 + LCR_MIGCAP ints: count, then env | k << 24) and resume over the big workspace at once; beyond the cap they take the redo pass
+#define LCR_MIGCAP 64
 #define LCR_NC_LOOP 5
 #define LCR_NC_BIG 16
 template <int NC> struct Scene {
@@ -204,8 +207,9 @@ struct LaunchNC {
   static int lockstep_warps(int warps);
   static void step_lockstep(const DevModel<T>* dm, const T* verts, DevState<T> s, StepIO io, Redo redo, int grid, int warps, int epc, int flags,
                             const int* perm, long long* prof, cudaStream_t st);
+  static void step_big_resume(const DevModel<T>* dm, const T* verts, DevState<T> s, const void* gws, StepIO io, const int* mig, cudaStream_t st);
   static int step_phased(int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, StepIO io, Redo redo, int env0, int cnt,
-                         const int* perm, cudaStream_t st);
+                         const int* perm, cudaStream_t st, int* mig, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join);
   static int flow_warps();
   static int flow_bigslots();
   static int flow_smem();

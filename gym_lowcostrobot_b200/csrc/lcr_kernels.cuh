@@ -1476,6 +1476,7 @@ __global__ void __launch_bounds__(32) k_ik(const DevModel<T>* __restrict__ dm, c
 #define LCR_LS_BAR_SOL 4      // barrier before the solver
 #define LCR_LS_SYNC_NEWTON 8  // barriers between Newton iterations
 #define LCR_LS_JOB_POOL 16    // CTA-wide narrowphase job pool
+#define LCR_LS_RESUME 32      // BIG pass over migrated envs: seats hold env | substep << 24, the env resumes from its parked substep-start state
 
 template <typename T, int NC>
 DI void cta_jobs(Ws<T, NC>* wsa, int W, const DevModel<T>& m, const T* __restrict__ verts, int* next) {
@@ -1555,7 +1556,7 @@ __global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__
 template <typename T, int NC, bool PROF>
 __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s, StepIO io, Redo redo,
                                                     int flags, const int* __restrict__ perm, int epc, long long* __restrict__ prof,
-                                                    const int* __restrict__ count) {
+                                                    const int* __restrict__ count, const void* __restrict__ parked = nullptr) {
   // blockDim.x / 32 warps, the first `epc` of them own an env (seat blockIdx.x * epc + warp), the others only help
   // with narrowphase jobs; shared memory holds epc workspaces
   Ws<T, NC>* wsa = reinterpret_cast<Ws<T, NC>*>(lcr_smem);
@@ -1563,7 +1564,9 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
   const int W = epc, warp = threadIdx.x >> 5, slot = blockIdx.x * epc + warp;
   const bool owner = warp < epc;
   // (count, optional: the seats are a device-side list of that many envs -- the BIG pass; seats beyond it are empty)
-  const int env = owner && !(count != nullptr && slot >= *count) ? (perm != nullptr ? perm[slot] : slot) : -1;  // -1 = empty seat
+  int env = owner && !(count != nullptr && slot >= *count) ? (perm != nullptr ? perm[slot] : slot) : -1;  // -1 = empty seat
+  int k0 = 0;  // first substep to run (LCR_LS_RESUME: the substep whose constraint rows outgrew the fast workspace)
+  if ((flags & LCR_LS_RESUME) && env >= 0) { k0 = (env >> 24) & 127; env &= 0xffffff; }
   const bool valid = env >= 0 && env < s.n;
   if (!__syncthreads_or(valid)) return;
   Ws<T, NC>& w = wsa[owner ? warp : 0];
@@ -1575,14 +1578,35 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
   if (PROF) t0 = clock64();
   bool go = false;
   if (valid) {
-    load_state(w, s, env);
-    go = env_step_begin(w, m, verts, io, env);
+    if (flags & LCR_LS_RESUME) {
+      // migrated from the phased chain: the state block (state, ints, diag, rng) of the parked fast workspace is the start state of
+      // substep k0 and has the same layout in both workspaces; the separating-axis cache comes along (performance only)
+      typedef Ws<T, (NC & 15)> WsF;
+      typedef Ws<T, NC> WsN;
+      static_assert(offsetof(WsF, xpos) == offsetof(WsN, xpos), "state block layout");
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(reinterpret_cast<const WsF*>(parked) + env);
+      for (int i = LANE; i < (int)offsetof(WsF, xpos) / 16; i += 32) reinterpret_cast<uint4*>(&w)[i] = reinterpret_cast<const uint4*>(src)[i];
+      for (int i = LANE; i < WsF::SA_BYTES / 16; i += 32)
+        reinterpret_cast<uint4*>(w.sa_dir)[i] = reinterpret_cast<const uint4*>(src + offsetof(WsF, sa_dir))[i];
+      if (LANE == 0) { w.ovf = 0; w.ncand = 0; w.redo_forward = 0; w.substep = 0; w.jobs_left = 0; }
+      __syncwarp();
+      go = true;
+    } else {
+      load_state(w, s, env);
+      go = env_step_begin(w, m, verts, io, env);
+    }
   }
   if (!go && owner) { if (LANE == 0) w.ncand = 0; __syncwarp(); }
   const T tol = solver_tol<T>(m);
   LCR_TICK(0);
+  if (flags & LCR_LS_RESUME) {  // (one env per CTA: its helper warps start at the same substep)
+    __shared__ int k0_cta;
+    if (threadIdx.x == 0) k0_cta = k0;
+    __syncthreads();
+    k0 = k0_cta;
+  }
 #pragma unroll 1
-  for (int k = 0; k < m.n_substeps; k++) {
+  for (int k = k0; k < m.n_substeps; k++) {
     if (flags & LCR_LS_BAR_TOP) __syncthreads();
     LCR_TICK(1);  // wait at the top of the substep
     if (go) { check_state(w, m); kinematics(w, m); inertia_and_bias(w, m); }
@@ -1754,7 +1778,8 @@ __global__ void __launch_bounds__(32, 16) k_ph_job(const DevModel<T>* __restrict
 }
 
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0, const int* __restrict__ perm) {
+__global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0, const int* __restrict__ perm,
+                                                   int substep, int* __restrict__ mig) {
   typedef Ws<T, NC> WsT;
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = ph_env(perm, env0 + blockIdx.x);
@@ -1766,6 +1791,18 @@ __global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict
   __syncwarp();
   make_constraints(w, *dm, verts, true);
   __syncwarp();
+  if (w.ovf && mig) {
+    // the rows of this substep do not fit the fast workspace: the env migrates to the big one NOW (mig[0] = count, then env | substep << 24;
+    // one list per chain and substep, consumed by the BIG pass launched behind this kernel) and resumes there from the parked start
+    // state of this substep, beside the rest of the chain -- instead of being redone from the step start after the chain
+    int pos = 0;
+    if (LANE == 0) pos = atomicAdd(&mig[0], 1);
+    pos = __shfl_sync(FULLMASK, pos, 0);
+    if (pos < LCR_MIGCAP) {
+      if (LANE == 0) { mig[1 + pos] = env | (substep << 24); gws[env].skip = 1; }
+      return;
+    }
+  }
   // writes: diag (state block), contacts, row parameters, row -> contact maps, counts + cache, J
   store_ws_range(w, gws, env, 0, LCR_OFF(xpos));
   store_ws_range(w, gws, env, LCR_OFF(c_pos), LCR_OFF(e_jar));
@@ -1995,6 +2032,19 @@ void LaunchNC<T, S>::prepare() {
   cudaFuncSetAttribute(k_step_ls<T, S, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_flow<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_step<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  // phased chain: the SAME L1 / shared split for every kernel of the chain, including the narrowphase job kernel that uses no shared
+  // memory at all -- CTAs of kernels with different carve-outs cannot share an SM, so the job kernel of one env group could not start
+  // on an SM before the solver CTAs of the other group had drained from it (and vice versa): the chains of the groups did not overlap
+  if (!getenv("LCR_PH_CARVEOUT") || atoi(getenv("LCR_PH_CARVEOUT")) != 0) {
+    const int co = (int)cudaSharedmemCarveoutMaxShared;
+    cudaFuncSetAttribute(k_ph_begin<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_ph_dyn<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_ph_job<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_ph_col<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_ph_sol<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_ph_end<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    cudaFuncSetAttribute(k_step_ls<T, B, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+  }
 }
 template <typename T, int S> size_t LaunchNC<T, S>::ws_bytes() { return sizeof(Ws<T, S>); }
 
@@ -2013,6 +2063,14 @@ void LaunchNC<T, S>::step(const DevModel<T>* dm, const T* verts, DevState<T> s, 
 // list longer than the grid -- never seen -- is finished by the one-warp kernel from entry LCR_BIG_GRID on.
 #define LCR_BIG_WARPS 8
 #define LCR_BIG_GRID 2048
+// BIG pass over the envs that migrated out of the phased chain in one (group, substep): mig[0] = count, then env | substep << 24
+template <typename T, int S>
+void LaunchNC<T, S>::step_big_resume(const DevModel<T>* dm, const T* verts, DevState<T> s, const void* gws, StepIO io, const int* mig, cudaStream_t st) {
+  constexpr int B = S | LCR_NC_BIG;
+  k_step_ls<T, B, false><<<LCR_MIGCAP, 32 * LCR_BIG_WARPS, sizeof(Ws<T, B>), st>>>(dm, verts, s, io, Redo{nullptr, nullptr},
+                                                                                 LCR_LS_BAR_TOP | LCR_LS_BAR_CON | LCR_LS_JOB_POOL | LCR_LS_RESUME,
+                                                                                 mig + 1, 1, nullptr, mig, gws);
+}
 template <typename T, int S>
 void LaunchNC<T, S>::step_big(const DevModel<T>* dm, const T* verts, DevState<T> s, StepIO io, Redo list, cudaStream_t st) {
   constexpr int B = S | LCR_NC_BIG;
@@ -2036,22 +2094,33 @@ void LaunchNC<T, S>::step_lockstep(const DevModel<T>* dm, const T* verts, DevSta
   if (prof) k_step_ls<T, S, true><<<grid, 32 * warps, sizeof(Ws<T, S>) * epc, st>>>(dm, verts, s, io, redo, flags, perm, epc, prof, nullptr);
   else k_step_ls<T, S, false><<<grid, 32 * warps, sizeof(Ws<T, S>) * epc, st>>>(dm, verts, s, io, redo, flags, perm, epc, prof, nullptr);
 }
-// one chain of 2 + 4 * n_substeps launches over the env range [env0, env0 + cnt) on stream st
+// one chain of 2 + 4 * n_substeps launches over the env range [env0, env0 + cnt) on stream st.  mig (optional): [n_substeps][1 + LCR_MIGCAP]
+// migration lists of this chain (zeroed by the caller); behind the constraint-row kernel of substep k the BIG pass over list k is
+// launched on side[k] (forked from st by ev_fork[k]; the caller joins side[k] through ev_join[k])
 template <typename T, int S>
 int LaunchNC<T, S>::step_phased(int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws_, StepIO io, Redo redo, int env0, int cnt,
-                                const int* perm, cudaStream_t st) {
+                                const int* perm, cudaStream_t st, int* mig, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) {
   typedef Ws<T, S> W;
   W* gws = reinterpret_cast<W*>(gws_);
   const size_t sm = sizeof(W);
+  int nl = 2 + 4 * n_substeps;
   k_ph_begin<T, S><<<cnt, 32, sm, st>>>(dm, verts, s, gws, io, redo, env0, perm);
   for (int k = 0; k < n_substeps; k++) {
+    int* mk = mig ? mig + (size_t)k * (1 + LCR_MIGCAP) : nullptr;
     k_ph_dyn<T, S><<<cnt, 32, sm, st>>>(dm, verts, gws, k == 0, env0, perm);
     k_ph_job<T, S><<<cnt * LCR_NSLOT, 32, 0, st>>>(dm, verts, gws, env0, perm);
-    k_ph_col<T, S><<<cnt, 32, sm, st>>>(dm, verts, gws, env0, perm);
+    k_ph_col<T, S><<<cnt, 32, sm, st>>>(dm, verts, gws, env0, perm, k, mk);
+    if (mk) {
+      cudaEventRecord(ev_fork[k], st);
+      cudaStreamWaitEvent(side[k], ev_fork[k], 0);
+      step_big_resume(dm, verts, s, gws_, io, mk, side[k]);
+      cudaEventRecord(ev_join[k], side[k]);
+      nl++;
+    }
     k_ph_sol<T, S><<<cnt, 32, sm, st>>>(dm, gws, env0, perm);
   }
   k_ph_end<T, S><<<cnt, 32, sm, st>>>(dm, verts, s, gws, io, redo, env0, perm);
-  return 2 + 4 * n_substeps;
+  return nl;
 }
 // flow kernel: `warps` fast workspace slots per CTA (<= 16); BIG CTAs hold as many big workspaces as fit
 template <typename T, int S> int LaunchNC<T, S>::flow_warps() { return std::max(1, std::min(16, (int)((LCR_SMEM_MAX - 256) / sizeof(Ws<T, S>)))); }
