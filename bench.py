@@ -383,7 +383,7 @@ def main():
         sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         issue_frac = pf["inst_executed"] / (4 * 148 * sm_hz * r["kernel_ms"] * 1e-3) if pf.get("inst_executed") else None
         kernel = {"lockstep": "k_step_ls (+ k_sched, BIG redo pass)", "fused": "k_step (+ BIG redo pass)", "flow": "k_flow (+ k_sched_flow)",
-                  "phased": "k_ph_* chain (2 + 4 x 20 launches per env group, + BIG redo pass)"}[exec_mode]
+                  "phased": "k_ph_* chain (2 + 4 x 20 launches per env group, replayed as one CUDA graph; envs beyond the fast caps migrate to BIG passes beside it)"}[exec_mode]
         line = {
             "metric": METRIC, "value": r["value"], "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -1761,7 +1761,9 @@ __global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict
 }
 // narrowphase jobs: one warp per (env, slot); the workspace stays in HBM/L2 and is only read, results go to the
 // candidate result rows.  No shared memory, so the hull vertices stay L1 resident.
-#define LCR_NSLOT 4
+#ifndef LCR_NSLOT
+#define LCR_NSLOT 8
+#endif
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_job(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0, const int* __restrict__ perm) {
   const int env = ph_env(perm, env0 + blockIdx.x / LCR_NSLOT), slot = blockIdx.x % LCR_NSLOT;

@@ -107,13 +107,13 @@ class BatchedLowCostRobotEnv:
         """"auto" = the fastest mode measured on B200 for the batch size (profiles/README.md, stationary window): the lockstep
         kernel (one launch per step, CTAs of 16 envs aligned at the phase boundaries, CTA-wide narrowphase job pool) for small
         batches; the phased chain (one small kernel per mj_step phase over all envs, the whole step replayed as ONE CUDA graph)
-        from 2 048 envs (ReachCube mid-episode, ms per step phased / lockstep: 10.2 / 11.1 at 2 048 envs, 11.2 / 13.0 at 4 096;
-        profiles/r02b_sweep_groups.txt).  "flow" (one persistent kernel per step, phases run from
+        from 256 envs (ReachCube mid-episode, ms per step phased / lockstep: 5.4 / 5.9 at 256 envs, 6.5 / 8.7 at 512, 6.6 / 7.2 at
+        1 024, 8.8 / 13.0 at 4 096; profiles/r02b_sweep_groups.txt).  "flow" (one persistent kernel per step, phases run from
         device-side queues, csrc/lcr_flow.cuh) reaches 0.65 - 1.0 of them and is selectable.  All modes give bit-identical
         results (tests/test_gpu_parity.py)."""
         if exec_mode != "auto":
             return exec_mode
-        return "phased" if num_envs >= 2048 else "lockstep"
+        return "phased" if num_envs >= 256 else "lockstep"
 
     @property
     def obs_layout(self):

@@ -61,6 +61,14 @@ typedef struct OrcSim {
   Contact con[LCR_MAXCON_BIG];
   int ncon, nefc, niter, overflow, nan_resets, max_nefc;
   int peak_ncon, peak_nefc, peak_ncand, total_overflow; /* over the lifetime of the sim (test statistics) */
+  /* Named switches for the choices that could not be checked against MuJoCo's source ("MJ choices"): a
+   * mismatch against a MuJoCo fixture (tests/test_golden_mujoco.py) can be bisected by flipping them one at a time.
+   *   plane_hull_tilt           tilt of the 3 extra support directions of plane-vs-hull contacts (default 1e-3)
+   *   implicit_kv_when_clamped  1 (default): -kv stays in the implicitfast derivative when the servo force is clamped;
+   *                             0: a dof whose actuator force sits at actuatorfrcrange contributes only its damping
+   *   impratio                  > 0 overrides the compiled model's value (the <option> merge of the include chain) */
+  double sw_tilt, sw_impratio;
+  int sw_kv_clamped;
   int hist_nefc[32], hist_ncon[32]; /* env.steps by their max nefc / 16 and max ncon / 8 */
   int step_max_ncon;
   int sa_key[LCR_NSA], sa_next; /* separating-axis cache, see lcr_oracle_convex.inc */
@@ -441,7 +449,8 @@ static void collide_floor_mesh(OrcSim *s, int g) {
   mat_vec(c, s->xmat[b], m->mesh_center[g]);
   if (s->xpos[b][2] + c[2] - m->mesh_rbound[g] > 0) return; /* bounding sphere above the floor */
   const double n[3] = {0, 0, 1};
-  static const double dirs[4][3] = {{0, 0, -1}, {1e-3, 0, -1}, {-0.5e-3, 0.8660254037844386e-3, -1}, {-0.5e-3, -0.8660254037844386e-3, -1}};
+  const double tl = s->sw_tilt;
+  const double dirs[4][3] = {{0, 0, -1}, {tl, 0, -1}, {-0.5 * tl, 0.8660254037844386 * tl, -1}, {-0.5 * tl, -0.8660254037844386 * tl, -1}};
   int used[4], cnt = 0;
   for (int t = 0; t < 4; t++) {
     double p[3];
@@ -576,7 +585,7 @@ static void make_constraints(OrcSim *s) {
     Contact *c = &s->con[ci];
     int i = c->efc;
     if (c->dim > 1) {
-      s->efc_R[i + 1] = s->efc_R[i] / fmax(MINVAL, m->impratio);
+      s->efc_R[i + 1] = s->efc_R[i] / fmax(MINVAL, s->sw_impratio > 0 ? s->sw_impratio : m->impratio);
       for (int j = 1; j < c->dim; j++)
         s->efc_R[i + j] = s->efc_R[i + 1] * c->friction[0] * c->friction[0] / (c->friction[j - 1] * c->friction[j - 1]);
       c->mu = c->friction[0] * sqrt(s->efc_R[i + 1] / s->efc_R[i]);
@@ -828,7 +837,10 @@ static void substep_(OrcSim *s) {
     for (int d = 0; d < nv; d++) { t += s->M[i][d] * s->qacc[d]; A[i][d] = s->M[i][d]; }
     rhs[i] = t;
   }
-  for (int j = 0; j < LCR_NARM; j++) A[j][j] += h * (m->jnt_damping[j] + m->act_kv[j]);
+  for (int j = 0; j < LCR_NARM; j++) {
+    const int clamped = s->actuator[j] <= m->jnt_frcrange[j][0] || s->actuator[j] >= m->jnt_frcrange[j][1];
+    A[j][j] += h * (m->jnt_damping[j] + ((s->sw_kv_clamped || !clamped) ? m->act_kv[j] : 0.0));
+  }
   cholesky(nv, A, L);
   chol_solve(nv, L, rhs, a);
   for (int i = 0; i < nv; i++) s->qvel[i] += h * a[i];
@@ -1103,6 +1115,7 @@ void orc_step(OrcSim *s, const float *action, float *obs, float *reward, uint8_t
 OrcSim *orc_create(const LcrModel *m, const double *verts, const LcrEnvCfg *cfg) {
   OrcSim *s = (OrcSim *)calloc(1, sizeof(OrcSim));
   s->m = *m; s->cfg = *cfg;
+  s->sw_tilt = 1e-3; s->sw_kv_clamped = 1; s->sw_impratio = 0;
   s->verts = (double *)malloc(sizeof(double) * 3 * m->nvert);
   memcpy(s->verts, verts, sizeof(double) * 3 * m->nvert);
   reset_data(s);
@@ -1139,6 +1152,13 @@ void orc_set_state(OrcSim *s, const double *qpos, const double *qvel, const doub
   sa_clear(s); /* the separating-axis cache is not part of the checkpointed state */
 }
 /* lifetime peaks: contacts, constraint rows, convex candidates of one substep; total dropped contacts */
+int orc_set_switch(OrcSim *s, const char *name, double value) {
+  if (!strcmp(name, "plane_hull_tilt")) s->sw_tilt = value;
+  else if (!strcmp(name, "implicit_kv_when_clamped")) s->sw_kv_clamped = value != 0;
+  else if (!strcmp(name, "impratio")) s->sw_impratio = value;
+  else return -1;
+  return 0;
+}
 void orc_get_peaks(const OrcSim *s, int32_t *d) { d[0] = s->peak_ncon; d[1] = s->peak_nefc; d[2] = s->peak_ncand; d[3] = s->total_overflow; }
 void orc_get_hist(const OrcSim *s, int32_t *nefc16, int32_t *ncon8) { memcpy(nefc16, s->hist_nefc, sizeof s->hist_nefc); memcpy(ncon8, s->hist_ncon, sizeof s->hist_ncon); }
 void orc_get_diag(const OrcSim *s, int32_t *d) {

@@ -72,6 +72,14 @@ class Oracle:
             self.L.orc_destroy(self.h)
             self.h = None
 
+    # the choices that could not be checked against MuJoCo's source, as named switches (see OrcSim in lcr_oracle.c)
+    SWITCHES = {"plane_hull_tilt": 1e-3, "implicit_kv_when_clamped": 1, "impratio": 0}
+
+    def set_switch(self, name, value):
+        self.L.orc_set_switch.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        if self.L.orc_set_switch(self.h, name.encode(), float(value)) != 0:
+            raise KeyError(f"unknown switch {name!r}; available: {sorted(self.SWITCHES)}")
+
     def seed(self, seed):
         st = pcg64_state(seed)
         self.L.orc_seed(self.h, _p(st))

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-S = np.load(os.path.join(HERE, "golden", "independent_scene_push.npz"))
+S = np.load(os.path.join(HERE, "golden", "independent", "scene_push.npz"))
 NB, NG = len(S["body_parent"]), len(S["geom_body"])
 CORNERS = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float)
 LO = np.array([-3.14159, -1.5708, -1.48353, -1.91986, -2.96706, -1.74533])

@@ -1,6 +1,6 @@
 """A second, structurally different restatement of ONE mj_step of the PushCube scene in numpy, against the oracle.
 
-Everything the step needs is rebuilt from tests/golden/independent_scene_push.npz -- the raw MJCF numbers read by
+Everything the step needs is rebuilt from tests/golden/independent/scene_push.npz -- the raw MJCF numbers read by
 tools/make_independent_scene.py's own reader (masses, inertial frames, armature, damping, force ranges, kp / kv, per-geom
 friction / condim / priority / solref / solimp with the default classes resolved there) -- and from the published formulation
 of MuJoCo's computation pipeline, NOT from gym_lowcostrobot_b200/mjcf.py (the compiler the oracle and the kernels share) nor

@@ -1,6 +1,6 @@
 """A second, structurally different check of the collision pipeline: brute force in numpy / scipy against the oracle.
 
-Nothing here shares code or data with the oracle or the kernels: the scene comes from tests/golden/independent_scene_push.npz,
+Nothing here shares code or data with the oracle or the kernels: the scene comes from tests/golden/independent/scene_push.npz,
 written by tools/make_independent_scene.py with its own minimal MJCF / STL reader (hull vertices in the RAW mesh frames, not
 the recentred ones of gym_lowcostrobot_b200/mjcf.py), forward kinematics are restated below, and the contact SET is found by
 an exhaustive loop over every geom pair with exact tests -- no broadphase boxes, no separating-axis cache, no candidate /

@@ -7,7 +7,7 @@ pose; an independent reader has no reason to).  Usage (in the build container, w
 
     python tools/make_independent_scene.py [/root/reference/gym_lowcostrobot/assets/low_cost_robot_6dof]
 
-writes tests/golden/independent_scene_push.npz.
+writes tests/golden/independent/scene_push.npz.
 """
 import os
 import struct
@@ -120,7 +120,7 @@ def main(assets):
     opt = dict(scene.find("option").attrib)
     opt.update(arm.find("option").attrib)
     assert opt["cone"] == "elliptic" and opt["integrator"] == "implicitfast"
-    out = os.path.join(ROOT, "tests", "golden", "independent_scene_push.npz")
+    out = os.path.join(ROOT, "tests", "golden", "independent", "scene_push.npz")
     np.savez_compressed(
         out, body_parent=np.array([b["parent"] for b in bodies]), body_pos=np.stack([b["pos"] for b in bodies]),
         body_quat=np.stack([b["quat"] for b in bodies]), body_axis=np.stack([b["axis"] for b in bodies]),
