@@ -433,9 +433,9 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
   s->tbig = env_int("LCR_TBIG", cfg->exec_mode == 1 ? 97 : 100000);
   if (cfg->exec_mode == 1) {
     // measured on B200 in the stationary window (profiles/r02b_sweep_groups.txt): the chains of the groups overlap each other's launch
-    // tails; up to 8 192 envs 4 groups are best (PickPlace-ee 8 192: 16.6 / 16.0 / 15.7 ms per step with 1 / 2 / 4 groups, Stack 8 192:
-    // 20.4 / 19.6 / 18.8), at 16 384 envs 2 (PushCube: 21.6 / 20.5 / 21.0 / 21.8 with 1 / 2 / 4 / 8): more groups only shrink the launches
-    int g = env_int("LCR_GROUPS", n_envs <= 8192 ? 4 : 2);
+    // tails; ms per step with 1 / 2 / 4 groups: PushCube 16 384 15.9 / 15.2 / 14.9, StackTwoCubes 8 192 - / 13.5 / 12.6, PickPlace-ee
+    // 8 192 - / 16.4 / 15.9, ReachCube 4 096 - / 7.6 / 7.4; more groups only shrink the launches (8: +4 %, 16: +10 % at 16 384 envs)
+    int g = env_int("LCR_GROUPS", n_envs <= 16384 ? 4 : 2);
     g = std::max(1, std::min(16, std::min(g, n_envs)));
     for (int k = 0; k < g; k++) {
       LCR_CREATE_OK(cudaStreamCreateWithFlags(&s->gstream[k], cudaStreamNonBlocking));
