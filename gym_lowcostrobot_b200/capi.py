@@ -16,7 +16,7 @@ F32, F64 = 0, 1
 
 # every symbol declared in include/lcrsim.h
 SYMBOLS = (
-    "lcr_obs_dim", "lcr_action_dim", "lcr_create", "lcr_destroy", "lcr_seed", "lcr_reset", "lcr_step", "lcr_step_rec", "lcr_pack_outputs", "lcr_record_append",
+    "lcr_obs_dim", "lcr_action_dim", "lcr_create", "lcr_destroy", "lcr_seed", "lcr_reset", "lcr_step", "lcr_step_rec", "lcr_pack_outputs", "lcr_record_append", "lcr_pose_slots", "lcr_body_poses", "lcr_render",
     "lcr_get_state", "lcr_set_state", "lcr_substeps", "lcr_ik", "lcr_get_diag", "lcr_debug_contacts", "lcr_debug_phase_clocks",
     "lcr_debug_flow_stats", "lcr_flow_status", "lcr_n_envs", "lcr_kernel_launches", "lcr_last_error", "lcr_version", "lcr_sizeof_model",
     "lcr_sizeof_cfg",
@@ -45,6 +45,9 @@ def lib():
         L.lcr_step_rec.argtypes = [vp] * 9
         L.lcr_pack_outputs.argtypes = [vp] * 8
         L.lcr_record_append.argtypes = [vp, i, vp, i, vp, vp, i, i, vp, vp, vp, vp, vp, i, vp]
+        L.lcr_pose_slots.argtypes = [vp]
+        L.lcr_body_poses.argtypes = [vp, vp, vp]
+        L.lcr_render.argtypes = [vp, i, i, vp, i, vp, vp, i, i, i, vp, vp]
         L.lcr_get_state.argtypes = [vp] * 9
         L.lcr_set_state.argtypes = [vp] * 9
         L.lcr_substeps.argtypes = [vp, i, vp]

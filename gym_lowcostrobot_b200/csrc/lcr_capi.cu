@@ -648,6 +648,22 @@ int lcr_pack_outputs(LcrSim* sim, const float* d_obs, const float* d_reward, con
   return 0;
 }
 
+int lcr_pose_slots(const LcrSim* sim) {
+  if (!sim) return 0;
+  int n = 0;
+  LCR_DISPATCH_RET(float, sim->ncube, n, pose_slots());
+  return n;
+}
+
+int lcr_body_poses(LcrSim* sim, float* d_poses, void* stream) {
+  WITH_DEVICE(sim);
+  if (!d_poses) return fail("lcr_body_poses: null buffer");
+  LCR_RUN(sim, poses(sim->f.dm, sim->f.s, d_poses, (cudaStream_t)stream), poses(sim->d.dm, sim->d.s, d_poses, (cudaStream_t)stream));
+  sim->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int lcr_record_append(const float* d_obs, int obs_dim, const float* d_actions, int action_dim, const uint8_t* d_terminated, const uint8_t* d_truncated,
                       int n_envs, int horizon, float* d_traj, int32_t* d_len, float* d_pool, int32_t* d_pool_meta, int32_t* d_count, int pool_cap,
                       void* stream) {

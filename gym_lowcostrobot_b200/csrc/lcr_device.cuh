@@ -219,6 +219,8 @@ struct LaunchNC {
   static void substeps_big(const DevModel<T>* dm, const T* verts, DevState<T> s, int n, Redo list, cudaStream_t st);
   static void ik(const DevModel<T>* dm, const T* verts, DevState<T> s, const float* target, float* q_out, cudaStream_t st);
   static void debug_contacts(const DevModel<T>* dm, const T* verts, DevState<T> s, double* out, int32_t* ncon, cudaStream_t st);
+  static int pose_slots();
+  static void poses(const DevModel<T>* dm, DevState<T> s, float* out, cudaStream_t st);
 };
 template <typename T>
 struct Launch {

@@ -1882,6 +1882,23 @@ template <typename T> DI void sa_empty(DevState<T> s, int e) {
   for (int k = 0; k < 4; k++) next[k] = 0;
 }
 // row-major float64 <-> per-env records of T; rng = the PCG64 state of the env's reset stream (4 x u64)
+// world poses of the kinematic tree for the renderer (image observations, reach_cube_env.py:288-292): mj_kinematics on the current
+// state (nothing written back); out [n][NB][12] float32 = xpos[3] | xmat[9] of the 7 arm bodies, then the boxes (cubes, walls)
+template <typename T, int NC>
+__global__ void __launch_bounds__(32, 16) k_poses(const DevModel<T>* __restrict__ dm, DevState<T> s, float* __restrict__ out) {
+  Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  const int env = blockIdx.x;
+  load_state(w, s, env);
+  kinematics(w, *dm);
+  __syncwarp();
+  constexpr int NB = Ws<T, NC>::NB;
+  float* o = out + (size_t)env * NB * 12;
+  for (int i = LANE; i < NB * 12; i += 32) {
+    const int b = i / 12, k = i % 12;
+    o[i] = (float)(k < 3 ? w.xpos[b][k] : w.xmat[b][k - 3]);
+  }
+}
+
 template <typename T>
 __global__ void k_get_state(DevState<T> s, int nq, int nv, double* qpos, double* qvel, double* ctrl, double* warm, double* aux, int32_t* ints,
                             unsigned long long* rng) {
@@ -2019,6 +2036,7 @@ void LaunchNC<T, S>::prepare() {
   cudaFuncSetAttribute(k_substeps<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
   cudaFuncSetAttribute(k_substeps<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(k_ik<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
+  cudaFuncSetAttribute(k_poses<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
   cudaFuncSetAttribute(k_debug_contacts<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(k_ph_begin<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
   cudaFuncSetAttribute(k_ph_dyn<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast);
@@ -2151,6 +2169,11 @@ void LaunchNC<T, S>::substeps_big(const DevModel<T>* dm, const T* verts, DevStat
 template <typename T, int S>
 void LaunchNC<T, S>::ik(const DevModel<T>* dm, const T* verts, DevState<T> s, const float* target, float* q_out, cudaStream_t st) {
   k_ik<T, S><<<s.n, 32, sizeof(Ws<T, S>), st>>>(dm, verts, s, target, q_out);
+}
+template <typename T, int S> int LaunchNC<T, S>::pose_slots() { return Ws<T, S>::NB; }
+template <typename T, int S>
+void LaunchNC<T, S>::poses(const DevModel<T>* dm, DevState<T> s, float* out, cudaStream_t st) {
+  k_poses<T, S><<<s.n, 32, sizeof(Ws<T, S>), st>>>(dm, s, out);
 }
 template <typename T, int S>
 void LaunchNC<T, S>::debug_contacts(const DevModel<T>* dm, const T* verts, DevState<T> s, double* out, int32_t* ncon, cudaStream_t st) {

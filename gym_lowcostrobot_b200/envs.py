@@ -58,10 +58,10 @@ class BatchedLowCostRobotEnv:
                  target_xy_range=0.3, goal_z_range=0.1, n_substeps=20, render_mode=None, max_episode_steps=50,
                  autoreset=False, precision="float32", assets_path=None, collision_mask=model.COLLIDE_ALL,
                  env_offset=0, exec_mode="auto", seed=None):
-        if observation_mode != "state":
-            raise NotImplementedError("only observation_mode='state' is implemented (image rendering is out of scope)")
+        if observation_mode not in ("state", "image", "both"):
+            raise ValueError("observation_mode must be 'image', 'state' or 'both'")
         if render_mode is not None:
-            raise NotImplementedError("rendering is out of scope")
+            raise NotImplementedError("render_mode (interactive viewer / 640x640 rgb_array of camera_vizu) is out of scope")
         if not torch.cuda.is_available():
             raise capi.LcrError("CUDA device required: the simulator has no CPU fallback")
         self.num_envs = int(num_envs)
@@ -96,6 +96,19 @@ class BatchedLowCostRobotEnv:
         sub = {"arm_qpos": spaces.Box(-np.pi, np.pi, (6,)), "arm_qvel": spaces.Box(-10.0, 10.0, (6,))}
         for key, width in _OBS_LAYOUT[self.task][2:]:
             sub[key] = spaces.Box(-10.0, 10.0, (width,))
+        # observation keys by mode (reach_cube_env.py:281-295): the images replace the state-only keys (cube positions) in "image" mode
+        self._state_only = {"cube_pos", "cube_red_pos", "cube_blue_pos"}
+        self._renderer = None
+        if observation_mode in ("image", "both"):
+            from .render import HEIGHT, WIDTH, BatchRenderer
+
+            self._renderer = BatchRenderer(self)
+            keep = {k: v for k, v in sub.items() if k not in self._state_only}
+            keep["image_front"] = spaces.Box(0, 255, (HEIGHT, WIDTH, 3), np.uint8)
+            keep["image_top"] = spaces.Box(0, 255, (HEIGHT, WIDTH, 3), np.uint8)
+            if observation_mode == "both":
+                keep.update({k: v for k, v in sub.items() if k in self._state_only})
+            sub = keep
         self.single_observation_space = spaces.Dict(sub)
         self.action_space = spaces.batch_space(self.single_action_space, n)
         self.observation_space = spaces.batch_space(self.single_observation_space, n)
@@ -125,10 +138,15 @@ class BatchedLowCostRobotEnv:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _split(self, flat):
-        out, k = {}, 0
+        """observation dict of the mode, in the reference's key order: state keys, images, state-only keys"""
+        out, late, k = {}, {}, 0
         for key, width in _OBS_LAYOUT[self.task]:
-            out[key] = flat[:, k:k + width]
+            (late if key in self._state_only else out)[key] = flat[:, k:k + width]
             k += width
+        if self._renderer is not None:
+            out.update({key: img.clone() for key, img in self._renderer.render().items()})
+        if self.observation_mode != "image":
+            out.update(late)
         return out
 
     def seed(self, seed, mask=None):

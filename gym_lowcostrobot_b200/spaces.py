@@ -36,6 +36,11 @@ class Box:
 
 
 class Dict(dict):
+    @property
+    def spaces(self):
+        """the sub-spaces by key, like ``gymnasium.spaces.Dict.spaces``"""
+        return self
+
     def sample(self):
         return {k: v.sample() for k, v in self.items()}
 

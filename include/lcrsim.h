@@ -132,6 +132,24 @@ int lcr_record_append(const float* d_obs, int obs_dim, const float* d_actions, i
                       const uint8_t* d_truncated, int n_envs, int horizon, float* d_traj, int32_t* d_len, float* d_pool,
                       int32_t* d_pool_meta, int32_t* d_count, int pool_cap, void* stream);
 
+/* Image observations (reach_cube_env.py:109-112,288-292 and the same lines of the other envs: mujoco.Renderer +
+ * update_scene(camera="camera_front" | "camera_top") + render(), 240 x 320 x 3 uint8) in two calls:
+ *  lcr_body_poses  mj_kinematics on the current state of every env (nothing written back): d_poses [n][lcr_pose_slots()][12]
+ *                  float32 = xpos[3] | xmat[9] (row-major) of the 7 arm bodies, then the boxes (cubes, PushCubeLoop's rails);
+ *  lcr_render      stateless ray caster over convex geometry: d_geoms [n_geoms][LCR_RENDER_GEOM_WORDS] float32 = kind (0 hull,
+ *                  1 box), pose slot, first half-space, half-space count, bounding-sphere centre[3] (body frame), radius,
+ *                  box half sizes[3], rgb[3], 2 pad; d_planes [P][4] = half-spaces n . x + d <= 0 of the hulls in their body
+ *                  frame; h_cameras (HOST) [n_cams][13] = position[3], rotation[9] (row-major, columns = camera x / y / z axes;
+ *                  the camera looks along -z like MuJoCo's), fovy in degrees; d_images [n][n_cams][height][width][3] uint8.
+ * The floor plane (0.1 m checker), the headlight and the scene's point light are built in; see csrc/lcr_render.cu for what
+ * the images do and do not reproduce of MuJoCo's OpenGL renderer.  Returns 0 on success. */
+#define LCR_RENDER_GEOM_WORDS 16
+#define LCR_RENDER_MAXCAM 4
+int lcr_pose_slots(const LcrSim* sim);
+int lcr_body_poses(LcrSim* sim, float* d_poses, void* stream);
+int lcr_render(const float* d_poses, int n_envs, int n_slots, const float* d_geoms, int n_geoms, const float* d_planes,
+               const float* h_cameras, int n_cams, int height, int width, uint8_t* d_images, void* stream);
+
 /* Debug hook (lockstep mode): from the next lcr_step on, every env writes the SM clock cycles it spent in each phase
  * of the step to d_clocks [n][10] int64 = begin/end, wait top, dynamics+broadphase, wait, narrowphase jobs, wait,
  * constraint rows, wait, Newton solve, integrate (sums over the substeps).  NULL switches it off again. */

@@ -73,8 +73,8 @@ def test_env_api(env_id, keys, blocked, mode):
 
 
 def test_constructor_errors():
-    with pytest.raises(NotImplementedError):
-        glr.make("ReachCube-v0", num_envs=2, observation_mode="image")
+    with pytest.raises(ValueError):
+        glr.make("ReachCube-v0", num_envs=2, observation_mode="depth")
     with pytest.raises(NotImplementedError):
         glr.make("PushCubeLoop-v0", num_envs=2, render_mode="human")
     with pytest.raises(ValueError, match="Invalid action mode"):

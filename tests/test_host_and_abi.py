@@ -52,8 +52,8 @@ def test_create_fails_loudly_without_cuda():
         glr.make("PushCubeLoop-v0", num_envs=2)
     with pytest.raises(KeyError):
         glr.make("NoSuchTask-v0")
-    with pytest.raises(NotImplementedError):
-        glr.make("ReachCube-v0", observation_mode="image")
+    with pytest.raises(ValueError):
+        glr.make("ReachCube-v0", observation_mode="depth")
 
 
 def test_compiled_models_are_consistent():
