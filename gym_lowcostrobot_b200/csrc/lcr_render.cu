@@ -116,7 +116,18 @@ __global__ void __launch_bounds__(kTile* kTile) k_render(RenderArgs A) {
         if (tn > t0) { t0 = tn; n0[0] = n0[1] = n0[2] = 0; n0[k] = dl[k] > 0 ? -1.0f : 1.0f; }
         t1 = fminf(t1, tf);
       }
-    } else {  // hull: half-space list
+    } else {  // hull: half-space list, behind a slab test against the hull's bounding box in the body frame (rejection only)
+      {
+        float ta = 0.0f, tb = tbest;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const float h = g[8 + k] + 1e-5f, c = ol[k] - g[4 + k];
+          if (fabsf(dl[k]) < 1e-12f) { if (fabsf(c) > h) tb = -1.0f; continue; }
+          const float inv = 1.0f / dl[k], u = (-h - c) * inv, v = (h - c) * inv;
+          ta = fmaxf(ta, fminf(u, v)); tb = fminf(tb, fmaxf(u, v));
+        }
+        if (ta > tb) continue;
+      }
       const int p0 = (int)g[2], pn = (int)g[3];
       for (int p = p0; p < p0 + pn && t0 <= t1; p++) {
         const float4 pl = __ldg(reinterpret_cast<const float4*>(A.planes) + p);

@@ -58,8 +58,9 @@ def build_scene(compiled, task):
         v = m["verts"][int(m["mesh_vertadr"][g]): int(m["mesh_vertadr"][g]) + int(m["mesh_vertnum"][g])]
         pl = hull_planes(v)
         rgb = [0.1] * 3 if name.endswith("_motor") else [0.8] * 3
+        # (mesh_center / mesh_half: the hull's bounding box in the body frame, mesh_rbound its bounding sphere about the same centre)
         geoms.append([0, int(m["mesh_body"][g]), sum(len(p) for p in planes), len(pl), *m["mesh_center"][g], float(m["mesh_rbound"][g]),
-                      0, 0, 0, *rgb, 0, 0])
+                      *m["mesh_half"][g], *rgb, 0, 0])
         planes.append(pl)
     ncube = int(m["ncube"])
     colors = CUBE_RGB.get(task, ([0.5, 0, 0],))

@@ -138,7 +138,7 @@ int lcr_record_append(const float* d_obs, int obs_dim, const float* d_actions, i
  *                  float32 = xpos[3] | xmat[9] (row-major) of the 7 arm bodies, then the boxes (cubes, PushCubeLoop's rails);
  *  lcr_render      stateless ray caster over convex geometry: d_geoms [n_geoms][LCR_RENDER_GEOM_WORDS] float32 = kind (0 hull,
  *                  1 box), pose slot, first half-space, half-space count, bounding-sphere centre[3] (body frame), radius,
- *                  box half sizes[3], rgb[3], 2 pad; d_planes [P][4] = half-spaces n . x + d <= 0 of the hulls in their body
+ *                  half sizes[3] (the box itself, or the hull's bounding box about the same centre), rgb[3], 2 pad; d_planes [P][4] = half-spaces n . x + d <= 0 of the hulls in their body
  *                  frame; h_cameras (HOST) [n_cams][13] = position[3], rotation[9] (row-major, columns = camera x / y / z axes;
  *                  the camera looks along -z like MuJoCo's), fovy in degrees; d_images [n][n_cams][height][width][3] uint8.
  * The floor plane (0.1 m checker), the headlight and the scene's point light are built in; see csrc/lcr_render.cu for what

@@ -22,4 +22,5 @@ timeout 600 ncu --profile-from-start off --set full --clock-control none --impor
 done
 unset LCR_GRAPH
 timeout 200 python tools/ph_timeline.py push joint 16384 ${O}_timeline_push16384.json 2 > ${O}_timeline.log 2>&1
+timeout 120 python tools/img_time.py > ${O}_img_time.log 2>&1
 ls -la gpurun_out | tail -20
