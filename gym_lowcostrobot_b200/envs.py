@@ -57,7 +57,7 @@ class BatchedLowCostRobotEnv:
                  block_gripper=None, distance_threshold=0.05, height_threshold=0.1, cube_xy_range=0.3,
                  target_xy_range=0.3, goal_z_range=0.1, n_substeps=20, render_mode=None, max_episode_steps=50,
                  autoreset=False, precision="float32", assets_path=None, collision_mask=model.COLLIDE_ALL,
-                 env_offset=0, exec_mode="auto", seed=None):
+                 env_offset=0, exec_mode="auto", seed=None, report_failures=False):
         if observation_mode not in ("state", "image", "both"):
             raise ValueError("observation_mode must be 'image', 'state' or 'both'")
         if render_mode is not None:
@@ -65,6 +65,7 @@ class BatchedLowCostRobotEnv:
         if not torch.cuda.is_available():
             raise capi.LcrError("CUDA device required: the simulator has no CPU fallback")
         self.num_envs = int(num_envs)
+        self.report_failures = bool(report_failures)
         self.device = torch.device(device)
         self.observation_mode, self.action_mode, self.reward_type = observation_mode, action_mode, reward_type
         self.cfg = config.make_cfg(self.task, action_mode=action_mode, reward_type=reward_type, block_gripper=block_gripper,
@@ -209,7 +210,8 @@ class BatchedLowCostRobotEnv:
             info.update(self.failure_info())
         return self._split(obs.clone()), reward.clone(), te.bool(), tr.bool(), info
 
-    report_failures = False  # True: every step() adds failure_info() to info (one more tiny launch per step)
+    report_failures = False  # constructor kwarg; True: every step() adds failure_info() to info (one more tiny launch per step;
+                             # off by default so that info carries exactly the reference's keys)
     nvtx = False             # True: NVTX range around every step's enqueue (and around the all-gather in dist.ShardedEnv)
 
     def failure_info(self):
@@ -358,6 +360,8 @@ class PushCubeLoopEnv(BatchedLowCostRobotEnv):
     def step(self, actions):
         obs, reward, te, tr, su = self.step_flat(actions)
         info = {"timestamp": self._timestamp(), "success": su.to(torch.int64)}  # push_cube_loop_env.py:329
+        if self.report_failures:
+            info.update(self.failure_info())
         return self._split(obs.clone()), reward.clone(), te.bool(), tr.bool(), info
 
 

@@ -72,6 +72,25 @@ def test_env_api(env_id, keys, blocked, mode):
     env.close()
 
 
+def test_failure_reporting_in_info():
+    """per-env blow-up flag and counters in info, on request (the default info carries exactly the reference's keys)"""
+    for env_id in ("PushCube-v0", "PushCubeLoop-v0"):
+        env = glr.make(env_id, num_envs=16, report_failures=True)
+        env.reset(seed=0)
+        obs, reward, terminated, truncated, info = env.step(torch.zeros(16, env.action_dim, device="cuda"))
+        assert {"nan_reset", "nan_resets", "contact_overflow"} <= set(info)
+        assert info["nan_reset"].dtype == torch.bool and not info["nan_reset"].any() and int(info["contact_overflow"].sum()) == 0
+        # a poisoned state is detected, reset like mj_checkPos does, flagged once and counted
+        q = env.get_state()["qpos"]
+        q[3, 0] = float("nan")
+        env.set_state(qpos=q)
+        _, _, _, _, info = env.step(torch.zeros(16, env.action_dim, device="cuda"))
+        assert info["nan_reset"].tolist() == [i == 3 for i in range(16)] and int(info["nan_resets"][3]) >= 1
+        _, _, _, _, info = env.step(torch.zeros(16, env.action_dim, device="cuda"))
+        assert not info["nan_reset"].any() and int(info["nan_resets"][3]) >= 1
+        env.close()
+
+
 def test_constructor_errors():
     with pytest.raises(ValueError):
         glr.make("ReachCube-v0", num_envs=2, observation_mode="depth")
