@@ -248,6 +248,8 @@ struct LcrSim {
   int use_graph = 0, ph_striped = 1, graph_nodes = 0;
   // phased mode: migration lists [group][substep][1 + LCR_MIGCAP] and the side stream / fork / join events of every (group, substep)
   int* mig = nullptr;
+  int* jobq = nullptr;  // phased mode: narrowphase job queues, one per group (jobq_stride ints each)
+  int jobq_stride = 0;
   std::vector<cudaStream_t> mstream;
   std::vector<cudaEvent_t> mev_fork, mev_join;
   cudaStream_t cstream = nullptr;
@@ -354,8 +356,10 @@ int enqueue_step(LcrSim* sim, const StepIO& io, cudaStream_t st) {
       int* mg = sim->mig ? sim->mig + (size_t)g * nsub * (1 + LCR_MIGCAP) : nullptr;
       cudaStream_t* ms = sim->mig ? &sim->mstream[(size_t)g * nsub] : nullptr;
       cudaEvent_t *mf = sim->mig ? &sim->mev_fork[(size_t)g * nsub] : nullptr, *mj = sim->mig ? &sim->mev_join[(size_t)g * nsub] : nullptr;
-      if (f32) LCR_DISPATCH_RET(float, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g], mg, ms, mf, mj));
-      else LCR_DISPATCH_RET(double, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g], mg, ms, mf, mj));
+      int* jq = sim->jobq ? sim->jobq + (size_t)g * sim->jobq_stride : nullptr;
+      if (jq) CUDA_OK(cudaMemsetAsync(jq, 0, sizeof(int) * LCR_JOBQ_HEADER, sim->gstream[g]));  // (k_ph_col clears the counters after every substep; this covers a step that was cut short)
+      if (f32) LCR_DISPATCH_RET(float, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g], mg, ms, mf, mj, jq));
+      else LCR_DISPATCH_RET(double, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g], mg, ms, mf, mj, jq));
       sim->launches += nl;
       CUDA_OK(cudaEventRecord(sim->ev_done[g], sim->gstream[g]));
       CUDA_OK(cudaStreamWaitEvent(st, sim->ev_done[g], 0));
@@ -456,6 +460,18 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
         LCR_CREATE_OK(cudaEventCreateWithFlags(&s->mev_join[k], cudaEventDisableTiming));
       }
     }
+    // (experiment knob, off: one narrowphase job queue per chain, drained by a fixed grid of warps through an atomic ticket, instead of 8
+    // warps per env.  Measured on B200: PushCube 16 384 15.04 -> 14.93 ms per step, ReachCube 4 096 7.34 -> 7.85, StackTwoCubes 8 192
+    // 12.6 -> 13.0 -- the jobs of one env scatter over the SMs and lose the locality of its workspace and hull vertices)
+    if (env_int("LCR_PH_JOBQ", 0) != 0) {
+      const int per = (n_envs + s->ngroups - 1) / s->ngroups;
+      int words = 0;
+      if (precision == LCR_F32) LCR_DISPATCH_RET(float, s->ncube, words, jobq_words(per));
+      else LCR_DISPATCH_RET(double, s->ncube, words, jobq_words(per));
+      s->jobq_stride = (words + 31) & ~31;
+      LCR_CREATE_OK(cudaMalloc(&s->jobq, sizeof(int) * (size_t)s->jobq_stride * s->ngroups));
+      LCR_CREATE_OK(cudaMemset(s->jobq, 0, sizeof(int) * (size_t)s->jobq_stride * s->ngroups));
+    }
     s->ph_striped = env_int("LCR_PH_STRIPED", 1);  // 1: ranks dealt out to the groups like cards; 0: group 0 holds the heaviest envs
     s->use_graph = env_int("LCR_GRAPH", 1);
     if (s->use_graph) {
@@ -492,6 +508,7 @@ int lcr_destroy(LcrSim* sim) {
   for (cudaEvent_t x : sim->mev_fork) if (x) cudaEventDestroy(x);
   for (cudaEvent_t x : sim->mev_join) if (x) cudaEventDestroy(x);
   cudaFree(sim->mig);
+  cudaFree(sim->jobq);
   if (sim->gexec) cudaGraphExecDestroy(sim->gexec);
   if (sim->cstream) cudaStreamDestroy(sim->cstream);
   cudaFree(sim->act_buf);

@@ -29,6 +29,11 @@
 // phased chain: envs whose constraint rows outgrow the fast workspace in substep k of chain g are appended to the migration list (g, k)
 // (1 + LCR_MIGCAP ints: count, then env | k << 24) and resume over the big workspace at once; beyond the cap they take the redo pass
 #define LCR_MIGCAP 64
+// phased chain: narrowphase job queue of one chain (ints): entry count, next ticket (own cache lines), then the entries env << 6 | candidate
+#define LCR_JOBQ_COUNT 0
+#define LCR_JOBQ_NEXT 32
+#define LCR_JOBQ_ITEMS 64
+#define LCR_JOBQ_HEADER LCR_JOBQ_ITEMS
 #define LCR_NC_LOOP 5
 #define LCR_NC_BIG 16
 template <int NC> struct Scene {
@@ -209,7 +214,8 @@ struct LaunchNC {
                             const int* perm, long long* prof, cudaStream_t st);
   static void step_big_resume(const DevModel<T>* dm, const T* verts, DevState<T> s, const void* gws, StepIO io, const int* mig, cudaStream_t st);
   static int step_phased(int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, StepIO io, Redo redo, int env0, int cnt,
-                         const int* perm, cudaStream_t st, int* mig, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join);
+                         const int* perm, cudaStream_t st, int* mig, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join, int* jobq);
+  static int jobq_words(int cnt);
   static int flow_warps();
   static int flow_bigslots();
   static int flow_smem();

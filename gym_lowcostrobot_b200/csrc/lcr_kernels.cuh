@@ -1733,7 +1733,8 @@ __global__ void __launch_bounds__(32, 16) k_ph_begin(const DevModel<T>* __restri
 
 // [integrate the previous substep] -> checks -> kinematics -> inertia / bias -> smooth forces
 template <typename T, int NC>
-__global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int first, int env0, const int* __restrict__ perm) {
+__global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int first, int env0, const int* __restrict__ perm,
+                                                   int* __restrict__ jobq) {
   typedef Ws<T, NC> WsT;
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
   const int env = ph_env(perm, env0 + blockIdx.x);
@@ -1755,6 +1756,15 @@ __global__ void __launch_bounds__(32, 16) k_ph_dyn(const DevModel<T>* __restrict
   smooth_forces(w, m);
   collect_candidates(w, m);
   __syncwarp();
+  if (jobq) {  // one queue entry per convex candidate of this env: env << 6 | candidate (LCR_JOBQ_* layout, see k_ph_jobq)
+    const int nj = w.ncand < WsT::MAXCAND ? w.ncand : WsT::MAXCAND;
+    if (nj > 0) {
+      int base = 0;
+      if (LANE == 0) base = atomicAdd(&jobq[LCR_JOBQ_COUNT], nj);
+      base = __shfl_sync(FULLMASK, base, 0);
+      for (int k = LANE; k < nj; k += 32) jobq[LCR_JOBQ_ITEMS + base + k] = (env << 6) | k;
+    }
+  }
   // writes: state, kinematics, dynamics vectors, candidate block (+ the cache if mj_forward was re-run)
   store_ws_range(w, gws, env, 0, LCR_OFF(H));
   store_ws_range(w, gws, env, redone ? LCR_OFF(ncon) : LCR_OFF(cand_key), LCR_OFF(J));
@@ -1779,11 +1789,32 @@ __global__ void __launch_bounds__(32, 16) k_ph_job(const DevModel<T>* __restrict
   }
 }
 
+// The same jobs from ONE queue per chain (filled by k_ph_dyn, heaviest envs first): a fixed grid of warps pulls entries with an
+// atomic ticket until the queue is empty, so no warp is launched for an env without candidates and the jobs of a folded arm are
+// spread over as many warps as it has penetrating pairs.  jobq: [LCR_JOBQ_COUNT] entries, [LCR_JOBQ_NEXT] next ticket, items from
+// LCR_JOBQ_ITEMS; both counters are cleared by k_ph_col (which runs after this kernel and before the next k_ph_dyn).
+template <typename T, int NC>
+__global__ void __launch_bounds__(32, 16) k_ph_jobq(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int* __restrict__ jobq) {
+  const int total = *reinterpret_cast<volatile int*>(&jobq[LCR_JOBQ_COUNT]);
+  for (;;) {
+    int j = 0;
+    if (LANE == 0) j = atomicAdd(&jobq[LCR_JOBQ_NEXT], 1);
+    j = __shfl_sync(FULLMASK, j, 0);
+    if (j >= total) return;
+    const int item = jobq[LCR_JOBQ_ITEMS + j], env = item >> 6, k = item & 63;
+    Ws<T, NC>& w = gws[env];
+    T r[8];
+    narrowphase_job<T, NC, false>(w, *dm, verts, w.cand_key[k], r);
+    if (LANE < 8) cand_res(w)[k][LANE] = r[LANE];
+  }
+}
+
 template <typename T, int NC>
 __global__ void __launch_bounds__(32, 16) k_ph_col(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, Ws<T, NC>* __restrict__ gws, int env0, const int* __restrict__ perm,
-                                                   int substep, int* __restrict__ mig) {
+                                                   int substep, int* __restrict__ mig, int* __restrict__ jobq) {
   typedef Ws<T, NC> WsT;
   Ws<T, NC>& w = *reinterpret_cast<Ws<T, NC>*>(lcr_smem);
+  if (jobq && blockIdx.x == 0 && LANE == 0) { jobq[LCR_JOBQ_COUNT] = 0; jobq[LCR_JOBQ_NEXT] = 0; }  // (the job kernel of this substep is done)
   const int env = ph_env(perm, env0 + blockIdx.x);
   if (env < 0 || gws[env].skip) return;
   // reads: state, kinematics, the job results (they alias e_w / e_g / e_p), counts + cache, candidate block
@@ -2119,7 +2150,7 @@ void LaunchNC<T, S>::step_lockstep(const DevModel<T>* dm, const T* verts, DevSta
 // launched on side[k] (forked from st by ev_fork[k]; the caller joins side[k] through ev_join[k])
 template <typename T, int S>
 int LaunchNC<T, S>::step_phased(int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws_, StepIO io, Redo redo, int env0, int cnt,
-                                const int* perm, cudaStream_t st, int* mig, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) {
+                                const int* perm, cudaStream_t st, int* mig, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join, int* jobq) {
   typedef Ws<T, S> W;
   W* gws = reinterpret_cast<W*>(gws_);
   const size_t sm = sizeof(W);
@@ -2127,9 +2158,10 @@ int LaunchNC<T, S>::step_phased(int n_substeps, const DevModel<T>* dm, const T* 
   k_ph_begin<T, S><<<cnt, 32, sm, st>>>(dm, verts, s, gws, io, redo, env0, perm);
   for (int k = 0; k < n_substeps; k++) {
     int* mk = mig ? mig + (size_t)k * (1 + LCR_MIGCAP) : nullptr;
-    k_ph_dyn<T, S><<<cnt, 32, sm, st>>>(dm, verts, gws, k == 0, env0, perm);
-    k_ph_job<T, S><<<cnt * LCR_NSLOT, 32, 0, st>>>(dm, verts, gws, env0, perm);
-    k_ph_col<T, S><<<cnt, 32, sm, st>>>(dm, verts, gws, env0, perm, k, mk);
+    k_ph_dyn<T, S><<<cnt, 32, sm, st>>>(dm, verts, gws, k == 0, env0, perm, jobq);
+    if (jobq) k_ph_jobq<T, S><<<std::min(cnt * 2, 148 * 16), 32, 0, st>>>(dm, verts, gws, jobq);
+    else k_ph_job<T, S><<<cnt * LCR_NSLOT, 32, 0, st>>>(dm, verts, gws, env0, perm);
+    k_ph_col<T, S><<<cnt, 32, sm, st>>>(dm, verts, gws, env0, perm, k, mk, jobq);
     if (mk) {
       cudaEventRecord(ev_fork[k], st);
       cudaStreamWaitEvent(side[k], ev_fork[k], 0);
@@ -2142,6 +2174,7 @@ int LaunchNC<T, S>::step_phased(int n_substeps, const DevModel<T>* dm, const T* 
   k_ph_end<T, S><<<cnt, 32, sm, st>>>(dm, verts, s, gws, io, redo, env0, perm);
   return nl;
 }
+template <typename T, int S> int LaunchNC<T, S>::jobq_words(int cnt) { return LCR_JOBQ_ITEMS + cnt * Ws<T, S>::MAXCAND; }
 // flow kernel: `warps` fast workspace slots per CTA (<= 16); BIG CTAs hold as many big workspaces as fit
 template <typename T, int S> int LaunchNC<T, S>::flow_warps() { return std::max(1, std::min(16, (int)((LCR_SMEM_MAX - 256) / sizeof(Ws<T, S>)))); }
 template <typename T, int S> int LaunchNC<T, S>::flow_bigslots() { return std::max(1, std::min(16, (int)((LCR_SMEM_MAX - 256) / sizeof(Ws<T, S | LCR_NC_BIG>)))); }
