@@ -2155,6 +2155,9 @@ int LaunchNC<T, S>::step_phased(int n_substeps, const DevModel<T>* dm, const T* 
   W* gws = reinterpret_cast<W*>(gws_);
   const size_t sm = sizeof(W);
   int nl = 2 + 4 * n_substeps;
+  // (tried and removed: the Newton solve of substep k fused with the dynamics stage of substep k + 1 -- one launch and one staging
+  //  round trip less per substep, bit-identical -- PushCube 16 384 15.1 -> 20.3 ms per step, StackTwoCubes 8 192 12.8 -> 15.6: like the
+  //  col + sol merge of round 1, a larger heterogeneous kernel loses more in the instruction cache than the launch saves)
   k_ph_begin<T, S><<<cnt, 32, sm, st>>>(dm, verts, s, gws, io, redo, env0, perm);
   for (int k = 0; k < n_substeps; k++) {
     int* mk = mig ? mig + (size_t)k * (1 + LCR_MIGCAP) : nullptr;
