@@ -50,3 +50,20 @@ def world_geoms(qpos):
     return verts, cube
 
 
+
+
+def load_scene(task):
+    """the fixture of another scene file (same arm; `ncube` free cubes, then static wall boxes)"""
+    return np.load(os.path.join(HERE, "golden", "independent", f"scene_{task}.npz"))
+
+
+def world_boxes(Sc, qpos):
+    """world-space corner sets of the boxes of a scene: the free cubes (pose from qpos), then the static walls"""
+    out = []
+    ncube = int(Sc["ncube"])
+    for c in range(ncube):
+        p = qpos[6 + 7 * c: 13 + 7 * c]
+        out.append(p[:3] + (CORNERS * Sc["box_half"][c]) @ quat_mat(p[3:7]).T)
+    for w, pos in enumerate(Sc["wall_pos"]):
+        out.append(pos + CORNERS * Sc["box_half"][ncube + w])
+    return out

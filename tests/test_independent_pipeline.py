@@ -19,12 +19,13 @@ have a depth between the exact minimum and the hulls' overlap along its normal, 
 Reference: this is what `mujoco.mj_step` -> mj_collision does for the scene (reach_cube_env.py:276-277); SURVEY Appendix A.3.
 """
 import numpy as np
+import pytest
 from scipy.optimize import linprog
 from scipy.spatial import ConvexHull
 
 from oracle.oracle import Oracle
 
-from independent_scene import CORNERS, HI, LO, NB, NG, S, world_geoms
+from independent_scene import CORNERS, HI, LO, NB, NG, S, load_scene, world_boxes, world_geoms
 
 
 def may_collide(b1, b2):
@@ -52,34 +53,43 @@ def separation(A, B):
     return hull.equations[:, 3].max()  # all offsets <= 0 when the origin is inside; the largest is minus the depth
 
 
-def brute_force_pairs(qpos):
-    """{(g1, g2): signed separation} over ALL geom pairs; geom ids: 0..19 meshes, 20 floor, 21 cube"""
-    verts, cube = world_geoms(qpos)
+def brute_force_pairs(qpos, Sc=S):
+    """{(g1, g2): signed separation} over ALL geom pairs of the scene; geom ids: 0..19 meshes, 20 floor, 21.. boxes (the free cubes,
+    then the static walls).  Walls and the floor belong to the world, like base_link which is welded to it: no pairs among those."""
+    verts, _ = world_geoms(np.r_[qpos[:6], 0, 0, 0, 1, 0, 0, 0])
+    boxes = world_boxes(Sc, qpos)
+    ncube = int(Sc["ncube"])
     out = {}
     for g in range(NG):
-        if S["geom_body"][g] != 0:  # base_link is welded to the world like the floor
+        on_world = S["geom_body"][g] == 0
+        if not on_world:
             out[(g, NG)] = verts[g][:, 2].min()
-        out[(NG + 1, g)] = separation(cube, verts[g])
+        for b, box in enumerate(boxes):
+            if b < ncube or not on_world:
+                out[(NG + 1 + b, g)] = separation(box, verts[g])
         for h in range(g + 1, NG):
             if may_collide(int(S["geom_body"][g]), int(S["geom_body"][h])):
                 out[(g, h)] = separation(verts[g], verts[h])
-    out[(NG, NG + 1)] = cube[:, 2].min()
-    return out, verts, cube
+    for c in range(ncube):
+        out[(NG, NG + 1 + c)] = boxes[c][:, 2].min()
+        for b in range(c + 1, len(boxes)):
+            out[(NG + 1 + c, NG + 1 + b)] = separation(boxes[c], boxes[b])
+    return out, verts, boxes
 
 
 def oracle_contacts(o):
     return o.get("contacts").reshape(-1, 27)
 
 
-def check_state(o, qpos, stats):
+def check_state(o, qpos, stats, Sc=S):
     """compare the oracle's contact list (already computed for qpos) with the brute force"""
-    pairs, verts, cube = brute_force_pairs(qpos)
+    pairs, verts, boxes = brute_force_pairs(qpos, Sc)
     con = oracle_contacts(o)
     reported = {}
     for c in con:
         key = tuple(sorted((int(c[14]), int(c[15]))))
         reported.setdefault(key, []).append(c)
-    geom = lambda g: cube if g == NG + 1 else verts[g]
+    geom = lambda g: boxes[g - NG - 1] if g > NG else verts[g]
     for (g1, g2), sep in pairs.items():
         key = tuple(sorted((g1, g2)))
         if abs(sep) < 1e-6:
@@ -99,7 +109,7 @@ def check_state(o, qpos, stats):
             exact = -pairs[(int(c[14]), int(c[15]))] if (int(c[14]), int(c[15])) in pairs else -pairs[(int(c[15]), int(c[14]))]
             overlap = (A @ n).max() - (B @ n).min()
             assert abs(np.linalg.norm(n) - 1) < 1e-9
-            if len(cs) == 1:  # one MPR contact per convex pair (box-box pairs may carry several clipped points)
+            if len(cs) == 1 and min(key) < NG:  # one MPR contact per convex pair (box-box pairs: SAT + clipping, several points)
                 assert exact - 1e-5 <= depth <= overlap + 1e-6, (key, exact, depth, overlap)
             assert (B @ n).min() - 1e-6 <= c[0:3] @ n <= (A @ n).max() + 1e-6
             stats["depths"] += 1
@@ -147,7 +157,7 @@ def test_exhaustive_pair_loop_agrees_with_the_oracles_contact_set():
         check_state(o, qpos, stats)
         for c in oracle_contacts(o):
             a, b = int(c[14]), int(c[15])
-            kinds.add("floor" if NG in (a, b) else "cube" if NG + 1 in (a, b) else "self")
+            kinds.add("floor" if NG in (a, b) else "cube" if max(a, b) > NG else "self")
         if trial % 2 == 0:  # warm: a few substeps fill the cache, then the contact list of the state reached
             o.set_state(qvel=rng.normal(scale=0.3, size=12))
             o.substep(3)
@@ -156,3 +166,47 @@ def test_exhaustive_pair_loop_agrees_with_the_oracles_contact_set():
             check_state(o, q1, stats)
     print(stats, kinds)
     assert stats["hits"] >= 40 and stats["depths"] >= 15 and kinds == {"floor", "cube", "self"}, (stats, kinds)
+
+
+@pytest.mark.parametrize("task", ["stack", "push_loop"])
+def test_exhaustive_pair_loop_on_the_other_scene_classes(task):
+    """the same check on the two other scene classes of the kernels: two free cubes (cube-cube by SAT + clipping), and one cube
+    inside four static rails (wall-cube, wall-mesh)"""
+    Sc = load_scene(task)
+    rng = np.random.default_rng(9)
+    stats = dict(hits=0, depths=0, borderline=0)
+    seen = set()
+    ncube, nq = int(Sc["ncube"]), 6 + 7 * int(Sc["ncube"])
+    for trial in range(12):
+        qpos = np.zeros(nq)
+        qpos[:6] = rng.uniform(LO, HI)
+        if task == "push_loop" and trial % 2:
+            qpos[1], qpos[2] = rng.uniform(0.6, 1.1), rng.uniform(0.8, 1.5)  # gripper lowered towards the rails
+        verts, _ = world_geoms(np.r_[qpos[:6], 0, 0, 0, 1, 0, 0, 0])
+        for c in range(ncube):
+            p = qpos[6 + 7 * c: 13 + 7 * c]
+            if task == "push_loop":  # on / inside a rail or free in the pen
+                w = rng.integers(0, 4)
+                p[:3] = Sc["wall_pos"][w] + rng.uniform(-1, 1, 3) * (Sc["box_half"][1 + w] + 0.012) + [0, 0, 0.008] if trial % 3 else [rng.uniform(-0.1, 0.1), rng.uniform(0.1, 0.17), 0.015]
+            elif c == 0:
+                p[:3] = verts[rng.integers(3, NG)].mean(0) + rng.uniform(-0.02, 0.02, 3) if trial % 2 else [rng.uniform(-0.1, 0.1), rng.uniform(0.1, 0.25), rng.uniform(0.0, 0.03)]
+            else:  # the second cube on / inside / beside the first
+                p[:3] = qpos[6:9] + rng.uniform(-0.025, 0.025, 3) + [0, 0, 0.02 * (trial % 3)]
+            q = rng.normal(size=4)
+            p[3:7] = q / np.linalg.norm(q) if trial % 4 else [1, 0, 0, 0]
+        o = Oracle(task)
+        o.set_state(qpos=qpos, qvel=np.zeros(o.nv), ctrl=qpos[:6], warm=np.zeros(o.nv))
+        o.forward()
+        check_state(o, qpos, stats, Sc)
+        for c in oracle_contacts(o):
+            a, b = sorted((int(c[14]), int(c[15])))
+            seen.add("cube-cube" if a > NG and b <= NG + ncube else "wall-cube" if a > NG else "wall-mesh" if b > NG + ncube else "other")
+        if trial % 2 == 0:
+            o.set_state(qvel=rng.normal(scale=0.3, size=o.nv))
+            o.substep(3)
+            q1 = o.get_state()["qpos"]
+            o.forward()
+            check_state(o, q1, stats, Sc)
+    want = {"cube-cube"} if task == "stack" else {"wall-cube", "wall-mesh"}
+    print(task, stats, seen)
+    assert stats["hits"] >= 40 and want <= seen, (stats, seen)

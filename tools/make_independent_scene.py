@@ -1,4 +1,5 @@
-"""Fixture for tests/test_independent_pipeline.py: the scene of push_cube.xml read by a SEPARATE minimal reader.
+"""Fixture for tests/test_independent_pipeline.py: the scenes of push_cube.xml, stack_two_cubes.xml and
+push_cube_loop.xml read by a SEPARATE minimal reader.
 
 Deliberately shares nothing with gym_lowcostrobot_b200/mjcf.py (the model compiler that the oracle and the CUDA path both
 use): plain ElementTree walk of follower.xml + push_cube.xml, raw binary STL triangles, scipy's Qhull for the hull vertex
@@ -7,7 +8,7 @@ pose; an independent reader has no reason to).  Usage (in the build container, w
 
     python tools/make_independent_scene.py [/root/reference/gym_lowcostrobot/assets/low_cost_robot_6dof]
 
-writes tests/golden/independent/scene_push.npz.
+writes tests/golden/independent/scene_{push,stack,push_loop}.npz.
 """
 import os
 import struct
@@ -34,9 +35,12 @@ def vec(s, n):
     return np.array(v)
 
 
-def main(assets):
+SCENES = {"push": "push_cube.xml", "stack": "stack_two_cubes.xml", "push_loop": "push_cube_loop.xml"}
+
+
+def main(assets, task="push"):
     arm = ET.parse(os.path.join(assets, "follower.xml")).getroot()
-    scene = ET.parse(os.path.join(assets, "push_cube.xml")).getroot()
+    scene = ET.parse(os.path.join(assets, SCENES[task])).getroot()
     meshdir = os.path.join(assets, arm.find("compiler").get("meshdir"))
     files = {m.get("name"): m.get("file") for m in arm.find("asset").findall("mesh")}
     on_disk = {f.lower(): f for f in os.listdir(meshdir)}
@@ -109,8 +113,11 @@ def main(assets):
         hull_adr.append(hull_adr[-1] + len(hv))
     excl = [(e.get("body1"), e.get("body2")) for e in arm.find("contact").findall("exclude")]
     names = [b["name"] for b in bodies]
-    cube = next(b for b in scene.find("worldbody").findall("body") if b.get("name") == "cube")
-    floor = next(g for g in scene.find("worldbody").findall("geom") if g.get("name") == "floor")
+    # free bodies (one box geom each) = the cubes; box geoms directly in the worldbody that take part in collisions = static walls
+    cubes = [b for b in scene.find("worldbody").findall("body") if b.find("freejoint") is not None]
+    walls = [g for g in scene.find("worldbody").findall("geom") if g.get("type") == "box" and g.get("contype") != "0"]
+    cube = cubes[0]
+    floor = next(g for g in scene.find("worldbody").iter("geom") if g.get("name") == "floor")  # (PushCubeLoop wraps it in a jointless body)
     geom_par.append(contact_params(dict(floor.attrib)))              # geom 20: the floor plane
     geom_par.append(contact_params(dict(cube.find("geom").attrib)))  # geom 21: the cube
     cine = cube.find("inertial")
@@ -120,13 +127,15 @@ def main(assets):
     opt = dict(scene.find("option").attrib)
     opt.update(arm.find("option").attrib)
     assert opt["cone"] == "elliptic" and opt["integrator"] == "implicitfast"
-    out = os.path.join(ROOT, "tests", "golden", "independent", "scene_push.npz")
+    out = os.path.join(ROOT, "tests", "golden", "independent", f"scene_{task}.npz")
     np.savez_compressed(
         out, body_parent=np.array([b["parent"] for b in bodies]), body_pos=np.stack([b["pos"] for b in bodies]),
         body_quat=np.stack([b["quat"] for b in bodies]), body_axis=np.stack([b["axis"] for b in bodies]),
         geom_body=np.array([g[0] for g in geoms]), geom_mesh=np.array([g[1] for g in geoms]), hull_adr=np.array(hull_adr),
         hull_pts=np.concatenate(hull_pts), exclude=np.array([(names.index(a), names.index(b)) for a, b in excl]),
         cube_half=vec(cube.find("geom").get("size"), 3), body_names=np.array(names),
+        ncube=len(cubes), box_half=np.stack([vec(b.find("geom").get("size"), 3) for b in cubes] + [vec(g.get("size"), 3) for g in walls]),
+        wall_pos=np.stack([vec(g.get("pos"), 3) for g in walls]) if walls else np.zeros((0, 3)),
         inertial=np.stack(inertial), joints=np.stack(joints), geom_par=np.array(geom_par), cube_mass=float(cine.get("mass")),
         cube_diaginertia=vec(cine.get("diaginertia"), 3), cube_pos0=vec(cube.get("pos"), 3), act_kp=float(act["kp"]), act_kv=float(act["kv"]),
         timestep=float(opt["timestep"]), impratio=float(opt["impratio"]), site_pos=vec(arm.find("worldbody").find(".//site").get("pos"), 3))
@@ -134,4 +143,5 @@ def main(assets):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "/root/reference/gym_lowcostrobot/assets/low_cost_robot_6dof")
+    for t in SCENES:
+        main(sys.argv[1] if len(sys.argv) > 1 else "/root/reference/gym_lowcostrobot/assets/low_cost_robot_6dof", t)
