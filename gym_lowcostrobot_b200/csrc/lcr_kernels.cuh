@@ -1177,6 +1177,36 @@ __device__ __noinline__ void env_reset(Ws<T, NC>& w, const DevModel<T>& m, const
   forward(w, m, verts);
 }
 
+// one damped-least-squares update of the IK (reach_cube_env.py:191-218) from the kinematics in `w`: returns true (q untouched) if the site
+// is within 1 cm of the target, otherwise advances q (lane a < 6 holds joint a)
+template <typename T, int NC>
+DI bool ik_update(Ws<T, NC>& w, const DevModel<T>& m, const T* target, T& q) {
+  const int lane = LANE;
+  const T* site = w.site_xpos();
+  T err[3] = {target[0] - site[0], target[1] - site[1], target[2] - site[2]};
+  if (sqrt(dot3(err, err)) < (T)0.01) return true;
+  // lane a < 6: Jacobian column a, A[a][:] = J^T J + 0.15 I, rhs_a = J^T err
+  T col[3] = {0, 0, 0};
+  if (lane < m.site_body && lane < 6) {
+    T r[3] = {site[0] - w.xpos[lane + 1][0], site[1] - w.xpos[lane + 1][1], site[2] - w.xpos[lane + 1][2]};
+    cross3(col, w.axis[lane], r);
+  }
+  T rhs = dot3(col, err);
+  T ar[LCR_NARM], cr[LCR_NARM];
+#pragma unroll
+  for (int b = 0; b < 6; b++) {
+    T cb[3] = {__shfl_sync(FULLMASK, col[0], b), __shfl_sync(FULLMASK, col[1], b), __shfl_sync(FULLMASK, col[2], b)};
+    ar[b] = (lane < 6 && b <= lane) ? dot3(col, cb) + (lane == b ? (T)0.15 : (T)0) : (T)0;
+    cr[b] = 0;
+  }
+  chol_reg<T, LCR_NARM>(ar, cr);
+  T qd = chol_reg_solve<T, LCR_NARM>(ar, cr, rhs);
+  const T n = sqrt(warp_sum(lane < 6 ? qd * qd : (T)0));
+  if (n > 1) qd /= n;
+  if (lane < 6) q = clampT(q + (T)0.5 * qd, m.jnt_range[lane][0], m.jnt_range[lane][1]);
+  return false;
+}
+
 // damped least squares IK (reach_cube_env.py:148-221); teleport = faithful in-step behaviour
 template <typename T, int NC>
 __device__ __noinline__ void inverse_kinematics(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const T* target,
@@ -1189,28 +1219,7 @@ __device__ __noinline__ void inverse_kinematics(Ws<T, NC>& w, const DevModel<T>&
     if (lane < 6) qpos[lane] = q;
     __syncwarp();
     if (teleport) forward(w, m, verts); else kinematics(w, m);
-    const T* site = w.site_xpos();
-    T err[3] = {target[0] - site[0], target[1] - site[1], target[2] - site[2]};
-    if (sqrt(dot3(err, err)) < (T)0.01) break;
-    // lane a < 6: Jacobian column a, A[a][:] = J^T J + 0.15 I, rhs_a = J^T err
-    T col[3] = {0, 0, 0};
-    if (lane < m.site_body && lane < 6) {
-      T r[3] = {site[0] - w.xpos[lane + 1][0], site[1] - w.xpos[lane + 1][1], site[2] - w.xpos[lane + 1][2]};
-      cross3(col, w.axis[lane], r);
-    }
-    T rhs = dot3(col, err);
-    T ar[LCR_NARM], cr[LCR_NARM];
-#pragma unroll
-    for (int b = 0; b < 6; b++) {
-      T cb[3] = {__shfl_sync(FULLMASK, col[0], b), __shfl_sync(FULLMASK, col[1], b), __shfl_sync(FULLMASK, col[2], b)};
-      ar[b] = (lane < 6 && b <= lane) ? dot3(col, cb) + (lane == b ? (T)0.15 : (T)0) : (T)0;
-      cr[b] = 0;
-    }
-    chol_reg<T, LCR_NARM>(ar, cr);
-    T qd = chol_reg_solve<T, LCR_NARM>(ar, cr, rhs);
-    const T n = sqrt(warp_sum(lane < 6 ? qd * qd : (T)0));
-    if (n > 1) qd /= n;
-    if (lane < 6) q = clampT(q + (T)0.5 * qd, m.jnt_range[lane][0], m.jnt_range[lane][1]);
+    if (ik_update(w, m, target, q)) break;
     __syncwarp();
   }
   if (lane < 6) q_out[lane] = q;
@@ -1224,15 +1233,17 @@ __device__ __noinline__ void inverse_kinematics(Ws<T, NC>& w, const DevModel<T>&
 __device__ const double kTargetLow[6] = {-3.14159, -1.5708, -1.48353, -1.91986, -2.96706, -1.74533};
 __device__ const double kTargetHigh[6] = {3.14159, 1.22173, 1.74533, 1.91986, 2.96706, 0.0523599};
 
+// env_step_begin in two halves around the IK of the ee action mode, so that a CTA that owns ONE env (the BIG passes) can run the IK's
+// mj_forward passes with its helper warps (env_step_begin_cta); env_step_begin = the one-warp composition, same arithmetic.
+// step_pre: 0 = the env was auto-reset instead of stepped (outputs written), 1 = joint mode, ctrl set, 2 = ee mode: IK target in w.search[0..2]
 template <typename T, int NC>
-__device__ __noinline__ bool env_step_begin(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const StepIO& io, int env) {
-  // returns false if the env was auto-reset instead of stepped (outputs already written)
+__device__ __noinline__ int step_pre(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const StepIO& io, int env) {
   const int lane = LANE, task = m.task;
   if (m.autoreset && w.ints[1]) {
     env_reset(w, m, verts);
     if (Scene<NC>::BIG || !w.ovf) write_outputs(w, m, io, env, 0.0f, false, false, false);
     __syncwarp();
-    return false;
+    return 0;
   }
   if (lane == 0) w.diag[3] = 0;
   const int na = (m.action_mode ? 3 : 5) + (m.block_gripper ? 0 : 1);
@@ -1240,29 +1251,50 @@ __device__ __noinline__ bool env_step_begin(Ws<T, NC>& w, const DevModel<T>& m, 
   const bool gripper_task = task == LCR_TASK_LIFT || task == LCR_TASK_PICK_PLACE || task == LCR_TASK_STACK;
   T* qpos = w.qpos();
   T a = lane < na ? clampT((T)action[lane], (T)-1, (T)1) : (T)0;
-  T tq = 0;
   if (m.action_mode == 1) {
     T* sc = w.search;  // free before the first and after the last mj_forward of the IK loop
     const T* site = w.site_xpos();
     // `ee_action * 0.05` is a float32 product in the reference (float32 array times a Python float), rounded before the sum
     if (lane < 3) { T t = site[lane] + (T)__fmul_rn((float)a, 0.05f); if (lane == 2 && t < 0) t = 0; sc[lane] = t; }
     __syncwarp();
-    T tgt[3] = {sc[0], sc[1], sc[2]};
-    __syncwarp();
-    inverse_kinematics(w, m, verts, tgt, sc, true);
-    __syncwarp();
-    if (lane < 6) tq = sc[lane];
-    if (lane == 5 && !gripper_task) tq = 0;
-    // gripper (lift_cube_env.py:253-257): q6 + 0.2*a[3] clipped to ctrlrange
-    const T ga = na > 3 ? __shfl_sync(FULLMASK, a, 3) : (T)0;
-    if (lane == 5 && gripper_task) tq = clampT(qpos[5] + (T)__fmul_rn((float)ga, 0.2f), m.act_ctrlrange[5][0], m.act_ctrlrange[5][1]);
-  } else {
-    const T alast = __shfl_sync(FULLMASK, a, na - 1);
-    if (lane < 5) tq = clampT(a + qpos[lane], (T)kTargetLow[lane], (T)kTargetHigh[lane]);
-    else if (lane == 5) tq = gripper_task ? clampT(alast + qpos[5], (T)kTargetLow[5], (T)kTargetHigh[5]) : (T)0;
+    return 2;
   }
+  T tq = 0;
+  const T alast = __shfl_sync(FULLMASK, a, na - 1);
+  if (lane < 5) tq = clampT(a + qpos[lane], (T)kTargetLow[lane], (T)kTargetHigh[lane]);
+  else if (lane == 5) tq = gripper_task ? clampT(alast + qpos[5], (T)kTargetLow[5], (T)kTargetHigh[5]) : (T)0;
   if (lane < 6) w.ctrl()[lane] = tq;
   __syncwarp();
+  return 1;
+}
+// ee mode, after the IK: q (lane a < 6 = joint a) -> ctrl, gripper from the action (lift_cube_env.py:253-257)
+template <typename T, int NC>
+DI void step_post_ik(Ws<T, NC>& w, const DevModel<T>& m, const StepIO& io, int env, T q) {
+  const int lane = LANE, task = m.task;
+  const int na = 3 + (m.block_gripper ? 0 : 1);
+  const float* action = io.actions + (size_t)env * na;
+  const bool gripper_task = task == LCR_TASK_LIFT || task == LCR_TASK_PICK_PLACE || task == LCR_TASK_STACK;
+  const T a = lane < na ? clampT((T)action[lane], (T)-1, (T)1) : (T)0;
+  T tq = lane < 6 ? q : (T)0;
+  if (lane == 5 && !gripper_task) tq = 0;
+  const T ga = na > 3 ? __shfl_sync(FULLMASK, a, 3) : (T)0;
+  if (lane == 5 && gripper_task) tq = clampT(w.qpos()[5] + (T)__fmul_rn((float)ga, 0.2f), m.act_ctrlrange[5][0], m.act_ctrlrange[5][1]);
+  if (lane < 6) w.ctrl()[lane] = tq;
+  __syncwarp();
+}
+
+template <typename T, int NC>
+__device__ __noinline__ bool env_step_begin(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const StepIO& io, int env) {
+  // returns false if the env was auto-reset instead of stepped (outputs already written)
+  const int pre = step_pre(w, m, verts, io, env);
+  if (pre != 2) return pre != 0;
+  T* sc = w.search;
+  T tgt[3] = {sc[0], sc[1], sc[2]};
+  __syncwarp();
+  inverse_kinematics(w, m, verts, tgt, sc, true);
+  __syncwarp();
+  const T q = LANE < 6 ? sc[LANE] : (T)0;
+  step_post_ik(w, m, io, env, q);
   return true;
 }
 
@@ -1553,6 +1585,52 @@ __global__ void __launch_bounds__(1024) k_sched(DevState<T> s, int* __restrict__
   }
 }
 
+// env_step_begin for a CTA that owns ONE env (the BIG passes: warp 0 owns the env, the others help): the same arithmetic, but the
+// narrowphase jobs of the IK's mj_forward passes -- dozens of MPR runs per pass in the deeply penetrating poses that need the big
+// workspace, ten passes per step in the ee action mode -- are drained by all warps of the CTA instead of the owner alone.
+// Every warp of the CTA calls this; returns env_step_begin's value in the owner warp, false in the helpers.
+template <typename T, int NC>
+__device__ bool env_step_begin_cta(Ws<T, NC>& w, const DevModel<T>& m, const T* __restrict__ verts, const StepIO& io, int env, bool owner, int* job_next) {
+  __shared__ int flag;
+  if (owner) {
+    const int pre = step_pre(w, m, verts, io, env);
+    if (LANE == 0) flag = pre;
+  }
+  __syncthreads();
+  const int pre = flag;
+  if (pre != 2) return owner && pre != 0;
+  T tgt[3] = {0, 0, 0}, q = 0;
+  if (owner) {
+    tgt[0] = w.search[0]; tgt[1] = w.search[1]; tgt[2] = w.search[2];
+    q = LANE < 6 ? w.qpos()[LANE] : (T)0;
+  }
+  for (int it = 0; it < 10; it++) {
+    if (owner) {  // mj_forward, first half
+      if (LANE < 6) w.qpos()[LANE] = q;
+      __syncwarp();
+      kinematics(w, m);
+      inertia_and_bias(w, m);
+      collect_candidates(w, m);
+      if (LANE == 0) *job_next = 0;
+    }
+    __syncthreads();
+    cta_jobs(&w, 1, m, verts, job_next);
+    __syncthreads();
+    if (owner) {  // second half, then the IK update
+      make_constraints(w, m, verts, true);
+      smooth_forces(w, m);
+      solve_constraints<T, NC, false>(w, m, solver_tol<T>(m));
+      const bool converged = ik_update(w, m, tgt, q);
+      __syncwarp();
+      if (LANE == 0) flag = converged ? 0 : 1;
+    }
+    __syncthreads();
+    if (!flag) break;
+  }
+  if (owner) step_post_ik(w, m, io, env, q);
+  return owner;
+}
+
 template <typename T, int NC, bool PROF>
 __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restrict__ dm, const T* __restrict__ verts, DevState<T> s, StepIO io, Redo redo,
                                                     int flags, const int* __restrict__ perm, int epc, long long* __restrict__ prof,
@@ -1577,6 +1655,8 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
     const long long t1_ = clock64(); tp[k] += t1_ - t0; t0 = t1_; } } while (0)
   if (PROF) t0 = clock64();
   bool go = false;
+  // one env per CTA with helper warps (the BIG passes): the step begin (IK forward passes of the ee mode) is CTA-cooperative too
+  const bool coop_begin = Scene<NC>::BIG && W == 1 && (flags & LCR_LS_JOB_POOL) && !(flags & LCR_LS_RESUME);
   if (valid) {
     if (flags & LCR_LS_RESUME) {
       // migrated from the phased chain: the state block (state, ints, diag, rng) of the parked fast workspace is the start state of
@@ -1593,9 +1673,10 @@ __global__ void __launch_bounds__(512, 1) k_step_ls(const DevModel<T>* __restric
       go = true;
     } else {
       load_state(w, s, env);
-      go = env_step_begin(w, m, verts, io, env);
+      if (!coop_begin) go = env_step_begin(w, m, verts, io, env);
     }
   }
+  if (coop_begin) go = env_step_begin_cta(w, m, verts, io, env, owner, &job_next);
   if (!go && owner) { if (LANE == 0) w.ncand = 0; __syncwarp(); }
   const T tol = solver_tol<T>(m);
   LCR_TICK(0);

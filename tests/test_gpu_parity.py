@@ -365,6 +365,35 @@ def test_envs_beyond_the_fast_caps_take_the_big_path_in_every_mode(em):
         e.close()
 
 
+def test_big_path_in_the_ee_action_mode_is_bitwise_identical_across_begin_variants():
+    """ee action mode with arms lying in the floor: the IK's ten mj_forward passes run over the big workspace.  The BIG passes of the
+    phased chain (one CTA per env) run them CTA-cooperatively -- helper warps drain the narrowphase jobs of every pass
+    (env_step_begin_cta) -- the flow mode's BIG path runs the one-warp env_step_begin: outputs and states must agree bit for bit."""
+    n = 128
+    rng = np.random.default_rng(13)
+    envs = [glr.make("PickPlaceCube-v0", num_envs=n, action_mode="ee", exec_mode=m) for m in ("flow", "phased")]
+    qpos, qvel, ctrl = random_states("pick_place", n, rng, envs[0].nq, envs[0].nv)
+    qpos[:, 1] = rng.uniform(0.9, 1.22, n)
+    qpos[:, 2] = rng.uniform(1.2, 1.74, n)
+    for e in envs:
+        e.reset(seed=1)
+        e.set_state(qpos=qpos, qvel=0.2 * qvel, ctrl=qpos[:, :6], warm=np.zeros((n, e.nv)))
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    peak = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for t in range(3):
+        a = torch.rand(n, envs[0].action_dim, generator=gen, device="cuda") * 2 - 1
+        ra, rb = envs[0].step_packed(a), envs[1].step_packed(a)
+        assert envs[0].flow_status() == (0, 0)
+        assert torch.equal(ra, rb), t
+        peak = torch.maximum(peak, envs[1].diagnostics()["max_nefc"])
+    assert int((peak > 96).sum()) >= 4, "the states should push some envs beyond the fast caps"
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    for e in envs:
+        e.close()
+
+
 def test_f64_big_path_matches_the_oracle():
     """float64 kernels against the oracle on the same beyond-the-caps states, ONE mj_step (the comparison that is well posed in
     deeply interpenetrating poses, see test_f64_one_substep_map_from_random_states).  Envs with more than 96 constraint rows
