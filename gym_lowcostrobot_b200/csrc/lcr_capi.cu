@@ -248,6 +248,8 @@ struct LcrSim {
   int use_graph = 0, ph_striped = 1, graph_nodes = 0;
   // phased mode: migration lists [group][substep][1 + LCR_MIGCAP] and the side stream / fork / join events of every (group, substep)
   int* mig = nullptr;
+  int* early = nullptr;  // phased mode: per group [1 + per] list of the envs whose step begin outgrew the fast workspace
+  int early_stride = 0;
   int* jobq = nullptr;  // phased mode: narrowphase job queues, one per group (jobq_stride ints each)
   int jobq_stride = 0;
   std::vector<cudaStream_t> mstream;
@@ -346,25 +348,29 @@ int enqueue_step(LcrSim* sim, const StepIO& io, cudaStream_t st) {
     }
     if (predicted) start_big();
     const int nsub = std::max(1, sim->cfg.n_substeps);
-    if (sim->mig) CUDA_OK(cudaMemsetAsync(sim->mig, 0, sizeof(int) * (size_t)G * nsub * (1 + LCR_MIGCAP), st));
+    if (sim->mig) {
+      CUDA_OK(cudaMemsetAsync(sim->mig, 0, sizeof(int) * (size_t)G * (nsub + 1) * (1 + LCR_MIGCAP), st));
+      CUDA_OK(cudaMemsetAsync(sim->early, 0, sizeof(int) * (size_t)sim->early_stride * G, st));
+    }
     CUDA_OK(cudaEventRecord(sim->ev_begin, st));
     for (int g = 0; g < G; g++) {
       const int env0 = g * per, cnt = sim->perm ? per : std::min(per, sim->n - env0);
       if (env0 >= sim->n) break;
       CUDA_OK(cudaStreamWaitEvent(sim->gstream[g], sim->ev_begin, 0));
       int nl = 0;
-      int* mg = sim->mig ? sim->mig + (size_t)g * nsub * (1 + LCR_MIGCAP) : nullptr;
-      cudaStream_t* ms = sim->mig ? &sim->mstream[(size_t)g * nsub] : nullptr;
-      cudaEvent_t *mf = sim->mig ? &sim->mev_fork[(size_t)g * nsub] : nullptr, *mj = sim->mig ? &sim->mev_join[(size_t)g * nsub] : nullptr;
+      int* mg = sim->mig ? sim->mig + (size_t)g * (nsub + 1) * (1 + LCR_MIGCAP) : nullptr;
+      cudaStream_t* ms = sim->mig ? &sim->mstream[(size_t)g * (nsub + 1)] : nullptr;
+      cudaEvent_t *mf = sim->mig ? &sim->mev_fork[(size_t)g * (nsub + 1)] : nullptr, *mj = sim->mig ? &sim->mev_join[(size_t)g * (nsub + 1)] : nullptr;
+      int* er = sim->mig ? sim->early + (size_t)g * sim->early_stride : nullptr;
       int* jq = sim->jobq ? sim->jobq + (size_t)g * sim->jobq_stride : nullptr;
       if (jq) CUDA_OK(cudaMemsetAsync(jq, 0, sizeof(int) * LCR_JOBQ_HEADER, sim->gstream[g]));  // (k_ph_col clears the counters after every substep; this covers a step that was cut short)
-      if (f32) LCR_DISPATCH_RET(float, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g], mg, ms, mf, mj, jq));
-      else LCR_DISPATCH_RET(double, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g], mg, ms, mf, mj, jq));
+      if (f32) LCR_DISPATCH_RET(float, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->f.dm, sim->f.verts, sim->f.s, sim->f.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g], mg, ms, mf, mj, jq, er));
+      else LCR_DISPATCH_RET(double, sim->ncube, nl, step_phased(sim->cfg.n_substeps, sim->d.dm, sim->d.verts, sim->d.s, sim->d.gws, io, redo, env0, cnt, sim->perm, sim->gstream[g], mg, ms, mf, mj, jq, er));
       sim->launches += nl;
       CUDA_OK(cudaEventRecord(sim->ev_done[g], sim->gstream[g]));
       CUDA_OK(cudaStreamWaitEvent(st, sim->ev_done[g], 0));
       if (sim->mig)  // the BIG passes over the envs that migrated out of this chain
-        for (int k = 0; k < sim->cfg.n_substeps; k++) CUDA_OK(cudaStreamWaitEvent(st, mj[k], 0));
+        for (int k = 0; k <= sim->cfg.n_substeps; k++) CUDA_OK(cudaStreamWaitEvent(st, mj[k], 0));  // (k == n_substeps: the begin stage)
     }
   } else if (sim->cfg.exec_mode == 2) {
     int W = 0;
@@ -451,8 +457,11 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
     // first in every phase kernel, so that the long Newton solves / MPR jobs do not end up in the tail of the launch
     if (env_int("LCR_PH_SORT", 1) != 0) LCR_CREATE_OK(cudaMalloc(&s->perm, sizeof(int) * (2 * (size_t)n_envs + 16)));
     if (env_int("LCR_PH_MIGRATE", 1) != 0) {
-      const int nb = s->ngroups * std::max(1, cfg->n_substeps);
+      const int nsub1 = std::max(1, cfg->n_substeps) + 1;  // one side stream per substep, and one for the begin stage
+      const int nb = s->ngroups * nsub1;
       LCR_CREATE_OK(cudaMalloc(&s->mig, sizeof(int) * (size_t)nb * (1 + LCR_MIGCAP)));
+      s->early_stride = (((n_envs + s->ngroups - 1) / s->ngroups) + 1 + 31) & ~31;
+      LCR_CREATE_OK(cudaMalloc(&s->early, sizeof(int) * (size_t)s->early_stride * s->ngroups));
       s->mstream.assign(nb, nullptr); s->mev_fork.assign(nb, nullptr); s->mev_join.assign(nb, nullptr);
       for (int k = 0; k < nb; k++) {
         LCR_CREATE_OK(cudaStreamCreateWithFlags(&s->mstream[k], cudaStreamNonBlocking));
@@ -508,6 +517,7 @@ int lcr_destroy(LcrSim* sim) {
   for (cudaEvent_t x : sim->mev_fork) if (x) cudaEventDestroy(x);
   for (cudaEvent_t x : sim->mev_join) if (x) cudaEventDestroy(x);
   cudaFree(sim->mig);
+  cudaFree(sim->early);
   cudaFree(sim->jobq);
   if (sim->gexec) cudaGraphExecDestroy(sim->gexec);
   if (sim->cstream) cudaStreamDestroy(sim->cstream);

@@ -214,7 +214,7 @@ struct LaunchNC {
                             const int* perm, long long* prof, cudaStream_t st);
   static void step_big_resume(const DevModel<T>* dm, const T* verts, DevState<T> s, const void* gws, StepIO io, const int* mig, cudaStream_t st);
   static int step_phased(int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws, StepIO io, Redo redo, int env0, int cnt,
-                         const int* perm, cudaStream_t st, int* mig, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join, int* jobq);
+                         const int* perm, cudaStream_t st, int* mig, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join, int* jobq, int* early);
   static int jobq_words(int cnt);
   static int flow_warps();
   static int flow_bigslots();

@@ -2231,7 +2231,8 @@ void LaunchNC<T, S>::step_lockstep(const DevModel<T>* dm, const T* verts, DevSta
 // launched on side[k] (forked from st by ev_fork[k]; the caller joins side[k] through ev_join[k])
 template <typename T, int S>
 int LaunchNC<T, S>::step_phased(int n_substeps, const DevModel<T>* dm, const T* verts, DevState<T> s, void* gws_, StepIO io, Redo redo, int env0, int cnt,
-                                const int* perm, cudaStream_t st, int* mig, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join, int* jobq) {
+                                const int* perm, cudaStream_t st, int* mig, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join, int* jobq,
+                                int* early) {
   typedef Ws<T, S> W;
   W* gws = reinterpret_cast<W*>(gws_);
   const size_t sm = sizeof(W);
@@ -2239,7 +2240,18 @@ int LaunchNC<T, S>::step_phased(int n_substeps, const DevModel<T>* dm, const T* 
   // (tried and removed: the Newton solve of substep k fused with the dynamics stage of substep k + 1 -- one launch and one staging
   //  round trip less per substep, bit-identical -- PushCube 16 384 15.1 -> 20.3 ms per step, StackTwoCubes 8 192 12.8 -> 15.6: like the
   //  col + sol merge of round 1, a larger heterogeneous kernel loses more in the instruction cache than the launch saves)
-  k_ph_begin<T, S><<<cnt, 32, sm, st>>>(dm, verts, s, gws, io, redo, env0, perm);
+  // early (optional, with mig): [1 + cnt] list of the envs whose step BEGIN outgrew the fast workspace (the IK's forward passes of the ee
+  // mode, the forward pass of an autoreset): their BIG pass over the whole step starts right behind k_ph_begin on side[n_substeps],
+  // beside the chain, instead of after it with the redo pass
+  const Redo first = early ? Redo{early, early + 1} : redo;
+  k_ph_begin<T, S><<<cnt, 32, sm, st>>>(dm, verts, s, gws, io, first, env0, perm);
+  if (early) {
+    cudaEventRecord(ev_fork[n_substeps], st);
+    cudaStreamWaitEvent(side[n_substeps], ev_fork[n_substeps], 0);
+    step_big(dm, verts, s, io, first, side[n_substeps]);
+    cudaEventRecord(ev_join[n_substeps], side[n_substeps]);
+    nl++;
+  }
   for (int k = 0; k < n_substeps; k++) {
     int* mk = mig ? mig + (size_t)k * (1 + LCR_MIGCAP) : nullptr;
     k_ph_dyn<T, S><<<cnt, 32, sm, st>>>(dm, verts, gws, k == 0, env0, perm, jobq);
