@@ -39,12 +39,19 @@ CUBE_RGB = {"stack": ([0.5, 0, 0], [0, 0, 0.5])}  # stack_two_cubes.xml: cube_re
 
 
 def hull_planes(verts):
-    """unique half-spaces n . x + d <= 0 of the convex hull of ``verts`` (Qhull)"""
+    """unique half-spaces n . x + d <= 0 of the convex hull of ``verts`` (Qhull), largest faces first: a ray that misses the hull
+    leaves the clipping loop as soon as an entry crossing lies behind an exit crossing, which the big faces decide soonest"""
     from scipy.spatial import ConvexHull
 
-    eq = ConvexHull(np.asarray(verts, np.float64)).equations
-    _, idx = np.unique(np.round(eq, 7), axis=0, return_index=True)
-    return eq[np.sort(idx)]
+    v = np.asarray(verts, np.float64)
+    hull = ConvexHull(v)
+    tri = v[hull.simplices]
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    key, inv = np.unique(np.round(hull.equations, 7), axis=0, return_inverse=True)
+    total = np.bincount(inv.reshape(-1), weights=area, minlength=len(key))
+    first = np.array([np.flatnonzero(inv.reshape(-1) == k)[0] for k in range(len(key))])
+    order = np.argsort(-total, kind="stable")
+    return hull.equations[first[order]]
 
 
 def build_scene(compiled, task):
