@@ -8,7 +8,8 @@ from the oracle's intermediate arrays:
 
   mass matrix          sum over bodies of m Jv^T Jv + Jw^T I Jw at the body's centre of mass, + armature
   bias forces          Lagrange: d/dt(M) v - 1/2 grad_q(v^T M v) + grad_q V, by central differences of the own M(q), V(q)
-  smooth forces        position servo kp (ctrl - q) - kv v clamped to the joint's actuatorfrcrange, joint damping
+  smooth forces        position servo kp (clamp(ctrl, joint range: inheritrange=1) - q) - kv v clamped to the joint's
+                       actuatorfrcrange, joint damping
   model constants      dof_invweight0 / body_invweight0 from the own M^-1 at qpos0
   constraint rows      joint limits and the contacts of the oracle's list (positions / frames / distances / geom ids only: the
                        geometry is checked by test_independent_pipeline.py): contact parameter mixing from the raw geom
@@ -25,25 +26,40 @@ import numpy as np
 import pytest
 from scipy.optimize import minimize
 
-from independent_scene import HI, LO, NB, NG, S, body_frames, quat_mat
+from independent_scene import HI, LO, NB, NG, body_frames, load_scene, quat_mat
 from oracle.oracle import Oracle
 
-NV, H, G = 12, float(S["timestep"]), 9.81
+S = load_scene("push")
+NCUBE, NV, NQ = 1, 12, 13
+H, G = float(S["timestep"]), 9.81
 IMPRATIO = float(S["impratio"])
 MINVAL, MINIMP, MAXIMP, MINMU = 1e-15, 1e-4, 0.9999, 1e-5
 ARM = S["joints"]  # armature, damping, frcrange lo hi, range lo hi
+DOF_INVW = BODY_INVW = None
+
+
+def use_scene(task):
+    """switch the module to another scene fixture (same arm; bodies 7.. = the free cubes)"""
+    global S, NCUBE, NV, NQ, H, IMPRATIO, ARM, DOF_INVW, BODY_INVW
+    S = load_scene(task)
+    NCUBE = int(S["ncube"])
+    NV, NQ = 6 + 6 * NCUBE, 6 + 7 * NCUBE
+    H, IMPRATIO, ARM = float(S["timestep"]), float(S["impratio"]), S["joints"]
+    DOF_INVW, BODY_INVW = invweights()
 
 
 # ------------------------------------------------------------------------------------------------ kinematics, M, bias
 def point_jacobian(qpos, body, point):
-    """(Jp, Jr) 3 x 12 of a world point attached to `body` (1..6 arm links, 0 = welded base, 7 = cube, -1 = world)"""
+    """(Jp, Jr) 3 x NV of a world point attached to `body` (1..6 arm links, 0 = welded base, 7.. = the cubes, -1 = world)"""
     Jp, Jr = np.zeros((3, NV)), np.zeros((3, NV))
-    if body == 7:
-        R = quat_mat(qpos[9:13])
-        Jp[:, 6:9] = np.eye(3)
+    if body >= 7:
+        c = body - 7
+        R = quat_mat(qpos[9 + 7 * c:13 + 7 * c])
+        d0 = 6 + 6 * c
+        Jp[:, d0:d0 + 3] = np.eye(3)
         for k in range(3):  # rotational dofs of a free joint are in the body frame
-            Jp[:, 9 + k] = np.cross(R[:, k], point - qpos[6:9])
-            Jr[:, 9 + k] = R[:, k]
+            Jp[:, d0 + 3 + k] = np.cross(R[:, k], point - qpos[6 + 7 * c:9 + 7 * c])
+            Jr[:, d0 + 3 + k] = R[:, k]
     elif body >= 1:
         _, p, axes = body_frames(qpos)
         for j in range(body):  # joint j moves bodies j + 1 .. 6 (a serial chain)
@@ -54,7 +70,7 @@ def point_jacobian(qpos, body, point):
 
 def mass_matrix(qpos):
     R, p, _ = body_frames(qpos)
-    M = np.diag(np.r_[ARM[:, 0], np.full(3, float(S["cube_mass"])), S["cube_diaginertia"]])
+    M = np.diag(np.r_[ARM[:, 0], np.concatenate([np.r_[np.full(3, S["cube_masses"][c]), S["cube_diaginertias"][c]] for c in range(NCUBE)])])
     for b in range(1, NB):
         ine = S["inertial"][b]
         com = p[b] + R[b] @ ine[0:3]
@@ -77,36 +93,39 @@ def bias_forces(qpos, qvel, eps=1e-6):
     v = qvel[:6]
     dM = []
     for k in range(6):
-        e = np.zeros(13)
+        e = np.zeros(NQ)
         e[k] = eps
         dM.append((mass_matrix(qpos + e)[:6, :6] - mass_matrix(qpos - e)[:6, :6]) / (2 * eps))
         c[k] = (potential(qpos + e) - potential(qpos - e)) / (2 * eps) - 0.5 * v @ dM[k] @ v
     c[:6] += sum(dM[k] * v[k] for k in range(6)) @ v
-    c[8] = float(S["cube_mass"]) * G
+    for cb in range(NCUBE):
+        c[6 + 6 * cb + 2] = float(S["cube_masses"][cb]) * G
     return c
 
 
 def smooth_acceleration(qpos, qvel, ctrl, M):
-    act = np.clip(float(S["act_kp"]) * (ctrl - qpos[:6]) - float(S["act_kv"]) * qvel[:6], ARM[:, 2], ARM[:, 3])
+    # <position ... inheritrange="1"/>: the actuator's ctrlrange is the joint's range, and ctrl is clamped to it
+    u = np.clip(ctrl, ARM[:, 4], ARM[:, 5])
+    act = np.clip(float(S["act_kp"]) * (u - qpos[:6]) - float(S["act_kv"]) * qvel[:6], ARM[:, 2], ARM[:, 3])
     f = -bias_forces(qpos, qvel)
     f[:6] += act - ARM[:, 1] * qvel[:6]
     return np.linalg.solve(M, f)
 
 
 def invweights():
-    """dof_invweight0 of the 6 hinges and body_invweight0 (translation, rotation) of bodies 0..7 at qpos0"""
-    q0 = np.r_[np.zeros(6), S["cube_pos0"], 1, 0, 0, 0]
+    """dof_invweight0 of the 6 hinges and body_invweight0 (translation, rotation) of bodies 0..6 and the cubes at qpos0"""
+    q0 = np.r_[np.zeros(6), np.concatenate([np.r_[S["cube_pos0s"][c], 1, 0, 0, 0] for c in range(NCUBE)])]
     Minv = np.linalg.inv(mass_matrix(q0))
     R, p, _ = body_frames(q0)
-    body = np.zeros((8, 2))
-    for b in range(1, 8):
-        com = q0[6:9] if b == 7 else p[b] + R[b] @ S["inertial"][b][0:3]
+    body = np.zeros((7 + NCUBE, 2))
+    for b in range(1, 7 + NCUBE):
+        com = q0[6 + 7 * (b - 7):9 + 7 * (b - 7)] if b >= 7 else p[b] + R[b] @ S["inertial"][b][0:3]
         Jp, Jr = point_jacobian(q0, b, com)
         body[b] = np.trace(Jp @ Minv @ Jp.T) / 3, np.trace(Jr @ Minv @ Jr.T) / 3
     return np.diag(Minv)[:6].copy(), body
 
 
-DOF_INVW, BODY_INVW = invweights()
+use_scene("push")
 
 
 # ------------------------------------------------------------------------------------------------ constraint rows
@@ -144,7 +163,7 @@ def stiffness_damping(solref, dmax):
 
 
 def geom_body(g):
-    return int(S["geom_body"][g]) if g < NG else (-1 if g == NG else 7)
+    return int(S["geom_body"][g]) if g < NG else (-1 if g == NG else 7 + (g - NG - 1))
 
 
 def constraint_rows(qpos, qvel, contacts):
@@ -225,25 +244,26 @@ def integrate(qpos, qvel, qacc, M):
     v = qvel + H * np.linalg.solve(M - H * np.diag(Dv), M @ qacc)
     q = qpos.copy()
     q[:6] += H * v[:6]
-    q[6:9] += H * v[6:9]
-    w = v[9:12]
-    ang = np.linalg.norm(w) * H
-    if ang > 0:
-        ax = w / np.linalg.norm(w)
-        dq = np.r_[np.cos(ang / 2), np.sin(ang / 2) * ax]
-        a0, b0 = qpos[9:13], dq
-        q[9:13] = np.r_[a0[0] * b0[0] - a0[1:] @ b0[1:], a0[0] * b0[1:] + b0[0] * a0[1:] + np.cross(a0[1:], b0[1:])]
-        q[9:13] /= np.linalg.norm(q[9:13])
+    for c in range(NCUBE):
+        p0, d0 = 6 + 7 * c, 6 + 6 * c
+        q[p0:p0 + 3] += H * v[d0:d0 + 3]
+        w = v[d0 + 3:d0 + 6]
+        ang = np.linalg.norm(w) * H
+        if ang > 0:
+            ax = w / np.linalg.norm(w)
+            a0, b0 = qpos[p0 + 3:p0 + 7], np.r_[np.cos(ang / 2), np.sin(ang / 2) * ax]
+            q[p0 + 3:p0 + 7] = np.r_[a0[0] * b0[0] - a0[1:] @ b0[1:], a0[0] * b0[1:] + b0[0] * a0[1:] + np.cross(a0[1:], b0[1:])]
+            q[p0 + 3:p0 + 7] /= np.linalg.norm(q[p0 + 3:p0 + 7])
     return q, v
 
 
 # ------------------------------------------------------------------------------------------------ states
-def harvested_states():
+def harvested_states(task):
     """mid-episode states of oracle rollouts with random actions, and constructed contact-rich ones"""
     rng = np.random.default_rng(17)
     out = []
     for seed in range(4):
-        o = Oracle("push")
+        o = Oracle(task)
         o.reset(seed=seed)
         for t in range(18):
             o.step(rng.uniform(-1, 1, o.na).astype(np.float32))
@@ -251,7 +271,7 @@ def harvested_states():
                 st = o.get_state()
                 out.append((st["qpos"], st["qvel"], st["ctrl"]))
     for k in range(10):
-        q = np.zeros(13)
+        q = np.zeros(NQ)
         q[:6] = rng.uniform(LO, HI)
         if k % 2:
             q[1], q[2] = rng.uniform(0.8, 1.22), rng.uniform(1.0, 1.74)  # arm in the floor
@@ -261,14 +281,20 @@ def harvested_states():
         q[6:9] = p[rng.integers(4, 7)] + rng.uniform(-0.03, 0.03, 3) if k % 3 else [rng.uniform(-0.1, 0.1), rng.uniform(0.1, 0.25), 0.013]
         quat = rng.normal(size=4)
         q[9:13] = quat / np.linalg.norm(quat)
+        if NCUBE == 2:  # the second cube on / inside / beside the first (cube-cube contacts)
+            q[13:16] = q[6:9] + rng.uniform(-0.02, 0.02, 3) + [0, 0, 0.02 * (k % 2)]
+            quat = rng.normal(size=4)
+            q[16:20] = quat / np.linalg.norm(quat) if k % 3 else q[9:13]
         out.append((q, rng.normal(scale=0.5, size=NV), rng.uniform(LO, HI)))
     return out
 
 
-def test_one_substep_from_an_independent_restatement():
-    checked = rows_checked = cone_states = limit_rows = 0
-    for qpos, qvel, ctrl in harvested_states():
-        o = Oracle("push")
+@pytest.mark.parametrize("task", ["push", "stack"])
+def test_one_substep_from_an_independent_restatement(task):
+    use_scene(task)
+    checked = rows_checked = cone_states = limit_rows = cube_cube = 0
+    for qpos, qvel, ctrl in harvested_states(task):
+        o = Oracle(task)
         o.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, warm=np.zeros(NV))
         o.forward()
         d = o.diag()
@@ -289,6 +315,7 @@ def test_one_substep_from_an_independent_restatement():
             np.testing.assert_allclose(o.get("efc_aref"), aref, rtol=1e-8, atol=1e-7)
             for c, (dim, mu, fr) in zip(con, units):
                 assert int(c[13]) == dim and abs(c[16] - mu) < 1e-12 * max(1, mu) and np.allclose(c[17:22], fr, rtol=1e-12)
+                cube_cube += min(int(c[14]), int(c[15])) > NG
             rows_checked += nefc
             limit_rows += nlim
         # (3) the oracle's qacc is a stationary point and a minimiser of the own objective (own a0: the oracle's agrees to 1e-6)
@@ -312,3 +339,4 @@ def test_one_substep_from_an_independent_restatement():
         np.testing.assert_allclose(st["qpos"], q1, rtol=0, atol=1e-11)
         checked += 1
     assert checked >= 20 and rows_checked >= 300 and cone_states >= 10 and limit_rows >= 1, (checked, rows_checked, cone_states, limit_rows)
+    assert task != "stack" or cube_cube >= 8, cube_cube

@@ -119,7 +119,10 @@ def main(assets, task="push"):
     cube = cubes[0]
     floor = next(g for g in scene.find("worldbody").iter("geom") if g.get("name") == "floor")  # (PushCubeLoop wraps it in a jointless body)
     geom_par.append(contact_params(dict(floor.attrib)))              # geom 20: the floor plane
-    geom_par.append(contact_params(dict(cube.find("geom").attrib)))  # geom 21: the cube
+    for b in cubes:                                                   # geoms 21..: the cubes, then the static walls
+        geom_par.append(contact_params(dict(b.find("geom").attrib)))
+    for g in walls:
+        geom_par.append(contact_params(dict(g.attrib)))
     cine = cube.find("inertial")
     act = resolved("position", "follower", {})
     # <option>: the include is expanded in place, so follower.xml's <option> comes after push_cube.xml's and wins where both set
@@ -136,6 +139,9 @@ def main(assets, task="push"):
         cube_half=vec(cube.find("geom").get("size"), 3), body_names=np.array(names),
         ncube=len(cubes), box_half=np.stack([vec(b.find("geom").get("size"), 3) for b in cubes] + [vec(g.get("size"), 3) for g in walls]),
         wall_pos=np.stack([vec(g.get("pos"), 3) for g in walls]) if walls else np.zeros((0, 3)),
+        cube_masses=np.array([float(b.find("inertial").get("mass")) for b in cubes]),
+        cube_diaginertias=np.stack([vec(b.find("inertial").get("diaginertia"), 3) for b in cubes]),
+        cube_pos0s=np.stack([vec(b.get("pos"), 3) for b in cubes]),
         inertial=np.stack(inertial), joints=np.stack(joints), geom_par=np.array(geom_par), cube_mass=float(cine.get("mass")),
         cube_diaginertia=vec(cine.get("diaginertia"), 3), cube_pos0=vec(cube.get("pos"), 3), act_kp=float(act["kp"]), act_kv=float(act["kv"]),
         timestep=float(opt["timestep"]), impratio=float(opt["impratio"]), site_pos=vec(arm.find("worldbody").find(".//site").get("pos"), 3))
