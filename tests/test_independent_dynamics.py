@@ -138,7 +138,9 @@ def mix(g1, g2):
     else:
         mixw = a[12] / (a[12] + b[12])
         fr, dim = np.maximum(a[0:3], b[0:3]), int(max(a[3], b[3]))
-        solref, solimp = mixw * a[5:7] + (1 - mixw) * b[5:7], mixw * a[7:12] + (1 - mixw) * b[7:12]
+        # solref: weighted like solimp when both are in the (timeconst, dampratio) form, otherwise the element-wise minimum
+        solref = mixw * a[5:7] + (1 - mixw) * b[5:7] if a[5] > 0 and b[5] > 0 else np.minimum(a[5:7], b[5:7])
+        solimp = mixw * a[7:12] + (1 - mixw) * b[7:12]
     fr = np.maximum(MINMU, fr)
     return np.array([fr[0], fr[0], fr[1], fr[2], fr[2]]), dim, solref, solimp
 
@@ -158,12 +160,16 @@ def impedance(solimp, dist):
 
 
 def stiffness_damping(solref, dmax):
+    if solref[0] <= 0:  # direct form (-stiffness, -damping); PushCubeLoop's floor has solref = "0 0": no reference acceleration at all
+        return -solref[0] / max(MINVAL, dmax * dmax), -solref[1] / max(MINVAL, dmax)
     tc, dr = max(solref[0], 2 * H), solref[1]  # refsafe
     return 1 / max(MINVAL, dmax * dmax * tc * tc * dr * dr), 2 / max(MINVAL, dmax * tc)
 
 
 def geom_body(g):
-    return int(S["geom_body"][g]) if g < NG else (-1 if g == NG else 7 + (g - NG - 1))
+    if g < NG:
+        return int(S["geom_body"][g])
+    return 7 + (g - NG - 1) if NG < g <= NG + NCUBE else -1  # the floor and the static walls belong to the world
 
 
 def constraint_rows(qpos, qvel, contacts):
@@ -281,6 +287,9 @@ def harvested_states(task):
         q[6:9] = p[rng.integers(4, 7)] + rng.uniform(-0.03, 0.03, 3) if k % 3 else [rng.uniform(-0.1, 0.1), rng.uniform(0.1, 0.25), 0.013]
         quat = rng.normal(size=4)
         q[9:13] = quat / np.linalg.norm(quat)
+        if task == "push_loop" and k % 2 == 0:  # the cube against / inside one of the rails
+            wl = rng.integers(0, 4)
+            q[6:9] = S["wall_pos"][wl] + rng.uniform(-1, 1, 3) * (S["box_half"][1 + wl] + 0.01) + [0, 0, 0.008]
         if NCUBE == 2:  # the second cube on / inside / beside the first (cube-cube contacts)
             q[13:16] = q[6:9] + rng.uniform(-0.02, 0.02, 3) + [0, 0, 0.02 * (k % 2)]
             quat = rng.normal(size=4)
@@ -289,10 +298,10 @@ def harvested_states(task):
     return out
 
 
-@pytest.mark.parametrize("task", ["push", "stack"])
+@pytest.mark.parametrize("task", ["push", "stack", "push_loop"])
 def test_one_substep_from_an_independent_restatement(task):
     use_scene(task)
-    checked = rows_checked = cone_states = limit_rows = cube_cube = 0
+    checked = rows_checked = cone_states = limit_rows = cube_cube = wall_rows = 0
     for qpos, qvel, ctrl in harvested_states(task):
         o = Oracle(task)
         o.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, warm=np.zeros(NV))
@@ -316,6 +325,7 @@ def test_one_substep_from_an_independent_restatement(task):
             for c, (dim, mu, fr) in zip(con, units):
                 assert int(c[13]) == dim and abs(c[16] - mu) < 1e-12 * max(1, mu) and np.allclose(c[17:22], fr, rtol=1e-12)
                 cube_cube += min(int(c[14]), int(c[15])) > NG
+                wall_rows += max(int(c[14]), int(c[15])) > NG + NCUBE
             rows_checked += nefc
             limit_rows += nlim
         # (3) the oracle's qacc is a stationary point and a minimiser of the own objective (own a0: the oracle's agrees to 1e-6)
@@ -340,3 +350,4 @@ def test_one_substep_from_an_independent_restatement(task):
         checked += 1
     assert checked >= 20 and rows_checked >= 300 and cone_states >= 10 and limit_rows >= 1, (checked, rows_checked, cone_states, limit_rows)
     assert task != "stack" or cube_cube >= 8, cube_cube
+    assert task != "push_loop" or wall_rows >= 8, wall_rows
