@@ -1961,8 +1961,10 @@ __global__ void __launch_bounds__(32, 16) k_ph_end(const DevModel<T>* __restrict
   __syncwarp();
   if (moved(w)) { redo_push(redo, env); return; }  // a substep outgrew the fast workspace: redone over the big one
   const DevModel<T>& m = *dm;
-  if (w.redo_forward) forward(w, m, verts);
-  integrate(w, m);
+  if (m.n_substeps > 0) {  // the integration of the last substep (with n_substeps == 0 there is none: mj_step was never called)
+    if (w.redo_forward) forward(w, m, verts);
+    integrate(w, m);
+  }
   env_step_end(w, m, io, env);
   store_state(w, s, env);
 }

@@ -394,6 +394,37 @@ def test_big_path_in_the_ee_action_mode_is_bitwise_identical_across_begin_varian
         e.close()
 
 
+@pytest.mark.parametrize("n_substeps", [0, 3])
+def test_phased_graph_replay_with_changing_buffers_and_odd_substep_counts(n_substeps, monkeypatch):
+    """The phased step is replayed as a CUDA graph that is re-captured when the caller's output pointers change, and its side
+    streams are sized by n_substeps: alternate between two record buffers and a None record, with 0 and 3 substeps per step
+    (the reference-glue fixtures use n_substeps=0), against the fused kernel and against the chain launched without a graph."""
+    n = 300
+    mk = lambda em: glr.make("PickPlaceCube-v0", num_envs=n, action_mode="ee", exec_mode=em, n_substeps=n_substeps, autoreset=True, max_episode_steps=4)
+    a_env, b_env = mk("fused"), mk("phased")
+    monkeypatch.setenv("LCR_GRAPH", "0")
+    c_env = mk("phased")
+    monkeypatch.delenv("LCR_GRAPH")
+    for e in (a_env, b_env, c_env):
+        e.reset(seed=9)
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    bufs = [torch.empty(n, b_env.obs_dim + 4, device="cuda") for _ in range(2)]
+    for t in range(9):
+        a = torch.rand(n, a_env.action_dim, generator=gen, device="cuda") * 2 - 1
+        ref = a_env.step_packed(a).clone()
+        if t % 3 == 2:
+            obs, rew, te, tr, su = b_env.step_flat(a)  # no record at all: another graph key
+            assert torch.equal(obs, ref[:, :b_env.obs_dim]) and torch.equal(rew, ref[:, b_env.obs_dim])
+        else:
+            assert torch.equal(b_env.step_packed(a, out=bufs[t % 2]), ref), t
+        assert torch.equal(c_env.step_packed(a), ref), t
+    sa, sb, sc = a_env.get_state(), b_env.get_state(), c_env.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]) and torch.equal(sa[k], sc[k]), k
+    for e in (a_env, b_env, c_env):
+        e.close()
+
+
 def test_f64_big_path_matches_the_oracle():
     """float64 kernels against the oracle on the same beyond-the-caps states, ONE mj_step (the comparison that is well posed in
     deeply interpenetrating poses, see test_f64_one_substep_map_from_random_states).  Envs with more than 96 constraint rows
