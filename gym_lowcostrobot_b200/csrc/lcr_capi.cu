@@ -418,6 +418,7 @@ int lcr_create(const LcrModel* model, const double* hull_verts, const LcrEnvCfg*
     return fail("lcr_create: static wall boxes are the four rails of the PushCubeLoop scene (one cube)");
   if (precision != LCR_F32 && precision != LCR_F64) return fail("lcr_create: precision must be LCR_F32 or LCR_F64");
   if (cfg->exec_mode < 0 || cfg->exec_mode > 3) return fail("lcr_create: exec_mode must be 0 (fused), 1 (phased), 2 (lockstep) or 3 (flow)");
+  if (cfg->exec_mode == 3 && cfg->n_substeps < 1) return fail("lcr_create: the flow mode needs n_substeps >= 1 (its phase queues always run the first substep)");
   int ndev = 0;
   CUDA_OK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail("lcr_create: no such CUDA device");
