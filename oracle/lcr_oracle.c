@@ -17,9 +17,11 @@
  * (with stand-ins for the two absent third-party packages and n_substeps=0) and records reset sampling, action maps,
  * IK iterations, observations, rewards, success flags and PushCubeLoop's goal switching; tests/test_reference_glue.py
  * replays those fixtures through this file (to 1e-9) and through the CUDA path.
- * (2) is pinned by analytic known-answer tests (tests/test_oracle_known_answers.py, incl. an independent numpy
- * restatement of the kinematics / inertia and Lagrangian finite differences), not by MuJoCo outputs.
- * tools/dump_mujoco_golden.py produces MuJoCo golden vectors wherever MuJoCo exists.
+ * (2) is pinned by analytic known-answer tests (tests/test_oracle_known_answers.py) and by a second, structurally independent
+ * numpy restatement built from the raw MJCF numbers by a separate reader (tests/test_independent_pipeline.py: the contact
+ * SET by brute force; tests/test_independent_dynamics.py: one mj_step on all three scene classes), not by MuJoCo outputs.
+ * tools/dump_mujoco_golden.py produces MuJoCo fixtures wherever MuJoCo exists; tests/test_golden_mujoco.py compares this
+ * file and the CUDA path with them and reports which of the named switches (orc_set_switch) repair a differing step.
  *
  * Plain C99, one environment per OrcSim, scalar double arithmetic.
  */
